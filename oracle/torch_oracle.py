@@ -1,0 +1,428 @@
+"""TEST INFRASTRUCTURE ONLY — CPU restatement of the Frido sampling hot path.
+
+A dependency-free, functional, plain-PyTorch fp32 restatement of the
+reference algorithm (SURVEY.md §8a rows a1–a16).  It is the CHECKER for the
+CUDA path and the `cpu_baseline` ("port") leg of bench.py; it is never on the
+product path (frido_b200/ does not import oracle/).
+
+Parity pin: the reference has no tests or golden vectors ("parity unpinned" by
+the reference itself).  This restatement is instead pinned
+against OUTPUTS OF THE REFERENCE ITSELF, run in the build container by
+oracle/make_golden.py and committed under tests/golden/ (see
+tests/test_oracle_golden.py).
+
+Everything works on a flat state dict with the reference's own key names; the
+network structure is recovered from the keys, not from the reference's
+constructors.  All `file:line` citations are into /root/reference.
+"""
+import math
+import re
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+# --------------------------------------------------------------------------
+# small helpers
+# --------------------------------------------------------------------------
+
+
+def _has(sd, key):
+    return key in sd
+
+
+def _conv(x, sd, p, stride=1, padding=1):
+    return F.conv2d(x, sd[p + ".weight"], sd.get(p + ".bias"), stride=stride, padding=padding)
+
+
+def _linear(x, sd, p):
+    return F.linear(x, sd[p + ".weight"], sd.get(p + ".bias"))
+
+
+def _gn(x, sd, p, eps):
+    return F.group_norm(x, 32, sd[p + ".weight"], sd[p + ".bias"], eps)
+
+
+def _ln(x, sd, p):
+    return F.layer_norm(x, (x.shape[-1],), sd[p + ".weight"], sd[p + ".bias"], 1e-5)
+
+
+def _norm(x, cond, sd, p, eps):
+    """GroupNorm32 (util.py:214, eps 1e-5) / Normalize (attention.py:76, eps 1e-6),
+    optionally wrapped in SPADE (spade_norm.py:44-60)."""
+    if _has(sd, p + ".param_free_norm.weight"):
+        normalized = _gn(x, sd, p + ".param_free_norm", eps)
+        if cond is None:
+            return normalized  # spade_norm.py:45-46
+        c = F.interpolate(cond, size=x.shape[2:], mode="nearest")  # :52
+        actv = F.relu(_conv(c, sd, p + ".mlp_shared.0"))  # :37-40,53
+        gamma = _conv(actv, sd, p + ".mlp_gamma")  # :54
+        beta = _conv(actv, sd, p + ".mlp_beta")  # :55
+        return normalized * (1 + gamma) + beta  # :58
+    return _gn(x, sd, p, eps)
+
+
+# --------------------------------------------------------------------------
+# a7: timestep / stage embedding  (util.py:151-171, pyunet.py:561-565,882-896)
+# --------------------------------------------------------------------------
+
+
+def timestep_embedding(t, dim, max_period=10000):
+    half = dim // 2
+    freqs = torch.exp(-math.log(max_period) * torch.arange(half, dtype=torch.float32) / half)
+    args = t[:, None].float() * freqs[None]
+    emb = torch.cat([torch.cos(args), torch.sin(args)], dim=-1)
+    if dim % 2:
+        emb = torch.cat([emb, torch.zeros_like(emb[:, :1])], dim=-1)
+    return emb
+
+
+def unet_emb(sd, pre, t, stage):
+    mc = sd[pre + "time_embed.0.weight"].shape[1]
+    emb = _linear(timestep_embedding(t, mc), sd, pre + "time_embed.0")
+    emb = _linear(F.silu(emb), sd, pre + "time_embed.2")
+    if _has(sd, pre + "stage_emb.weight"):
+        emb = emb + sd[pre + "stage_emb.weight"][stage][None]  # pyunet.py:890-896
+    return emb
+
+
+# --------------------------------------------------------------------------
+# a8: ResBlock / Upsample / Downsample  (pyunet.py:94-163, 262-300)
+# --------------------------------------------------------------------------
+
+
+def resblock(x, emb, cond, sd, p):
+    h = _norm(x, cond, sd, p + ".in_layers.0", 1e-5)
+    h = _conv(F.silu(h), sd, p + ".in_layers.2")
+    h = h + _linear(F.silu(emb), sd, p + ".emb_layers.1")[:, :, None, None]  # :280-293
+    h = _norm(h, cond, sd, p + ".out_layers.0", 1e-5)
+    h = _conv(F.silu(h), sd, p + ".out_layers.3")
+    if _has(sd, p + ".skip_connection.weight"):
+        w = sd[p + ".skip_connection.weight"]
+        x = F.conv2d(x, w, sd[p + ".skip_connection.bias"], padding=w.shape[-1] // 2)
+    return x + h  # :300
+
+
+# --------------------------------------------------------------------------
+# a10/a11: SpatialTransformer / CrossAttention / GEGLU  (attention.py)
+# --------------------------------------------------------------------------
+
+
+def cross_attention(x, ctx, sd, p):
+    """attention.py:170-193; legacy=True => 1 head, d_head = inner dim."""
+    q = F.linear(x, sd[p + ".to_q.weight"])
+    ctx = x if ctx is None else ctx
+    k = F.linear(ctx, sd[p + ".to_k.weight"])
+    v = F.linear(ctx, sd[p + ".to_v.weight"])
+    scale = q.shape[-1] ** -0.5
+    sim = torch.einsum("bid,bjd->bij", q, k) * scale  # :180
+    attn = sim.softmax(dim=-1)
+    out = torch.einsum("bij,bjd->bid", attn, v)
+    return _linear(out, sd, p + ".to_out.0")
+
+
+def transformer_block(x, ctx, sd, p):
+    x = cross_attention(_ln(x, sd, p + ".norm1"), None, sd, p + ".attn1") + x  # :224
+    x = cross_attention(_ln(x, sd, p + ".norm2"), ctx, sd, p + ".attn2") + x  # :225
+    h = _linear(_ln(x, sd, p + ".norm3"), sd, p + ".ff.net.0.proj")  # GEGLU :37-44
+    a, g = h.chunk(2, dim=-1)
+    h = a * F.gelu(g)
+    return _linear(h, sd, p + ".ff.net.2") + x  # :226
+
+
+def spatial_transformer(x, ctx, cond, sd, p):
+    b, c, hh, ww = x.shape
+    x_in = x
+    x = _norm(x, cond, sd, p + ".norm", 1e-6)  # attention.py:292-296
+    x = _conv(x, sd, p + ".proj_in", padding=0)
+    x = x.permute(0, 2, 3, 1).reshape(b, hh * ww, -1)
+    d = 0
+    while _has(sd, f"{p}.transformer_blocks.{d}.norm1.weight"):
+        x = transformer_block(x, ctx, sd, f"{p}.transformer_blocks.{d}")
+        d += 1
+    x = x.reshape(b, hh, ww, -1).permute(0, 3, 1, 2)
+    return _conv(x, sd, p + ".proj_out", padding=0) + x_in
+
+
+# --------------------------------------------------------------------------
+# a6: PyUNetModel.forward  (pyunet.py:867-950)
+# --------------------------------------------------------------------------
+
+
+def _seq(x, emb, ctx, cond, sd, p):
+    """TimestepEmbedSequential (pyunet.py:75-91); layer kinds recovered from keys."""
+    j = 0
+    while True:
+        q = f"{p}.{j}"
+        if _has(sd, q + ".in_layers.2.weight"):
+            x = resblock(x, emb, cond, sd, q)
+        elif _has(sd, q + ".proj_in.weight"):
+            x = spatial_transformer(x, ctx, cond, sd, q)
+        elif _has(sd, q + ".op.weight"):  # Downsample :152-156 (stride 2, pad 1)
+            x = _conv(x, sd, q + ".op", stride=2, padding=1)
+        elif _has(sd, q + ".conv.weight"):  # Upsample :119-121
+            x = _conv(F.interpolate(x, scale_factor=2, mode="nearest"), sd, q + ".conv")
+        elif _has(sd, q + ".weight"):  # bare conv (pre_input blocks)
+            x = _conv(x, sd, q)
+        else:
+            return x
+        j += 1
+
+
+def _count(sd, pat):
+    r = re.compile(pat)
+    idx = {int(m.group(1)) for k in sd for m in [r.match(k)] if m}
+    return max(idx) + 1 if idx else 0
+
+
+def unet_forward(sd, x, t, context, stage, split, pre="model.diffusion_model.", spade=True):
+    """x: [B, sum(split[:stage+1]), H, W] NCHW; returns eps for group `stage`."""
+    emb = unet_emb(sd, pre, t, stage)
+    cond_ch = sum(split[:stage]) if spade else 0  # :900-904
+    in_ch = sum(split[: stage + 1])
+    h_cond = x[:, :cond_ch]
+    h = x[:, cond_ch:in_ch]
+    h = _seq(h, emb, context, None, sd, f"{pre}pre_input_blocks.{stage}")
+    if cond_ch:
+        h_cond = _seq(h_cond, emb, context, None, sd, f"{pre}pre_input_cond_blocks.{stage - 1}")
+    else:
+        h_cond = None
+    hs = [h]
+    n_in = _count(sd, re.escape(pre) + r"input_blocks\.(\d+)\.")
+    n_out = _count(sd, re.escape(pre) + r"output_blocks\.(\d+)\.")
+    for i in range(n_in):
+        h = _seq(h, emb, context, h_cond, sd, f"{pre}input_blocks.{i}")
+        hs.append(h)
+    h = _seq(h, emb, context, h_cond, sd, f"{pre}middle_block")
+    for i in range(n_out):
+        h = torch.cat([h, hs.pop()], dim=1)  # :939
+        h = _seq(h, emb, context, h_cond, sd, f"{pre}output_blocks.{i}")
+    o = f"{pre}out.{stage}"
+    return _conv(F.silu(_gn(h, sd, o + ".0", 1e-5)), sd, o + ".2")  # :947
+
+
+# --------------------------------------------------------------------------
+# a1: schedules  (util.py:21-25,46-74; frido.py:127-147; ddim.py:25-54)
+# --------------------------------------------------------------------------
+
+
+def alphas_cumprod(timesteps=1000, linear_start=0.0015, linear_end=0.0155):
+    betas = torch.linspace(linear_start**0.5, linear_end**0.5, timesteps, dtype=torch.float64).numpy() ** 2
+    return np.cumprod(1.0 - betas, axis=0)  # fp64; the reference stores fp32 (frido.py:147)
+
+
+def ddim_schedule(S, eta, acp_fp32, T=1000):
+    """Returns dict of per-index fp32 scalars exactly as p_sample_ddim reads them
+    (ddim.py:233-240): a_t, a_prev, sigma_t, sqrt_one_minus_at."""
+    c = T // S
+    ts = np.asarray(list(range(0, T, c))) + 1  # util.py:46-60
+    acp = acp_fp32.astype(np.float32)
+    alphas = acp[ts]  # fp32 values (util.py:65 indexes the fp32 buffer moved to cpu)
+    alphas_prev = np.asarray([acp[0]] + acp[ts[:-1]].tolist())  # fp64 array of fp32 values
+    # util.py:69 mixes an fp64 ndarray (alphas_prev) with an fp32 tensor (alphas): `1 - alphas`
+    # is evaluated in fp32, and `ndarray / tensor` dispatches to Tensor.__rtruediv__ =
+    # other * self.reciprocal(), i.e. an fp32 reciprocal promoted to fp64.
+    recip = (np.float32(1.0) / (np.float32(1.0) - alphas)).astype(np.float64)
+    sigmas = eta * np.sqrt((1 - alphas_prev) * recip * (1 - alphas.astype(np.float64) / alphas_prev))
+    sqrt_1m = np.sqrt(1.0 - alphas)  # fp32 (ddim.py:50 on an fp32 tensor)
+    return dict(
+        timesteps=ts,
+        a_t=alphas.astype(np.float32),
+        a_prev=alphas_prev.astype(np.float32),
+        sigma=sigmas.astype(np.float32),
+        sqrt_1m=sqrt_1m.astype(np.float32),
+    )
+
+
+# --------------------------------------------------------------------------
+# a3/a4: DDIM / PLMS update  (ddim.py:189-273, plms.py:196-303)
+# --------------------------------------------------------------------------
+
+
+def ddim_update(x, e_t, sch, index, start, noise=None, temperature=1.0):
+    """x: [B, end, H, W]; e_t: [B, end-start, H, W] (active group only).
+    Returns (x_prev, pred_x0) with groups < start frozen."""
+    f32 = lambda v: torch.tensor(float(v), dtype=torch.float32)
+    a_t, a_prev = f32(sch["a_t"][index]), f32(sch["a_prev"][index])
+    sigma, s1m = f32(sch["sigma"][index]), f32(sch["sqrt_1m"][index])
+    e = torch.cat([torch.zeros_like(x[:, :start]), e_t], dim=1)  # ddim.py:200-202
+    pred_x0 = (x - s1m * e) / a_t.sqrt()  # :243
+    pred_x0[:, :start] = x[:, :start]  # :246
+    dir_xt = (1.0 - a_prev - sigma**2).sqrt() * e  # :258
+    nz = sigma * (noise if noise is not None else torch.zeros_like(x)) * temperature
+    x_prev = a_prev.sqrt() * pred_x0 + dir_xt + nz  # :263
+    x_prev[:, :start] = pred_x0[:, :start]  # :266
+    return x_prev, pred_x0
+
+
+def plms_eps_prime(e_t, old_eps, e_t_next=None):
+    """plms.py:285-299."""
+    if len(old_eps) == 0:
+        return (e_t + e_t_next) / 2
+    if len(old_eps) == 1:
+        return (3 * e_t - old_eps[-1]) / 2
+    if len(old_eps) == 2:
+        return (23 * e_t - 16 * old_eps[-1] + 5 * old_eps[-2]) / 12
+    return (55 * e_t - 59 * old_eps[-1] + 37 * old_eps[-2] - 9 * old_eps[-3]) / 24
+
+
+def stage_snap(img, start, end, n):
+    """ddim.py:177-185: avg_pool2d(2) n times then nearest x2 n times on one group."""
+    tmp = img[:, start:end].clone()
+    for _ in range(n):
+        tmp = F.avg_pool2d(tmp, 2, 2)
+    for _ in range(n):
+        tmp = F.interpolate(tmp, scale_factor=2, mode="nearest")
+    img = img.clone()
+    img[:, start:end] = tmp
+    return img
+
+
+def cfg_combine(e_c, e_u, scale):
+    return e_u + scale * (e_c - e_u)  # ddim.py:226
+
+
+def sample(sd, split, context, x_init, S, eta=0.0, sampler="ddim", noises=None, uc=None, cfg_scale=1.0,
+           acp=None, spade=True, steps_limit=None, trace=None):
+    """a2: DDIMSampler.ddim_sampling / PLMSSampler.plms_sampling (ddim.py:117-186,
+    plms.py:117-194) with the start noise injected (x_init = the tensor the
+    reference draws at ddim.py:128).  steps_limit truncates every stage to its
+    first N steps (test economy); trace, if a list, receives (stage, index, x_prev, pred_x0, eps)."""
+    if acp is None:
+        acp = alphas_cumprod()
+    sch = ddim_schedule(S, eta, acp.astype(np.float32))
+    time_range = np.flip(sch["timesteps"])
+    total = len(time_range)
+    B = x_init.shape[0]
+    num_stage = len(split)
+    img = None
+    k = 0
+    for s in range(num_stage):
+        start, end = sum(split[:s]), sum(split[: s + 1])
+        img = x_init[:, :end].clone() if s == 0 else torch.cat([img, x_init[:, start:end]], dim=1)
+        old_eps = []
+
+        def model_out(xx, tt):
+            e = unet_forward(sd, xx, tt, context, s, split, spade=spade)
+            if cfg_scale != 1.0:
+                e_u = unet_forward(sd, xx, tt, uc, s, split, spade=spade)
+                e = cfg_combine(e, e_u, cfg_scale)
+            return e
+
+        for i, step in enumerate(time_range):
+            if steps_limit is not None and i >= steps_limit:
+                break
+            index = total - i - 1
+            ts = torch.full((B,), int(step), dtype=torch.long)
+            nz = None if noises is None else noises[k]
+            k += 1
+            e_t = model_out(img, ts)
+            if sampler == "ddim":
+                img, pred_x0 = ddim_update(img, e_t, sch, index, start, nz)
+            else:
+                if len(old_eps) == 0:
+                    x_prev, _ = ddim_update(img, e_t, sch, index, start, nz)
+                    t_next = torch.full((B,), int(time_range[min(i + 1, total - 1)]), dtype=torch.long)
+                    e_next = model_out(x_prev, t_next)
+                    e_p = plms_eps_prime(e_t, old_eps, e_next)
+                else:
+                    e_p = plms_eps_prime(e_t, old_eps)
+                img, pred_x0 = ddim_update(img, e_p, sch, index, start, nz)
+                old_eps.append(e_t)
+                if len(old_eps) >= 4:
+                    old_eps.pop(0)
+            if trace is not None:
+                trace.append((s, index, img.clone(), pred_x0.clone(), e_t.clone()))
+        if num_stage != 1:
+            img = stage_snap(img, start, end, num_stage - s - 1)
+    return img
+
+
+# --------------------------------------------------------------------------
+# a14: VectorQuantizer2.forward  (quantize.py:267-308)
+# --------------------------------------------------------------------------
+
+
+def vq_lookup(z, codebook):
+    """z: [B,C,H,W]; returns (z_q NCHW, indices int64 [B*H*W])."""
+    zp = z.permute(0, 2, 3, 1).contiguous()
+    zf = zp.view(-1, codebook.shape[1])
+    d = (
+        torch.sum(zf**2, dim=1, keepdim=True)
+        + torch.sum(codebook**2, dim=1)
+        - 2 * torch.einsum("bd,dn->bn", zf, codebook.t())
+    )  # :276-278
+    idx = torch.argmin(d, dim=1)  # :280 (first minimum)
+    z_q = codebook[idx].view(zp.shape)
+    z_q = zp + (z_q - zp)  # :294 straight-through rounding
+    return z_q.permute(0, 3, 1, 2).contiguous(), idx
+
+
+# --------------------------------------------------------------------------
+# a15: taming Decoder  (taming/modules/diffusionmodules/model.py:38-53,78-192,548-649)
+# --------------------------------------------------------------------------
+
+
+def _t_resblock(x, sd, p):
+    h = _conv(F.silu(_gn(x, sd, p + ".norm1", 1e-6)), sd, p + ".conv1")
+    h = _conv(F.silu(_gn(h, sd, p + ".norm2", 1e-6)), sd, p + ".conv2")
+    if _has(sd, p + ".nin_shortcut.weight"):
+        x = _conv(x, sd, p + ".nin_shortcut", padding=0)
+    elif _has(sd, p + ".conv_shortcut.weight"):
+        x = _conv(x, sd, p + ".conv_shortcut")
+    return x + h
+
+
+def _t_attn(x, sd, p):
+    h = _gn(x, sd, p + ".norm", 1e-6)
+    q, k, v = (_conv(h, sd, f"{p}.{n}", padding=0) for n in "qkv")
+    b, c, hh, ww = q.shape
+    q = q.reshape(b, c, hh * ww).permute(0, 2, 1)
+    k = k.reshape(b, c, hh * ww)
+    w_ = torch.bmm(q, k) * (int(c) ** (-0.5))  # :179-180
+    w_ = F.softmax(w_, dim=2)
+    v = v.reshape(b, c, hh * ww)
+    h = torch.bmm(v, w_.permute(0, 2, 1)).reshape(b, c, hh, ww)
+    return x + _conv(h, sd, p + ".proj_out", padding=0)
+
+
+def decoder_forward(sd, z, pre="first_stage_model.decoder."):
+    h = _conv(z, sd, pre + "conv_in")
+    h = _t_resblock(h, sd, pre + "mid.block_1")
+    h = _t_attn(h, sd, pre + "mid.attn_1")
+    h = _t_resblock(h, sd, pre + "mid.block_2")
+    n_lvl = _count(sd, re.escape(pre) + r"up\.(\d+)\.")
+    for lvl in reversed(range(n_lvl)):
+        j = 0
+        while _has(sd, f"{pre}up.{lvl}.block.{j}.conv1.weight"):
+            h = _t_resblock(h, sd, f"{pre}up.{lvl}.block.{j}")
+            if _has(sd, f"{pre}up.{lvl}.attn.{j}.q.weight"):
+                h = _t_attn(h, sd, f"{pre}up.{lvl}.attn.{j}")
+            j += 1
+        if lvl != 0:
+            h = _conv(F.interpolate(h, scale_factor=2.0, mode="nearest"), sd, f"{pre}up.{lvl}.upsample.conv")
+    h = F.silu(_gn(h, sd, pre + "norm_out", 1e-6))
+    return _conv(h, sd, pre + "conv_out")
+
+
+# --------------------------------------------------------------------------
+# a12/a13: decode_first_stage + VQModelInterface.decode (frido.py:823-891, msvqgan.py:376-399)
+# --------------------------------------------------------------------------
+
+
+def decode_first_stage(sd, z, embed_dim, scale_factor, pre="first_stage_model."):
+    z = z.clone()
+    start = 0
+    for i, e in enumerate(embed_dim):  # frido.py:832-838
+        z[:, start : start + e] *= 1.0 / scale_factor[i]
+        start += e
+    quants, codes = [], []
+    start = 0
+    for i, e in enumerate(embed_dim):
+        q, idx = vq_lookup(z[:, start : start + e], sd[f"{pre}ms_quantize.{i}.embedding.weight"])
+        quants.append(q)
+        codes.append(idx.reshape(z.shape[0], -1))
+        start += e
+    quant = torch.cat(quants[::-1], dim=1)  # msvqgan.py:392-393 (fine -> coarse)
+    quant = _conv(quant, sd, pre + "post_quant_conv", padding=0)
+    return decoder_forward(sd, quant, pre + "decoder."), codes

@@ -1,0 +1,101 @@
+"""Pins oracle/torch_oracle.py (the CPU restatement) against outputs of the
+UNMODIFIED reference, generated in the build container by oracle/make_golden.py
+(the reference itself has no tests or golden vectors — SURVEY.md §4)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import synth
+from oracle import torch_oracle as O
+
+torch.set_grad_enabled(False)
+TOL = 2e-5  # same algorithm, same fp32 CPU kernels; only op-order differences
+
+
+def _load(golden_dir, name):
+    p = os.path.join(golden_dir, name)
+    if not os.path.exists(p):
+        pytest.skip(f"{name} not generated")
+    return torch.load(p, weights_only=False)
+
+
+def test_schedule_tables(golden_dir):
+    g = _load(golden_dir, "sched.pt")
+    acp = O.alphas_cumprod()
+    assert np.array_equal(acp.astype(np.float32), g["alphas_cumprod"].numpy())
+    for S in (200, 250, 100, 50, 4):
+        for eta in (0.0, 1.0):
+            ref = g[f"S{S}_eta{eta}"]
+            sch = O.ddim_schedule(S, eta, acp.astype(np.float32))
+            assert np.array_equal(sch["timesteps"], ref["timesteps"].numpy())
+            tab = np.stack([sch["a_t"], sch["a_prev"], sch["sigma"], sch["sqrt_1m"]], 1)
+            # bit-exact: these scalars feed every step
+            assert np.array_equal(tab, ref["table"].numpy()), (S, eta)
+
+
+@pytest.mark.parametrize("tag", ["tiny2", "tiny3"])
+def test_tiny_model_vs_reference(golden_dir, tag):
+    g = _load(golden_dir, f"{tag}.pt")
+    sd = synth.synth_state_dict(g["manifest"], g["seed"])
+    split, B = g["split"], g["B"]
+    ns = len(split)
+    C = sum(split)
+    ctx = synth.synth_input("ctx", (B, 5, 24), 1)
+    uc = synth.synth_input("uc", (B, 5, 24), 2)
+    for s in range(ns):
+        x = synth.synth_input(f"x{s}", (B, 3 * (s + 1), 8, 8), 4)
+        for t in (996, 1):
+            e = O.unet_forward(sd, x, torch.full((B,), t, dtype=torch.long), ctx, s, split)
+            assert (e - g[f"eps_s{s}_t{t}"]).abs().max() < TOL
+    tr = []
+    out = O.sample(sd, split, ctx, g["ddim4_xinit"], 4, trace=tr)
+    assert (out - g["ddim4_out"]).abs().max() < 1e-4
+    assert (tr[0][2] - g["ddim4_xinter1"]).abs().max() < 1e-4
+    assert (tr[0][3] - g["ddim4_predx0_1"]).abs().max() < 2e-3  # /sqrt(a_t): ~x30 amplification at t=751
+    noises = [synth.synth_input(f"nz{k}", (B, C, 8, 8), 5) for k in range(4 * ns)]
+    noises_s = []
+    for s in range(ns):
+        for i in range(4):
+            noises_s.append(noises[s * 4 + i][:, : sum(split[: s + 1])])
+    out = O.sample(sd, split, ctx, g["ddim4e_xinit"], 4, eta=0.7, noises=noises_s)
+    assert (out - g["ddim4e_out"]).abs().max() < 1e-4
+    out = O.sample(sd, split, ctx, g["plms5_xinit"], 5, sampler="plms")
+    assert (out - g["plms5_out"]).abs().max() < 1e-4
+    out = O.sample(sd, split, ctx, g["cfg2_xinit"], 2, uc=uc, cfg_scale=1.5)
+    assert (out - g["cfg2_out"]).abs().max() < 1e-4
+    out = O.sample(sd, split, ctx, g["plmscfg4_xinit"], 4, sampler="plms", uc=uc, cfg_scale=1.5)
+    assert (out - g["plmscfg4_out"]).abs().max() < 1e-4
+    # decode: indices bit-exact, image close
+    for zk, ik, ck in (("ddim4_out", "dec_img", "dec_codes"), ("dec2_z", "dec2_img", "dec2_codes")):
+        img, codes = O.decode_first_stage(sd, g[zk], split, g["scale_factor"].tolist())
+        for a, b in zip(codes, g[ck]):
+            assert torch.equal(a, b)
+        assert (img - g[ik]).abs().max() < 1e-4
+
+
+@pytest.mark.slow
+def test_full_size_l2i_unet_step_and_decoder(golden_dir):
+    """BASELINE config 1: single DDIM step on the full-size 511 M-parameter
+    UNet at a 32x32 latent, plus the full-size f8f4 decoder."""
+    g = _load(golden_dir, "l2i32.pt")
+    sd = synth.synth_state_dict(g["manifest"], g["seed"])
+    ctx = synth.synth_input("ctx", (1, 26, 640), 1)
+    acp = O.alphas_cumprod().astype(np.float32)
+    sch = O.ddim_schedule(200, 0.0, acp)
+    for s in (0, 1):
+        x = synth.synth_input(f"x{s}", (1, 3 * (s + 1), 32, 32), 2)
+        for t in (996, 1):
+            e = O.unet_forward(sd, x, torch.full((1,), t, dtype=torch.long), ctx, s, [3, 3])
+            assert (e - g[f"eps_s{s}_t{t}"]).abs().max() < 5e-5
+            if t == 996:
+                xp, p0 = O.ddim_update(x, e, sch, 199, 3 * s)
+                assert (xp - g[f"step_s{s}_xprev"]).abs().max() < 1e-5
+                assert (p0 - g[f"step_s{s}_predx0"]).abs().max() < 2e-3
+    del sd
+    sd = synth.synth_state_dict(g["dec_manifest"], g["seed"])
+    img, codes = O.decode_first_stage(sd, g["dec_z"], [3, 3], g["scale_factor"].tolist())
+    for a, b in zip(codes, g["dec_codes"]):
+        assert torch.equal(a, b)
+    assert (img - g["dec_img"]).abs().max() < 1e-4
