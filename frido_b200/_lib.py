@@ -1,0 +1,157 @@
+"""ctypes binding of libfrido_b200.so (include/frido_b200.h).
+
+There is NO fallback: if the shared library is missing or a launcher returns an
+error the caller gets an exception.  The structures below mirror the header
+field for field; `frido_sizeof_op()` is checked at load time.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libfrido_b200.so")
+
+c_f = C.c_float
+c_i = C.c_int32
+c_l = C.c_int64
+c_p = C.c_void_p
+
+ACT_NONE, ACT_RELU, ACT_SILU, ACT_GEGLU = 0, 1, 2, 3
+(OP_CONV, OP_GN_STATS, OP_NORM_ACT, OP_LAYERNORM, OP_SOFTMAX, OP_TIME_EMBED, OP_STEP_BEGIN, OP_UPDATE, OP_SNAP, OP_VQ,
+ OP_ZERO) = range(1, 12)
+
+
+class ConvParams(C.Structure):
+    _fields_ = [
+        ("a0", c_p), ("a1", c_p), ("c0", c_i), ("c1", c_i),
+        ("a0_sb", c_l), ("a0_sy", c_l), ("a0_sx", c_l), ("a0_sc", c_l),
+        ("a1_sb", c_l), ("a1_sy", c_l), ("a1_sx", c_l), ("a1_sc", c_l),
+        ("B", c_i), ("Hin", c_i), ("Win", c_i), ("ups", c_i),
+        ("ksize", c_i), ("stride", c_i), ("pad", c_i), ("Hout", c_i), ("Wout", c_i),
+        ("w", c_p), ("w_sb", c_l), ("w_ld", c_l), ("Cout", c_i),
+        ("bias", c_p), ("rowvec", c_p), ("rowvec_sb", c_l), ("res", c_p),
+        ("alpha", c_f), ("act", c_i), ("out", c_p),
+        ("o_sb", c_l), ("o_sp", c_l), ("o_sn", c_l), ("round_tf32", c_i), ("engine", c_i),
+    ]
+
+
+class GnStatsParams(C.Structure):
+    _fields_ = [("a0", c_p), ("a1", c_p), ("c0", c_i), ("c1", c_i), ("B", c_i), ("HW", c_i), ("groups", c_i),
+                ("sums", c_p)]
+
+
+class NormActParams(C.Structure):
+    _fields_ = [("a0", c_p), ("a1", c_p), ("c0", c_i), ("c1", c_i), ("B", c_i), ("HW", c_i), ("groups", c_i),
+                ("sums", c_p), ("eps", c_f), ("gamma", c_p), ("beta", c_p), ("gb", c_p), ("silu", c_i),
+                ("round_tf32", c_i), ("out", c_p)]
+
+
+class LayerNormParams(C.Structure):
+    _fields_ = [("x", c_p), ("rows", c_l), ("C", c_i), ("eps", c_f), ("gamma", c_p), ("beta", c_p),
+                ("round_tf32", c_i), ("out", c_p)]
+
+
+class SoftmaxParams(C.Structure):
+    _fields_ = [("s", c_p), ("rows", c_l), ("n", c_i), ("ld", c_l), ("scale", c_f), ("round_tf32", c_i), ("out", c_p)]
+
+
+class TimeEmbedParams(C.Structure):
+    _fields_ = [("t", c_p), ("B", c_i), ("dim", c_i), ("max_period", c_f), ("out", c_p)]
+
+
+class StepBeginParams(C.Structure):
+    _fields_ = [("step", c_p), ("t_table", c_p), ("use_next", c_i), ("T", c_i), ("ts", c_p), ("B", c_i)]
+
+
+class UpdateParams(C.Structure):
+    _fields_ = [
+        ("x", c_p), ("eps", c_p), ("eps_uncond", c_p), ("cfg_scale", c_f),
+        ("B", c_i), ("c_start", c_i), ("c_end", c_i), ("HW", c_i),
+        ("coef", c_p), ("step", c_p), ("advance", c_i), ("plms_order", c_i), ("plms_mode", c_i),
+        ("hist", c_p), ("eps_save", c_p), ("noise", c_p), ("seed", C.c_uint64), ("seed_dev", c_p), ("temperature", c_f),
+        ("x_prev", c_p), ("x_dup", c_p), ("pred_x0", c_p),
+    ]
+
+
+class SnapParams(C.Structure):
+    _fields_ = [("x", c_p), ("B", c_i), ("C", c_i), ("H", c_i), ("W", c_i), ("c_start", c_i), ("c_end", c_i), ("n", c_i)]
+
+
+class VqParams(C.Structure):
+    _fields_ = [("z", c_p), ("B", c_i), ("C_total", c_i), ("HW", c_i), ("c_start", c_i), ("e_dim", c_i),
+                ("scale_factor", c_f), ("codebook", c_p), ("n_e", c_i), ("out", c_p), ("out_C", c_i),
+                ("out_coff", c_i), ("indices", c_p)]
+
+
+class ZeroParams(C.Structure):
+    _fields_ = [("ptr", c_p), ("nbytes", c_l)]
+
+
+class _OpU(C.Union):
+    _fields_ = [("conv", ConvParams), ("gn_stats", GnStatsParams), ("norm_act", NormActParams),
+                ("layernorm", LayerNormParams), ("softmax", SoftmaxParams), ("time_embed", TimeEmbedParams),
+                ("step_begin", StepBeginParams), ("update", UpdateParams), ("snap", SnapParams), ("vq", VqParams),
+                ("zero", ZeroParams)]
+
+
+class Op(C.Structure):
+    _fields_ = [("kind", c_i), ("tag", c_i), ("u", _OpU)]
+
+
+_KIND_FIELD = {OP_CONV: "conv", OP_GN_STATS: "gn_stats", OP_NORM_ACT: "norm_act", OP_LAYERNORM: "layernorm",
+               OP_SOFTMAX: "softmax", OP_TIME_EMBED: "time_embed", OP_STEP_BEGIN: "step_begin", OP_UPDATE: "update",
+               OP_SNAP: "snap", OP_VQ: "vq", OP_ZERO: "zero"}
+
+EXPORTS = [
+    "frido_conv2d", "frido_gn_stats", "frido_norm_act", "frido_layernorm", "frido_softmax", "frido_time_embed",
+    "frido_step_begin", "frido_sampler_update", "frido_stage_snap", "frido_vq_lookup", "frido_zero",
+    "frido_round_tf32", "frido_run_program", "frido_abi_version", "frido_sizeof_op", "frido_last_error",
+    "frido_launch_count", "frido_check_device",
+]
+
+_lib = None
+
+
+class FridoError(RuntimeError):
+    pass
+
+
+def lib():
+    """Load (once) and return the shared library; raises if it is not built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise FridoError(
+            f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(make -C frido_b200/csrc). There is no CPU or PyTorch fallback."
+        )
+    L = C.CDLL(LIB_PATH)
+    for name in EXPORTS:
+        if not hasattr(L, name):
+            raise FridoError(f"{LIB_PATH} does not export {name}")
+    L.frido_last_error.restype = C.c_char_p
+    L.frido_launch_count.restype = C.c_int64
+    L.frido_run_program.argtypes = [C.c_void_p, c_i, c_p]
+    L.frido_zero.argtypes = [c_p, c_l, c_p]
+    L.frido_round_tf32.argtypes = [c_p, c_p, c_l, c_p]
+    for name in ("frido_conv2d", "frido_gn_stats", "frido_norm_act", "frido_layernorm", "frido_softmax",
+                 "frido_time_embed", "frido_step_begin", "frido_sampler_update", "frido_stage_snap", "frido_vq_lookup"):
+        getattr(L, name).argtypes = [c_p, c_p]
+    if L.frido_sizeof_op() != C.sizeof(Op):
+        raise FridoError(f"ABI mismatch: sizeof(FridoOp) C={L.frido_sizeof_op()} python={C.sizeof(Op)}")
+    _lib = L
+    return L
+
+
+def check(rc, what=""):
+    if rc != 0:
+        msg = lib().frido_last_error().decode(errors="replace")
+        raise FridoError(f"{what} failed (rc={rc}): {msg}")
+
+
+def make_op(kind, params, tag=0):
+    op = Op()
+    op.kind = kind
+    op.tag = tag
+    setattr(op.u, _KIND_FIELD[kind], params)
+    return op

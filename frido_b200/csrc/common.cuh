@@ -1,0 +1,53 @@
+// Shared helpers for the frido_b200 CUDA library (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/frido_b200.h"
+
+namespace frido {
+
+extern char g_last_error[512];
+extern long long g_launch_count;
+
+inline int set_error(int code, const char* msg) {
+  snprintf(g_last_error, sizeof(g_last_error), "%s", msg);
+  return code;
+}
+
+inline int check_launch(const char* what) {
+  ++g_launch_count;
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    snprintf(g_last_error, sizeof(g_last_error), "%s: %s", what, cudaGetErrorString(e));
+    return FRIDO_E_LAUNCH;
+  }
+  return FRIDO_OK;
+}
+
+__device__ __forceinline__ float round_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+
+__device__ __forceinline__ float silu_f(float v) { return v / (1.0f + __expf(-v)); }
+// exact-erf GELU (attention.py:44 F.gelu default)
+__device__ __forceinline__ float gelu_erf(float v) { return 0.5f * v * (1.0f + erff(v * 0.70710678118654752440f)); }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+int conv2d_simt(const FridoConvParams* p, cudaStream_t s);
+int conv2d_tc(const FridoConvParams* p, cudaStream_t s);
+
+}  // namespace frido

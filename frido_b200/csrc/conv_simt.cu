@@ -1,0 +1,213 @@
+// SIMT fp32 implicit-GEMM engine: every conv / linear / batched matmul shape the
+// path has, exact fp32 FFMA accumulation.  It carries the odd shapes the tcgen05
+// engine does not take (C_in = 3/6, C_out = 3, K tails, NCHW latents in/out)
+// and is the numerical yardstick for the tensor-core engine.
+//
+// out[b,p,n] = act(alpha * sum_k A(b,p,k) W[n,k] + bias[n] + rowvec[b,n] + res[b,p,n])
+// k = tap * Cin + c ; tap = dy*ksize+dx ; A gathers from up to two channel-
+// concatenated NHWC (or arbitrarily strided) sources.
+#include "common.cuh"
+
+namespace frido {
+
+constexpr int BM = 64, BN = 64, BK = 16, NT = 256;
+
+struct ALoad {
+  float v[4];
+};
+
+template <bool VEC_A, bool VEC_W>
+__global__ void __launch_bounds__(NT) conv_simt_kernel(const FridoConvParams p) {
+  __shared__ __align__(16) float As[2][BK][BM + 4];
+  __shared__ __align__(16) float Ws[2][BK][BN + 4];
+
+  const int tid = threadIdx.x;
+  const int b = blockIdx.z;
+  const int m0 = blockIdx.x * BM;
+  const int n0 = blockIdx.y * BN;
+  const int HWout = p.Hout * p.Wout;
+  const int Cin = p.c0 + p.c1;
+  const int taps = p.ksize * p.ksize;
+  const int Ktot = taps * Cin;
+
+  // loader role: one (row, 4 consecutive k) per thread for A and for W
+  const int lrow = tid >> 2;        // 0..63
+  const int lk = (tid & 3) * 4;     // 0,4,8,12
+  const int pm = m0 + lrow;
+  const bool m_ok = pm < HWout;
+  const int oy = m_ok ? pm / p.Wout : 0;
+  const int ox = m_ok ? pm - oy * p.Wout : 0;
+  const int Hl = p.Hin * p.ups, Wl = p.Win * p.ups;  // logical (post-upsample) input grid
+  const int ush = p.ups == 2 ? 1 : 0;
+  const float* __restrict__ a0 = p.a0 + (int64_t)b * p.a0_sb;
+  const float* __restrict__ a1 = p.a1 ? p.a1 + (int64_t)b * p.a1_sb : nullptr;
+  const int wn = n0 + lrow;
+  const bool n_ok = wn < p.Cout;
+  const float* __restrict__ wrow = p.w + (int64_t)b * p.w_sb + (int64_t)(n_ok ? wn : 0) * (p.w_ld ? p.w_ld : (int64_t)Ktot);
+
+  auto load_a = [&](int k0, float (&v)[4]) {
+    const int k = k0 + lk;
+    v[0] = v[1] = v[2] = v[3] = 0.f;
+    if (!m_ok || k >= Ktot) return;
+    if (VEC_A) {
+      const int tap = k / Cin;
+      const int c = k - tap * Cin;
+      const int dy = tap / p.ksize, dx = tap - dy * p.ksize;
+      const int iy = oy * p.stride + dy - p.pad, ix = ox * p.stride + dx - p.pad;
+      if (iy < 0 || iy >= Hl || ix < 0 || ix >= Wl) return;
+      const int sy = iy >> ush, sx = ix >> ush;
+      const float* src = (c < p.c0) ? a0 + (int64_t)sy * p.a0_sy + (int64_t)sx * p.a0_sx + c
+                                    : a1 + (int64_t)sy * p.a1_sy + (int64_t)sx * p.a1_sx + (c - p.c0);
+      const float4 t = __ldg(reinterpret_cast<const float4*>(src));
+      v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int kk = k + j;
+        if (kk >= Ktot) break;
+        const int tap = kk / Cin;
+        const int c = kk - tap * Cin;
+        const int dy = tap / p.ksize, dx = tap - dy * p.ksize;
+        const int iy = oy * p.stride + dy - p.pad, ix = ox * p.stride + dx - p.pad;
+        if (iy < 0 || iy >= Hl || ix < 0 || ix >= Wl) continue;
+        const int sy = iy >> ush, sx = ix >> ush;
+        v[j] = (c < p.c0) ? __ldg(a0 + (int64_t)sy * p.a0_sy + (int64_t)sx * p.a0_sx + (int64_t)c * p.a0_sc)
+                          : __ldg(a1 + (int64_t)sy * p.a1_sy + (int64_t)sx * p.a1_sx + (int64_t)(c - p.c0) * p.a1_sc);
+      }
+    }
+  };
+  auto load_w = [&](int k0, float (&v)[4]) {
+    const int k = k0 + lk;
+    v[0] = v[1] = v[2] = v[3] = 0.f;
+    if (!n_ok || k >= Ktot) return;
+    if (VEC_W) {
+      const float4 t = __ldg(reinterpret_cast<const float4*>(wrow + k));
+      v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (k + j < Ktot) v[j] = __ldg(wrow + k + j);
+    }
+  };
+
+  // compute role: 4x4 micro-tile
+  const int tx = tid & 15, ty = tid >> 4;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  float ra[4], rw[4];
+  load_a(0, ra);
+  load_w(0, rw);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    As[0][lk + j][lrow] = ra[j];
+    Ws[0][lk + j][lrow] = rw[j];
+  }
+  __syncthreads();
+
+  const int nk = (Ktot + BK - 1) / BK;
+  for (int kt = 0; kt < nk; ++kt) {
+    const int cur = kt & 1;
+    if (kt + 1 < nk) {
+      load_a((kt + 1) * BK, ra);
+      load_w((kt + 1) * BK, rw);
+    }
+#pragma unroll
+    for (int k = 0; k < BK; ++k) {
+      const float4 av = *reinterpret_cast<const float4*>(&As[cur][k][ty * 4]);
+      const float4 wv = *reinterpret_cast<const float4*>(&Ws[cur][k][tx * 4]);
+      const float a[4] = {av.x, av.y, av.z, av.w};
+      const float w[4] = {wv.x, wv.y, wv.z, wv.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], w[j], acc[i][j]);
+    }
+    if (kt + 1 < nk) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        As[cur ^ 1][lk + j][lrow] = ra[j];
+        Ws[cur ^ 1][lk + j][lrow] = rw[j];
+      }
+    }
+    __syncthreads();
+  }
+
+  // epilogue
+  float* __restrict__ out = p.out + (int64_t)b * p.o_sb;
+  const float* __restrict__ res = p.res ? p.res + (int64_t)b * p.o_sb : nullptr;
+  const float* __restrict__ rv = p.rowvec ? p.rowvec + (int64_t)b * p.rowvec_sb : nullptr;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int pmo = m0 + ty * 4 + i;
+    if (pmo >= HWout) continue;
+    float v[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + tx * 4 + j;
+      float t = acc[i][j] * p.alpha;
+      if (n < p.Cout) {
+        if (p.bias) t += __ldg(p.bias + n);
+        if (rv) t += __ldg(rv + n);
+      }
+      v[j] = t;
+    }
+    if (p.act == FRIDO_ACT_GEGLU) {
+#pragma unroll
+      for (int j = 0; j < 4; j += 2) {
+        const int n = n0 + tx * 4 + j;
+        if (n + 1 < p.Cout) {
+          const int no = n >> 1;
+          float t = v[j] * gelu_erf(v[j + 1]);
+          const int64_t o = (int64_t)pmo * p.o_sp + (int64_t)no * p.o_sn;
+          if (res) t += res[o];
+          out[o] = p.round_tf32 ? round_tf32(t) : t;
+        }
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int n = n0 + tx * 4 + j;
+        if (n < p.Cout) {
+          float t = v[j];
+          const int64_t o = (int64_t)pmo * p.o_sp + (int64_t)n * p.o_sn;
+          if (res) t += res[o];
+          if (p.act == FRIDO_ACT_RELU) t = fmaxf(t, 0.f);
+          else if (p.act == FRIDO_ACT_SILU) t = silu_f(t);
+          out[o] = p.round_tf32 ? round_tf32(t) : t;
+        }
+      }
+    }
+  }
+}
+
+static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+int conv2d_simt(const FridoConvParams* p, cudaStream_t s) {
+  if (!p || !p->a0 || !p->w || !p->out) return set_error(FRIDO_E_ARG, "conv2d: null pointer");
+  if (p->B <= 0 || p->Hout <= 0 || p->Wout <= 0 || p->Cout <= 0 || p->c0 <= 0 || p->c1 < 0)
+    return set_error(FRIDO_E_ARG, "conv2d: bad shape");
+  if ((p->c1 > 0) != (p->a1 != nullptr)) return set_error(FRIDO_E_ARG, "conv2d: a1/c1 mismatch");
+  if (p->ups != 1 && p->ups != 2) return set_error(FRIDO_E_ARG, "conv2d: ups must be 1 or 2");
+  if (p->ksize != 1 && p->ksize != 3) return set_error(FRIDO_E_ARG, "conv2d: ksize must be 1 or 3");
+  if (p->act == FRIDO_ACT_GEGLU && (p->Cout & 1)) return set_error(FRIDO_E_ARG, "conv2d: GEGLU needs even Cout");
+  const int Cin = p->c0 + p->c1;
+  const int64_t Ktot = (int64_t)p->ksize * p->ksize * Cin;
+  bool vecA = (Cin % 4 == 0) && (p->c0 % 4 == 0) && p->a0_sc == 1 && aligned16(p->a0) && p->a0_sb % 4 == 0 &&
+              p->a0_sy % 4 == 0 && p->a0_sx % 4 == 0;
+  if (p->a1)
+    vecA = vecA && p->a1_sc == 1 && aligned16(p->a1) && p->a1_sb % 4 == 0 && p->a1_sy % 4 == 0 && p->a1_sx % 4 == 0;
+  const bool vecW = (Ktot % 4 == 0) && aligned16(p->w) && (p->w_sb % 4 == 0) && (p->w_ld % 4 == 0);
+  dim3 grid((p->Hout * p->Wout + BM - 1) / BM, (p->Cout + BN - 1) / BN, p->B);
+  if (grid.y > 65535 || grid.z > 65535) return set_error(FRIDO_E_ARG, "conv2d: grid too large");
+  if (vecA && vecW) conv_simt_kernel<true, true><<<grid, NT, 0, s>>>(*p);
+  else if (vecA) conv_simt_kernel<true, false><<<grid, NT, 0, s>>>(*p);
+  else if (vecW) conv_simt_kernel<false, true><<<grid, NT, 0, s>>>(*p);
+  else conv_simt_kernel<false, false><<<grid, NT, 0, s>>>(*p);
+  return check_launch("conv2d_simt");
+}
+
+}  // namespace frido

@@ -1,0 +1,325 @@
+// HBM-bound row/group kernels of the path: GroupNorm statistics, the fused
+// normalise(+SPADE)(+SiLU) pass, LayerNorm, row softmax and the sinusoidal
+// timestep embedding.  All NHWC fp32, float4 accesses, one pass over the data
+// per kernel (softmax: three cached passes over one row).
+#include "common.cuh"
+
+namespace frido {
+
+// ----------------------------------------------------------------------------
+// GroupNorm statistics: fp32 per-thread partials over a pixel chunk, fp64
+// shared + global atomics for the cross-thread reduction.
+// ----------------------------------------------------------------------------
+constexpr int GN_THREADS = 256;
+constexpr int GN_MAXQPT = 4;  // quads (float4) of one pixel owned by one thread: C <= 4096
+
+__global__ void __launch_bounds__(GN_THREADS) gn_stats_kernel(const FridoGnStatsParams p, int pix_per_cta) {
+  __shared__ double s_sum[64], s_sq[64];
+  const int C = p.c0 + p.c1;
+  const int Q = C >> 2;
+  const int cg = C / p.groups;
+  const int b = blockIdx.y;
+  const int tid = threadIdx.x;
+  if (tid < p.groups) { s_sum[tid] = 0.0; s_sq[tid] = 0.0; }
+  __syncthreads();
+  const int Qe = Q < GN_THREADS ? Q : GN_THREADS;  // quads covered per pixel pass
+  const int PL = GN_THREADS / Qe;                  // pixel lanes
+  const int pl = tid / Qe, ql = tid - pl * Qe;
+  const int pix0 = blockIdx.x * pix_per_cta;
+  const int pix1 = min(pix0 + pix_per_cta, p.HW);
+  float s[GN_MAXQPT][4], ss[GN_MAXQPT][4];
+#pragma unroll
+  for (int j = 0; j < GN_MAXQPT; ++j)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) s[j][e] = ss[j][e] = 0.f;
+  if (pl < PL) {
+    const float* a0 = p.a0 + (int64_t)b * p.HW * p.c0;
+    const float* a1 = p.a1 ? p.a1 + (int64_t)b * p.HW * p.c1 : nullptr;
+    for (int pix = pix0 + pl; pix < pix1; pix += PL) {
+#pragma unroll
+      for (int j = 0; j < GN_MAXQPT; ++j) {
+        const int q = ql + j * GN_THREADS;
+        if (q < Q) {
+          const int c = q << 2;
+          const float4 v = (c < p.c0) ? __ldg(reinterpret_cast<const float4*>(a0 + (int64_t)pix * p.c0 + c))
+                                      : __ldg(reinterpret_cast<const float4*>(a1 + (int64_t)pix * p.c1 + (c - p.c0)));
+          s[j][0] += v.x; ss[j][0] += v.x * v.x;
+          s[j][1] += v.y; ss[j][1] += v.y * v.y;
+          s[j][2] += v.z; ss[j][2] += v.z * v.z;
+          s[j][3] += v.w; ss[j][3] += v.w * v.w;
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < GN_MAXQPT; ++j) {
+      const int q = ql + j * GN_THREADS;
+      if (q < Q) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int g = ((q << 2) + e) / cg;
+          atomicAdd(&s_sum[g], (double)s[j][e]);
+          atomicAdd(&s_sq[g], (double)ss[j][e]);
+        }
+      }
+    }
+  }
+  __syncthreads();
+  if (tid < p.groups) {
+    double* o = p.sums + ((int64_t)b * p.groups + tid) * 2;
+    atomicAdd(o, s_sum[tid]);
+    atomicAdd(o + 1, s_sq[tid]);
+  }
+}
+
+static int gn_chunk(int B, int HW) {
+  // aim for >= ~4 CTAs per SM overall, at least 16 pixels per CTA
+  int target = (148 * 4 + B - 1) / B;
+  int ppc = (HW + target - 1) / target;
+  if (ppc < 16) ppc = 16;
+  return ppc;
+}
+
+// ----------------------------------------------------------------------------
+// normalise + affine (+SPADE) (+SiLU)
+// ----------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) norm_act_kernel(const FridoNormActParams p, int pix_per_cta) {
+  __shared__ float s_mean[64], s_rstd[64];
+  const int C = p.c0 + p.c1;
+  const int Q = C >> 2;
+  const int cg = C / p.groups;
+  const int b = blockIdx.y;
+  if (threadIdx.x < p.groups) {
+    const double* sm = p.sums + ((int64_t)b * p.groups + threadIdx.x) * 2;
+    const double cnt = (double)cg * (double)p.HW;
+    const double mean = sm[0] / cnt;
+    double var = sm[1] / cnt - mean * mean;
+    if (var < 0.0) var = 0.0;
+    s_mean[threadIdx.x] = (float)mean;
+    s_rstd[threadIdx.x] = (float)(1.0 / sqrt(var + (double)p.eps));
+  }
+  __syncthreads();
+  const int pix0 = blockIdx.x * pix_per_cta;
+  const int pix1 = min(pix0 + pix_per_cta, p.HW);
+  const int64_t n = (int64_t)(pix1 - pix0) * Q;
+  const float* a0 = p.a0 + (int64_t)b * p.HW * p.c0;
+  const float* a1 = p.a1 ? p.a1 + (int64_t)b * p.HW * p.c1 : nullptr;
+  const float* gb = p.gb ? p.gb + (int64_t)b * p.HW * 2 * C : nullptr;
+  float* out = p.out + (int64_t)b * p.HW * C;
+  for (int64_t e = threadIdx.x; e < n; e += blockDim.x) {
+    const int pix = pix0 + (int)(e / Q);
+    const int c = ((int)(e % Q)) << 2;
+    const float4 xv = (c < p.c0) ? __ldg(reinterpret_cast<const float4*>(a0 + (int64_t)pix * p.c0 + c))
+                                 : __ldg(reinterpret_cast<const float4*>(a1 + (int64_t)pix * p.c1 + (c - p.c0)));
+    const float4 gm = __ldg(reinterpret_cast<const float4*>(p.gamma + c));
+    const float4 bt = __ldg(reinterpret_cast<const float4*>(p.beta + c));
+    float x[4] = {xv.x, xv.y, xv.z, xv.w};
+    const float g4[4] = {gm.x, gm.y, gm.z, gm.w};
+    const float b4[4] = {bt.x, bt.y, bt.z, bt.w};
+    float sg[4] = {0, 0, 0, 0}, sb[4] = {0, 0, 0, 0};
+    if (gb) {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(gb + (int64_t)pix * 2 * C + c));
+      const float4 d = __ldg(reinterpret_cast<const float4*>(gb + (int64_t)pix * 2 * C + C + c));
+      sg[0] = a.x; sg[1] = a.y; sg[2] = a.z; sg[3] = a.w;
+      sb[0] = d.x; sb[1] = d.y; sb[2] = d.z; sb[3] = d.w;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int g = (c + j) / cg;
+      float y = (x[j] - s_mean[g]) * s_rstd[g] * g4[j] + b4[j];
+      if (gb) y = y * (1.0f + sg[j]) + sb[j];
+      if (p.silu) y = silu_f(y);
+      x[j] = p.round_tf32 ? round_tf32(y) : y;
+    }
+    *reinterpret_cast<float4*>(out + (int64_t)pix * C + c) = make_float4(x[0], x[1], x[2], x[3]);
+  }
+}
+
+// ----------------------------------------------------------------------------
+// LayerNorm: one warp per row, row cached in registers (C <= 1024), two-pass var
+// ----------------------------------------------------------------------------
+constexpr int LN_MAXQ = 8;
+__global__ void __launch_bounds__(256) layernorm_kernel(const FridoLayerNormParams p) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= p.rows) return;
+  const int Q = p.C >> 2;
+  const float* x = p.x + (int64_t)warp * p.C;
+  float4 v[LN_MAXQ];
+  float s = 0.f;
+#pragma unroll
+  for (int j = 0; j < LN_MAXQ; ++j) {
+    const int q = lane + j * 32;
+    if (q < Q) {
+      v[j] = __ldg(reinterpret_cast<const float4*>(x) + q);
+      s += (v[j].x + v[j].y) + (v[j].z + v[j].w);
+    }
+  }
+  const float mean = warp_sum(s) / (float)p.C;
+  float ss = 0.f;
+#pragma unroll
+  for (int j = 0; j < LN_MAXQ; ++j) {
+    const int q = lane + j * 32;
+    if (q < Q) {
+      const float a = v[j].x - mean, b = v[j].y - mean, c = v[j].z - mean, d = v[j].w - mean;
+      ss += (a * a + b * b) + (c * c + d * d);
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(ss) / (float)p.C + p.eps);
+  float* out = p.out + (int64_t)warp * p.C;
+#pragma unroll
+  for (int j = 0; j < LN_MAXQ; ++j) {
+    const int q = lane + j * 32;
+    if (q < Q) {
+      const float4 g = __ldg(reinterpret_cast<const float4*>(p.gamma) + q);
+      const float4 b = __ldg(reinterpret_cast<const float4*>(p.beta) + q);
+      float4 o;
+      o.x = (v[j].x - mean) * rstd * g.x + b.x;
+      o.y = (v[j].y - mean) * rstd * g.y + b.y;
+      o.z = (v[j].z - mean) * rstd * g.z + b.z;
+      o.w = (v[j].w - mean) * rstd * g.w + b.w;
+      if (p.round_tf32) { o.x = round_tf32(o.x); o.y = round_tf32(o.y); o.z = round_tf32(o.z); o.w = round_tf32(o.w); }
+      reinterpret_cast<float4*>(out)[q] = o;
+    }
+  }
+}
+
+// ----------------------------------------------------------------------------
+// Row softmax.  n <= 1024: one warp per row; else one CTA per row.
+// ----------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) softmax_warp_kernel(const FridoSoftmaxParams p) {
+  const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= p.rows) return;
+  const float* s = p.s + row * p.ld;
+  float* o = p.out + row * p.ld;
+  float m = -INFINITY;
+  for (int j = lane; j < p.n; j += 32) m = fmaxf(m, s[j] * p.scale);
+  m = warp_max(m);
+  float sum = 0.f;
+  for (int j = lane; j < p.n; j += 32) sum += __expf(s[j] * p.scale - m);
+  sum = warp_sum(sum);
+  const float inv = 1.0f / sum;
+  for (int j = lane; j < p.n; j += 32) {
+    const float v = __expf(s[j] * p.scale - m) * inv;
+    o[j] = p.round_tf32 ? round_tf32(v) : v;
+  }
+}
+
+__global__ void __launch_bounds__(256) softmax_cta_kernel(const FridoSoftmaxParams p) {
+  __shared__ float red[8];
+  __shared__ float bc;
+  const int64_t row = blockIdx.x;
+  const float* s = p.s + row * p.ld;
+  float* o = p.out + row * p.ld;
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const int n4 = p.n >> 2;
+  float m = -INFINITY;
+  for (int j = tid; j < n4; j += 256) {
+    const float4 v = reinterpret_cast<const float4*>(s)[j];
+    m = fmaxf(m, fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w)) * p.scale);
+  }
+  for (int j = (n4 << 2) + tid; j < p.n; j += 256) m = fmaxf(m, s[j] * p.scale);
+  m = warp_max(m);
+  if (lane == 0) red[w] = m;
+  __syncthreads();
+  if (tid == 0) { float t = red[0]; for (int i = 1; i < 8; ++i) t = fmaxf(t, red[i]); bc = t; }
+  __syncthreads();
+  m = bc;
+  float sum = 0.f;
+  for (int j = tid; j < n4; j += 256) {
+    const float4 v = reinterpret_cast<const float4*>(s)[j];
+    sum += (__expf(v.x * p.scale - m) + __expf(v.y * p.scale - m)) + (__expf(v.z * p.scale - m) + __expf(v.w * p.scale - m));
+  }
+  for (int j = (n4 << 2) + tid; j < p.n; j += 256) sum += __expf(s[j] * p.scale - m);
+  sum = warp_sum(sum);
+  __syncthreads();
+  if (lane == 0) red[w] = sum;
+  __syncthreads();
+  if (tid == 0) { float t = 0.f; for (int i = 0; i < 8; ++i) t += red[i]; bc = t; }
+  __syncthreads();
+  const float inv = 1.0f / bc;
+  for (int j = tid; j < n4; j += 256) {
+    float4 v = reinterpret_cast<const float4*>(s)[j];
+    v.x = __expf(v.x * p.scale - m) * inv; v.y = __expf(v.y * p.scale - m) * inv;
+    v.z = __expf(v.z * p.scale - m) * inv; v.w = __expf(v.w * p.scale - m) * inv;
+    if (p.round_tf32) { v.x = round_tf32(v.x); v.y = round_tf32(v.y); v.z = round_tf32(v.z); v.w = round_tf32(v.w); }
+    reinterpret_cast<float4*>(o)[j] = v;
+  }
+  for (int j = (n4 << 2) + tid; j < p.n; j += 256) {
+    const float v = __expf(s[j] * p.scale - m) * inv;
+    o[j] = p.round_tf32 ? round_tf32(v) : v;
+  }
+}
+
+// ----------------------------------------------------------------------------
+// timestep embedding
+// ----------------------------------------------------------------------------
+__global__ void time_embed_kernel(const FridoTimeEmbedParams p) {
+  const int half = p.dim / 2;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= p.B * half) return;
+  const int b = i / half, j = i - b * half;
+  // util.py:160-166: freqs = exp(-ln(max_period) * j / half) in fp32; args = t.float() * freqs
+  const float nl = (float)(-log((double)p.max_period));  // python float -> fp32 scalar
+  const float f = expf(nl * (float)j / (float)half);
+  const float a = (float)p.t[b] * f;
+  p.out[(int64_t)b * p.dim + j] = cosf(a);
+  p.out[(int64_t)b * p.dim + half + j] = sinf(a);
+  if ((p.dim & 1) && j == 0) p.out[(int64_t)b * p.dim + p.dim - 1] = 0.f;
+}
+
+}  // namespace frido
+
+using namespace frido;
+
+extern "C" int frido_gn_stats(const FridoGnStatsParams* p, void* stream) {
+  if (!p || !p->a0 || !p->sums) return set_error(FRIDO_E_ARG, "gn_stats: null pointer");
+  const int C = p->c0 + p->c1;
+  if (p->groups <= 0 || p->groups > 64 || C % p->groups || (C & 3) || (p->c0 & 3) || C > GN_THREADS * 4 * GN_MAXQPT)
+    return set_error(FRIDO_E_ARG, "gn_stats: unsupported channel count");
+  if ((p->c1 > 0) != (p->a1 != nullptr)) return set_error(FRIDO_E_ARG, "gn_stats: a1/c1 mismatch");
+  const int ppc = gn_chunk(p->B, p->HW);
+  dim3 grid((p->HW + ppc - 1) / ppc, p->B);
+  gn_stats_kernel<<<grid, GN_THREADS, 0, (cudaStream_t)stream>>>(*p, ppc);
+  return check_launch("gn_stats");
+}
+
+extern "C" int frido_norm_act(const FridoNormActParams* p, void* stream) {
+  if (!p || !p->a0 || !p->sums || !p->out || !p->gamma || !p->beta) return set_error(FRIDO_E_ARG, "norm_act: null pointer");
+  const int C = p->c0 + p->c1;
+  if (p->groups <= 0 || p->groups > 64 || C % p->groups || (C & 3) || (p->c0 & 3))
+    return set_error(FRIDO_E_ARG, "norm_act: unsupported channel count");
+  if ((p->c1 > 0) != (p->a1 != nullptr)) return set_error(FRIDO_E_ARG, "norm_act: a1/c1 mismatch");
+  const int ppc = gn_chunk(p->B, p->HW);
+  dim3 grid((p->HW + ppc - 1) / ppc, p->B);
+  norm_act_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(*p, ppc);
+  return check_launch("norm_act");
+}
+
+extern "C" int frido_layernorm(const FridoLayerNormParams* p, void* stream) {
+  if (!p || !p->x || !p->out || !p->gamma || !p->beta) return set_error(FRIDO_E_ARG, "layernorm: null pointer");
+  if ((p->C & 3) || p->C > LN_MAXQ * 128 || p->rows <= 0) return set_error(FRIDO_E_ARG, "layernorm: unsupported C");
+  const int64_t blocks = (p->rows + 7) / 8;
+  layernorm_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(*p);
+  return check_launch("layernorm");
+}
+
+extern "C" int frido_softmax(const FridoSoftmaxParams* p, void* stream) {
+  if (!p || !p->s || !p->out || p->rows <= 0 || p->n <= 0) return set_error(FRIDO_E_ARG, "softmax: bad argument");
+  if (p->n <= 1024) {
+    const int64_t blocks = (p->rows + 7) / 8;
+    softmax_warp_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(*p);
+  } else {
+    if ((p->ld & 3) || (reinterpret_cast<uintptr_t>(p->s) & 15) || (reinterpret_cast<uintptr_t>(p->out) & 15))
+      return set_error(FRIDO_E_ARG, "softmax: wide rows need 16B-aligned rows");
+    softmax_cta_kernel<<<(unsigned)p->rows, 256, 0, (cudaStream_t)stream>>>(*p);
+  }
+  return check_launch("softmax");
+}
+
+extern "C" int frido_time_embed(const FridoTimeEmbedParams* p, void* stream) {
+  if (!p || !p->t || !p->out || p->dim < 2) return set_error(FRIDO_E_ARG, "time_embed: bad argument");
+  const int n = p->B * (p->dim / 2);
+  time_embed_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(*p);
+  return check_launch("time_embed");
+}

@@ -1,0 +1,233 @@
+"""MS-VQGAN decode side — drop-in mirror of taming/models/msvqgan.py
+(`VQModelInterface.decode`, :376-399) with the taming Decoder
+(taming/modules/diffusionmodules/model.py:548-649) and VectorQuantizer2
+(taming/modules/vqvae/quantize.py:267-308) scheduled as one libfrido_b200 program:
+
+  per-scale rescale + VQ argmin/gather (written straight into the fine->coarse
+  concatenated NHWC tensor) -> post_quant_conv -> conv_in -> mid (Res, Attn, Res)
+  -> up levels (Res [+Attn]) with nearest-x2 folded into the upsample conv
+  -> GroupNorm+swish -> conv_out written NCHW.
+
+The encoder half (msvqgan.py:116-154,326-374) is outside the sampling hot path
+ and is not instantiated; its checkpoint keys are ignored on load.
+"""
+import torch
+from torch import nn
+
+from . import _lib as L
+from . import modules as M
+from .program import Program, Src
+from .unet import _pack_conv
+
+
+class VQModelInterface(nn.Module):
+    def __init__(self, embed_dim, edconfig=None, ddconfig=None, lossconfig=None, n_embed=None, channel_range=[],
+                 fusion="concat", ckpt_path=None, ignore_keys=[], image_key="image", colorize_nlabels=None, monitor=None,
+                 remap=None, sane_index_shape=False, on_vit=[], use_aux_loss=False, unsample_type="nearest",
+                 quant_beta=0.25, legacy=True, init_normal=False, **kwargs):
+        super().__init__()
+        if remap is not None or fusion != "concat":
+            raise NotImplementedError("remap / non-concat fusion are outside the B200 hot path")
+        self.embed_dim = [int(e) for e in embed_dim]
+        self.n_embed = [int(n) for n in n_embed]
+        assert len(self.n_embed) == len(self.embed_dim), "multiscale mode. dim of n_embed is incorrect."
+        self.channel_range = channel_range
+        self.image_key = image_key
+        self.ddconfig = dict(ddconfig)
+        self.edconfig = dict(edconfig) if edconfig is not None else None
+        self.decoder = M.TDecoder(**self.ddconfig)
+        self.ms_quantize = nn.ModuleList([M.VectorQuantizer(n, e, init_normal) for n, e in zip(self.n_embed, self.embed_dim)])
+        self.post_quant_conv = nn.Conv2d(sum(self.embed_dim), self.ddconfig["z_channels"], 1)
+        # frido.py:609 reads len(first_stage_model.res_list)
+        if self.edconfig is not None:
+            nres = len(self.edconfig["ch_mult"])
+            self.res_list = [self.edconfig["resolution"] / 2 ** (nres - i - 1) for i in range(self.edconfig["multiscale"])]
+        else:
+            self.res_list = [0] * len(self.embed_dim)
+        self._plans = {}
+        self._pack_version = 0
+        if ckpt_path is not None:
+            self.init_from_ckpt(ckpt_path, ignore_keys=ignore_keys)
+
+    def init_from_ckpt(self, path, ignore_keys=list()):
+        sd = torch.load(path, map_location="cpu")["state_dict"]
+        for k in list(sd.keys()):
+            if any(k.startswith(ik) for ik in ignore_keys):
+                del sd[k]
+        missing, unexpected = self.load_state_dict(sd, strict=False)
+        print(f"Restored from {path} with {len(missing)} missing and {len(unexpected)} unexpected keys")
+        self.invalidate()
+
+    def invalidate(self):
+        self._pack_version += 1
+        for p in self._plans.values():
+            p.repack()
+
+    def encode(self, x):
+        raise NotImplementedError("MS-VQGAN encode is outside the B200 sampling hot path (SURVEY.md §8f.3)")
+
+    @torch.no_grad()
+    def decode(self, h_in, force_not_quantize=False, return_code=False, scale_factor=None):
+        """msvqgan.py:376-399.  `scale_factor` (list, one per scale) folds
+        decode_first_stage's per-group 1/scale (frido.py:832-838) into the VQ kernel."""
+        if not h_in.is_cuda:
+            raise L.FridoError("VQModelInterface.decode runs on a CUDA device only (no CPU path)")
+        B, C, H, W = h_in.shape
+        sf = tuple(float(s) for s in (scale_factor if scale_factor is not None else [1.0] * len(self.embed_dim)))
+        key = (B, H, W, sf)
+        plan = self._plans.get(key)
+        if plan is None:
+            plan = DecodePlan(self, B, H, W, sf)
+            self._plans[key] = plan
+        plan.repack_if_stale()
+        plan.z.copy_(h_in)
+        plan.prog.run()
+        dec = plan.image.clone()
+        if return_code:
+            code = [idx.view(B, -1).tolist() for idx in plan.indices]  # msvqgan.py:390
+            return dec, code
+        return dec
+
+
+class DecodePlan:
+    def __init__(self, fs: VQModelInterface, B, H, W, sf):
+        self.fs, self.B, self.H, self.W = fs, B, H, W
+        dev = next(fs.parameters()).device
+        self.dev = dev
+        self.packers = []
+        self.version = fs._pack_version
+        Ct = sum(fs.embed_dim)
+        self.z = torch.zeros(B, Ct, H, W, dtype=torch.float32, device=dev)
+        self.indices = [torch.zeros(B * H * W, dtype=torch.int64, device=dev) for _ in fs.embed_dim]
+        P = self.prog = Program(dev, "decode")
+        dec = fs.decoder
+        n_gn = sum(1 for m in dec.modules() if isinstance(m, nn.GroupNorm))
+        self._sums = torch.zeros(n_gn + 1, B, 32, 2, dtype=torch.float64, device=dev)
+        self._slot = 0
+        P.zero(self._sums, tag="gn.zero")
+        # a14: VQ per scale, written fine->coarse (msvqgan.py:392-393)
+        quant = P.buf(B, H * W, Ct)
+        start = 0
+        for i, e in enumerate(fs.embed_dim):
+            coff = sum(fs.embed_dim[i + 1:])
+            P.vq(self.z, self._vec(fs.ms_quantize[i].embedding.weight), quant, self.indices[i], B=B, C_total=Ct, HW=H * W,
+                 c_start=start, e_dim=e, scale_factor=sf[i], out_C=Ct, out_coff=coff, tag=f"vq{i}")
+            start += e
+        zc = fs.post_quant_conv.weight.shape[0]
+        pq = P.buf(B, H * W, zc)
+        P.conv(Src.nhwc(quant, H, W), self._packed(lambda: fs.post_quant_conv.weight.detach().view(zc, Ct).clone()), pq, B=B,
+               Hin=H, Win=W, Hout=H, Wout=W, Cout=zc, bias=self._vec(fs.post_quant_conv.bias), tag="post_quant_conv")
+        c = dec.conv_in.weight.shape[0]
+        h = P.buf(B, H * W, c)
+        P.conv(Src.nhwc(pq, H, W), self._conv_w(dec.conv_in), h, B=B, Hin=H, Win=W, Hout=H, Wout=W, Cout=c, ksize=3, pad=1,
+               bias=self._vec(dec.conv_in.bias), tag="dec.conv_in")
+        hh, ww = H, W
+        h = self._res(dec.mid.block_1, h, hh, ww)
+        h = self._attn(dec.mid.attn_1, h, hh, ww)
+        h = self._res(dec.mid.block_2, h, hh, ww)
+        for lvl in reversed(range(dec.num_resolutions)):
+            up = dec.up[lvl]
+            for j, blk in enumerate(up.block):
+                h = self._res(blk, h, hh, ww)
+                if len(up.attn) > 0:
+                    h = self._attn(up.attn[j], h, hh, ww)
+            if lvl != 0:
+                c = up.upsample.conv.weight.shape[0]
+                o = P.buf(B, 4 * hh * ww, c)
+                P.conv(Src.nhwc(h, hh, ww), self._conv_w(up.upsample.conv), o, B=B, Hin=hh, Win=ww, Hout=2 * hh, Wout=2 * ww,
+                       Cout=c, ksize=3, pad=1, ups=2, bias=self._vec(up.upsample.conv.bias), tag="dec.up")
+                P.release(h)
+                h, hh, ww = o, 2 * hh, 2 * ww
+        c = dec.norm_out.weight.shape[0]
+        t = self._gn(h, c, hh, ww, dec.norm_out, 1)
+        P.release(h)
+        oc = dec.conv_out.weight.shape[0]
+        self.image = torch.zeros(B, oc, hh, ww, dtype=torch.float32, device=dev)
+        P.conv(Src.nhwc(t, hh, ww), self._conv_w(dec.conv_out), self.image, B=B, Hin=hh, Win=ww, Hout=hh, Wout=ww, Cout=oc,
+               ksize=3, pad=1, bias=self._vec(dec.conv_out.bias), o_sb=oc * hh * ww, o_sp=1, o_sn=hh * ww, tag="dec.conv_out")
+
+    # packing -------------------------------------------------------------
+    def _packed(self, fn):
+        dst = fn().to(self.dev).contiguous()
+        self.packers.append((dst, fn))
+        return dst
+
+    def _vec(self, p):
+        return self._packed(lambda: p.detach().clone())
+
+    def _conv_w(self, conv):
+        return self._packed(lambda: _pack_conv(conv.weight))
+
+    def repack(self):
+        for dst, fn in self.packers:
+            dst.copy_(fn())
+        self.version = self.fs._pack_version
+
+    def repack_if_stale(self):
+        if self.version != self.fs._pack_version:
+            self.repack()
+
+    # blocks --------------------------------------------------------------
+    def _gn(self, x, c, h, w, norm, silu):
+        P, B = self.prog, self.B
+        sums = self._sums[self._slot]
+        self._slot += 1
+        P.gn_stats(x, c, sums, B=B, HW=h * w)
+        out = P.buf(B, h * w, c)
+        P.norm_act(x, c, sums, self._vec(norm.weight), self._vec(norm.bias), out, B=B, HW=h * w, eps=1e-6, silu=silu,
+                   tag="dec.norm")
+        return out
+
+    def _res(self, rb, x, h, w):
+        """taming ResnetBlock (model.py:115-137), temb is None in the decoder."""
+        P, B = self.prog, self.B
+        cin, cout = rb.in_channels, rb.out_channels
+        t1 = self._gn(x, cin, h, w, rb.norm1, 1)
+        h1 = P.buf(B, h * w, cout)
+        P.conv(Src.nhwc(t1, h, w), self._conv_w(rb.conv1), h1, B=B, Hin=h, Win=w, Hout=h, Wout=w, Cout=cout, ksize=3, pad=1,
+               bias=self._vec(rb.conv1.bias), tag="dec.res.conv1")
+        P.release(t1)
+        t2 = self._gn(h1, cout, h, w, rb.norm2, 1)
+        P.release(h1)
+        res, sk = x, None
+        if cin != cout:
+            sk = P.buf(B, h * w, cout)
+            P.conv(Src.nhwc(x, h, w), self._packed(lambda: rb.nin_shortcut.weight.detach().view(cout, cin).clone()), sk, B=B,
+                   Hin=h, Win=w, Hout=h, Wout=w, Cout=cout, bias=self._vec(rb.nin_shortcut.bias), tag="dec.res.nin")
+            res = sk
+        out = P.buf(B, h * w, cout)
+        P.conv(Src.nhwc(t2, h, w), self._conv_w(rb.conv2), out, B=B, Hin=h, Win=w, Hout=h, Wout=w, Cout=cout, ksize=3, pad=1,
+               bias=self._vec(rb.conv2.bias), res=res, tag="dec.res.conv2")
+        P.release(t2)
+        if sk is not None:
+            P.release(sk)
+        P.release(x)
+        return out
+
+    def _attn(self, ab, x, h, w):
+        """taming AttnBlock (model.py:166-192): single head, d = C, softmax over keys."""
+        P, B = self.prog, self.B
+        C = ab.q.weight.shape[0]
+        N = h * w
+        t = self._gn(x, C, h, w, ab.norm, 0)
+        wqk = self._packed(lambda: torch.cat([ab.q.weight.detach().view(C, C), ab.k.weight.detach().view(C, C)], 0))
+        bqk = self._packed(lambda: torch.cat([ab.q.bias.detach(), ab.k.bias.detach()], 0))
+        qk = P.buf(B, N, 2 * C)
+        P.linear(t, wqk, qk, M=B * N, K=C, N=2 * C, bias=bqk, tag="dec.attn.qk")
+        vT = P.buf(B, C, N)
+        P.conv(Src(t, C, N * C, 0, C, 1), self._packed(lambda: ab.v.weight.detach().view(C, C).clone()), vT, B=B, Hin=1, Win=N,
+               Hout=1, Wout=N, Cout=C, bias=self._vec(ab.v.bias), o_sb=C * N, o_sp=1, o_sn=N, tag="dec.attn.vT")
+        P.release(t)
+        sc = P.buf(B, N, N)
+        P.conv(Src(qk, C, N * 2 * C, 0, 2 * C, 1), qk, sc, B=B, Hin=1, Win=N, Hout=1, Wout=N, Cout=N, w_sb=N * 2 * C,
+               w_ld=2 * C, w_off=C, tag="dec.attn.qk^T")
+        P.softmax(sc, rows=B * N, n=N, ld=N, scale=float(int(C) ** (-0.5)), tag="dec.attn.softmax")
+        o = P.buf(B, N, C)
+        P.conv(Src(sc, N, N * N, 0, N, 1), vT, o, B=B, Hin=1, Win=N, Hout=1, Wout=N, Cout=C, w_sb=C * N, w_ld=N,
+               tag="dec.attn.pv")
+        P.release(qk); P.release(vT); P.release(sc)
+        out = P.buf(B, N, C)
+        P.linear(o, self._packed(lambda: ab.proj_out.weight.detach().view(C, C).clone()), out, M=B * N, K=C, N=C,
+                 bias=self._vec(ab.proj_out.bias), res=x, tag="dec.attn.proj_out")
+        P.release(o); P.release(x)
+        return out

@@ -1,0 +1,227 @@
+"""Host runtime: flat op programs over static device buffers.
+
+A `Program` is built once per (network, stage, batch, geometry), owns every
+intermediate buffer it touches, and is executed by the native executor
+`frido_run_program` (one C call) — normally inside a captured CUDA graph, so a
+sampler step is a single graph launch.  Nothing here computes on the host.
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib as L
+
+
+def _ptr(t):
+    return 0 if t is None else t.data_ptr()
+
+
+class Src:
+    """A strided view used as a conv A-source: element strides (image,row,col,channel)."""
+
+    __slots__ = ("t", "C", "sb", "sy", "sx", "sc", "off")
+
+    def __init__(self, t, C_, sb, sy, sx, sc, off=0):
+        self.t, self.C, self.sb, self.sy, self.sx, self.sc, self.off = t, C_, sb, sy, sx, sc, off
+
+    @staticmethod
+    def nhwc(t, H, W, C_=None, sub=1, c_off=0, c_total=None):
+        """t is a contiguous [B,H,W,Ct] tensor; take channels [c_off, c_off+C_); `sub`
+        subsamples rows/cols (nearest down-resize: picks index i*sub)."""
+        Ct = c_total if c_total is not None else t.shape[-1]
+        C_ = C_ if C_ is not None else Ct
+        return Src(t, C_, H * W * Ct, W * Ct * sub, Ct * sub, 1, c_off)
+
+    @staticmethod
+    def nchw(t, H, W, c0, c1):
+        Ct = t.shape[1]
+        return Src(t, c1 - c0, Ct * H * W, W, 1, H * W, c0 * H * W)
+
+    @property
+    def ptr(self):
+        return self.t.data_ptr() + 4 * self.off
+
+
+class Program:
+    def __init__(self, device, name=""):
+        self.device = torch.device(device)
+        self.name = name
+        self.ops = []
+        self.tags = []
+        self.keep = []  # every tensor referenced by an op (keeps storage alive)
+        self._pool = {}
+        self._arr = None
+        self.graph = None
+        self.flops = 0  # algorithmic multiply-add*2 of conv/linear/matmul ops
+        self.tc_flops = 0
+
+    # ---- buffers -------------------------------------------------------
+    def buf(self, *shape, dtype=torch.float32, zero=False):
+        n = 1
+        for s in shape:
+            n *= int(s)
+        key = (n, dtype)
+        lst = self._pool.get(key)
+        if lst and not zero:
+            t = lst.pop().view(*shape)
+        else:
+            t = (torch.zeros if zero else torch.empty)(*shape, dtype=dtype, device=self.device)
+        self.keep.append(t)
+        return t
+
+    def release(self, t):
+        """Return a buffer to the pool: later ops may overwrite it (stream order makes that safe)."""
+        self._pool.setdefault((t.numel(), t.dtype), []).append(t.view(-1))
+
+    def hold(self, *ts):
+        for t in ts:
+            if t is not None:
+                self.keep.append(t)
+
+    # ---- op emitters ---------------------------------------------------
+    def _add(self, kind, params, tag):
+        self.ops.append(L.make_op(kind, params, len(self.tags)))
+        self.tags.append(tag)
+        self._arr = None
+
+    def conv(self, a0, w, out, *, B, Hin, Win, Hout, Wout, Cout, ksize=1, stride=1, pad=0, ups=1, a1=None,
+             bias=None, rowvec=None, rowvec_sb=0, res=None, alpha=1.0, act=L.ACT_NONE, o_sb=None, o_sp=None, o_sn=1,
+             w_sb=0, w_ld=0, w_off=0, out_off=0, round_tf32=0, engine=0, tag="conv"):
+        p = L.ConvParams()
+        p.a0, p.c0 = a0.ptr, a0.C
+        p.a0_sb, p.a0_sy, p.a0_sx, p.a0_sc = a0.sb, a0.sy, a0.sx, a0.sc
+        if a1 is not None:
+            p.a1, p.c1 = a1.ptr, a1.C
+            p.a1_sb, p.a1_sy, p.a1_sx, p.a1_sc = a1.sb, a1.sy, a1.sx, a1.sc
+        p.B, p.Hin, p.Win, p.ups = B, Hin, Win, ups
+        p.ksize, p.stride, p.pad, p.Hout, p.Wout = ksize, stride, pad, Hout, Wout
+        p.w, p.w_sb, p.w_ld, p.Cout = w.data_ptr() + 4 * w_off, w_sb, w_ld, Cout
+        p.bias, p.rowvec, p.rowvec_sb, p.res = _ptr(bias), _ptr(rowvec), rowvec_sb, _ptr(res)
+        p.alpha, p.act = alpha, act
+        n_out = Cout // 2 if act == L.ACT_GEGLU else Cout
+        p.out = out.data_ptr() + 4 * out_off
+        p.o_sp = n_out if o_sp is None else o_sp
+        p.o_sb = Hout * Wout * p.o_sp if o_sb is None else o_sb
+        p.o_sn = o_sn
+        p.round_tf32, p.engine = round_tf32, engine
+        self.hold(a0.t, None if a1 is None else a1.t, w, out, bias, rowvec, res)
+        fl = 2 * B * Hout * Wout * Cout * ksize * ksize * (a0.C + (a1.C if a1 is not None else 0))
+        self.flops += fl
+        if engine == 1:
+            self.tc_flops += fl
+        self._add(L.OP_CONV, p, tag)
+
+    def linear(self, a, w, out, *, M, K, N, bias=None, res=None, act=L.ACT_NONE, a_ld=None, a_off=0, out_ld=None,
+               rowvec=None, round_tf32=0, engine=0, tag="linear"):
+        """out[M,N] = act(a[M,K] @ w[N,K]^T + bias (+rowvec) (+res))  — rows are 'pixels' of one image."""
+        a_ld = K if a_ld is None else a_ld
+        src = Src(a, K, 0, 0, a_ld, 1, a_off)
+        self.conv(src, w, out, B=1, Hin=1, Win=M, Hout=1, Wout=M, Cout=N, bias=bias, res=res, act=act,
+                  rowvec=rowvec, o_sp=out_ld, round_tf32=round_tf32, engine=engine, tag=tag)
+
+    def zero(self, t, tag="zero"):
+        p = L.ZeroParams()
+        p.ptr, p.nbytes = t.data_ptr(), t.numel() * t.element_size()
+        self.hold(t)
+        self._add(L.OP_ZERO, p, tag)
+
+    def gn_stats(self, a0, c0, sums, *, B, HW, a1=None, c1=0, groups=32, tag="gn_stats"):
+        p = L.GnStatsParams()
+        p.a0, p.a1, p.c0, p.c1, p.B, p.HW, p.groups, p.sums = _ptr(a0), _ptr(a1), c0, c1, B, HW, groups, sums.data_ptr()
+        self.hold(a0, a1, sums)
+        self._add(L.OP_GN_STATS, p, tag)
+
+    def norm_act(self, a0, c0, sums, gamma, beta, out, *, B, HW, eps, a1=None, c1=0, gb=None, silu=1, groups=32,
+                 round_tf32=0, tag="norm_act"):
+        p = L.NormActParams()
+        p.a0, p.a1, p.c0, p.c1, p.B, p.HW, p.groups = _ptr(a0), _ptr(a1), c0, c1, B, HW, groups
+        p.sums, p.eps, p.gamma, p.beta, p.gb = sums.data_ptr(), eps, gamma.data_ptr(), beta.data_ptr(), _ptr(gb)
+        p.silu, p.round_tf32, p.out = silu, round_tf32, out.data_ptr()
+        self.hold(a0, a1, sums, gamma, beta, gb, out)
+        self._add(L.OP_NORM_ACT, p, tag)
+
+    def layernorm(self, x, gamma, beta, out, *, rows, Cdim, eps=1e-5, round_tf32=0, tag="layernorm"):
+        p = L.LayerNormParams()
+        p.x, p.rows, p.C, p.eps, p.gamma, p.beta = x.data_ptr(), rows, Cdim, eps, gamma.data_ptr(), beta.data_ptr()
+        p.round_tf32, p.out = round_tf32, out.data_ptr()
+        self.hold(x, gamma, beta, out)
+        self._add(L.OP_LAYERNORM, p, tag)
+
+    def softmax(self, s, *, rows, n, ld, scale, out=None, round_tf32=0, tag="softmax"):
+        out = s if out is None else out
+        p = L.SoftmaxParams()
+        p.s, p.rows, p.n, p.ld, p.scale, p.round_tf32, p.out = s.data_ptr(), rows, n, ld, scale, round_tf32, out.data_ptr()
+        self.hold(s, out)
+        self._add(L.OP_SOFTMAX, p, tag)
+
+    def time_embed(self, ts, out, *, B, dim, max_period=10000.0, tag="time_embed"):
+        p = L.TimeEmbedParams()
+        p.t, p.B, p.dim, p.max_period, p.out = ts.data_ptr(), B, dim, max_period, out.data_ptr()
+        self.hold(ts, out)
+        self._add(L.OP_TIME_EMBED, p, tag)
+
+    def step_begin(self, step, t_table, ts, *, B, T, use_next=0, tag="step_begin"):
+        p = L.StepBeginParams()
+        p.step, p.t_table, p.use_next, p.T, p.ts, p.B = step.data_ptr(), t_table.data_ptr(), use_next, T, ts.data_ptr(), B
+        self.hold(step, t_table, ts)
+        self._add(L.OP_STEP_BEGIN, p, tag)
+
+    def update(self, x, eps, coef, step, x_prev, *, B, c_start, c_end, HW, eps_uncond=None, cfg_scale=1.0, advance=1,
+               plms_order=0, plms_mode=0, hist=None, eps_save=None, noise=None, seed=0, seed_dev=None, temperature=1.0, x_dup=None,
+               pred_x0=None, tag="sampler_update"):
+        p = L.UpdateParams()
+        p.x, p.eps, p.eps_uncond, p.cfg_scale = x.data_ptr(), eps.data_ptr(), _ptr(eps_uncond), cfg_scale
+        p.B, p.c_start, p.c_end, p.HW = B, c_start, c_end, HW
+        p.coef, p.step, p.advance = coef.data_ptr(), step.data_ptr(), advance
+        p.plms_order, p.plms_mode, p.hist, p.eps_save = plms_order, plms_mode, _ptr(hist), _ptr(eps_save)
+        p.noise, p.seed, p.seed_dev, p.temperature = _ptr(noise), seed, _ptr(seed_dev), temperature
+        p.x_prev, p.x_dup, p.pred_x0 = x_prev.data_ptr(), _ptr(x_dup), _ptr(pred_x0)
+        self.hold(x, eps, eps_uncond, coef, step, hist, eps_save, noise, seed_dev, x_prev, x_dup, pred_x0)
+        self._add(L.OP_UPDATE, p, tag)
+
+    def snap(self, x, *, B, Ctot, H, W, c_start, c_end, n, tag="stage_snap"):
+        p = L.SnapParams()
+        p.x, p.B, p.C, p.H, p.W, p.c_start, p.c_end, p.n = x.data_ptr(), B, Ctot, H, W, c_start, c_end, n
+        self.hold(x)
+        self._add(L.OP_SNAP, p, tag)
+
+    def vq(self, z, codebook, out, indices, *, B, C_total, HW, c_start, e_dim, scale_factor, out_C, out_coff, tag="vq"):
+        p = L.VqParams()
+        p.z, p.B, p.C_total, p.HW, p.c_start, p.e_dim = z.data_ptr(), B, C_total, HW, c_start, e_dim
+        p.scale_factor, p.codebook, p.n_e = scale_factor, codebook.data_ptr(), codebook.shape[0]
+        p.out, p.out_C, p.out_coff, p.indices = out.data_ptr(), out_C, out_coff, indices.data_ptr()
+        self.hold(z, codebook, out, indices)
+        self._add(L.OP_VQ, p, tag)
+
+    # ---- execution -----------------------------------------------------
+    def _array(self):
+        if self._arr is None:
+            self._arr = (L.Op * len(self.ops))(*self.ops)
+        return self._arr
+
+    def run(self, stream=None):
+        """Enqueue all ops on `stream` (default: torch's current stream)."""
+        if not self.ops:
+            return
+        s = torch.cuda.current_stream(self.device).cuda_stream if stream is None else stream
+        rc = L.lib().frido_run_program(C.cast(self._array(), C.c_void_p), len(self.ops), C.c_void_p(s))
+        L.check(rc, f"program {self.name}")
+
+    def capture(self):
+        """Capture the program into a CUDA graph (after one eager warm-up run)."""
+        self.run()
+        torch.cuda.synchronize(self.device)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self.run()
+        self.graph = g
+        return g
+
+    def replay(self):
+        if self.graph is None:
+            self.run()
+        else:
+            self.graph.replay()
+
+    def __len__(self):
+        return len(self.ops)

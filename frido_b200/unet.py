@@ -1,0 +1,454 @@
+"""PyUNetModel — drop-in mirror of frido/modules/diffusionmodules/pyunet.py:447-950.
+
+Same constructor keywords, attributes and state-dict keys as the reference;
+`forward(x, timesteps, context, y, stage)` returns the same tensor.  The body
+of forward is a *program* of libfrido_b200 launches (see UNetPlan):
+
+  * activations NHWC fp32; tokens of a SpatialTransformer are the same memory;
+  * skip concat, nearest x2 upsampling, SPADE's nearest down-resize are folded
+    into conv addressing (no copies);
+  * step-invariant work is hoisted into a per-stage PROLOGUE program: the
+    SPADE gamma/beta maps of all norm sites (they depend only on the frozen
+    coarse channels, ddim.py:246,266 + pyunet.py:906-911) and the
+    cross-attention K/V of the context (attention.py:175-176);
+  * the 22 ResBlock timestep projections run as one GEMM.
+"""
+import math
+
+import torch
+from torch import nn
+
+from . import _lib as L
+from . import modules as M
+from .program import Program, Src
+
+
+class PyUNetModel(nn.Module):
+    def __init__(self, image_size, in_channels, model_channels, out_channels, num_res_blocks, attention_resolutions,
+                 dropout=0, channel_mult=(1, 2, 4, 8), conv_resample=True, dims=2, num_classes=None,
+                 use_checkpoint=False, use_fp16=False, num_heads=-1, num_head_channels=-1, num_heads_upsample=-1,
+                 use_scale_shift_norm=False, use_embed=False, num_stage=1, resblock_updown=False,
+                 use_new_attention_order=False, use_spatial_transformer=False, transformer_depth=1, context_dim=None,
+                 n_embed=None, legacy=True, use_split_head=False, split_embed_dim_list=[], use_SPADE_norm=False,
+                 use_pos_embed=False, use_mscond=False, use_stage_expert=False):
+        super().__init__()
+        # the shipped configs (configs/frido/**) use exactly this subset; anything else is refused loudly
+        unsupported = dict(dims=(dims, 2), num_classes=(num_classes, None), use_scale_shift_norm=(use_scale_shift_norm, False),
+                           resblock_updown=(resblock_updown, False), n_embed=(n_embed, None), legacy=(legacy, True),
+                           use_pos_embed=(use_pos_embed, False), use_mscond=(use_mscond, False),
+                           use_stage_expert=(use_stage_expert, False), use_fp16=(use_fp16, False),
+                           conv_resample=(conv_resample, True))
+        for k, (v, want) in unsupported.items():
+            if v != want:
+                raise NotImplementedError(f"PyUNetModel({k}={v!r}) is outside the B200 hot path (supported: {want!r})")
+        if not use_spatial_transformer or context_dim is None:
+            raise NotImplementedError("only use_spatial_transformer=True with a context_dim is supported")
+        if not use_split_head:
+            raise NotImplementedError("only use_split_head=True (Frido split heads) is supported")
+        if isinstance(context_dim, (list, tuple)):
+            context_dim = list(context_dim)[0]
+        split = [int(v) for v in split_embed_dim_list]
+        assert len(split) != 0, "specify split head embed dim."
+        assert sum(split) == in_channels
+        self.image_size, self.in_channels, self.model_channels = image_size, in_channels, model_channels
+        self.out_channels, self.num_res_blocks = out_channels, num_res_blocks
+        self.attention_resolutions = [int(a) for a in attention_resolutions]
+        self.dropout, self.channel_mult = dropout, [int(c) for c in channel_mult]
+        self.num_classes, self.num_stage = num_classes, num_stage
+        self.use_split_head, self.split_embed_dim_list = use_split_head, split
+        self.use_SPADE_norm, self.context_dim = use_SPADE_norm, context_dim
+        self.transformer_depth = transformer_depth
+        self.dtype = torch.float32
+        spade = use_SPADE_norm
+        mc = model_channels
+        ted = mc * 4
+        self.time_embed = M.Seq(nn.Linear(mc, ted), M.Marker(), nn.Linear(ted, ted))
+        if num_stage > 1:
+            self.stage_emb = nn.Embedding(num_stage, ted)
+        if spade:
+            self.pre_input_cond_blocks = nn.ModuleList(
+                [M.Seq(nn.Conv2d(sum(split[: i + 1]), mc, 3, padding=1)) for i in range(len(split) - 1)])
+            self.pre_input_blocks = nn.ModuleList([M.Seq(nn.Conv2d(split[i], mc, 3, padding=1)) for i in range(len(split))])
+        else:
+            self.pre_input_blocks = nn.ModuleList(
+                [M.Seq(nn.Conv2d(sum(split[: i + 1]), mc, 3, padding=1)) for i in range(len(split))])
+
+        def st(ch):
+            return M.SpatialTransformer(ch, mc, transformer_depth, context_dim, spade)
+
+        self.input_blocks = nn.ModuleList([])
+        chans = [mc]
+        ch, ds = mc, 1
+        for level, mult in enumerate(self.channel_mult):
+            for _ in range(num_res_blocks):
+                layers = [M.ResBlock(ch, mc, ted, mult * mc, spade)]
+                ch = mult * mc
+                if ds in self.attention_resolutions:
+                    layers.append(st(ch))
+                self.input_blocks.append(M.Seq(*layers))
+                chans.append(ch)
+            if level != len(self.channel_mult) - 1:
+                self.input_blocks.append(M.Seq(M.Downsample(ch, ch)))
+                chans.append(ch)
+                ds *= 2
+        self.middle_block = M.Seq(M.ResBlock(ch, mc, ted, ch, spade), st(ch), M.ResBlock(ch, mc, ted, ch, spade))
+        self.output_blocks = nn.ModuleList([])
+        for level, mult in list(enumerate(self.channel_mult))[::-1]:
+            for i in range(num_res_blocks + 1):
+                ich = chans.pop()
+                layers = [M.ResBlock(ch + ich, mc, ted, mc * mult, spade)]
+                ch = mc * mult
+                if ds in self.attention_resolutions:
+                    layers.append(st(ch))
+                if level and i == num_res_blocks:
+                    layers.append(M.Upsample(ch, ch))
+                    ds //= 2
+                self.output_blocks.append(M.Seq(*layers))
+        self.out = nn.ModuleList([M.Seq(M.gn(ch, 1e-5), M.Marker(), M._zero(nn.Conv2d(mc, split[i], 3, padding=1)))
+                                  for i in range(len(split))])
+        self._plans = {}
+        self._pack_version = 0
+
+    # ------------------------------------------------------------------
+    def invalidate(self):
+        """Weights changed under us (EMA swap writes through .data.copy_, ema.py:51,76 —
+        invisible to pointer/version checks): re-pack on next use."""
+        self._pack_version += 1
+        for plan in self._plans.values():
+            plan.repack()
+
+    def plan(self, stage, B, H, W, L_ctx):
+        key = (stage, B, H, W, L_ctx)
+        p = self._plans.get(key)
+        if p is None:
+            p = UNetPlan(self, stage, B, H, W, L_ctx)
+            self._plans[key] = p
+        return p
+
+    @torch.no_grad()
+    def forward(self, x, timesteps=None, context=None, y=None, stage=None, **kwargs):
+        assert y is None, "must specify y if and only if the model is class-conditional"
+        if not x.is_cuda:
+            raise L.FridoError("PyUNetModel runs on a CUDA device only (no CPU path)")
+        stage = 0 if stage is None else int(stage)
+        B, C, H, W = x.shape
+        assert C >= sum(self.split_embed_dim_list[: stage + 1])
+        plan = self.plan(stage, B, H, W, context.shape[1])
+        plan.repack_if_stale()
+        plan.x_in[:, : plan.c_end].copy_(x[:, : plan.c_end])
+        plan.ts.copy_(timesteps.to(torch.int64))
+        plan.ctx.copy_(context)
+        plan.prologue.run()
+        plan.step.run()
+        return plan.eps.clone()
+
+
+def _pack_conv(w):
+    """OIHW -> [O][kh*kw][I] (K-major rows for the implicit GEMM)."""
+    return w.detach().permute(0, 2, 3, 1).contiguous().view(w.shape[0], -1)
+
+
+class UNetPlan:
+    """Programs + static buffers for one (stage, batch, geometry)."""
+
+    def __init__(self, net: PyUNetModel, stage, B, H, W, Lc):
+        self.net, self.stage, self.B, self.H, self.W, self.Lc = net, stage, B, H, W, Lc
+        dev = next(net.parameters()).device
+        self.dev = dev
+        split = net.split_embed_dim_list
+        self.spade = net.use_SPADE_norm
+        self.c_cond = sum(split[:stage]) if self.spade else 0
+        self.c_end = sum(split[: stage + 1])
+        self.e_s = split[stage]
+        self.packers = []
+        self.version = net._pack_version
+        f32 = dict(dtype=torch.float32, device=dev)
+        self.x_in = torch.zeros(B, self.c_end, H, W, **f32)
+        self.ts = torch.zeros(B, dtype=torch.int64, device=dev)
+        self.ctx = torch.zeros(B, Lc, net.context_dim, **f32)
+        self.eps = torch.zeros(B, self.e_s, H, W, **f32)
+        self.Lp = (Lc + 31) // 32 * 32
+        self.prologue = Program(dev, f"unet.s{stage}.prologue")
+        self.step = Program(dev, f"unet.s{stage}.step")
+        self._gn_slots = []
+        self._build()
+
+    # ---- weight packing (re-runnable: same destination pointers) -------
+    def _packed(self, fn):
+        dst = fn().to(self.dev).contiguous()
+        self.packers.append((dst, fn))
+        return dst
+
+    def repack(self):
+        for dst, fn in self.packers:
+            dst.copy_(fn())
+        self.version = self.net._pack_version
+
+    def repack_if_stale(self):
+        if self.version != self.net._pack_version:
+            self.repack()
+
+    def _conv_w(self, conv):
+        return self._packed(lambda: _pack_conv(conv.weight))
+
+    def _vec(self, p):
+        return self._packed(lambda: p.detach().clone())
+
+    # ---- helpers ---------------------------------------------------------
+    def _gn_slot(self, prog):
+        t = self._sums_all[len(self._gn_slots)]
+        self._gn_slots.append(t)
+        return t
+
+    def _norm(self, prog, xs, cs, h, w, norm, eps, silu, site):
+        """GroupNorm(+SPADE)(+SiLU) over the (possibly concatenated) NHWC sources xs -> new buffer."""
+        B = self.B
+        hw = h * w
+        C = sum(cs)
+        sums = self._gn_slot(prog)
+        a1 = xs[1] if len(xs) > 1 else None
+        c1 = cs[1] if len(xs) > 1 else 0
+        prog.gn_stats(xs[0], cs[0], sums, B=B, HW=hw, a1=a1, c1=c1)
+        is_spade = isinstance(norm, M.SPADE)
+        g = norm.param_free_norm if is_spade else norm
+        gb = self._spade_site(norm, C, h, w) if (is_spade and self.c_cond) else None
+        out = prog.buf(B, hw, C)
+        prog.norm_act(xs[0], cs[0], sums, self._vec(g.weight), self._vec(g.bias), out, B=B, HW=hw, eps=eps, a1=a1,
+                      c1=c1, gb=gb, silu=silu, tag=site)
+        return out
+
+    def _spade_site(self, sp, C, h, w):
+        """Prologue: gamma|beta = conv3x3(ReLU(conv3x3(nearest_resize(h_cond)))) (spade_norm.py:52-55)."""
+        P, B = self.prologue, self.B
+        hw = h * w
+        sub = self.H // h
+        assert sub * h == self.H and sub * w == self.W
+        mc = self.net.model_channels
+        nh = sp.mlp_shared[0].weight.shape[0]
+        actv = P.buf(B, hw, nh)
+        P.conv(Src.nhwc(self.h_cond, self.H, self.W, mc, sub=sub), self._conv_w(sp.mlp_shared[0]), actv, B=B, Hin=h,
+               Win=w, Hout=h, Wout=w, Cout=nh, ksize=3, pad=1, bias=self._vec(sp.mlp_shared[0].bias), act=L.ACT_RELU,
+               tag="spade.shared")
+        wgb = self._packed(lambda: torch.cat([_pack_conv(sp.mlp_gamma.weight), _pack_conv(sp.mlp_beta.weight)], 0))
+        bgb = self._packed(lambda: torch.cat([sp.mlp_gamma.bias.detach(), sp.mlp_beta.bias.detach()], 0))
+        gb = torch.empty(B, hw, 2 * C, dtype=torch.float32, device=self.dev)  # lives across steps: not pooled
+        P.conv(Src.nhwc(actv, h, w), wgb, gb, B=B, Hin=h, Win=w, Hout=h, Wout=w, Cout=2 * C, ksize=3, pad=1, bias=bgb,
+               tag="spade.gamma_beta")
+        P.release(actv)
+        return gb
+
+    def _resblock(self, rb, xs, cs, h, w):
+        S, B = self.step, self.B
+        hw = h * w
+        cout = rb.out_channels
+        t1 = self._norm(S, xs, cs, h, w, rb.in_layers[0], 1e-5, 1, "res.norm1")
+        h1 = S.buf(B, hw, cout)
+        off = self._emb_off[id(rb)]
+        S.conv(Src.nhwc(t1, h, w), self._conv_w(rb.in_layers[2]), h1, B=B, Hin=h, Win=w, Hout=h, Wout=w, Cout=cout,
+               ksize=3, pad=1, bias=self._vec(rb.in_layers[2].bias), rowvec=self.emb_all[:, off:], rowvec_sb=self.emb_total,
+               tag="res.conv1")
+        S.release(t1)
+        t2 = self._norm(S, [h1], [cout], h, w, rb.out_layers[0], 1e-5, 1, "res.norm2")
+        S.release(h1)
+        a1 = Src.nhwc(xs[1], h, w) if len(xs) > 1 else None
+        if isinstance(rb.skip_connection, nn.Conv2d):
+            sk = S.buf(B, hw, cout)
+            S.conv(Src.nhwc(xs[0], h, w), self._conv_w(rb.skip_connection), sk, B=B, Hin=h, Win=w, Hout=h, Wout=w,
+                   Cout=cout, a1=a1, bias=self._vec(rb.skip_connection.bias), tag="res.skip")
+            res = sk
+        else:
+            assert len(xs) == 1
+            res, sk = xs[0], None
+        out = S.buf(B, hw, cout)
+        S.conv(Src.nhwc(t2, h, w), self._conv_w(rb.out_layers[3]), out, B=B, Hin=h, Win=w, Hout=h, Wout=w, Cout=cout,
+               ksize=3, pad=1, bias=self._vec(rb.out_layers[3].bias), res=res, tag="res.conv2")
+        S.release(t2)
+        if sk is not None:
+            S.release(sk)
+        return out
+
+    def _attention(self, x, C, N, ca, ctx_kv, tag):
+        """x: LayerNorm-ed tokens [B,N,C]; returns attention output before to_out."""
+        S, B = self.step, self.B
+        scale = float(C) ** -0.5
+        if ctx_kv is None:  # self-attention: fused q|k projection, V written transposed
+            wqk = self._packed(lambda: torch.cat([ca.to_q.weight.detach(), ca.to_k.weight.detach()], 0))
+            qk = S.buf(B, N, 2 * C)
+            S.linear(x, wqk, qk, M=B * N, K=C, N=2 * C, tag=tag + ".qk")
+            vT = S.buf(B, C, N)
+            S.conv(Src(x, C, N * C, 0, C, 1), self._vec(ca.to_v.weight), vT, B=B, Hin=1, Win=N, Hout=1, Wout=N, Cout=C,
+                   o_sb=C * N, o_sp=1, o_sn=N, tag=tag + ".vT")
+            Nk, Nkp = N, N
+            q_src = Src(qk, C, N * 2 * C, 0, 2 * C, 1)
+            k_t, k_off, k_sb, k_ld = qk, C, N * 2 * C, 2 * C
+            v_t, v_sb = vT, C * N
+        else:
+            kc, vTc = ctx_kv
+            q = S.buf(B, N, C)
+            S.linear(x, self._vec(ca.to_q.weight), q, M=B * N, K=C, N=C, tag=tag + ".q")
+            Nk, Nkp = self.Lc, self.Lp
+            q_src = Src(q, C, N * C, 0, C, 1)
+            k_t, k_off, k_sb, k_ld = kc, 0, self.Lp * C, C
+            v_t, v_sb = vTc, C * self.Lp
+            qk = q
+        # scores: pad columns [Nk, Nkp) stay zero forever (zero-initialised, never written)
+        sc = torch.zeros(B, N, Nkp, dtype=torch.float32, device=self.dev) if Nkp != Nk else S.buf(B, N, Nkp)
+        S.hold(sc)
+        S.conv(q_src, k_t, sc, B=B, Hin=1, Win=N, Hout=1, Wout=N, Cout=Nk, w_sb=k_sb, w_ld=k_ld, w_off=k_off,
+               o_sb=N * Nkp, o_sp=Nkp, tag=tag + ".qk^T")
+        S.softmax(sc, rows=B * N, n=Nk, ld=Nkp, scale=scale, tag=tag + ".softmax")
+        o = S.buf(B, N, C)
+        S.conv(Src(sc, Nk, N * Nkp, 0, Nkp, 1), v_t, o, B=B, Hin=1, Win=N, Hout=1, Wout=N, Cout=C, w_sb=v_sb, w_ld=Nkp,
+               tag=tag + ".pv")
+        S.release(qk)
+        if ctx_kv is None:
+            S.release(vT)
+        if Nkp == Nk:
+            S.release(sc)
+        return o
+
+    def _ctx_kv(self, ca, C):
+        """Prologue: K = ctx Wk^T [B,Lp,C] (rows >= Lc zero), V^T [B,C,Lp] (attention.py:175-176)."""
+        P, B, Lc, Lp = self.prologue, self.B, self.Lc, self.Lp
+        D = self.net.context_dim
+        kc = torch.zeros(B, Lp, C, dtype=torch.float32, device=self.dev)
+        vT = torch.zeros(B, C, Lp, dtype=torch.float32, device=self.dev)
+        P.conv(Src(self.ctx, D, Lc * D, 0, D, 1), self._vec(ca.to_k.weight), kc, B=B, Hin=1, Win=Lc, Hout=1, Wout=Lc,
+               Cout=C, o_sb=Lp * C, o_sp=C, tag="ctx.k")
+        P.conv(Src(self.ctx, D, Lc * D, 0, D, 1), self._vec(ca.to_v.weight), vT, B=B, Hin=1, Win=Lc, Hout=1, Wout=Lc,
+               Cout=C, o_sb=C * Lp, o_sp=1, o_sn=Lp, tag="ctx.vT")
+        return kc, vT
+
+    def _transformer(self, st, x, C, h, w):
+        S, B = self.step, self.B
+        N = h * w
+        t = self._norm(S, [x], [C], h, w, st.norm, 1e-6, 0, "st.norm")
+        hcur = S.buf(B, N, C)
+        S.linear(t, self._packed(lambda: st.proj_in.weight.detach().view(C, C).clone()), hcur, M=B * N, K=C, N=C,
+                 bias=self._vec(st.proj_in.bias), tag="st.proj_in")
+        S.release(t)
+        for blk in st.transformer_blocks:
+            ln = S.buf(B, N, C)
+            S.layernorm(hcur, self._vec(blk.norm1.weight), self._vec(blk.norm1.bias), ln, rows=B * N, Cdim=C)
+            o = self._attention(ln, C, N, blk.attn1, None, "attn1")
+            S.release(ln)
+            h1 = S.buf(B, N, C)
+            S.linear(o, self._vec(blk.attn1.to_out[0].weight), h1, M=B * N, K=C, N=C, bias=self._vec(blk.attn1.to_out[0].bias),
+                     res=hcur, tag="attn1.out")
+            S.release(o); S.release(hcur)
+            ln = S.buf(B, N, C)
+            S.layernorm(h1, self._vec(blk.norm2.weight), self._vec(blk.norm2.bias), ln, rows=B * N, Cdim=C)
+            o = self._attention(ln, C, N, blk.attn2, self._ctx_kv(blk.attn2, C), "attn2")
+            S.release(ln)
+            h2 = S.buf(B, N, C)
+            S.linear(o, self._vec(blk.attn2.to_out[0].weight), h2, M=B * N, K=C, N=C, bias=self._vec(blk.attn2.to_out[0].bias),
+                     res=h1, tag="attn2.out")
+            S.release(o); S.release(h1)
+            ln = S.buf(B, N, C)
+            S.layernorm(h2, self._vec(blk.norm3.weight), self._vec(blk.norm3.bias), ln, rows=B * N, Cdim=C)
+            proj = blk.ff.net[0].proj
+            inner = proj.weight.shape[0] // 2
+
+            def _inter(p=proj, inner=inner):  # GEGLU (attention.py:42-44): rows (value_j, gate_j) interleaved
+                wv, wg = p.weight.detach()[:inner], p.weight.detach()[inner:]
+                return torch.stack([wv, wg], 1).reshape(2 * inner, -1).contiguous()
+
+            def _inter_b(p=proj, inner=inner):
+                return torch.stack([p.bias.detach()[:inner], p.bias.detach()[inner:]], 1).reshape(-1).contiguous()
+
+            ff = S.buf(B, N, inner)
+            S.linear(ln, self._packed(_inter), ff, M=B * N, K=C, N=2 * inner, bias=self._packed(_inter_b), act=L.ACT_GEGLU,
+                     tag="ff.geglu")
+            S.release(ln)
+            h3 = S.buf(B, N, C)
+            S.linear(ff, self._vec(blk.ff.net[2].weight), h3, M=B * N, K=inner, N=C, bias=self._vec(blk.ff.net[2].bias),
+                     res=h2, tag="ff.out")
+            S.release(ff); S.release(h2)
+            hcur = h3
+        out = S.buf(B, N, C)
+        S.linear(hcur, self._packed(lambda: st.proj_out.weight.detach().view(C, C).clone()), out, M=B * N, K=C, N=C,
+                 bias=self._vec(st.proj_out.bias), res=x, tag="st.proj_out")
+        S.release(hcur)
+        return out
+
+    def _run_seq(self, seq, xs, cs, h, w):
+        """One TimestepEmbedSequential (pyunet.py:75-91). xs: list of NHWC sources (skip concat)."""
+        S, B = self.step, self.B
+        for layer in seq:
+            if isinstance(layer, M.ResBlock):
+                x = self._resblock(layer, xs, cs, h, w)
+                xs, cs = [x], [layer.out_channels]
+            elif isinstance(layer, M.SpatialTransformer):
+                x = self._transformer(layer, xs[0], cs[0], h, w)
+                xs = [x]
+            elif isinstance(layer, M.Downsample):
+                ho, wo = (h + 1) // 2, (w + 1) // 2
+                x = S.buf(B, ho * wo, cs[0])
+                S.conv(Src.nhwc(xs[0], h, w), self._conv_w(layer.op), x, B=B, Hin=h, Win=w, Hout=ho, Wout=wo, Cout=cs[0],
+                       ksize=3, stride=2, pad=1, bias=self._vec(layer.op.bias), tag="down")
+                xs, h, w = [x], ho, wo
+            elif isinstance(layer, M.Upsample):
+                x = S.buf(B, 4 * h * w, cs[0])
+                S.conv(Src.nhwc(xs[0], h, w), self._conv_w(layer.conv), x, B=B, Hin=h, Win=w, Hout=2 * h, Wout=2 * w,
+                       Cout=cs[0], ksize=3, pad=1, ups=2, bias=self._vec(layer.conv.bias), tag="up")
+                xs, h, w = [x], 2 * h, 2 * w
+            else:
+                raise TypeError(type(layer))
+        return xs[0], cs[0], h, w
+
+    # ---- the program -----------------------------------------------------
+    def _build(self):
+        net, B, H, W, s = self.net, self.B, self.H, self.W, self.stage
+        P, S = self.prologue, self.step
+        mc = net.model_channels
+        ted = mc * 4
+        # GN statistics slots: one [B,32,2] fp64 block per norm site, zeroed once per step
+        n_norm = sum(1 for m in net.modules() if isinstance(m, (nn.GroupNorm,)))
+        self._sums_all = torch.zeros(n_norm + 2, B, 32, 2, dtype=torch.float64, device=self.dev)
+        S.zero(self._sums_all, tag="gn.zero")
+        # --- embedding (a7) ---
+        te = S.buf(B, mc)
+        S.time_embed(self.ts, te, B=B, dim=mc)
+        e1 = S.buf(B, ted)
+        S.linear(te, self._vec(net.time_embed[0].weight), e1, M=B, K=mc, N=ted, bias=self._vec(net.time_embed[0].bias),
+                 act=L.ACT_SILU, tag="time_embed.0")
+        semb = S.buf(B, ted)  # SiLU(emb): every consumer applies SiLU first (pyunet.py:226)
+        stage_row = self._packed(lambda: net.stage_emb.weight.detach()[s].clone()) if net.num_stage > 1 else None
+        S.linear(e1, self._vec(net.time_embed[2].weight), semb, M=B, K=ted, N=ted, bias=self._vec(net.time_embed[2].bias),
+                 rowvec=stage_row, act=L.ACT_SILU, tag="time_embed.2")
+        rbs = [m for m in net.modules() if isinstance(m, M.ResBlock)]
+        self._emb_off, off = {}, 0
+        for rb in rbs:
+            self._emb_off[id(rb)] = off
+            off += rb.out_channels
+        self.emb_total = off
+        self.emb_all = S.buf(B, off)
+        S.linear(semb, self._packed(lambda: torch.cat([rb.emb_layers[1].weight.detach() for rb in rbs], 0)), self.emb_all,
+                 M=B, K=ted, N=off, bias=self._packed(lambda: torch.cat([rb.emb_layers[1].bias.detach() for rb in rbs], 0)),
+                 tag="emb_layers(all)")
+        # --- split head (pyunet.py:899-914) ---
+        if self.c_cond:
+            pc = net.pre_input_cond_blocks[s - 1][0]
+            self.h_cond = torch.empty(B, H * W, mc, dtype=torch.float32, device=self.dev)
+            P.conv(Src.nchw(self.x_in, H, W, 0, self.c_cond), self._conv_w(pc), self.h_cond, B=B, Hin=H, Win=W, Hout=H,
+                   Wout=W, Cout=mc, ksize=3, pad=1, bias=self._vec(pc.bias), tag="pre_input_cond")
+        pi = net.pre_input_blocks[s][0]
+        c_lo = self.c_cond if self.spade else 0
+        h = S.buf(B, H * W, mc)
+        S.conv(Src.nchw(self.x_in, H, W, c_lo, self.c_end), self._conv_w(pi), h, B=B, Hin=H, Win=W, Hout=H, Wout=W,
+               Cout=mc, ksize=3, pad=1, bias=self._vec(pi.bias), tag="pre_input")
+        hs = [(h, mc, H, W)]
+        c, hh, ww = mc, H, W
+        for blk in net.input_blocks:
+            h, c, hh, ww = self._run_seq(blk, [h], [c], hh, ww)
+            hs.append((h, c, hh, ww))
+        h, c, hh, ww = self._run_seq(net.middle_block, [h], [c], hh, ww)
+        for blk in net.output_blocks:
+            sk, sc, sh, sw = hs.pop()
+            assert (sh, sw) == (hh, ww)
+            h, c, hh, ww = self._run_seq(blk, [h, sk], [c, sc], hh, ww)
+        # --- out head (pyunet.py:947) ---
+        oh = net.out[s]
+        t = self._norm(S, [h], [c], hh, ww, oh[0], 1e-5, 1, "out.norm")
+        S.conv(Src.nhwc(t, hh, ww), self._conv_w(oh[2]), self.eps, B=B, Hin=hh, Win=ww, Hout=hh, Wout=ww, Cout=self.e_s,
+               ksize=3, pad=1, bias=self._vec(oh[2].bias), o_sb=self.e_s * H * W, o_sp=1, o_sn=H * W, tag="out.conv")

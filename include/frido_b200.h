@@ -1,0 +1,225 @@
+/* frido_b200 — C ABI of the B200-native Frido sampling hot path.
+ *
+ * The reference (davidhalladay/Frido) has no FFI: its "operators" are stock
+ * PyTorch calls made from Python classes resolved out of YAML `target:` strings
+ * (SURVEY.md §8b).  This header is the boundary a maintainer binds instead: one
+ * launcher per fused device op of the path, plain pointers + sizes, no torch
+ * types.  Every launcher enqueues on `stream` (a cudaStream_t passed as void*),
+ * never synchronises, never allocates, and returns 0 or a negative FRIDO_E_*.
+ * All pointers are DEVICE pointers unless stated.  Activations are fp32 NHWC
+ * ("[B,H,W,C]"; tokens "[B,N,C]" are the same memory); latents at the sampler
+ * level are fp32 NCHW exactly as the reference's tensors.
+ *
+ * Each entry cites the reference code it replaces (paths into the reference).
+ */
+#ifndef FRIDO_B200_H
+#define FRIDO_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FRIDO_ABI_VERSION 1
+
+#define FRIDO_OK 0
+#define FRIDO_E_ARG (-1)     /* bad argument / unsupported shape */
+#define FRIDO_E_LAUNCH (-2)  /* CUDA launch error (see frido_last_error) */
+#define FRIDO_E_ARCH (-3)    /* device is not sm_100 */
+
+/* activation codes for FridoConvParams.act */
+#define FRIDO_ACT_NONE 0
+#define FRIDO_ACT_RELU 1
+#define FRIDO_ACT_SILU 2
+#define FRIDO_ACT_GEGLU 3 /* columns (2j,2j+1) = (value,gate) -> out[j] = value*gelu_erf(gate) */
+
+/* ---------------------------------------------------------------------------
+ * Implicit-GEMM convolution / linear / batched matmul.
+ *   out[b,p,n] = act( alpha * sum_{tap,c} A[b, pix(p,tap), c] * W[n, tap, c]
+ *                     + bias[n] + rowvec[b,n] + res[b,p,n] )
+ * Replaces nn.Conv2d 3x3/1x1 (pyunet.py:211,237,248,154,110; spade_norm.py:37-42;
+ * taming/modules/diffusionmodules/model.py:43,88,98,570,612; msvqgan.py:75),
+ * nn.Linear (pyunet.py:561-565,225-231; attention.py:40,60,161-168), the
+ * channel concat th.cat([h, hs.pop()],1) (pyunet.py:939, via a0|a1), nearest x2
+ * upsampling (pyunet.py:119, via ups=2), SPADE's nearest down-resize
+ * (spade_norm.py:52, via scaled strides) and the attention einsums
+ * (attention.py:180-191; model.py:176-188, via per-image weights w_sb != 0).
+ * ------------------------------------------------------------------------- */
+typedef struct FridoConvParams {
+  const float* a0;          /* source 0 */
+  const float* a1;          /* source 1 (channel-concatenated after source 0) or NULL */
+  int32_t c0, c1;           /* channels taken from each source; K per tap = c0 + c1 */
+  int64_t a0_sb, a0_sy, a0_sx, a0_sc; /* element strides: image, row, col, channel */
+  int64_t a1_sb, a1_sy, a1_sx, a1_sc;
+  int32_t B, Hin, Win;      /* source grid (before the optional x2 upsample) */
+  int32_t ups;              /* 1, or 2 = nearest-neighbour x2 folded into addressing */
+  int32_t ksize, stride, pad;
+  int32_t Hout, Wout;
+  const float* w;           /* [Cout][ksize*ksize][c0+c1], K contiguous */
+  int64_t w_sb;             /* 0 = shared weights; else per-image weight stride (batched matmul) */
+  int64_t w_ld;             /* element stride between weight rows; 0 = dense (ksize*ksize*(c0+c1)) */
+  int32_t Cout;
+  const float* bias;        /* [Cout] or NULL */
+  const float* rowvec;      /* per-image vector (timestep embedding) or NULL */
+  int64_t rowvec_sb;
+  const float* res;         /* residual, addressed like out, or NULL */
+  float alpha;
+  int32_t act;
+  float* out;
+  int64_t o_sb, o_sp, o_sn; /* out[b*o_sb + p*o_sp + n*o_sn], p = oy*Wout + ox */
+  int32_t round_tf32;       /* round stored values to TF32 (rna) */
+  int32_t engine;           /* 0 = SIMT fp32 engine, 1 = tcgen05 TF32 engine (aligned shapes only) */
+} FridoConvParams;
+
+int frido_conv2d(const FridoConvParams* p, void* stream);
+
+/* GroupNorm statistics over an NHWC tensor that may be the concat of two
+ * sources: per (image, group) sum and sum of squares in fp64.
+ * Replaces the reduction half of nn.GroupNorm(32) (util.py:214; attention.py:76;
+ * taming model.py:34).  `sums` [B][groups][2] must be zero on entry. */
+typedef struct FridoGnStatsParams {
+  const float* a0; const float* a1; int32_t c0, c1;
+  int32_t B, HW, groups;
+  double* sums;
+} FridoGnStatsParams;
+int frido_gn_stats(const FridoGnStatsParams* p, void* stream);
+
+/* Normalise + affine [+ SPADE modulation] [+ SiLU], writing one NHWC tensor.
+ *   y = ((x-mean)*rstd*gamma[c]+beta[c]);  if gb: y = y*(1+gb[b,p,c]) + gb[b,p,C+c];
+ *   if silu: y = y*sigmoid(y)
+ * Replaces the apply half of GroupNorm, SPADE.forward's modulation
+ * (spade_norm.py:58) and nn.SiLU / swish (pyunet.py:210,234; model.py:29). */
+typedef struct FridoNormActParams {
+  const float* a0; const float* a1; int32_t c0, c1;
+  int32_t B, HW, groups;
+  const double* sums; float eps;
+  const float* gamma; const float* beta;  /* [C] */
+  const float* gb;                        /* [B,HW,2C] SPADE (gamma|beta) or NULL */
+  int32_t silu;
+  int32_t round_tf32;
+  float* out;                             /* [B,HW,C] */
+} FridoNormActParams;
+int frido_norm_act(const FridoNormActParams* p, void* stream);
+
+/* nn.LayerNorm over the last dim (attention.py:203-205), eps 1e-5. */
+typedef struct FridoLayerNormParams {
+  const float* x; int64_t rows; int32_t C; float eps;
+  const float* gamma; const float* beta; int32_t round_tf32; float* out;
+} FridoLayerNormParams;
+int frido_layernorm(const FridoLayerNormParams* p, void* stream);
+
+/* Row softmax of scale*S (attention.py:180,189; model.py:180-181), in place allowed. */
+typedef struct FridoSoftmaxParams {
+  const float* s; int64_t rows; int32_t n; int64_t ld; float scale; int32_t round_tf32; float* out;
+} FridoSoftmaxParams;
+int frido_softmax(const FridoSoftmaxParams* p, void* stream);
+
+/* timestep_embedding (util.py:151-171): out[b] = [cos(t_b f_j), sin(t_b f_j)], j < dim/2. */
+typedef struct FridoTimeEmbedParams {
+  const int64_t* t; int32_t B; int32_t dim; float max_period; float* out;
+} FridoTimeEmbedParams;
+int frido_time_embed(const FridoTimeEmbedParams* p, void* stream);
+
+/* Sampler state kept on the device so that one captured step can be replayed:
+ *   step[0] = running step counter i (0..T-1) of the current stage.
+ * frido_step_begin writes ts[b] = t_table[i] (ddim.py:157). */
+typedef struct FridoStepBeginParams {
+  const int32_t* step; const int64_t* t_table; int32_t use_next; int32_t T; int64_t* ts; int32_t B;
+} FridoStepBeginParams;
+int frido_step_begin(const FridoStepBeginParams* p, void* stream);
+
+/* Fused DDIM / PLMS x_{t-1} update (ddim.py:200-268; plms.py:247-301):
+ * zero-pad eps to the frozen groups, optional classifier-free guidance
+ * (ddim.py:226), optional Adams-Bashforth combination of the eps history
+ * (plms.py:285-299), x0 prediction, direction, sigma*noise, group masking, and
+ * (single thread) step counter increment.  NCHW fp32.
+ *   coef[i] = {a_t, a_prev, sigma_t, sqrt(1-a_t)} for step i (index = T-1-i). */
+typedef struct FridoUpdateParams {
+  const float* x;            /* [B, c_end, H, W] */
+  const float* eps;          /* [B, c_act, H, W] conditional (or only) model output */
+  const float* eps_uncond;   /* same shape or NULL */
+  float cfg_scale;
+  int32_t B, c_start, c_end, HW;
+  const float* coef;         /* [T][4] */
+  int32_t* step;             /* device step counter */
+  int32_t advance;           /* 1: increment *step after the update */
+  int32_t plms_order;        /* 0 = DDIM; 1..4 = multistep order cap (uses min(order, i+1) unless forced) */
+  int32_t plms_mode;         /* 0 plain, 1 = "first half" (x_prev from e_t only, history untouched),
+                                2 = "second half" (e' = (hist_new + eps)/2 where eps is e(t_next)) */
+  float* hist;               /* [3][B, c_act, H, W] eps ring (PLMS) or NULL */
+  float* eps_save;           /* PLMS mode 1: where e_t is parked; mode 2: read back */
+  const float* noise;        /* injected N(0,1) [B, c_end, H, W] or NULL */
+  uint64_t seed;             /* Philox seed used when noise == NULL and sigma != 0 */
+  const uint64_t* seed_dev;  /* optional device word XORed into seed (fresh per sample() call; graph-safe) */
+  float temperature;
+  float* x_prev;             /* [B, c_end, H, W] (may alias x) */
+  float* x_dup;              /* optional second copy of x_prev (CFG 2B batch) or NULL */
+  float* pred_x0;            /* optional or NULL */
+} FridoUpdateParams;
+int frido_sampler_update(const FridoUpdateParams* p, void* stream);
+
+/* Inter-stage snap (ddim.py:177-185): avg_pool2d(2) n times then nearest x2 n times
+ * on channels [c_start,c_end) of an NCHW tensor, in place. */
+typedef struct FridoSnapParams {
+  float* x; int32_t B, C, H, W, c_start, c_end, n;
+} FridoSnapParams;
+int frido_stage_snap(const FridoSnapParams* p, void* stream);
+
+/* decode_first_stage rescale + VectorQuantizer2.forward for one scale
+ * (frido.py:832-838; quantize.py:272-297): z*(1/scale) -> argmin_j (|z|^2+|e_j|^2-2 z.e_j)
+ * (first minimum) -> z + (e_idx - z), written NHWC at channel offset out_coff of
+ * a [B,HW,out_C] tensor (msvqgan.py:392-393 reverses the group order). */
+typedef struct FridoVqParams {
+  const float* z;            /* NCHW [B, C_total, H, W] */
+  int32_t B, C_total, HW, c_start, e_dim;
+  float scale_factor;
+  const float* codebook;     /* [n_e][e_dim] */
+  int32_t n_e;
+  float* out; int32_t out_C, out_coff;
+  int64_t* indices;          /* [B*HW] */
+} FridoVqParams;
+int frido_vq_lookup(const FridoVqParams* p, void* stream);
+
+/* Fill `n` bytes with zero (graph-capturable helper for the GN sums). */
+int frido_zero(void* ptr, int64_t nbytes, void* stream);
+
+/* tcgen05 engine weight packing: W[Cout][K] fp32 -> TF32-rounded (rna) copy.
+ * (The layout itself is unchanged; TMA tiles it.) */
+int frido_round_tf32(const float* src, float* dst, int64_t n, void* stream);
+
+/* ---------------------------------------------------------------------------
+ * Native op-program executor: the host runtime builds a flat array of ops once
+ * per (stage, batch) and replays it (inside a CUDA graph) every step.
+ * ------------------------------------------------------------------------- */
+enum FridoOpKind {
+  FRIDO_OP_CONV = 1, FRIDO_OP_GN_STATS = 2, FRIDO_OP_NORM_ACT = 3, FRIDO_OP_LAYERNORM = 4,
+  FRIDO_OP_SOFTMAX = 5, FRIDO_OP_TIME_EMBED = 6, FRIDO_OP_STEP_BEGIN = 7, FRIDO_OP_UPDATE = 8,
+  FRIDO_OP_SNAP = 9, FRIDO_OP_VQ = 10, FRIDO_OP_ZERO = 11
+};
+typedef struct FridoZeroParams { void* ptr; int64_t nbytes; } FridoZeroParams;
+typedef struct FridoOp {
+  int32_t kind;
+  int32_t tag; /* free for the host (profiling label index) */
+  union {
+    FridoConvParams conv; FridoGnStatsParams gn_stats; FridoNormActParams norm_act;
+    FridoLayerNormParams layernorm; FridoSoftmaxParams softmax; FridoTimeEmbedParams time_embed;
+    FridoStepBeginParams step_begin; FridoUpdateParams update; FridoSnapParams snap; FridoVqParams vq;
+    FridoZeroParams zero;
+  } u;
+} FridoOp;
+/* Launches ops[0..n) in order on `stream`; returns 0 or (-(1000+i)) if op i failed. */
+int frido_run_program(const FridoOp* ops, int32_t n, void* stream);
+
+int frido_abi_version(void);
+int frido_sizeof_op(void);
+const char* frido_last_error(void);
+/* number of kernel launches issued through this library since load (bench's gpu_launches) */
+int64_t frido_launch_count(void);
+/* 0 if the current device is sm_100 and the tcgen05 engine is usable */
+int frido_check_device(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
