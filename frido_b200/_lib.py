@@ -17,7 +17,7 @@ c_p = C.c_void_p
 
 ACT_NONE, ACT_RELU, ACT_SILU, ACT_GEGLU = 0, 1, 2, 3
 (OP_CONV, OP_GN_STATS, OP_NORM_ACT, OP_LAYERNORM, OP_SOFTMAX, OP_TIME_EMBED, OP_STEP_BEGIN, OP_UPDATE, OP_SNAP, OP_VQ,
- OP_ZERO) = range(1, 12)
+ OP_ZERO, OP_UPSAMPLE) = range(1, 13)
 
 
 class ConvParams(C.Structure):
@@ -55,7 +55,7 @@ class SoftmaxParams(C.Structure):
 
 
 class TimeEmbedParams(C.Structure):
-    _fields_ = [("t", c_p), ("B", c_i), ("dim", c_i), ("max_period", c_f), ("out", c_p)]
+    _fields_ = [("t", c_p), ("B", c_i), ("dim", c_i), ("max_period", c_f), ("freqs", c_p), ("out", c_p)]
 
 
 class StepBeginParams(C.Structure):
@@ -86,11 +86,15 @@ class ZeroParams(C.Structure):
     _fields_ = [("ptr", c_p), ("nbytes", c_l)]
 
 
+class UpsampleParams(C.Structure):
+    _fields_ = [("x", c_p), ("B", c_i), ("H", c_i), ("W", c_i), ("C", c_i), ("round_tf32", c_i), ("out", c_p)]
+
+
 class _OpU(C.Union):
     _fields_ = [("conv", ConvParams), ("gn_stats", GnStatsParams), ("norm_act", NormActParams),
                 ("layernorm", LayerNormParams), ("softmax", SoftmaxParams), ("time_embed", TimeEmbedParams),
                 ("step_begin", StepBeginParams), ("update", UpdateParams), ("snap", SnapParams), ("vq", VqParams),
-                ("zero", ZeroParams)]
+                ("zero", ZeroParams), ("upsample", UpsampleParams)]
 
 
 class Op(C.Structure):
@@ -99,12 +103,12 @@ class Op(C.Structure):
 
 _KIND_FIELD = {OP_CONV: "conv", OP_GN_STATS: "gn_stats", OP_NORM_ACT: "norm_act", OP_LAYERNORM: "layernorm",
                OP_SOFTMAX: "softmax", OP_TIME_EMBED: "time_embed", OP_STEP_BEGIN: "step_begin", OP_UPDATE: "update",
-               OP_SNAP: "snap", OP_VQ: "vq", OP_ZERO: "zero"}
+               OP_SNAP: "snap", OP_VQ: "vq", OP_ZERO: "zero", OP_UPSAMPLE: "upsample"}
 
 EXPORTS = [
     "frido_conv2d", "frido_gn_stats", "frido_norm_act", "frido_layernorm", "frido_softmax", "frido_time_embed",
     "frido_step_begin", "frido_sampler_update", "frido_stage_snap", "frido_vq_lookup", "frido_zero",
-    "frido_round_tf32", "frido_run_program", "frido_abi_version", "frido_sizeof_op", "frido_last_error",
+    "frido_round_tf32", "frido_upsample2x", "frido_run_program", "frido_abi_version", "frido_sizeof_op", "frido_last_error",
     "frido_launch_count", "frido_check_device",
 ]
 
@@ -135,7 +139,8 @@ def lib():
     L.frido_zero.argtypes = [c_p, c_l, c_p]
     L.frido_round_tf32.argtypes = [c_p, c_p, c_l, c_p]
     for name in ("frido_conv2d", "frido_gn_stats", "frido_norm_act", "frido_layernorm", "frido_softmax",
-                 "frido_time_embed", "frido_step_begin", "frido_sampler_update", "frido_stage_snap", "frido_vq_lookup"):
+                 "frido_time_embed", "frido_step_begin", "frido_sampler_update", "frido_stage_snap", "frido_vq_lookup",
+                 "frido_upsample2x"):
         getattr(L, name).argtypes = [c_p, c_p]
     if L.frido_sizeof_op() != C.sizeof(Op):
         raise FridoError(f"ABI mismatch: sizeof(FridoOp) C={L.frido_sizeof_op()} python={C.sizeof(Op)}")

@@ -10,7 +10,7 @@ using namespace frido;
 
 extern "C" int frido_conv2d(const FridoConvParams* p, void* stream) {
   if (!p) return set_error(FRIDO_E_ARG, "conv2d: null params");
-  if (p->engine == 1) return conv2d_tc(p, (cudaStream_t)stream);
+  if (p->engine == 1 || p->engine == 2) return conv2d_tc(p, (cudaStream_t)stream);
   return conv2d_simt(p, (cudaStream_t)stream);
 }
 
@@ -38,6 +38,7 @@ extern "C" int frido_run_program(const FridoOp* ops, int32_t n, void* stream) {
       case FRIDO_OP_UPDATE: rc = frido_sampler_update(&op.u.update, stream); break;
       case FRIDO_OP_SNAP: rc = frido_stage_snap(&op.u.snap, stream); break;
       case FRIDO_OP_VQ: rc = frido_vq_lookup(&op.u.vq, stream); break;
+      case FRIDO_OP_UPSAMPLE: rc = frido_upsample2x(&op.u.upsample, stream); break;
       case FRIDO_OP_ZERO: rc = frido_zero(op.u.zero.ptr, op.u.zero.nbytes, stream); break;
       default: rc = set_error(FRIDO_E_ARG, "run_program: unknown op kind");
     }

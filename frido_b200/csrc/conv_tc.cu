@@ -1,8 +1,517 @@
-// tcgen05 TF32 implicit-GEMM engine (placeholder until the kernel lands).
+// tcgen05 TF32 implicit-GEMM engine (sm_100a): conv3x3 / conv1x1 / linear /
+// batched matmul on the 5th-gen tensor cores.
+//
+//   D[128 x BN] (fp32, TMEM) += A[128 x 32] (fp32 read as TF32, smem) * W[BN x 32]^T
+//
+// * persistent CTAs (grid = min(tiles, #SM)), 192 threads:
+//     warp 0   : TMA producer   (cp.async.bulk.tensor, 4-stage mbarrier ring)
+//     warp 1   : TMEM allocator + single-thread tcgen05.mma issuer
+//     warps 2-5: epilogue       (tcgen05.ld -> bias/emb/residual/act -> global)
+// * A tile = one TMA box of an NHWC tensor: {32 channels, TW, TH, TB} pixels
+//   (128 rows), loaded per filter tap at shifted coordinates; TMA zero-fills the
+//   out-of-bounds halo, so the conv padding costs nothing.  Two A sources give
+//   the channel concat (skip connections) for free.
+// * W tile = TMA box {32 k, BN rows} of the K-major weight matrix (optionally
+//   one matrix per image: attention QK^T / PV).
+// * both tiles land in the canonical K-major SWIZZLE_128B layout, so the UMMA
+//   shared-memory descriptors are (start, SBO=1024B, swizzle=128B) and K-steps
+//   of 8 TF32 advance the start address by 32 bytes.
+// * accumulators are double-buffered in TMEM (2 x 256 columns): the epilogue of
+//   tile i overlaps the main loop of tile i+1.
+#include <cuda.h>
+
 #include "common.cuh"
+
 namespace frido {
-int conv2d_tc(const FridoConvParams* p, cudaStream_t s) {
-  (void)p; (void)s;
-  return set_error(FRIDO_E_ARG, "conv2d: tcgen05 engine not built");
+
+constexpr int TC_BM = 128;
+constexpr int TC_BK = 32;             // fp32 elements per stage row = 128 bytes = one swizzle row
+constexpr int TC_MAX_STAGES = 6;
+constexpr int TC_MAX_BN = 256;
+constexpr int TC_A_BYTES = TC_BM * TC_BK * 4;       // 16 KB
+constexpr int TC_SMEM_BUDGET = 216 * 1024;          // operand ring; + 1 KB align slack + barriers < 227 KB
+constexpr int TC_SMEM_BYTES = TC_SMEM_BUDGET + 1024 + 256;
+constexpr int TC_THREADS = 192;                     // TMA, MMA, 4 epilogue warps
+constexpr int TC_THREADS_X3 = 320;                  // + 4 splitter warps (3xTF32 mode)
+
+struct TcParams {
+  int B, Hout, Wout, Cout;
+  int c0, c1;           // channels per source (multiples of 32)
+  int ksize, pad, stride;
+  int TW, TH, TB;       // tile = TW*TH*TB = 128 pixels
+  int tiles_x, tiles_y, tiles_b, tiles_n;
+  int BN;
+  int stages;           // depth of the smem ring
+  int w_batched;        // weights have a per-image leading dim
+  const float* bias;
+  const float* rowvec; long long rowvec_sb;
+  const float* res;
+  float alpha;
+  int act;
+  float* out; long long o_sb, o_sp, o_sn;
+  int round_tf32;
+};
+
+// ---------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
 }
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra WAIT_DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "WAIT_DONE:\n"
+      "}\n" ::"r"(bar), "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(dst),
+      "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst),
+      "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor):
+// start>>4 [0,14) | LBO>>4 [16,30) | SBO>>4 [32,46) | version=1 [46,48) | layout=2 (SW128) [61,64)
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;                 // LBO (unused for swizzled K-major) = 1
+  d |= (uint64_t)(1024 >> 4) << 32;       // SBO: 8 rows * 128 B
+  d |= (uint64_t)1 << 46;                 // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;                 // SWIZZLE_128B
+  return d;
+}
+// kind::tf32 instruction descriptor (cute::UMMA::InstrDescriptor): D=F32, A=B=TF32, K-major both
+__device__ __forceinline__ uint32_t umma_idesc_tf32(int M, int N) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// ----------------------------------------------------------------------------
+// X3 = error-compensated 3xTF32: every operand tile is split in shared memory into hi = rna_tf32(v) and
+// lo = v - hi by four extra warps, and each K-step issues hi*hi + lo*hi + hi*lo (fp32-faithful, ~2^-21).
+template <bool X3>
+__global__ void __launch_bounds__(X3 ? TC_THREADS_X3 : TC_THREADS, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
+               const __grid_constant__ CUtensorMap map_w, const TcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // SWIZZLE_128B atoms need 1024 B alignment
+  const uint32_t b_bytes = (uint32_t)p.BN * TC_BK * 4;
+  // stage layout: A | W            (X3: A_hi | A_lo | W_hi | W_lo)
+  const uint32_t stage_bytes = (TC_A_BYTES + b_bytes) * (X3 ? 2u : 1u);
+  const uint32_t off_alo = TC_A_BYTES;
+  const uint32_t off_w = X3 ? 2u * TC_A_BYTES : (uint32_t)TC_A_BYTES;
+  const uint32_t off_wlo = off_w + b_bytes;
+  const uint32_t bar_base = smem_base + TC_SMEM_BUDGET;
+  // barrier layout: full[6] | empty[6] | split[6] | tmem_full[2] | tmem_empty[2] | tmem_ptr
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (TC_MAX_STAGES + s); };
+  auto split_bar = [&](int s) { return bar_base + 8u * (2 * TC_MAX_STAGES + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (3 * TC_MAX_STAGES + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (3 * TC_MAX_STAGES + 2 + a); };
+  const uint32_t tmem_slot = bar_base + 8u * (3 * TC_MAX_STAGES + 4);
+  const int NS = p.stages;
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  const int Cin = p.c0 + p.c1;
+  const int kchunks = Cin / TC_BK;
+  const int taps = p.ksize * p.ksize;
+  const int ksteps = taps * kchunks;
+  const int m_tiles = p.tiles_x * p.tiles_y * p.tiles_b;
+  const int total_tiles = m_tiles * p.tiles_n;
+  const uint32_t stage_tx = TC_A_BYTES + b_bytes;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&map_a0);
+    if (p.c1) prefetch_tmap(&map_a1);
+    prefetch_tmap(&map_w);
+    for (int s = 0; s < NS; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+      mbar_init(split_bar(s), 4);  // one arrive per splitter warp
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull_bar(a), 1);
+      mbar_init(tempty_bar(a), 4);  // one arrive per epilogue warp
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int nt = tile % p.tiles_n;
+        int mt = tile / p.tiles_n;
+        const int tx = mt % p.tiles_x; mt /= p.tiles_x;
+        const int ty = mt % p.tiles_y;
+        const int tb = mt / p.tiles_y;
+        const int ox0 = tx * p.TW, oy0 = ty * p.TH, b0 = tb * p.TB;
+        const int n0 = nt * p.BN;
+        for (int ks = 0; ks < ksteps; ++ks) {
+          const int tap = ks / kchunks;
+          const int kc = ks - tap * kchunks;
+          const int dy = tap / p.ksize, dx = tap - dy * p.ksize;
+          mbar_wait(empty_bar(stage), phase ^ 1);
+          const uint32_t sa = smem_base + stage * stage_bytes;
+          const uint32_t sb = sa + off_w;
+          mbar_expect_tx(full_bar(stage), stage_tx);
+          const int ch = kc * TC_BK;
+          const int cx = ox0 * p.stride + dx - p.pad, cy = oy0 * p.stride + dy - p.pad;
+          if (ch < p.c0) tma_load_4d(sa, &map_a0, full_bar(stage), ch, cx, cy, b0);
+          else           tma_load_4d(sa, &map_a1, full_bar(stage), ch - p.c0, cx, cy, b0);
+          tma_load_3d(sb, &map_w, full_bar(stage), tap * Cin + ch, n0, p.w_batched ? b0 : 0);
+          if (++stage == NS) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_tf32(TC_BM, p.BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1);  // epilogue has drained this accumulator
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * TC_MAX_BN);
+        for (int ks = 0; ks < ksteps; ++ks) {
+          mbar_wait(X3 ? split_bar(stage) : full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t sa = smem_base + stage * stage_bytes;
+          const uint32_t sb = sa + off_w;
+#pragma unroll
+          for (int k = 0; k < TC_BK / 8; ++k) {
+            const uint64_t ad = umma_desc_sw128(sa + k * 32);
+            const uint64_t bd = umma_desc_sw128(sb + k * 32);
+            umma_tf32(d_tmem, ad, bd, idesc, (ks | k) ? 1u : 0u);
+            if (X3) {
+              const uint64_t al = umma_desc_sw128(sa + off_alo + k * 32);
+              const uint64_t bl = umma_desc_sw128(sa + off_wlo + k * 32);
+              umma_tf32(d_tmem, al, bd, idesc, 1u);
+              umma_tf32(d_tmem, ad, bl, idesc, 1u);
+            }
+          }
+          umma_commit(empty_bar(stage));  // frees the smem slot when these MMAs retire
+          if (++stage == NS) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(tfull_bar(acc));  // accumulator ready for the epilogue
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else if (warp < 6) {
+    // ===================== epilogue (warps 2..5) =====================
+    const int q = warp & 3;            // TMEM lane quarter this warp may access
+    const int row = q * 32 + lane;     // tile row owned by this thread
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int nt = tile % p.tiles_n;
+      int mt = tile / p.tiles_n;
+      const int tx = mt % p.tiles_x; mt /= p.tiles_x;
+      const int ty = mt % p.tiles_y;
+      const int tb = mt / p.tiles_y;
+      const int tw = row % p.TW;
+      const int th = (row / p.TW) % p.TH;
+      const int tbb = row / (p.TW * p.TH);
+      const int ox = tx * p.TW + tw, oy = ty * p.TH + th, b = tb * p.TB + tbb;
+      const bool valid = ox < p.Wout && oy < p.Hout && b < p.B;
+      const int n0 = nt * p.BN;
+      const long long pix = (long long)oy * p.Wout + ox;
+      float* __restrict__ orow = p.out + (long long)b * p.o_sb + pix * p.o_sp;
+      const float* __restrict__ rrow = p.res ? p.res + (long long)b * p.o_sb + pix * p.o_sp : nullptr;
+      const float* __restrict__ rv = p.rowvec ? p.rowvec + (long long)b * p.rowvec_sb : nullptr;
+
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after();
+      const uint32_t t_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * TC_MAX_BN);
+      for (int c = 0; c < p.BN; c += 32) {
+        uint32_t r[32];
+        tmem_ld32(t_base + c, r);
+        if (valid) {
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int n = n0 + c + j;
+            float t = __uint_as_float(r[j]) * p.alpha;
+            if (p.bias) t += __ldg(p.bias + n);
+            if (rv) t += __ldg(rv + n);
+            v[j] = t;
+          }
+          if (p.act == FRIDO_ACT_GEGLU) {
+            const int no = (n0 + c) >> 1;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              float t = v[2 * j] * gelu_erf(v[2 * j + 1]);
+              if (rrow) t += rrow[(long long)(no + j) * p.o_sn];
+              orow[(long long)(no + j) * p.o_sn] = p.round_tf32 ? round_tf32(t) : t;
+            }
+          } else if (p.o_sn == 1) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              float4 t = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+              if (rrow) {
+                const float4 rr = *reinterpret_cast<const float4*>(rrow + n0 + c + j);
+                t.x += rr.x; t.y += rr.y; t.z += rr.z; t.w += rr.w;
+              }
+              if (p.act == FRIDO_ACT_RELU) { t.x = fmaxf(t.x, 0.f); t.y = fmaxf(t.y, 0.f); t.z = fmaxf(t.z, 0.f); t.w = fmaxf(t.w, 0.f); }
+              else if (p.act == FRIDO_ACT_SILU) { t.x = silu_f(t.x); t.y = silu_f(t.y); t.z = silu_f(t.z); t.w = silu_f(t.w); }
+              if (p.round_tf32) { t.x = round_tf32(t.x); t.y = round_tf32(t.y); t.z = round_tf32(t.z); t.w = round_tf32(t.w); }
+              *reinterpret_cast<float4*>(orow + n0 + c + j) = t;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const long long o = (long long)(n0 + c + j) * p.o_sn;
+              float t = v[j];
+              if (rrow) t += rrow[o];
+              if (p.act == FRIDO_ACT_RELU) t = fmaxf(t, 0.f);
+              else if (p.act == FRIDO_ACT_SILU) t = silu_f(t);
+              orow[o] = p.round_tf32 ? round_tf32(t) : t;
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(acc));
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  } else if (X3) {
+    // ===================== splitter (warps 6..9, 3xTF32 only) =====================
+    // In place: v -> hi = rna_tf32(v); lo = v - hi goes to the twin buffer at the same (swizzled) offset.
+    const int t = threadIdx.x - 192;  // 0..127
+    int stage = 0;
+    uint32_t phase = 0;
+    const int a_vec = TC_A_BYTES / 16, w_vec = (int)(b_bytes / 16);
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int ks = 0; ks < ksteps; ++ks) {
+        mbar_wait(full_bar(stage), phase);
+        uint8_t* sbase = smem_raw + (smem_base - smem_u32(smem_raw)) + (size_t)stage * stage_bytes;
+        float4* a_hi = reinterpret_cast<float4*>(sbase);
+        float4* a_lo = reinterpret_cast<float4*>(sbase + off_alo);
+        float4* w_hi = reinterpret_cast<float4*>(sbase + off_w);
+        float4* w_lo = reinterpret_cast<float4*>(sbase + off_wlo);
+#pragma unroll 4
+        for (int i = t; i < a_vec; i += 128) {
+          const float4 v = a_hi[i];
+          const float4 h = make_float4(round_tf32(v.x), round_tf32(v.y), round_tf32(v.z), round_tf32(v.w));
+          a_hi[i] = h;
+          a_lo[i] = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
+        }
+#pragma unroll 4
+        for (int i = t; i < w_vec; i += 128) {
+          const float4 v = w_hi[i];
+          const float4 h = make_float4(round_tf32(v.x), round_tf32(v.y), round_tf32(v.z), round_tf32(v.w));
+          w_hi[i] = h;
+          w_lo[i] = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
+        }
+        fence_proxy_async();  // generic-proxy writes -> visible to the tensor core (async proxy)
+        __syncwarp();
+        if (lane == 0) mbar_arrive(split_bar(stage));
+        if (++stage == NS) { stage = 0; phase ^= 1; }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  }
+  return fn;
+}
+
+static int next_pow2(int v) { int p = 1; while (p < v) p <<= 1; return p; }
+
+// rank-4 fp32 map (C, W, H, B) with a {32, bw, bh, bb} box, SWIZZLE_128B
+static bool make_map4(CUtensorMap* m, const float* base, uint64_t C, uint64_t W, uint64_t H, uint64_t Bn, int64_t sx, int64_t sy,
+                      int64_t sb, uint32_t bw, uint32_t bh, uint32_t bb, uint32_t es_xy) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return false;
+  cuuint64_t dims[4] = {C, W, H, Bn};
+  // strides of dims 1..3 in bytes; size-1 dims get a harmless natural stride
+  const int64_t s1 = sx, s2 = (H > 1 || sy) ? sy : sx * (int64_t)W, s3 = (Bn > 1 || sb) ? sb : (s2 ? s2 : sx * (int64_t)W) * (int64_t)H;
+  cuuint64_t strides[3] = {(cuuint64_t)s1 * 4, (cuuint64_t)(s2 ? s2 : s1 * (int64_t)W) * 4, (cuuint64_t)(s3 ? s3 : s1 * (int64_t)W * (int64_t)H) * 4};
+  // traversal stride es_xy (stride-2 convs): the box spans bw*es input columns and yields bw of them
+  cuuint32_t box[4] = {TC_BK, bw * es_xy, bh * es_xy, bb};
+  cuuint32_t es[4] = {1, es_xy, es_xy, 1};
+  return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(base), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+static bool make_map3(CUtensorMap* m, const float* base, uint64_t K, uint64_t N, uint64_t Bn, int64_t ld, int64_t sb, uint32_t bn) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return false;
+  cuuint64_t dims[3] = {K, N, Bn};
+  cuuint64_t strides[2] = {(cuuint64_t)ld * 4, (cuuint64_t)(sb ? sb : ld * (int64_t)N) * 4};
+  cuuint32_t box[3] = {TC_BK, bn, 1};
+  cuuint32_t es[3] = {1, 1, 1};
+  return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+static bool a16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+int conv2d_tc(const FridoConvParams* p, cudaStream_t s) {
+  if (!p->a0 || !p->w || !p->out) return set_error(FRIDO_E_ARG, "conv2d_tc: null pointer");
+  if (p->ups != 1) return set_error(FRIDO_E_ARG, "conv2d_tc: ups must be 1 (materialise the upsample first)");
+  if (p->stride != 1 && !(p->stride == 2 && p->ksize == 3)) return set_error(FRIDO_E_ARG, "conv2d_tc: stride must be 1, or 2 for 3x3");
+  if (p->ksize != 1 && p->ksize != 3) return set_error(FRIDO_E_ARG, "conv2d_tc: ksize must be 1 or 3");
+  if (p->pad != p->ksize / 2) return set_error(FRIDO_E_ARG, "conv2d_tc: pad must be ksize/2");
+  if (p->c0 % TC_BK || p->c1 % TC_BK || p->c0 <= 0) return set_error(FRIDO_E_ARG, "conv2d_tc: channels must be multiples of 32");
+  if ((p->c1 > 0) != (p->a1 != nullptr)) return set_error(FRIDO_E_ARG, "conv2d_tc: a1/c1 mismatch");
+  if (p->Cout % 64) return set_error(FRIDO_E_ARG, "conv2d_tc: Cout must be a multiple of 64");
+  if (p->a0_sc != 1 || (p->a1 && p->a1_sc != 1)) return set_error(FRIDO_E_ARG, "conv2d_tc: channel stride must be 1");
+  if (p->Hout != (p->Hin + p->stride - 1) / p->stride || p->Wout != (p->Win + p->stride - 1) / p->stride)
+    return set_error(FRIDO_E_ARG, "conv2d_tc: output size must be ceil(in/stride)");
+  if (!a16(p->a0) || !a16(p->w) || (p->a1 && !a16(p->a1)) || !a16(p->out) || (p->res && !a16(p->res)))
+    return set_error(FRIDO_E_ARG, "conv2d_tc: pointers must be 16-byte aligned");
+  if (p->a0_sx % 4 || p->a0_sy % 4 || p->a0_sb % 4 || (p->a1 && (p->a1_sx % 4 || p->a1_sy % 4 || p->a1_sb % 4)))
+    return set_error(FRIDO_E_ARG, "conv2d_tc: strides must be multiples of 16 bytes");
+  const int Cin = p->c0 + p->c1;
+  const int64_t Ktot = (int64_t)p->ksize * p->ksize * Cin;
+  const int64_t w_ld = p->w_ld ? p->w_ld : Ktot;
+  if (w_ld % 4 || p->w_sb % 4) return set_error(FRIDO_E_ARG, "conv2d_tc: weight strides must be multiples of 16 bytes");
+  if (p->act == FRIDO_ACT_GEGLU && p->o_sn != 1) return set_error(FRIDO_E_ARG, "conv2d_tc: GEGLU needs a dense output");
+  if (p->o_sn == 1 && (p->o_sp % 4 || p->o_sb % 4)) return set_error(FRIDO_E_ARG, "conv2d_tc: output rows must be 16-byte aligned");
+
+  TcParams t;
+  t.B = p->B; t.Hout = p->Hout; t.Wout = p->Wout; t.Cout = p->Cout;
+  t.c0 = p->c0; t.c1 = p->c1; t.ksize = p->ksize; t.pad = p->pad; t.stride = p->stride;
+  t.TW = next_pow2(p->Wout) < TC_BM ? next_pow2(p->Wout) : TC_BM;
+  t.TH = next_pow2(p->Hout) < TC_BM / t.TW ? next_pow2(p->Hout) : TC_BM / t.TW;
+  t.TB = TC_BM / (t.TW * t.TH);
+  t.tiles_x = (p->Wout + t.TW - 1) / t.TW;
+  t.tiles_y = (p->Hout + t.TH - 1) / t.TH;
+  t.tiles_b = (p->B + t.TB - 1) / t.TB;
+  if (p->w_sb && t.TB != 1) return set_error(FRIDO_E_ARG, "conv2d_tc: per-image weights need >= 128 rows per image");
+  const int m_tiles = t.tiles_x * t.tiles_y * t.tiles_b;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  int bn = 64;
+  const int cands[4] = {256, 192, 128, 64};
+  for (int i = 0; i < 4; ++i)
+    if (p->Cout % cands[i] == 0 && (int64_t)m_tiles * (p->Cout / cands[i]) >= sms) { bn = cands[i]; break; }
+  t.BN = bn;
+  t.tiles_n = p->Cout / bn;
+  t.w_batched = p->w_sb != 0;
+  t.bias = p->bias; t.rowvec = p->rowvec; t.rowvec_sb = p->rowvec_sb; t.res = p->res;
+  t.alpha = p->alpha; t.act = p->act; t.out = p->out; t.o_sb = p->o_sb; t.o_sp = p->o_sp; t.o_sn = p->o_sn;
+  t.round_tf32 = p->round_tf32;
+
+  CUtensorMap ma0, ma1, mw;
+  if (!make_map4(&ma0, p->a0, p->c0, p->Win, p->Hin, p->B, p->a0_sx, p->a0_sy, p->a0_sb, t.TW, t.TH, t.TB, (uint32_t)p->stride))
+    return set_error(FRIDO_E_ARG, "conv2d_tc: cuTensorMapEncodeTiled(a0) failed");
+  if (p->a1) {
+    if (!make_map4(&ma1, p->a1, p->c1, p->Win, p->Hin, p->B, p->a1_sx, p->a1_sy, p->a1_sb, t.TW, t.TH, t.TB, (uint32_t)p->stride))
+      return set_error(FRIDO_E_ARG, "conv2d_tc: cuTensorMapEncodeTiled(a1) failed");
+  } else {
+    ma1 = ma0;
+  }
+  if (!make_map3(&mw, p->w, Ktot, p->Cout, p->w_sb ? p->B : 1, w_ld, p->w_sb, bn))
+    return set_error(FRIDO_E_ARG, "conv2d_tc: cuTensorMapEncodeTiled(w) failed");
+
+  static bool attr = false;
+  if (!attr) {
+    if (cudaFuncSetAttribute(conv_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES) != cudaSuccess ||
+        cudaFuncSetAttribute(conv_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES) != cudaSuccess)
+      return set_error(FRIDO_E_LAUNCH, "conv2d_tc: cannot opt in to dynamic shared memory");
+    attr = true;
+  }
+  const bool x3 = p->engine == 2;
+  const int stage_bytes = (TC_A_BYTES + bn * TC_BK * 4) * (x3 ? 2 : 1);
+  t.stages = TC_SMEM_BUDGET / stage_bytes;
+  if (t.stages > TC_MAX_STAGES) t.stages = TC_MAX_STAGES;
+  const int total = m_tiles * t.tiles_n;
+  const int grid = total < sms ? total : sms;
+  if (x3) conv_tc_kernel<true><<<grid, TC_THREADS_X3, TC_SMEM_BYTES, s>>>(ma0, ma1, mw, t);
+  else conv_tc_kernel<false><<<grid, TC_THREADS, TC_SMEM_BYTES, s>>>(ma0, ma1, mw, t);
+  return check_launch(x3 ? "conv2d_tc(3xTF32)" : "conv2d_tc");
+}
+
 }  // namespace frido

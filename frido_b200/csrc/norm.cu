@@ -261,16 +261,41 @@ __global__ void time_embed_kernel(const FridoTimeEmbedParams p) {
   const int b = i / half, j = i - b * half;
   // util.py:160-166: freqs = exp(-ln(max_period) * j / half) in fp32; args = t.float() * freqs
   const float nl = (float)(-log((double)p.max_period));  // python float -> fp32 scalar
-  const float f = expf(nl * (float)j / (float)half);
+  const float f = p.freqs ? p.freqs[j] : expf(nl * (float)j / (float)half);
   const float a = (float)p.t[b] * f;
   p.out[(int64_t)b * p.dim + j] = cosf(a);
   p.out[(int64_t)b * p.dim + half + j] = sinf(a);
   if ((p.dim & 1) && j == 0) p.out[(int64_t)b * p.dim + p.dim - 1] = 0.f;
 }
 
+// nearest x2 upsample, NHWC, one float4 per thread
+__global__ void __launch_bounds__(256) upsample2x_kernel(const FridoUpsampleParams p) {
+  const int Q = p.C >> 2;
+  const int64_t total = (int64_t)p.B * 4 * p.H * p.W * Q;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int q = (int)(e % Q);
+    int64_t r = e / Q;
+    const int ox = (int)(r % (2 * p.W)); r /= (2 * p.W);
+    const int oy = (int)(r % (2 * p.H));
+    const int b = (int)(r / (2 * p.H));
+    float4 v = __ldg(reinterpret_cast<const float4*>(p.x + (((int64_t)b * p.H + (oy >> 1)) * p.W + (ox >> 1)) * p.C) + q);
+    if (p.round_tf32) { v.x = round_tf32(v.x); v.y = round_tf32(v.y); v.z = round_tf32(v.z); v.w = round_tf32(v.w); }
+    reinterpret_cast<float4*>(p.out + (((int64_t)b * 2 * p.H + oy) * 2 * p.W + ox) * p.C)[q] = v;
+  }
+}
+
 }  // namespace frido
 
 using namespace frido;
+
+extern "C" int frido_upsample2x(const FridoUpsampleParams* p, void* stream) {
+  if (!p || !p->x || !p->out || (p->C & 3)) return set_error(FRIDO_E_ARG, "upsample2x: bad argument");
+  const int64_t total = (int64_t)p->B * 4 * p->H * p->W * (p->C >> 2);
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  upsample2x_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(*p);
+  return check_launch("upsample2x");
+}
 
 extern "C" int frido_gn_stats(const FridoGnStatsParams* p, void* stream) {
   if (!p || !p->a0 || !p->sums) return set_error(FRIDO_E_ARG, "gn_stats: null pointer");

@@ -17,6 +17,7 @@ from torch import nn
 from . import _lib as L
 from . import modules as M
 from .program import Program, Src
+from .program import round_tf32_
 from .unet import _pack_conv
 
 
@@ -104,6 +105,7 @@ class DecodePlan:
         n_gn = sum(1 for m in dec.modules() if isinstance(m, nn.GroupNorm))
         self._sums = torch.zeros(n_gn + 1, B, 32, 2, dtype=torch.float64, device=dev)
         self._slot = 0
+        self._mma_ids = set()
         P.zero(self._sums, tag="gn.zero")
         # a14: VQ per scale, written fine->coarse (msvqgan.py:392-393)
         quant = P.buf(B, H * W, Ct)
@@ -134,8 +136,15 @@ class DecodePlan:
             if lvl != 0:
                 c = up.upsample.conv.weight.shape[0]
                 o = P.buf(B, 4 * hh * ww, c)
-                P.conv(Src.nhwc(h, hh, ww), self._conv_w(up.upsample.conv), o, B=B, Hin=hh, Win=ww, Hout=2 * hh, Wout=2 * ww,
-                       Cout=c, ksize=3, pad=1, ups=2, bias=self._vec(up.upsample.conv.bias), tag="dec.up")
+                if P.tc_code and c % 64 == 0:
+                    u2 = P.buf(B, 4 * hh * ww, c)
+                    P.upsample2x(h, u2, B=B, H=hh, W=ww, Cdim=c, round_tf32=P.R)
+                    P.conv(Src.nhwc(u2, 2 * hh, 2 * ww), self._conv_w(up.upsample.conv), o, B=B, Hin=2 * hh, Win=2 * ww,
+                           Hout=2 * hh, Wout=2 * ww, Cout=c, ksize=3, pad=1, bias=self._vec(up.upsample.conv.bias), tag="dec.up")
+                    P.release(u2)
+                else:
+                    P.conv(Src.nhwc(h, hh, ww), self._conv_w(up.upsample.conv), o, B=B, Hin=hh, Win=ww, Hout=2 * hh, Wout=2 * ww,
+                           Cout=c, ksize=3, pad=1, ups=2, bias=self._vec(up.upsample.conv.bias), tag="dec.up")
                 P.release(h)
                 h, hh, ww = o, 2 * hh, 2 * ww
         c = dec.norm_out.weight.shape[0]
@@ -145,6 +154,10 @@ class DecodePlan:
         self.image = torch.zeros(B, oc, hh, ww, dtype=torch.float32, device=dev)
         P.conv(Src.nhwc(t, hh, ww), self._conv_w(dec.conv_out), self.image, B=B, Hin=hh, Win=ww, Hout=hh, Wout=ww, Cout=oc,
                ksize=3, pad=1, bias=self._vec(dec.conv_out.bias), o_sb=oc * hh * ww, o_sp=1, o_sn=hh * ww, tag="dec.conv_out")
+        self._mma_ids = {id(t) for t in P.mma_weights} if P.R else set()
+        for dst, _ in self.packers:
+            if id(dst) in self._mma_ids:
+                round_tf32_(dst)
 
     # packing -------------------------------------------------------------
     def _packed(self, fn):
@@ -161,6 +174,8 @@ class DecodePlan:
     def repack(self):
         for dst, fn in self.packers:
             dst.copy_(fn())
+            if id(dst) in self._mma_ids:
+                round_tf32_(dst)
         self.version = self.fs._pack_version
 
     def repack_if_stale(self):
@@ -175,7 +190,7 @@ class DecodePlan:
         P.gn_stats(x, c, sums, B=B, HW=h * w)
         out = P.buf(B, h * w, c)
         P.norm_act(x, c, sums, self._vec(norm.weight), self._vec(norm.bias), out, B=B, HW=h * w, eps=1e-6, silu=silu,
-                   tag="dec.norm")
+                   round_tf32=P.R, tag="dec.norm")
         return out
 
     def _res(self, rb, x, h, w):
@@ -213,18 +228,18 @@ class DecodePlan:
         wqk = self._packed(lambda: torch.cat([ab.q.weight.detach().view(C, C), ab.k.weight.detach().view(C, C)], 0))
         bqk = self._packed(lambda: torch.cat([ab.q.bias.detach(), ab.k.bias.detach()], 0))
         qk = P.buf(B, N, 2 * C)
-        P.linear(t, wqk, qk, M=B * N, K=C, N=2 * C, bias=bqk, tag="dec.attn.qk")
+        P.linear(t, wqk, qk, M=B * N, K=C, N=2 * C, bias=bqk, round_tf32=P.R, tag="dec.attn.qk")
         vT = P.buf(B, C, N)
         P.conv(Src(t, C, N * C, 0, C, 1), self._packed(lambda: ab.v.weight.detach().view(C, C).clone()), vT, B=B, Hin=1, Win=N,
-               Hout=1, Wout=N, Cout=C, bias=self._vec(ab.v.bias), o_sb=C * N, o_sp=1, o_sn=N, tag="dec.attn.vT")
+               Hout=1, Wout=N, Cout=C, bias=self._vec(ab.v.bias), o_sb=C * N, o_sp=1, o_sn=N, round_tf32=P.R, tag="dec.attn.vT")
         P.release(t)
         sc = P.buf(B, N, N)
         P.conv(Src(qk, C, N * 2 * C, 0, 2 * C, 1), qk, sc, B=B, Hin=1, Win=N, Hout=1, Wout=N, Cout=N, w_sb=N * 2 * C,
                w_ld=2 * C, w_off=C, tag="dec.attn.qk^T")
-        P.softmax(sc, rows=B * N, n=N, ld=N, scale=float(int(C) ** (-0.5)), tag="dec.attn.softmax")
+        P.softmax(sc, rows=B * N, n=N, ld=N, scale=float(int(C) ** (-0.5)), round_tf32=P.R, tag="dec.attn.softmax")
         o = P.buf(B, N, C)
         P.conv(Src(sc, N, N * N, 0, N, 1), vT, o, B=B, Hin=1, Win=N, Hout=1, Wout=N, Cout=C, w_sb=C * N, w_ld=N,
-               tag="dec.attn.pv")
+               round_tf32=P.R, tag="dec.attn.pv")
         P.release(qk); P.release(vT); P.release(sc)
         out = P.buf(B, N, C)
         P.linear(o, self._packed(lambda: ab.proj_out.weight.detach().view(C, C).clone()), out, M=B * N, K=C, N=C,

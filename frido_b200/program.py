@@ -6,6 +6,7 @@ intermediate buffer it touches, and is executed by the native executor
 sampler step is a single graph launch.  Nothing here computes on the host.
 """
 import ctypes as C
+import os
 
 import torch
 
@@ -14,6 +15,26 @@ from . import _lib as L
 
 def _ptr(t):
     return 0 if t is None else t.data_ptr()
+
+
+def default_engine():
+    """'tc3'  = tcgen05 error-compensated 3xTF32 wherever a shape is eligible (fp32-faithful, default);
+    'tc'   = tcgen05 single-pass TF32 (operands rounded to 10 mantissa bits, ~1e-3 relative);
+    'simt' = everything on the fp32 SIMT engine (numerical yardstick / debugging).
+    Shapes the tensor-core engine does not take always run on the SIMT engine."""
+    e = os.environ.get("FRIDO_ENGINE", "tc3")
+    if e not in ("tc3", "tc", "simt"):
+        raise ValueError(f"FRIDO_ENGINE={e!r}: expected tc3, tc or simt")
+    return e
+
+
+def round_tf32_(t):
+    """In-place round-to-nearest (ties away) to TF32 of a device tensor: MMA operands are rounded once
+    by their producer so the tensor core's mantissa truncation never bites."""
+    if t.is_cuda:
+        s = torch.cuda.current_stream(t.device).cuda_stream
+        L.check(L.lib().frido_round_tf32(C.c_void_p(t.data_ptr()), C.c_void_p(t.data_ptr()), t.numel(), C.c_void_p(s)), "round_tf32")
+    return t
 
 
 class Src:
@@ -43,7 +64,7 @@ class Src:
 
 
 class Program:
-    def __init__(self, device, name=""):
+    def __init__(self, device, name="", engine=None):
         self.device = torch.device(device)
         self.name = name
         self.ops = []
@@ -54,6 +75,10 @@ class Program:
         self.graph = None
         self.flops = 0  # algorithmic multiply-add*2 of conv/linear/matmul ops
         self.tc_flops = 0
+        self.mma_weights = []  # tensors consumed as the W operand of a tcgen05 conv
+        self.engine = default_engine() if engine is None else engine
+        self.R = 1 if self.engine == "tc" else 0  # single-pass TF32: producers of MMA operands round to TF32
+        self.tc_code = {"tc": 1, "tc3": 2}.get(self.engine, 0)
 
     # ---- buffers -------------------------------------------------------
     def buf(self, *shape, dtype=torch.float32, zero=False):
@@ -86,7 +111,10 @@ class Program:
 
     def conv(self, a0, w, out, *, B, Hin, Win, Hout, Wout, Cout, ksize=1, stride=1, pad=0, ups=1, a1=None,
              bias=None, rowvec=None, rowvec_sb=0, res=None, alpha=1.0, act=L.ACT_NONE, o_sb=None, o_sp=None, o_sn=1,
-             w_sb=0, w_ld=0, w_off=0, out_off=0, round_tf32=0, engine=0, tag="conv"):
+             w_sb=0, w_ld=0, w_off=0, out_off=0, round_tf32=0, engine=None, tag="conv"):
+        if engine is None:
+            engine = self.tc_code if (self.tc_code and self._tc_ok(a0, a1, B, Hin, Win, Hout, Wout, Cout, ksize, stride, pad, ups, w,
+                                                               w_sb, w_ld, w_off, act, o_sb, o_sp, o_sn, out, out_off, res)) else 0
         p = L.ConvParams()
         p.a0, p.c0 = a0.ptr, a0.C
         p.a0_sb, p.a0_sy, p.a0_sx, p.a0_sc = a0.sb, a0.sy, a0.sx, a0.sc
@@ -107,12 +135,59 @@ class Program:
         self.hold(a0.t, None if a1 is None else a1.t, w, out, bias, rowvec, res)
         fl = 2 * B * Hout * Wout * Cout * ksize * ksize * (a0.C + (a1.C if a1 is not None else 0))
         self.flops += fl
-        if engine == 1:
+        if engine in (1, 2):
             self.tc_flops += fl
+            self.mma_weights.append(w)
         self._add(L.OP_CONV, p, tag)
 
+    @staticmethod
+    def _tc_ok(a0, a1, B, Hin, Win, Hout, Wout, Cout, ksize, stride, pad, ups, w, w_sb, w_ld, w_off, act, o_sb, o_sp, o_sn,
+               out, out_off, res):
+        """Shape contract of conv2d_tc (csrc/conv_tc.cu); everything else runs on the SIMT engine."""
+        if ups != 1 or ksize not in (1, 3) or pad != ksize // 2:
+            return False
+        if not (stride == 1 or (stride == 2 and ksize == 3 and os.environ.get('FRIDO_TC_STRIDE2', '1') == '1')):
+            return False
+        if (Hout, Wout) != ((Hin + stride - 1) // stride, (Win + stride - 1) // stride):
+            return False
+        if stride == 2 and (2 * min(128, 1 << (Wout - 1).bit_length()) > 256):
+            return False
+        if a0.C % 32 or (a1 is not None and a1.C % 32) or Cout % 64:
+            return False
+        if Hout * Wout * B < 128:  # less than one tile of rows: latency-bound, SIMT is as good
+            return False
+        srcs = [a0] + ([a1] if a1 is not None else [])
+        for s in srcs:
+            if s.sc != 1 or s.sx % 4 or s.sy % 4 or s.sb % 4 or (s.ptr & 15):
+                return False
+        Ktot = ksize * ksize * sum(s.C for s in srcs)
+        ld = w_ld or Ktot
+        if ld % 4 or w_sb % 4 or ((w.data_ptr() + 4 * w_off) & 15):
+            return False
+        if w_sb:  # per-image weights: a 128-row tile must not straddle images
+            tw = min(128, 1 << (Wout - 1).bit_length())
+            th = min(128 // tw, 1 << (Hout - 1).bit_length())
+            if tw * th != 128:
+                return False
+        n_out = Cout // 2 if act == L.ACT_GEGLU else Cout
+        o_sp_ = n_out if o_sp is None else o_sp
+        o_sb_ = Hout * Wout * o_sp_ if o_sb is None else o_sb
+        if act == L.ACT_GEGLU and o_sn != 1:
+            return False
+        if o_sn == 1 and (o_sp_ % 4 or o_sb_ % 4):
+            return False
+        if (out.data_ptr() + 4 * out_off) & 15 or (res is not None and res.data_ptr() & 15):
+            return False
+        return True
+
+    def upsample2x(self, x, out, *, B, H, W, Cdim, round_tf32=0, tag="upsample2x"):
+        p = L.UpsampleParams()
+        p.x, p.B, p.H, p.W, p.C, p.round_tf32, p.out = x.data_ptr(), B, H, W, Cdim, round_tf32, out.data_ptr()
+        self.hold(x, out)
+        self._add(L.OP_UPSAMPLE, p, tag)
+
     def linear(self, a, w, out, *, M, K, N, bias=None, res=None, act=L.ACT_NONE, a_ld=None, a_off=0, out_ld=None,
-               rowvec=None, round_tf32=0, engine=0, tag="linear"):
+               rowvec=None, round_tf32=0, engine=None, tag="linear"):
         """out[M,N] = act(a[M,K] @ w[N,K]^T + bias (+rowvec) (+res))  — rows are 'pixels' of one image."""
         a_ld = K if a_ld is None else a_ld
         src = Src(a, K, 0, 0, a_ld, 1, a_off)
@@ -155,9 +230,13 @@ class Program:
         self._add(L.OP_SOFTMAX, p, tag)
 
     def time_embed(self, ts, out, *, B, dim, max_period=10000.0, tag="time_embed"):
+        import math
+        half = dim // 2
+        # util.py:160-162, evaluated by the same CPU torch ops as the reference, then shipped to the device
+        freqs = torch.exp(-math.log(max_period) * torch.arange(start=0, end=half, dtype=torch.float32) / half).to(self.device)
         p = L.TimeEmbedParams()
-        p.t, p.B, p.dim, p.max_period, p.out = ts.data_ptr(), B, dim, max_period, out.data_ptr()
-        self.hold(ts, out)
+        p.t, p.B, p.dim, p.max_period, p.freqs, p.out = ts.data_ptr(), B, dim, max_period, freqs.data_ptr(), out.data_ptr()
+        self.hold(ts, out, freqs)
         self._add(L.OP_TIME_EMBED, p, tag)
 
     def step_begin(self, step, t_table, ts, *, B, T, use_next=0, tag="step_begin"):

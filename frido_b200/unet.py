@@ -20,7 +20,7 @@ from torch import nn
 
 from . import _lib as L
 from . import modules as M
-from .program import Program, Src
+from .program import Program, Src, round_tf32_
 
 
 class PyUNetModel(nn.Module):
@@ -171,7 +171,9 @@ class UNetPlan:
         self.prologue = Program(dev, f"unet.s{stage}.prologue")
         self.step = Program(dev, f"unet.s{stage}.step")
         self._gn_slots = []
+        self._mma_ids = set()
         self._build()
+        self._finalize_weights()
 
     # ---- weight packing (re-runnable: same destination pointers) -------
     def _packed(self, fn):
@@ -182,7 +184,16 @@ class UNetPlan:
     def repack(self):
         for dst, fn in self.packers:
             dst.copy_(fn())
+            if id(dst) in self._mma_ids:
+                round_tf32_(dst)
         self.version = self.net._pack_version
+
+    def _finalize_weights(self):
+        """Weights that feed the tcgen05 engine are rounded to TF32 once, here (and on every repack)."""
+        self._mma_ids = {id(t) for prog in (self.prologue, self.step) if prog.R for t in prog.mma_weights}
+        for dst, _ in self.packers:
+            if id(dst) in self._mma_ids:
+                round_tf32_(dst)
 
     def repack_if_stale(self):
         if self.version != self.net._pack_version:
@@ -214,7 +225,7 @@ class UNetPlan:
         gb = self._spade_site(norm, C, h, w) if (is_spade and self.c_cond) else None
         out = prog.buf(B, hw, C)
         prog.norm_act(xs[0], cs[0], sums, self._vec(g.weight), self._vec(g.bias), out, B=B, HW=hw, eps=eps, a1=a1,
-                      c1=c1, gb=gb, silu=silu, tag=site)
+                      c1=c1, gb=gb, silu=silu, round_tf32=prog.R, tag=site)
         return out
 
     def _spade_site(self, sp, C, h, w):
@@ -228,7 +239,7 @@ class UNetPlan:
         actv = P.buf(B, hw, nh)
         P.conv(Src.nhwc(self.h_cond, self.H, self.W, mc, sub=sub), self._conv_w(sp.mlp_shared[0]), actv, B=B, Hin=h,
                Win=w, Hout=h, Wout=w, Cout=nh, ksize=3, pad=1, bias=self._vec(sp.mlp_shared[0].bias), act=L.ACT_RELU,
-               tag="spade.shared")
+               round_tf32=P.R, tag="spade.shared")
         wgb = self._packed(lambda: torch.cat([_pack_conv(sp.mlp_gamma.weight), _pack_conv(sp.mlp_beta.weight)], 0))
         bgb = self._packed(lambda: torch.cat([sp.mlp_gamma.bias.detach(), sp.mlp_beta.bias.detach()], 0))
         gb = torch.empty(B, hw, 2 * C, dtype=torch.float32, device=self.dev)  # lives across steps: not pooled
@@ -274,10 +285,10 @@ class UNetPlan:
         if ctx_kv is None:  # self-attention: fused q|k projection, V written transposed
             wqk = self._packed(lambda: torch.cat([ca.to_q.weight.detach(), ca.to_k.weight.detach()], 0))
             qk = S.buf(B, N, 2 * C)
-            S.linear(x, wqk, qk, M=B * N, K=C, N=2 * C, tag=tag + ".qk")
+            S.linear(x, wqk, qk, M=B * N, K=C, N=2 * C, round_tf32=S.R, tag=tag + ".qk")
             vT = S.buf(B, C, N)
             S.conv(Src(x, C, N * C, 0, C, 1), self._vec(ca.to_v.weight), vT, B=B, Hin=1, Win=N, Hout=1, Wout=N, Cout=C,
-                   o_sb=C * N, o_sp=1, o_sn=N, tag=tag + ".vT")
+                   o_sb=C * N, o_sp=1, o_sn=N, round_tf32=S.R, tag=tag + ".vT")
             Nk, Nkp = N, N
             q_src = Src(qk, C, N * 2 * C, 0, 2 * C, 1)
             k_t, k_off, k_sb, k_ld = qk, C, N * 2 * C, 2 * C
@@ -285,7 +296,7 @@ class UNetPlan:
         else:
             kc, vTc = ctx_kv
             q = S.buf(B, N, C)
-            S.linear(x, self._vec(ca.to_q.weight), q, M=B * N, K=C, N=C, tag=tag + ".q")
+            S.linear(x, self._vec(ca.to_q.weight), q, M=B * N, K=C, N=C, round_tf32=S.R, tag=tag + ".q")
             Nk, Nkp = self.Lc, self.Lp
             q_src = Src(q, C, N * C, 0, C, 1)
             k_t, k_off, k_sb, k_ld = kc, 0, self.Lp * C, C
@@ -296,10 +307,12 @@ class UNetPlan:
         S.hold(sc)
         S.conv(q_src, k_t, sc, B=B, Hin=1, Win=N, Hout=1, Wout=N, Cout=Nk, w_sb=k_sb, w_ld=k_ld, w_off=k_off,
                o_sb=N * Nkp, o_sp=Nkp, tag=tag + ".qk^T")
-        S.softmax(sc, rows=B * N, n=Nk, ld=Nkp, scale=scale, tag=tag + ".softmax")
+        S.softmax(sc, rows=B * N, n=Nk, ld=Nkp, scale=scale, round_tf32=S.R, tag=tag + ".softmax")
         o = S.buf(B, N, C)
-        S.conv(Src(sc, Nk, N * Nkp, 0, Nkp, 1), v_t, o, B=B, Hin=1, Win=N, Hout=1, Wout=N, Cout=C, w_sb=v_sb, w_ld=Nkp,
-               tag=tag + ".pv")
+        # K runs over the padded key count when that makes the tensor-core engine eligible (pad columns are zero)
+        Kpv = Nkp if Nkp % 32 == 0 else Nk
+        S.conv(Src(sc, Kpv, N * Nkp, 0, Nkp, 1), v_t, o, B=B, Hin=1, Win=N, Hout=1, Wout=N, Cout=C, w_sb=v_sb, w_ld=Nkp,
+               round_tf32=S.R, tag=tag + ".pv")
         S.release(qk)
         if ctx_kv is None:
             S.release(vT)
@@ -314,9 +327,9 @@ class UNetPlan:
         kc = torch.zeros(B, Lp, C, dtype=torch.float32, device=self.dev)
         vT = torch.zeros(B, C, Lp, dtype=torch.float32, device=self.dev)
         P.conv(Src(self.ctx, D, Lc * D, 0, D, 1), self._vec(ca.to_k.weight), kc, B=B, Hin=1, Win=Lc, Hout=1, Wout=Lc,
-               Cout=C, o_sb=Lp * C, o_sp=C, tag="ctx.k")
+               Cout=C, o_sb=Lp * C, o_sp=C, round_tf32=P.R, tag="ctx.k")
         P.conv(Src(self.ctx, D, Lc * D, 0, D, 1), self._vec(ca.to_v.weight), vT, B=B, Hin=1, Win=Lc, Hout=1, Wout=Lc,
-               Cout=C, o_sb=C * Lp, o_sp=1, o_sn=Lp, tag="ctx.vT")
+               Cout=C, o_sb=C * Lp, o_sp=1, o_sn=Lp, round_tf32=P.R, tag="ctx.vT")
         return kc, vT
 
     def _transformer(self, st, x, C, h, w):
@@ -329,7 +342,7 @@ class UNetPlan:
         S.release(t)
         for blk in st.transformer_blocks:
             ln = S.buf(B, N, C)
-            S.layernorm(hcur, self._vec(blk.norm1.weight), self._vec(blk.norm1.bias), ln, rows=B * N, Cdim=C)
+            S.layernorm(hcur, self._vec(blk.norm1.weight), self._vec(blk.norm1.bias), ln, rows=B * N, Cdim=C, round_tf32=S.R)
             o = self._attention(ln, C, N, blk.attn1, None, "attn1")
             S.release(ln)
             h1 = S.buf(B, N, C)
@@ -337,7 +350,7 @@ class UNetPlan:
                      res=hcur, tag="attn1.out")
             S.release(o); S.release(hcur)
             ln = S.buf(B, N, C)
-            S.layernorm(h1, self._vec(blk.norm2.weight), self._vec(blk.norm2.bias), ln, rows=B * N, Cdim=C)
+            S.layernorm(h1, self._vec(blk.norm2.weight), self._vec(blk.norm2.bias), ln, rows=B * N, Cdim=C, round_tf32=S.R)
             o = self._attention(ln, C, N, blk.attn2, self._ctx_kv(blk.attn2, C), "attn2")
             S.release(ln)
             h2 = S.buf(B, N, C)
@@ -345,7 +358,7 @@ class UNetPlan:
                      res=h1, tag="attn2.out")
             S.release(o); S.release(h1)
             ln = S.buf(B, N, C)
-            S.layernorm(h2, self._vec(blk.norm3.weight), self._vec(blk.norm3.bias), ln, rows=B * N, Cdim=C)
+            S.layernorm(h2, self._vec(blk.norm3.weight), self._vec(blk.norm3.bias), ln, rows=B * N, Cdim=C, round_tf32=S.R)
             proj = blk.ff.net[0].proj
             inner = proj.weight.shape[0] // 2
 
@@ -358,7 +371,7 @@ class UNetPlan:
 
             ff = S.buf(B, N, inner)
             S.linear(ln, self._packed(_inter), ff, M=B * N, K=C, N=2 * inner, bias=self._packed(_inter_b), act=L.ACT_GEGLU,
-                     tag="ff.geglu")
+                     round_tf32=S.R, tag="ff.geglu")
             S.release(ln)
             h3 = S.buf(B, N, C)
             S.linear(ff, self._vec(blk.ff.net[2].weight), h3, M=B * N, K=inner, N=C, bias=self._vec(blk.ff.net[2].bias),
@@ -389,8 +402,16 @@ class UNetPlan:
                 xs, h, w = [x], ho, wo
             elif isinstance(layer, M.Upsample):
                 x = S.buf(B, 4 * h * w, cs[0])
-                S.conv(Src.nhwc(xs[0], h, w), self._conv_w(layer.conv), x, B=B, Hin=h, Win=w, Hout=2 * h, Wout=2 * w,
-                       Cout=cs[0], ksize=3, pad=1, ups=2, bias=self._vec(layer.conv.bias), tag="up")
+                if S.tc_code and cs[0] % 64 == 0:
+                    # tensor-core path: materialise the nearest x2 copy (TF32-rounded), then a plain 3x3 conv
+                    up = S.buf(B, 4 * h * w, cs[0])
+                    S.upsample2x(xs[0], up, B=B, H=h, W=w, Cdim=cs[0], round_tf32=S.R)
+                    S.conv(Src.nhwc(up, 2 * h, 2 * w), self._conv_w(layer.conv), x, B=B, Hin=2 * h, Win=2 * w, Hout=2 * h,
+                           Wout=2 * w, Cout=cs[0], ksize=3, pad=1, bias=self._vec(layer.conv.bias), tag="up")
+                    S.release(up)
+                else:
+                    S.conv(Src.nhwc(xs[0], h, w), self._conv_w(layer.conv), x, B=B, Hin=h, Win=w, Hout=2 * h, Wout=2 * w,
+                           Cout=cs[0], ksize=3, pad=1, ups=2, bias=self._vec(layer.conv.bias), tag="up")
                 xs, h, w = [x], 2 * h, 2 * w
             else:
                 raise TypeError(type(layer))

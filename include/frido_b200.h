@@ -69,7 +69,8 @@ typedef struct FridoConvParams {
   float* out;
   int64_t o_sb, o_sp, o_sn; /* out[b*o_sb + p*o_sp + n*o_sn], p = oy*Wout + ox */
   int32_t round_tf32;       /* round stored values to TF32 (rna) */
-  int32_t engine;           /* 0 = SIMT fp32 engine, 1 = tcgen05 TF32 engine (aligned shapes only) */
+  int32_t engine;           /* 0 = SIMT fp32; 1 = tcgen05 TF32; 2 = tcgen05 3xTF32 (error-compensated, fp32-faithful);
+                               1 and 2 take aligned shapes only (see csrc/conv_tc.cu) */
 } FridoConvParams;
 
 int frido_conv2d(const FridoConvParams* p, void* stream);
@@ -117,7 +118,9 @@ int frido_softmax(const FridoSoftmaxParams* p, void* stream);
 
 /* timestep_embedding (util.py:151-171): out[b] = [cos(t_b f_j), sin(t_b f_j)], j < dim/2. */
 typedef struct FridoTimeEmbedParams {
-  const int64_t* t; int32_t B; int32_t dim; float max_period; float* out;
+  const int64_t* t; int32_t B; int32_t dim; float max_period;
+  const float* freqs; /* optional [dim/2] host-computed f_j (bit-identical to the reference's torch.exp); NULL = compute */
+  float* out;
 } FridoTimeEmbedParams;
 int frido_time_embed(const FridoTimeEmbedParams* p, void* stream);
 
@@ -181,6 +184,11 @@ typedef struct FridoVqParams {
 } FridoVqParams;
 int frido_vq_lookup(const FridoVqParams* p, void* stream);
 
+/* F.interpolate(scale_factor=2, mode="nearest") on an NHWC tensor (pyunet.py:119; taming
+ * model.py:50) — used in front of the tcgen05 engine (the SIMT engine folds it into addressing). */
+typedef struct FridoUpsampleParams { const float* x; int32_t B, H, W, C; int32_t round_tf32; float* out; } FridoUpsampleParams;
+int frido_upsample2x(const FridoUpsampleParams* p, void* stream);
+
 /* Fill `n` bytes with zero (graph-capturable helper for the GN sums). */
 int frido_zero(void* ptr, int64_t nbytes, void* stream);
 
@@ -195,7 +203,7 @@ int frido_round_tf32(const float* src, float* dst, int64_t n, void* stream);
 enum FridoOpKind {
   FRIDO_OP_CONV = 1, FRIDO_OP_GN_STATS = 2, FRIDO_OP_NORM_ACT = 3, FRIDO_OP_LAYERNORM = 4,
   FRIDO_OP_SOFTMAX = 5, FRIDO_OP_TIME_EMBED = 6, FRIDO_OP_STEP_BEGIN = 7, FRIDO_OP_UPDATE = 8,
-  FRIDO_OP_SNAP = 9, FRIDO_OP_VQ = 10, FRIDO_OP_ZERO = 11
+  FRIDO_OP_SNAP = 9, FRIDO_OP_VQ = 10, FRIDO_OP_ZERO = 11, FRIDO_OP_UPSAMPLE = 12
 };
 typedef struct FridoZeroParams { void* ptr; int64_t nbytes; } FridoZeroParams;
 typedef struct FridoOp {
@@ -205,7 +213,7 @@ typedef struct FridoOp {
     FridoConvParams conv; FridoGnStatsParams gn_stats; FridoNormActParams norm_act;
     FridoLayerNormParams layernorm; FridoSoftmaxParams softmax; FridoTimeEmbedParams time_embed;
     FridoStepBeginParams step_begin; FridoUpdateParams update; FridoSnapParams snap; FridoVqParams vq;
-    FridoZeroParams zero;
+    FridoZeroParams zero; FridoUpsampleParams upsample;
   } u;
 } FridoOp;
 /* Launches ops[0..n) in order on `stream`; returns 0 or (-(1000+i)) if op i failed. */

@@ -243,14 +243,21 @@ def ddim_update(x, e_t, sch, index, start, noise=None, temperature=1.0):
     """x: [B, end, H, W]; e_t: [B, end-start, H, W] (active group only).
     Returns (x_prev, pred_x0) with groups < start frozen."""
     f32 = lambda v: torch.tensor(float(v), dtype=torch.float32)
-    a_t, a_prev = f32(sch["a_t"][index]), f32(sch["a_prev"][index])
+    a_t, a_prev = np.float32(sch["a_t"][index]), np.float32(sch["a_prev"][index])
     sigma, s1m = f32(sch["sigma"][index]), f32(sch["sqrt_1m"][index])
+    # The three per-step square roots are taken with IEEE correctly-rounded fp32 sqrt (numpy), which
+    # is what the reference's CUDA tensors get (sqrtf.rn).  torch's *CPU* fp32 sqrt (Sleef u05) is
+    # off by one ulp on near-ties (e.g. sqrt(0.009843762f)), so `a_t.sqrt()` on a CPU tensor would
+    # pin the oracle to a host-library quirk instead of to the algorithm.
+    sqrt_at, sqrt_ap = f32(np.sqrt(a_t)), f32(np.sqrt(a_prev))
+    sig32 = np.float32(sch["sigma"][index])
+    dir_c = f32(np.sqrt(np.float32(np.float32(np.float32(1.0) - a_prev) - np.float32(sig32 * sig32))))
     e = torch.cat([torch.zeros_like(x[:, :start]), e_t], dim=1)  # ddim.py:200-202
-    pred_x0 = (x - s1m * e) / a_t.sqrt()  # :243
+    pred_x0 = (x - s1m * e) / sqrt_at  # :243
     pred_x0[:, :start] = x[:, :start]  # :246
-    dir_xt = (1.0 - a_prev - sigma**2).sqrt() * e  # :258
+    dir_xt = dir_c * e  # :258
     nz = sigma * (noise if noise is not None else torch.zeros_like(x)) * temperature
-    x_prev = a_prev.sqrt() * pred_x0 + dir_xt + nz  # :263
+    x_prev = sqrt_ap * pred_x0 + dir_xt + nz  # :263
     x_prev[:, :start] = pred_x0[:, :start]  # :266
     return x_prev, pred_x0
 
