@@ -14,3 +14,16 @@ from .unet import PyUNetModel  # noqa: F401
 
 __all__ = ["FridoDiffusion", "DiffusionWrapper", "LitEma", "PyUNetModel", "VQModelInterface", "DDIMSampler",
            "PLMSSampler", "FridoError", "instantiate_from_config", "lib"]
+
+
+def install_aliases():
+    """Make the reference's import paths (`frido.models.diffusion.ddim`, `taming.models.msvqgan`, ...) and YAML
+    `target:` strings resolve to this package (see frido_b200/compat/README.md)."""
+    import os
+    import sys
+
+    p = os.path.join(os.path.dirname(os.path.abspath(__file__)), "compat")
+    if p not in sys.path:
+        sys.path.insert(0, p)
+    for k in [k for k in sys.modules if k.split(".")[0] in ("frido", "taming")]:
+        del sys.modules[k]

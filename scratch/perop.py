@@ -1,0 +1,47 @@
+import sys, os, ctypes as C, json, collections
+sys.path.insert(0, '/root/repo')
+import torch
+torch.set_grad_enabled(False)
+import frido_b200 as fb
+from frido_b200 import configs, _lib as L
+dev = torch.device('cuda:0')
+model, cfg = configs.build('l2i_coco', dev)
+B = int(os.environ.get('PB', '16'))
+unet = model.model.diffusion_model
+stage = int(os.environ.get('PSTAGE', '1'))
+plan = unet.plan(stage, B, 64, 64, 26)
+plan.prologue.run(); plan.step.run(); torch.cuda.synchronize()
+lib = L.lib()
+ops, tags = plan.step.ops, plan.step.tags
+stream = torch.cuda.current_stream(); sptr = C.c_void_p(stream.cuda_stream)
+best = {}
+for rep in range(3):
+    evs = []
+    for i, op in enumerate(ops):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream); L.check(lib.frido_run_program(C.byref(op), 1, sptr), 'op'); b.record(stream)
+        evs.append((a, b))
+    torch.cuda.synchronize()
+    for i, (a, b) in enumerate(evs):
+        t = a.elapsed_time(b)
+        best[i] = min(best.get(i, 1e9), t)
+rows = []
+agg = collections.defaultdict(lambda: [0.0, 0.0, 0])
+for i, op in enumerate(ops):
+    t = best[i]
+    if op.kind == L.OP_CONV:
+        c = op.u.conv
+        fl = 2 * c.B * c.Hout * c.Wout * c.Cout * c.ksize * c.ksize * (c.c0 + c.c1)
+        key = f"{tags[i]} e{c.engine}"
+        rows.append((t, f"{tags[i]:16s} eng{c.engine} B{c.B} {c.Hout}x{c.Wout} cin{c.c0}+{c.c1} cout{c.Cout} k{c.ksize} s{c.stride}  {t*1e3:8.1f} us  {fl/t/1e9:8.1f} TF/s"))
+    else:
+        fl = 0; key = tags[i] if op.kind != L.OP_GN_STATS else 'gn_stats'
+    agg[key][0] += t; agg[key][1] += fl; agg[key][2] += 1
+tot = sum(best.values())
+print(f"stage {stage} B {B}: total eager per-op sum {tot:.2f} ms over {len(ops)} ops")
+for k, (t, fl, n) in sorted(agg.items(), key=lambda kv: -kv[1][0]):
+    print(f"{k:24s} n={n:3d} {t:8.3f} ms {100*t/tot:5.1f}%  {fl/t/1e9 if t else 0:8.1f} TF/s")
+print('--- slowest convs')
+for t, r in sorted(rows, reverse=True)[:25]:
+    print(r)
+print('--- least efficient big convs')

@@ -75,8 +75,9 @@ def test_conv_simt_matches_torch(dev, case):
     P.run()
     got = out.view(B, Ho, Wo, Cout).permute(0, 3, 1, 2).cpu()
     got2 = out2.view(B, Ho, Wo, Cout).permute(0, 3, 1, 2).cpu()
-    assert (got - ref).abs().max() < 2e-5
-    assert (got2 - ref2).abs().max() < 2e-5
+    tol = 2e-5 + 3e-8 * Cin * k * k  # fp32 accumulation-order noise grows with K
+    assert (got - ref).abs().max() < tol
+    assert (got2 - ref2).abs().max() < tol
 
 
 def test_conv_concat_nchw_in_out_and_geglu(dev):
