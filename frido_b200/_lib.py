@@ -27,7 +27,7 @@ class ConvParams(C.Structure):
         ("a1_sb", c_l), ("a1_sy", c_l), ("a1_sx", c_l), ("a1_sc", c_l),
         ("B", c_i), ("Hin", c_i), ("Win", c_i), ("ups", c_i),
         ("ksize", c_i), ("stride", c_i), ("pad", c_i), ("Hout", c_i), ("Wout", c_i),
-        ("w", c_p), ("w_sb", c_l), ("w_ld", c_l), ("Cout", c_i),
+        ("w", c_p), ("w_sb", c_l), ("w_ld", c_l), ("w_lo", c_p), ("Cout", c_i),
         ("bias", c_p), ("rowvec", c_p), ("rowvec_sb", c_l), ("res", c_p),
         ("alpha", c_f), ("act", c_i), ("out", c_p),
         ("o_sb", c_l), ("o_sp", c_l), ("o_sn", c_l), ("round_tf32", c_i), ("engine", c_i),
@@ -108,7 +108,7 @@ _KIND_FIELD = {OP_CONV: "conv", OP_GN_STATS: "gn_stats", OP_NORM_ACT: "norm_act"
 EXPORTS = [
     "frido_conv2d", "frido_gn_stats", "frido_norm_act", "frido_layernorm", "frido_softmax", "frido_time_embed",
     "frido_step_begin", "frido_sampler_update", "frido_stage_snap", "frido_vq_lookup", "frido_zero",
-    "frido_round_tf32", "frido_upsample2x", "frido_run_program", "frido_abi_version", "frido_sizeof_op", "frido_last_error",
+    "frido_round_tf32", "frido_split_bf16", "frido_upsample2x", "frido_run_program", "frido_abi_version", "frido_sizeof_op", "frido_last_error",
     "frido_launch_count", "frido_check_device",
 ]
 
@@ -138,6 +138,7 @@ def lib():
     L.frido_run_program.argtypes = [C.c_void_p, c_i, c_p]
     L.frido_zero.argtypes = [c_p, c_l, c_p]
     L.frido_round_tf32.argtypes = [c_p, c_p, c_l, c_p]
+    L.frido_split_bf16.argtypes = [c_p, c_p, c_p, c_l, c_p]
     for name in ("frido_conv2d", "frido_gn_stats", "frido_norm_act", "frido_layernorm", "frido_softmax",
                  "frido_time_embed", "frido_step_begin", "frido_sampler_update", "frido_stage_snap", "frido_vq_lookup",
                  "frido_upsample2x"):

@@ -10,7 +10,7 @@ using namespace frido;
 
 extern "C" int frido_conv2d(const FridoConvParams* p, void* stream) {
   if (!p) return set_error(FRIDO_E_ARG, "conv2d: null params");
-  if (p->engine == 1 || p->engine == 2) return conv2d_tc(p, (cudaStream_t)stream);
+  if (p->engine >= 1 && p->engine <= 3) return conv2d_tc(p, (cudaStream_t)stream);
   return conv2d_simt(p, (cudaStream_t)stream);
 }
 

@@ -108,6 +108,38 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
   d |= (uint64_t)2 << 61;                 // SWIZZLE_128B
   return d;
 }
+// K-major, SWIZZLE_64B descriptor (64-byte rows: 32 bf16 of K per row; 8-row atoms of 512 B)
+__device__ __forceinline__ uint64_t umma_desc_sw64(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(512 >> 4) << 32;        // SBO: 8 rows * 64 B
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)4 << 61;                 // SWIZZLE_64B
+  return d;
+}
+// kind::f16 instruction descriptor with BF16 operands, F32 accumulate
+__device__ __forceinline__ uint32_t umma_idesc_bf16(int M, int N) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo_elem, float hi_elem) {
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi_elem), "f"(lo_elem));  // first source -> upper half
+  return r;
+}
+__device__ __forceinline__ float bf16_lo_to_f32(uint32_t packed) { return __uint_as_float(packed << 16); }
+__device__ __forceinline__ float bf16_hi_to_f32(uint32_t packed) { return __uint_as_float(packed & 0xFFFF0000u); }
+
 // kind::tf32 instruction descriptor (cute::UMMA::InstrDescriptor): D=F32, A=B=TF32, K-major both
 __device__ __forceinline__ uint32_t umma_idesc_tf32(int M, int N) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
@@ -139,19 +171,26 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
 }
 
 // ----------------------------------------------------------------------------
-// X3 = error-compensated 3xTF32: every operand tile is split in shared memory into hi = rna_tf32(v) and
-// lo = v - hi by four extra warps, and each K-step issues hi*hi + lo*hi + hi*lo (fp32-faithful, ~2^-21).
-template <bool X3>
-__global__ void __launch_bounds__(X3 ? TC_THREADS_X3 : TC_THREADS, 1)
+// MODE 0: single-pass TF32.
+// MODE 1: error-compensated 3xTF32: every operand tile is split in shared memory into hi = rna_tf32(v) and
+//         lo = v - hi by four extra warps, and each K-step issues hi*hi + lo*hi + hi*lo (products ~2^-21).
+// MODE 2: error-compensated BF16x3 at twice the TF32 issue rate: the fp32 A tile is split in shared memory into
+//         bf16 hi/lo tiles (SWIZZLE_64B), the weights arrive PRE-SPLIT from HBM as two bf16 matrices (two TMA maps);
+//         hi*hi + lo*hi + hi*lo with fp32 accumulation (products ~2^-16).
+template <int MODE>
+__global__ void __launch_bounds__(MODE ? TC_THREADS_X3 : TC_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
-               const __grid_constant__ CUtensorMap map_w, const TcParams p) {
+               const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_wlo, const TcParams p) {
+  constexpr bool X3 = MODE == 1;
+  constexpr bool BF = MODE == 2;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // SWIZZLE_128B atoms need 1024 B alignment
-  const uint32_t b_bytes = (uint32_t)p.BN * TC_BK * 4;
-  // stage layout: A | W            (X3: A_hi | A_lo | W_hi | W_lo)
-  const uint32_t stage_bytes = (TC_A_BYTES + b_bytes) * (X3 ? 2u : 1u);
-  const uint32_t off_alo = TC_A_BYTES;
-  const uint32_t off_w = X3 ? 2u * TC_A_BYTES : (uint32_t)TC_A_BYTES;
+  // stage layout  MODE 0: A | W      MODE 1: A_hi | A_lo | W_hi | W_lo      MODE 2: A_raw(fp32) | A_hi | A_lo | W_hi | W_lo (bf16)
+  const uint32_t b_bytes = BF ? (uint32_t)p.BN * TC_BK * 2 : (uint32_t)p.BN * TC_BK * 4;
+  const uint32_t stage_bytes = BF ? (2u * TC_A_BYTES + 2u * b_bytes) : (TC_A_BYTES + b_bytes) * (X3 ? 2u : 1u);
+  const uint32_t off_ahi = BF ? (uint32_t)TC_A_BYTES : 0u;
+  const uint32_t off_alo = BF ? (uint32_t)TC_A_BYTES + TC_A_BYTES / 2 : (uint32_t)TC_A_BYTES;
+  const uint32_t off_w = (X3 || BF) ? 2u * TC_A_BYTES : (uint32_t)TC_A_BYTES;
   const uint32_t off_wlo = off_w + b_bytes;
   const uint32_t bar_base = smem_base + TC_SMEM_BUDGET;
   // barrier layout: full[6] | empty[6] | split[6] | tmem_full[2] | tmem_empty[2] | tmem_ptr
@@ -173,12 +212,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
   const int ksteps = taps * kchunks;
   const int m_tiles = p.tiles_x * p.tiles_y * p.tiles_b;
   const int total_tiles = m_tiles * p.tiles_n;
-  const uint32_t stage_tx = TC_A_BYTES + b_bytes;
+  const uint32_t stage_tx = TC_A_BYTES + b_bytes * (BF ? 2u : 1u);
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&map_a0);
     if (p.c1) prefetch_tmap(&map_a1);
     prefetch_tmap(&map_w);
+    if (BF) prefetch_tmap(&map_wlo);
     for (int s = 0; s < NS; ++s) {
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);
@@ -225,6 +265,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
           if (ch < p.c0) tma_load_4d(sa, &map_a0, full_bar(stage), ch, cx, cy, b0);
           else           tma_load_4d(sa, &map_a1, full_bar(stage), ch - p.c0, cx, cy, b0);
           tma_load_3d(sb, &map_w, full_bar(stage), tap * Cin + ch, n0, p.w_batched ? b0 : 0);
+          if (BF) tma_load_3d(sa + off_wlo, &map_wlo, full_bar(stage), tap * Cin + ch, n0, p.w_batched ? b0 : 0);
           if (++stage == NS) { stage = 0; phase ^= 1; }
         }
       }
@@ -232,7 +273,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
-      const uint32_t idesc = umma_idesc_tf32(TC_BM, p.BN);
+      const uint32_t idesc = BF ? umma_idesc_bf16(TC_BM, p.BN) : umma_idesc_tf32(TC_BM, p.BN);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -242,10 +283,20 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * TC_MAX_BN);
         for (int ks = 0; ks < ksteps; ++ks) {
-          mbar_wait(X3 ? split_bar(stage) : full_bar(stage), phase);
+          mbar_wait(MODE ? split_bar(stage) : full_bar(stage), phase);
           tc_fence_after();
           const uint32_t sa = smem_base + stage * stage_bytes;
           const uint32_t sb = sa + off_w;
+          if (BF) {
+#pragma unroll
+            for (int k = 0; k < TC_BK / 16; ++k) {  // 2 K-steps of 16 bf16 (32 B) inside the 64 B swizzle row
+              const uint64_t ah = umma_desc_sw64(sa + off_ahi + k * 32), al = umma_desc_sw64(sa + off_alo + k * 32);
+              const uint64_t bh = umma_desc_sw64(sb + k * 32), bl = umma_desc_sw64(sa + off_wlo + k * 32);
+              umma_bf16(d_tmem, ah, bh, idesc, (ks | k) ? 1u : 0u);
+              umma_bf16(d_tmem, al, bh, idesc, 1u);
+              umma_bf16(d_tmem, ah, bl, idesc, 1u);
+            }
+          } else
 #pragma unroll
           for (int k = 0; k < TC_BK / 8; ++k) {
             const uint64_t ad = umma_desc_sw128(sa + k * 32);
@@ -343,6 +394,39 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
       if (lane == 0) mbar_arrive(tempty_bar(acc));
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
+  } else if (BF) {
+    // ===================== splitter (warps 6..9), BF16x3: fp32 A tile -> bf16 hi / lo tiles =====================
+    // source: 128 rows x 128 B, SWIZZLE_128B (16-B chunk c of row r sits at chunk c ^ (r & 7));
+    // destination: 128 rows x 64 B, SWIZZLE_64B (16-B chunk q of row r sits at chunk q ^ ((r >> 1) & 3)).
+    const int t = threadIdx.x - 192;  // 0..127
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int ks = 0; ks < ksteps; ++ks) {
+        mbar_wait(full_bar(stage), phase);
+        uint8_t* sbase = smem_raw + (smem_base - smem_u32(smem_raw)) + (size_t)stage * stage_bytes;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int item = t + 128 * j;   // (row, out-chunk) pairs: 128 x 4
+          const int r = item >> 2, q = item & 3;
+          const float4 v0 = *reinterpret_cast<const float4*>(sbase + r * 128 + (((2 * q) ^ (r & 7)) << 4));
+          const float4 v1 = *reinterpret_cast<const float4*>(sbase + r * 128 + (((2 * q + 1) ^ (r & 7)) << 4));
+          uint4 h, l;
+          h.x = pack_bf16x2(v0.x, v0.y); h.y = pack_bf16x2(v0.z, v0.w); h.z = pack_bf16x2(v1.x, v1.y); h.w = pack_bf16x2(v1.z, v1.w);
+          l.x = pack_bf16x2(v0.x - bf16_lo_to_f32(h.x), v0.y - bf16_hi_to_f32(h.x));
+          l.y = pack_bf16x2(v0.z - bf16_lo_to_f32(h.y), v0.w - bf16_hi_to_f32(h.y));
+          l.z = pack_bf16x2(v1.x - bf16_lo_to_f32(h.z), v1.y - bf16_hi_to_f32(h.z));
+          l.w = pack_bf16x2(v1.z - bf16_lo_to_f32(h.w), v1.w - bf16_hi_to_f32(h.w));
+          const uint32_t o = (uint32_t)r * 64 + ((q ^ ((r >> 1) & 3)) << 4);
+          *reinterpret_cast<uint4*>(sbase + off_ahi + o) = h;
+          *reinterpret_cast<uint4*>(sbase + off_alo + o) = l;
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(split_bar(stage));
+        if (++stage == NS) { stage = 0; phase ^= 1; }
+      }
+    }
   } else if (X3) {
     // ===================== splitter (warps 6..9, 3xTF32 only) =====================
     // In place: v -> hi = rna_tf32(v); lo = v - hi goes to the twin buffer at the same (swizzled) offset.
@@ -423,15 +507,18 @@ static bool make_map4(CUtensorMap* m, const float* base, uint64_t C, uint64_t W,
              CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-static bool make_map3(CUtensorMap* m, const float* base, uint64_t K, uint64_t N, uint64_t Bn, int64_t ld, int64_t sb, uint32_t bn) {
+static bool make_map3(CUtensorMap* m, const void* base, uint64_t K, uint64_t N, uint64_t Bn, int64_t ld, int64_t sb, uint32_t bn,
+                      bool bf16) {
   EncodeTiledFn enc = get_encode();
   if (!enc) return false;
+  const int es_bytes = bf16 ? 2 : 4;
   cuuint64_t dims[3] = {K, N, Bn};
-  cuuint64_t strides[2] = {(cuuint64_t)ld * 4, (cuuint64_t)(sb ? sb : ld * (int64_t)N) * 4};
+  cuuint64_t strides[2] = {(cuuint64_t)ld * es_bytes, (cuuint64_t)(sb ? sb : ld * (int64_t)N) * es_bytes};
   cuuint32_t box[3] = {TC_BK, bn, 1};
   cuuint32_t es[3] = {1, 1, 1};
-  return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+  return enc(m, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(base), dims, strides,
+             box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, bf16 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+             CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 static bool a16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
@@ -455,6 +542,10 @@ int conv2d_tc(const FridoConvParams* p, cudaStream_t s) {
   const int Cin = p->c0 + p->c1;
   const int64_t Ktot = (int64_t)p->ksize * p->ksize * Cin;
   const int64_t w_ld = p->w_ld ? p->w_ld : Ktot;
+  const bool bf = p->engine == 3;
+  if (bf && !p->w_lo) return set_error(FRIDO_E_ARG, "conv2d_tc: engine 3 (bf16x3) needs pre-split weights (w = bf16 hi, w_lo = bf16 lo)");
+  if (bf && (w_ld % 8 || p->w_sb % 8 || !a16(p->w_lo)))
+    return set_error(FRIDO_E_ARG, "conv2d_tc: bf16 weight strides must be multiples of 16 bytes");
   if (w_ld % 4 || p->w_sb % 4) return set_error(FRIDO_E_ARG, "conv2d_tc: weight strides must be multiples of 16 bytes");
   if (p->act == FRIDO_ACT_GEGLU && p->o_sn != 1) return set_error(FRIDO_E_ARG, "conv2d_tc: GEGLU needs a dense output");
   if (p->o_sn == 1 && (p->o_sp % 4 || p->o_sb % 4)) return set_error(FRIDO_E_ARG, "conv2d_tc: output rows must be 16-byte aligned");
@@ -484,7 +575,7 @@ int conv2d_tc(const FridoConvParams* p, cudaStream_t s) {
   t.alpha = p->alpha; t.act = p->act; t.out = p->out; t.o_sb = p->o_sb; t.o_sp = p->o_sp; t.o_sn = p->o_sn;
   t.round_tf32 = p->round_tf32;
 
-  CUtensorMap ma0, ma1, mw;
+  CUtensorMap ma0, ma1, mw, mwlo;
   if (!make_map4(&ma0, p->a0, p->c0, p->Win, p->Hin, p->B, p->a0_sx, p->a0_sy, p->a0_sb, t.TW, t.TH, t.TB, (uint32_t)p->stride))
     return set_error(FRIDO_E_ARG, "conv2d_tc: cuTensorMapEncodeTiled(a0) failed");
   if (p->a1) {
@@ -493,25 +584,33 @@ int conv2d_tc(const FridoConvParams* p, cudaStream_t s) {
   } else {
     ma1 = ma0;
   }
-  if (!make_map3(&mw, p->w, Ktot, p->Cout, p->w_sb ? p->B : 1, w_ld, p->w_sb, bn))
+  if (!make_map3(&mw, p->w, Ktot, p->Cout, p->w_sb ? p->B : 1, w_ld, p->w_sb, bn, bf))
     return set_error(FRIDO_E_ARG, "conv2d_tc: cuTensorMapEncodeTiled(w) failed");
+  if (bf) {
+    if (!make_map3(&mwlo, p->w_lo, Ktot, p->Cout, p->w_sb ? p->B : 1, w_ld, p->w_sb, bn, true))
+      return set_error(FRIDO_E_ARG, "conv2d_tc: cuTensorMapEncodeTiled(w_lo) failed");
+  } else {
+    mwlo = mw;
+  }
 
   static bool attr = false;
   if (!attr) {
-    if (cudaFuncSetAttribute(conv_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES) != cudaSuccess ||
-        cudaFuncSetAttribute(conv_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES) != cudaSuccess)
+    if (cudaFuncSetAttribute(conv_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES) != cudaSuccess ||
+        cudaFuncSetAttribute(conv_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES) != cudaSuccess ||
+        cudaFuncSetAttribute(conv_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES) != cudaSuccess)
       return set_error(FRIDO_E_LAUNCH, "conv2d_tc: cannot opt in to dynamic shared memory");
     attr = true;
   }
   const bool x3 = p->engine == 2;
-  const int stage_bytes = (TC_A_BYTES + bn * TC_BK * 4) * (x3 ? 2 : 1);
+  const int stage_bytes = bf ? (2 * TC_A_BYTES + 2 * bn * TC_BK * 2) : (TC_A_BYTES + bn * TC_BK * 4) * (x3 ? 2 : 1);
   t.stages = TC_SMEM_BUDGET / stage_bytes;
   if (t.stages > TC_MAX_STAGES) t.stages = TC_MAX_STAGES;
   const int total = m_tiles * t.tiles_n;
   const int grid = total < sms ? total : sms;
-  if (x3) conv_tc_kernel<true><<<grid, TC_THREADS_X3, TC_SMEM_BYTES, s>>>(ma0, ma1, mw, t);
-  else conv_tc_kernel<false><<<grid, TC_THREADS, TC_SMEM_BYTES, s>>>(ma0, ma1, mw, t);
-  return check_launch(x3 ? "conv2d_tc(3xTF32)" : "conv2d_tc");
+  if (bf) conv_tc_kernel<2><<<grid, TC_THREADS_X3, TC_SMEM_BYTES, s>>>(ma0, ma1, mw, mwlo, t);
+  else if (x3) conv_tc_kernel<1><<<grid, TC_THREADS_X3, TC_SMEM_BYTES, s>>>(ma0, ma1, mw, mwlo, t);
+  else conv_tc_kernel<0><<<grid, TC_THREADS, TC_SMEM_BYTES, s>>>(ma0, ma1, mw, mwlo, t);
+  return check_launch(bf ? "conv2d_tc(bf16x3)" : x3 ? "conv2d_tc(3xTF32)" : "conv2d_tc");
 }
 
 }  // namespace frido

@@ -184,9 +184,31 @@ __global__ void round_tf32_kernel(const float* __restrict__ src, float* __restri
     dst[i] = round_tf32(src[i]);
 }
 
+__global__ void split_bf16_kernel(const float* __restrict__ src, uint16_t* __restrict__ hi, uint16_t* __restrict__ lo, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float v = src[i];
+    uint32_t h;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(h) : "f"(0.f), "f"(v));
+    const float hf = __uint_as_float(h << 16);
+    uint32_t l;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(l) : "f"(0.f), "f"(v - hf));
+    hi[i] = (uint16_t)(h & 0xFFFF);
+    lo[i] = (uint16_t)(l & 0xFFFF);
+  }
+}
+
 }  // namespace frido
 
 using namespace frido;
+
+extern "C" int frido_split_bf16(const float* src, void* hi, void* lo, int64_t n, void* stream) {
+  if (!src || !hi || !lo || n < 0) return set_error(FRIDO_E_ARG, "split_bf16: bad argument");
+  if (n == 0) return FRIDO_OK;
+  int blocks = (int)((n + 255) / 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  split_bf16_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(src, (uint16_t*)hi, (uint16_t*)lo, n);
+  return check_launch("split_bf16");
+}
 
 extern "C" int frido_step_begin(const FridoStepBeginParams* p, void* stream) {
   if (!p || !p->step || !p->t_table || !p->ts || p->B <= 0 || p->T <= 0) return set_error(FRIDO_E_ARG, "step_begin: bad argument");

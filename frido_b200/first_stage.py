@@ -158,6 +158,7 @@ class DecodePlan:
         for dst, _ in self.packers:
             if id(dst) in self._mma_ids:
                 round_tf32_(dst)
+        P.prepare_weights()
 
     # packing -------------------------------------------------------------
     def _packed(self, fn):
@@ -176,6 +177,7 @@ class DecodePlan:
             dst.copy_(fn())
             if id(dst) in self._mma_ids:
                 round_tf32_(dst)
+        self.prog.prepare_weights()
         self.version = self.fs._pack_version
 
     def repack_if_stale(self):

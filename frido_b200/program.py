@@ -18,13 +18,15 @@ def _ptr(t):
 
 
 def default_engine():
-    """'tc3'  = tcgen05 error-compensated 3xTF32 wherever a shape is eligible (fp32-faithful, default);
-    'tc'   = tcgen05 single-pass TF32 (operands rounded to 10 mantissa bits, ~1e-3 relative);
-    'simt' = everything on the fp32 SIMT engine (numerical yardstick / debugging).
+    """'bf16x3' = tcgen05 error-compensated BF16x3 (hi*hi + lo*hi + hi*lo, fp32 accumulate; products ~2^-16) for every
+               eligible conv/linear with shared weights, 3xTF32 for the attention matmuls (default);
+    'tc3'    = tcgen05 error-compensated 3xTF32 everywhere eligible (products ~2^-21, 2x slower than bf16x3);
+    'tc'     = tcgen05 single-pass TF32 (operands rounded to 10 mantissa bits, ~1e-3 relative);
+    'simt'   = everything on the fp32 SIMT engine (numerical yardstick / debugging).
     Shapes the tensor-core engine does not take always run on the SIMT engine."""
-    e = os.environ.get("FRIDO_ENGINE", "tc3")
-    if e not in ("tc3", "tc", "simt"):
-        raise ValueError(f"FRIDO_ENGINE={e!r}: expected tc3, tc or simt")
+    e = os.environ.get("FRIDO_ENGINE", "bf16x3")
+    if e not in ("bf16x3", "tc3", "tc", "simt"):
+        raise ValueError(f"FRIDO_ENGINE={e!r}: expected bf16x3, tc3, tc or simt")
     return e
 
 
@@ -78,7 +80,9 @@ class Program:
         self.mma_weights = []  # tensors consumed as the W operand of a tcgen05 conv
         self.engine = default_engine() if engine is None else engine
         self.R = 1 if self.engine == "tc" else 0  # single-pass TF32: producers of MMA operands round to TF32
-        self.tc_code = {"tc": 1, "tc3": 2}.get(self.engine, 0)
+        self.tc_code = {"tc": 1, "tc3": 2, "bf16x3": 3}.get(self.engine, 0)
+        self.split_list = []   # (fp32 packed weight, bf16 hi, bf16 lo) of every BF16x3 conv
+        self._split_ids = {}
 
     # ---- buffers -------------------------------------------------------
     def buf(self, *shape, dtype=torch.float32, zero=False):
@@ -115,6 +119,8 @@ class Program:
         if engine is None:
             engine = self.tc_code if (self.tc_code and self._tc_ok(a0, a1, B, Hin, Win, Hout, Wout, Cout, ksize, stride, pad, ups, w,
                                                                w_sb, w_ld, w_off, act, o_sb, o_sp, o_sn, out, out_off, res)) else 0
+        if engine == 3 and w_sb:
+            engine = 2  # per-image "weights" are activations (attention): no pre-split copy exists -> 3xTF32
         p = L.ConvParams()
         p.a0, p.c0 = a0.ptr, a0.C
         p.a0_sb, p.a0_sy, p.a0_sx, p.a0_sc = a0.sb, a0.sy, a0.sx, a0.sc
@@ -124,6 +130,15 @@ class Program:
         p.B, p.Hin, p.Win, p.ups = B, Hin, Win, ups
         p.ksize, p.stride, p.pad, p.Hout, p.Wout = ksize, stride, pad, Hout, Wout
         p.w, p.w_sb, p.w_ld, p.Cout = w.data_ptr() + 4 * w_off, w_sb, w_ld, Cout
+        if engine == 3:
+            ent = self._split_ids.get(id(w))
+            if ent is None:
+                ent = (w, torch.empty(w.shape, dtype=torch.bfloat16, device=w.device),
+                       torch.empty(w.shape, dtype=torch.bfloat16, device=w.device))
+                self._split_ids[id(w)] = ent
+                self.split_list.append(ent)
+            p.w, p.w_lo = ent[1].data_ptr() + 2 * w_off, ent[2].data_ptr() + 2 * w_off
+            self.hold(ent[1], ent[2])
         p.bias, p.rowvec, p.rowvec_sb, p.res = _ptr(bias), _ptr(rowvec), rowvec_sb, _ptr(res)
         p.alpha, p.act = alpha, act
         n_out = Cout // 2 if act == L.ACT_GEGLU else Cout
@@ -135,7 +150,7 @@ class Program:
         self.hold(a0.t, None if a1 is None else a1.t, w, out, bias, rowvec, res)
         fl = 2 * B * Hout * Wout * Cout * ksize * ksize * (a0.C + (a1.C if a1 is not None else 0))
         self.flops += fl
-        if engine in (1, 2):
+        if engine in (1, 2, 3):
             self.tc_flops += fl
             self.mma_weights.append(w)
         self._add(L.OP_CONV, p, tag)
@@ -271,6 +286,14 @@ class Program:
         p.out, p.out_C, p.out_coff, p.indices = out.data_ptr(), out_C, out_coff, indices.data_ptr()
         self.hold(z, codebook, out, indices)
         self._add(L.OP_VQ, p, tag)
+
+    def prepare_weights(self):
+        """(Re)compute the bf16 hi/lo copies of every weight a BF16x3 conv reads (after packing / re-packing)."""
+        for w, hi, lo in self.split_list:
+            if w.is_cuda:
+                s = torch.cuda.current_stream(w.device).cuda_stream
+                L.check(L.lib().frido_split_bf16(C.c_void_p(w.data_ptr()), C.c_void_p(hi.data_ptr()), C.c_void_p(lo.data_ptr()),
+                                                 w.numel(), C.c_void_p(s)), "split_bf16")
 
     # ---- execution -----------------------------------------------------
     def _array(self):

@@ -186,6 +186,8 @@ class UNetPlan:
             dst.copy_(fn())
             if id(dst) in self._mma_ids:
                 round_tf32_(dst)
+        self.prologue.prepare_weights()
+        self.step.prepare_weights()
         self.version = self.net._pack_version
 
     def _finalize_weights(self):
@@ -194,6 +196,8 @@ class UNetPlan:
         for dst, _ in self.packers:
             if id(dst) in self._mma_ids:
                 round_tf32_(dst)
+        self.prologue.prepare_weights()
+        self.step.prepare_weights()
 
     def repack_if_stale(self):
         if self.version != self.net._pack_version:

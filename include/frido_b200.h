@@ -59,6 +59,8 @@ typedef struct FridoConvParams {
   const float* w;           /* [Cout][ksize*ksize][c0+c1], K contiguous */
   int64_t w_sb;             /* 0 = shared weights; else per-image weight stride (batched matmul) */
   int64_t w_ld;             /* element stride between weight rows; 0 = dense (ksize*ksize*(c0+c1)) */
+  const void* w_lo;         /* engine 3 only: `w` is then the bf16 HIGH part and w_lo the bf16 LOW part of the
+                               weights (W = hi + lo, same [Cout][K] layout, see frido_split_bf16); else NULL */
   int32_t Cout;
   const float* bias;        /* [Cout] or NULL */
   const float* rowvec;      /* per-image vector (timestep embedding) or NULL */
@@ -69,8 +71,9 @@ typedef struct FridoConvParams {
   float* out;
   int64_t o_sb, o_sp, o_sn; /* out[b*o_sb + p*o_sp + n*o_sn], p = oy*Wout + ox */
   int32_t round_tf32;       /* round stored values to TF32 (rna) */
-  int32_t engine;           /* 0 = SIMT fp32; 1 = tcgen05 TF32; 2 = tcgen05 3xTF32 (error-compensated, fp32-faithful);
-                               1 and 2 take aligned shapes only (see csrc/conv_tc.cu) */
+  int32_t engine;           /* 0 = SIMT fp32; 1 = tcgen05 TF32; 2 = tcgen05 3xTF32 (error-compensated, ~2^-21 products);
+                               3 = tcgen05 BF16x3 (error-compensated, ~2^-16 products, pre-split weights, 2x the TF32
+                               issue rate); 1-3 take aligned shapes only (see csrc/conv_tc.cu) */
 } FridoConvParams;
 
 int frido_conv2d(const FridoConvParams* p, void* stream);
@@ -191,6 +194,9 @@ int frido_upsample2x(const FridoUpsampleParams* p, void* stream);
 
 /* Fill `n` bytes with zero (graph-capturable helper for the GN sums). */
 int frido_zero(void* ptr, int64_t nbytes, void* stream);
+
+/* BF16x3 weight packing: hi = bf16_rn(w), lo = bf16_rn(w - hi), element-wise (device pointers). */
+int frido_split_bf16(const float* src, void* hi, void* lo, int64_t n, void* stream);
 
 /* tcgen05 engine weight packing: W[Cout][K] fp32 -> TF32-rounded (rna) copy.
  * (The layout itself is unchanged; TMA tiles it.) */

@@ -10,7 +10,7 @@ def build(g, eng):
     p["first_stage_config"]["params"]["ckpt_path"] = None
     m = fb.FridoDiffusion(**p); synth.fill_module_(m, g["seed"]); m.scale_factor.copy_(g["scale_factor"]); m = m.to(dev)
     return m, fb
-for eng in ('tc3', 'tc'):
+for eng in ('bf16x3', 'tc3'):
     for tag in ('tiny2', 'tiny3'):
         g = torch.load(f'tests/golden/{tag}.pt', weights_only=False)
         m, fb = build(g, eng)

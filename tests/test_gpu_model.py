@@ -18,10 +18,10 @@ import torch
 pytestmark = pytest.mark.gpu
 torch.set_grad_enabled(False)
 
-# engine -> (eps tolerance, output tolerance).  tc3 (default product path) and simt meet the north-star
+# engine -> (eps tolerance, output tolerance).  bf16x3 (default product path), tc3 and simt meet the north-star
 # |delta| < 1e-3 everywhere; single-pass TF32 ("tc", opt-in fast mode) is bounded by its operand rounding.
-TOLS = {"tc3": (1e-3, 1e-3), "simt": (1e-4, 1e-3), "tc": (1e-2, 5e-2)}
-ENGINES = ["tc3", "simt", "tc"]
+TOLS = {"bf16x3": (1e-3, 1e-3), "tc3": (1e-3, 1e-3), "simt": (1e-4, 1e-3), "tc": (1e-2, 5e-2)}
+ENGINES = ["bf16x3", "tc3", "simt", "tc"]
 
 
 @pytest.fixture(params=ENGINES)

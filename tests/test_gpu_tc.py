@@ -34,6 +34,7 @@ def _pack(w):
 
 
 def _run(P, dev):
+    P.prepare_weights()
     P.run()
     torch.cuda.synchronize(dev)
 
@@ -51,7 +52,7 @@ CASES = [
 ]
 
 
-@pytest.mark.parametrize("eng", [1, 2])
+@pytest.mark.parametrize("eng", [1, 2, 3])
 @pytest.mark.parametrize("case", CASES)
 def test_conv_tc_matches_torch(dev, case, eng):
     from frido_b200 import _lib as L
@@ -82,11 +83,11 @@ def test_conv_tc_matches_torch(dev, case, eng):
     got2 = out2.view(B, H, W, Cout).permute(0, 3, 1, 2).cpu()
     e1, e2 = (got - ref).abs().max().item(), (got2 - ref2).abs().max().item()
     print(f"case {case} engine {eng}: err {e1:.3e} {e2:.3e} (ref absmax {ref.abs().max():.2f})")
-    tol = TOL if eng == 1 else tol3(Cin * k * k, ref.abs().max().item())
+    tol = TOL if eng == 1 else tol3(Cin * k * k, ref.abs().max().item()) + (1e-4 if eng == 3 else 0.0)  # bf16x3 products ~2^-16
     assert e1 < tol and e2 < tol, (case, e1, e2)
 
 
-@pytest.mark.parametrize("eng", [1, 2])
+@pytest.mark.parametrize("eng", [1, 2, 3])
 def test_tc_geglu_and_attention_shapes(dev, eng):
     from frido_b200 import _lib as L
     from frido_b200.program import Program, Src
@@ -126,7 +127,7 @@ def test_tc_geglu_and_attention_shapes(dev, eng):
     errs = [(outg.cpu() - refg).abs().max().item(), (sc.cpu() - S).abs().max().item() / 8,
             (vT.cpu() - vT_ref).abs().max().item(), (o.cpu() - o_ref).abs().max().item()]
     print("engine", eng, "geglu/qk/vT/pv errs", errs)
-    assert max(errs) < (3e-2 if eng == 1 else 3e-5), errs
+    assert max(errs) < {1: 3e-2, 2: 3e-5, 3: 2e-4}[eng], errs
 
 
 @pytest.mark.parametrize("B,C,H,W", [(2, 64, 16, 16), (3, 192, 64, 64), (2, 96, 9, 7)])
