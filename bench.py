@@ -121,7 +121,7 @@ def time_tc_launches(plan_step, reps=2):
     ops = plan_step.ops
     stream = torch.cuda.current_stream()
     sptr = C.c_void_p(stream.cuda_stream)
-    tc = [i for i, op in enumerate(ops) if op.kind == L.OP_CONV and op.u.conv.engine in (1, 2)]
+    tc = [i for i, op in enumerate(ops) if op.kind == L.OP_CONV and op.u.conv.engine in (1, 2, 3)]
     best = None
     for _ in range(reps + 1):
         evs = {i: (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for i in tc}
@@ -245,7 +245,9 @@ def run_ours(args):
             else f"images/sec {cfg['sampler'].upper()}-{S} ({args.config}, sampling + decode)",
             "value": round(value, 4), "unit": "images/sec", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": round(ms / args.steps, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": {"tc3": "tf32x3 (error-compensated 3xTF32 operands, fp32 accumulate: fp32-faithful)",
+            "dtype": {"bf16x3": "bf16x3 (error-compensated: bf16 hi/lo operand split, 3 MMAs per product, fp32 accumulate; "
+                                "attention matmuls tf32x3) - fp32-faithful to ~1e-4 on eps",
+                      "tc3": "tf32x3 (error-compensated 3xTF32 operands, fp32 accumulate: fp32-faithful)",
                       "tc": "tf32 (fp32 accumulate)", "simt": "f32"}[eng],
             "data": "synthetic (random-init weights with zero_module tensors re-drawn, N(0,1) context and start noise, eta=0)",
             "config": {"workload": f"{args.config}: latent {C}x{H}x{W}, context {Lc}x{D}, {cfg['sampler'].upper()}-{S} x {ns} stages "
@@ -260,11 +262,12 @@ def run_ours(args):
             "clocks": clk,
             "roofline": {"bound": "tensor", "achieved": round(achieved, 2), "peak": peaks["bf16"], "unit": "TFLOP/s",
                          "frac": round(achieved / peaks["bf16"], 4), "traffic": None,
-                         "kernel": "frido::conv_tc_kernel" + ("<true> (3xTF32)" if eng == "tc3" else "<false> (TF32)"),
+                         "kernel": "frido::conv_tc_kernel" + {"bf16x3": "<2> (BF16x3)", "tc3": "<1> (3xTF32)", "tc": "<0> (TF32)"}.get(eng, ""),
                          "note": f"algorithmic FLOPs (1x) of the {tc_n} tcgen05 conv launches of one stage-{ns - 1} UNet step at batch {B} "
                                  f"/ their summed CUDA-event time ({tc_ms:.2f} ms of a {step_ms:.2f} ms eager step); peak = {peaks['source']} "
-                                 "dense bf16 sustained; TF32 issues at half the bf16 rate and 3xTF32 issues 3 MMAs per product, so the "
-                                 "ceiling for this kernel is peak/6 (tc3) or peak/2 (tc)",
+                                 "dense bf16 sustained; error-compensated modes issue 3 MMAs per product and TF32 issues at half the bf16 "
+                                 "rate, so the ceiling of this kernel in algorithmic TFLOP/s is peak/3 (bf16x3), peak/6 (tc3), peak/2 (tc)",
+                         "issued_tflops": round(achieved * {"bf16x3": 3, "tc3": 3}.get(eng, 1), 1),
                          "share_of_step": round(tc_ms / step_ms, 3)},
             "tflop_per_image": round(flops_per_img / 1e12, 3),
             "achieved_tflops_whole_job": round(flops_per_img * value / 1e12 / world, 2),

@@ -10,7 +10,7 @@
 
 namespace frido {
 
-constexpr int BM = 64, BN = 64, BK = 16, NT = 256;
+constexpr int BM = 64, BN = 64, BK = 32, NT = 256;
 
 struct ALoad {
   float v[4];
@@ -30,9 +30,9 @@ __global__ void __launch_bounds__(NT) conv_simt_kernel(const FridoConvParams p) 
   const int taps = p.ksize * p.ksize;
   const int Ktot = taps * Cin;
 
-  // loader role: one (row, 4 consecutive k) per thread for A and for W
+  // loader role: one (row, 2 x 4 consecutive k) per thread for A and for W
   const int lrow = tid >> 2;        // 0..63
-  const int lk = (tid & 3) * 4;     // 0,4,8,12
+  const int lk = (tid & 3) * 4;     // 0,4,8,12 (+16 for the second quad)
   const int pm = m0 + lrow;
   const bool m_ok = pm < HWout;
   const int oy = m_ok ? pm / p.Wout : 0;
@@ -98,13 +98,17 @@ __global__ void __launch_bounds__(NT) conv_simt_kernel(const FridoConvParams p) 
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
 
-  float ra[4], rw[4];
+  float ra[4], rw[4], ra2[4], rw2[4];
   load_a(0, ra);
   load_w(0, rw);
+  load_a(16, ra2);
+  load_w(16, rw2);
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
     As[0][lk + j][lrow] = ra[j];
     Ws[0][lk + j][lrow] = rw[j];
+    As[0][16 + lk + j][lrow] = ra2[j];
+    Ws[0][16 + lk + j][lrow] = rw2[j];
   }
   __syncthreads();
 
@@ -114,6 +118,8 @@ __global__ void __launch_bounds__(NT) conv_simt_kernel(const FridoConvParams p) 
     if (kt + 1 < nk) {
       load_a((kt + 1) * BK, ra);
       load_w((kt + 1) * BK, rw);
+      load_a((kt + 1) * BK + 16, ra2);
+      load_w((kt + 1) * BK + 16, rw2);
     }
 #pragma unroll
     for (int k = 0; k < BK; ++k) {
@@ -131,6 +137,8 @@ __global__ void __launch_bounds__(NT) conv_simt_kernel(const FridoConvParams p) 
       for (int j = 0; j < 4; ++j) {
         As[cur ^ 1][lk + j][lrow] = ra[j];
         Ws[cur ^ 1][lk + j][lrow] = rw[j];
+        As[cur ^ 1][16 + lk + j][lrow] = ra2[j];
+        Ws[cur ^ 1][16 + lk + j][lrow] = rw2[j];
       }
     }
     __syncthreads();
@@ -184,6 +192,69 @@ __global__ void __launch_bounds__(NT) conv_simt_kernel(const FridoConvParams p) 
   }
 }
 
+// Few output channels (UNet / decoder heads: C_out = 3): one thread per output pixel, all C_out accumulators in
+// registers, weights in shared memory.  The generic 64x64 tile would waste 61 of 64 columns here.
+constexpr int SC_MAXCOUT = 4;
+__global__ void __launch_bounds__(128) conv_smallcout_kernel(const FridoConvParams p) {
+  extern __shared__ float wsm[];  // [Cout][Ktot]
+  const int Cin = p.c0 + p.c1;
+  const int Ktot = p.ksize * p.ksize * Cin;
+  const int b = blockIdx.y;
+  const int64_t wld = p.w_ld ? p.w_ld : Ktot;
+  for (int i = threadIdx.x; i < p.Cout * Ktot; i += blockDim.x) wsm[i] = p.w[(int64_t)b * p.w_sb + (int64_t)(i / Ktot) * wld + (i % Ktot)];
+  __syncthreads();
+  const int HWout = p.Hout * p.Wout;
+  const int pix = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pix >= HWout) return;
+  const int oy = pix / p.Wout, ox = pix - oy * p.Wout;
+  const int Hl = p.Hin * p.ups, Wl = p.Win * p.ups, ush = p.ups == 2 ? 1 : 0;
+  const float* a0 = p.a0 + (int64_t)b * p.a0_sb;
+  const float* a1 = p.a1 ? p.a1 + (int64_t)b * p.a1_sb : nullptr;
+  float acc[SC_MAXCOUT] = {0.f, 0.f, 0.f, 0.f};
+  for (int tap = 0; tap < p.ksize * p.ksize; ++tap) {
+    const int dy = tap / p.ksize, dx = tap - dy * p.ksize;
+    const int iy = oy * p.stride + dy - p.pad, ix = ox * p.stride + dx - p.pad;
+    if (iy < 0 || iy >= Hl || ix < 0 || ix >= Wl) continue;
+    const int sy = iy >> ush, sx = ix >> ush;
+    const float4* s0 = reinterpret_cast<const float4*>(a0 + (int64_t)sy * p.a0_sy + (int64_t)sx * p.a0_sx);
+    const float* wt = wsm + tap * Cin;
+    for (int c4 = 0; c4 < p.c0 / 4; ++c4) {
+      const float4 v = __ldg(s0 + c4);
+#pragma unroll
+      for (int n = 0; n < SC_MAXCOUT; ++n)
+        if (n < p.Cout) {
+          const float4 w = *reinterpret_cast<const float4*>(wt + n * Ktot + 4 * c4);
+          acc[n] = fmaf(v.x, w.x, fmaf(v.y, w.y, fmaf(v.z, w.z, fmaf(v.w, w.w, acc[n]))));
+        }
+    }
+    if (a1) {
+      const float4* s1 = reinterpret_cast<const float4*>(a1 + (int64_t)sy * p.a1_sy + (int64_t)sx * p.a1_sx);
+      for (int c4 = 0; c4 < p.c1 / 4; ++c4) {
+        const float4 v = __ldg(s1 + c4);
+#pragma unroll
+        for (int n = 0; n < SC_MAXCOUT; ++n)
+          if (n < p.Cout) {
+            const float4 w = *reinterpret_cast<const float4*>(wt + n * Ktot + p.c0 + 4 * c4);
+            acc[n] = fmaf(v.x, w.x, fmaf(v.y, w.y, fmaf(v.z, w.z, fmaf(v.w, w.w, acc[n]))));
+          }
+      }
+    }
+  }
+  float* out = p.out + (int64_t)b * p.o_sb + (int64_t)pix * p.o_sp;
+  const float* res = p.res ? p.res + (int64_t)b * p.o_sb + (int64_t)pix * p.o_sp : nullptr;
+#pragma unroll
+  for (int n = 0; n < SC_MAXCOUT; ++n)
+    if (n < p.Cout) {
+      float t = acc[n] * p.alpha;
+      if (p.bias) t += __ldg(p.bias + n);
+      if (p.rowvec) t += __ldg(p.rowvec + (int64_t)b * p.rowvec_sb + n);
+      if (res) t += res[(int64_t)n * p.o_sn];
+      if (p.act == FRIDO_ACT_RELU) t = fmaxf(t, 0.f);
+      else if (p.act == FRIDO_ACT_SILU) t = silu_f(t);
+      out[(int64_t)n * p.o_sn] = p.round_tf32 ? round_tf32(t) : t;
+    }
+}
+
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 int conv2d_simt(const FridoConvParams* p, cudaStream_t s) {
@@ -201,6 +272,17 @@ int conv2d_simt(const FridoConvParams* p, cudaStream_t s) {
   if (p->a1)
     vecA = vecA && p->a1_sc == 1 && aligned16(p->a1) && p->a1_sb % 4 == 0 && p->a1_sy % 4 == 0 && p->a1_sx % 4 == 0;
   const bool vecW = (Ktot % 4 == 0) && aligned16(p->w) && (p->w_sb % 4 == 0) && (p->w_ld % 4 == 0);
+  if (vecA && p->Cout <= SC_MAXCOUT && p->act != FRIDO_ACT_GEGLU && (size_t)p->Cout * Ktot * 4 <= 96 * 1024 && Ktot % 4 == 0) {
+    const size_t smem = (size_t)p->Cout * Ktot * 4;
+    static bool attr = false;
+    if (!attr) {
+      cudaFuncSetAttribute(conv_smallcout_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+      attr = true;
+    }
+    dim3 g((p->Hout * p->Wout + 127) / 128, p->B);
+    conv_smallcout_kernel<<<g, 128, smem, s>>>(*p);
+    return check_launch("conv2d_smallcout");
+  }
   dim3 grid((p->Hout * p->Wout + BM - 1) / BM, (p->Cout + BN - 1) / BN, p->B);
   if (grid.y > 65535 || grid.z > 65535) return set_error(FRIDO_E_ARG, "conv2d: grid too large");
   if (vecA && vecW) conv_simt_kernel<true, true><<<grid, NT, 0, s>>>(*p);

@@ -29,16 +29,20 @@ constexpr int TC_BK = 32;             // fp32 elements per stage row = 128 bytes
 constexpr int TC_MAX_STAGES = 6;
 constexpr int TC_MAX_BN = 256;
 constexpr int TC_A_BYTES = TC_BM * TC_BK * 4;       // 16 KB
-constexpr int TC_SMEM_BUDGET = 216 * 1024;          // operand ring; + 1 KB align slack + barriers < 227 KB
-constexpr int TC_SMEM_BYTES = TC_SMEM_BUDGET + 1024 + 256;
+constexpr int TC_SMEM_BUDGET = 200 * 1024;          // operand ring
+constexpr int TC_STG_BYTES = 4 * 4096;              // epilogue transpose staging, 4 KB per epilogue warp
+constexpr int TC_SMEM_BYTES = TC_SMEM_BUDGET + TC_STG_BYTES + 256 /*barriers*/ + 1024 /*align slack*/;  // < 227 KB
 constexpr int TC_THREADS = 192;                     // TMA, MMA, 4 epilogue warps
-constexpr int TC_THREADS_X3 = 320;                  // + 4 splitter warps (3xTF32 mode)
+constexpr int TC_SPLIT_WARPS = 8;
+constexpr int TC_SPLIT_THREADS = TC_SPLIT_WARPS * 32;
+constexpr int TC_THREADS_X3 = 192 + TC_SPLIT_THREADS;  // + splitter warps (error-compensated modes)
 
 struct TcParams {
   int B, Hout, Wout, Cout;
   int c0, c1;           // channels per source (multiples of 32)
   int ksize, pad, stride;
-  int TW, TH, TB;       // tile = TW*TH*TB = 128 pixels
+  int TW, TH, TB;       // tile = TW*TH*TB = 128 pixels (powers of two)
+  int lTW, lTH;         // log2
   int tiles_x, tiles_y, tiles_b, tiles_n;
   int BN;
   int stages;           // depth of the smem ring
@@ -192,7 +196,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
   const uint32_t off_alo = BF ? (uint32_t)TC_A_BYTES + TC_A_BYTES / 2 : (uint32_t)TC_A_BYTES;
   const uint32_t off_w = (X3 || BF) ? 2u * TC_A_BYTES : (uint32_t)TC_A_BYTES;
   const uint32_t off_wlo = off_w + b_bytes;
-  const uint32_t bar_base = smem_base + TC_SMEM_BUDGET;
+  const uint32_t bar_base = smem_base + TC_SMEM_BUDGET + TC_STG_BYTES;
   // barrier layout: full[6] | empty[6] | split[6] | tmem_full[2] | tmem_empty[2] | tmem_ptr
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (TC_MAX_STAGES + s); };
@@ -222,7 +226,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
     for (int s = 0; s < NS; ++s) {
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);
-      mbar_init(split_bar(s), 4);  // one arrive per splitter warp
+      mbar_init(split_bar(s), TC_SPLIT_WARPS);  // one arrive per splitter warp
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
@@ -318,8 +322,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
     }
   } else if (warp < 6) {
     // ===================== epilogue (warps 2..5) =====================
+    // tcgen05.ld gives thread = accumulator row.  For NHWC outputs (o_sn == 1) each 32x32 chunk is transposed
+    // through a 4 KB per-warp shared staging tile so that every global access instruction covers 4 rows x 128
+    // contiguous bytes (bias / timestep row / residual / activation are applied in that coalesced arrangement).
+    // Transposed outputs (V^T: o_sp == 1) are already coalesced across lanes and go out directly.
     const int q = warp & 3;            // TMEM lane quarter this warp may access
     const int row = q * 32 + lane;     // tile row owned by this thread
+    float4* stg = reinterpret_cast<float4*>(smem_raw + (smem_base - smem_u32(smem_raw)) + TC_SMEM_BUDGET) + q * 256;
+    const int sub = lane >> 3, ck = lane & 7;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -328,59 +338,96 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
       const int tx = mt % p.tiles_x; mt /= p.tiles_x;
       const int ty = mt % p.tiles_y;
       const int tb = mt / p.tiles_y;
-      const int tw = row % p.TW;
-      const int th = (row / p.TW) % p.TH;
-      const int tbb = row / (p.TW * p.TH);
-      const int ox = tx * p.TW + tw, oy = ty * p.TH + th, b = tb * p.TB + tbb;
-      const bool valid = ox < p.Wout && oy < p.Hout && b < p.B;
       const int n0 = nt * p.BN;
-      const long long pix = (long long)oy * p.Wout + ox;
-      float* __restrict__ orow = p.out + (long long)b * p.o_sb + pix * p.o_sp;
-      const float* __restrict__ rrow = p.res ? p.res + (long long)b * p.o_sb + pix * p.o_sp : nullptr;
-      const float* __restrict__ rv = p.rowvec ? p.rowvec + (long long)b * p.rowvec_sb : nullptr;
-
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
       const uint32_t t_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * TC_MAX_BN);
-      for (int c = 0; c < p.BN; c += 32) {
-        uint32_t r[32];
-        tmem_ld32(t_base + c, r);
-        if (valid) {
-          float v[32];
+      if (p.o_sn == 1) {
+        // per-lane output rows of the coalesced arrangement (8 rows: rl = 4j + sub) are the same for every chunk
+        long long obase[8];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const int n = n0 + c + j;
-            float t = __uint_as_float(r[j]) * p.alpha;
-            if (p.bias) t += __ldg(p.bias + n);
-            if (rv) t += __ldg(rv + n);
-            v[j] = t;
-          }
-          if (p.act == FRIDO_ACT_GEGLU) {
-            const int no = (n0 + c) >> 1;
+        for (int j = 0; j < 8; ++j) {
+          const int rr = q * 32 + 4 * j + sub;
+          const int ox = tx * p.TW + (rr & (p.TW - 1));
+          const int oy = ty * p.TH + ((rr >> p.lTW) & (p.TH - 1));
+          const int b = tb * p.TB + (rr >> (p.lTW + p.lTH));
+          obase[j] = (ox < p.Wout && oy < p.Hout && b < p.B) ? (long long)b * p.o_sb + ((long long)oy * p.Wout + ox) * p.o_sp : -1;
+        }
+        const bool geglu = p.act == FRIDO_ACT_GEGLU;
+        for (int c = 0; c < p.BN; c += 32) {
+          // residual loads of this chunk are issued first so their latency overlaps the TMEM load + transpose
+          float4 rres[8];
+          if (p.res) {
+            const int nn = n0 + c + 4 * ck;
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              float t = v[2 * j] * gelu_erf(v[2 * j + 1]);
-              if (rrow) t += rrow[(long long)(no + j) * p.o_sn];
-              orow[(long long)(no + j) * p.o_sn] = p.round_tf32 ? round_tf32(t) : t;
-            }
-          } else if (p.o_sn == 1) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              float4 t = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-              if (rrow) {
-                const float4 rr = *reinterpret_cast<const float4*>(rrow + n0 + c + j);
-                t.x += rr.x; t.y += rr.y; t.z += rr.z; t.w += rr.w;
+            for (int j = 0; j < 8; ++j) {
+              rres[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (obase[j] >= 0) {
+                if (geglu) { const float2 t2 = *reinterpret_cast<const float2*>(p.res + obase[j] + (nn >> 1)); rres[j].x = t2.x; rres[j].y = t2.y; }
+                else rres[j] = *reinterpret_cast<const float4*>(p.res + obase[j] + nn);
               }
-              if (p.act == FRIDO_ACT_RELU) { t.x = fmaxf(t.x, 0.f); t.y = fmaxf(t.y, 0.f); t.z = fmaxf(t.z, 0.f); t.w = fmaxf(t.w, 0.f); }
-              else if (p.act == FRIDO_ACT_SILU) { t.x = silu_f(t.x); t.y = silu_f(t.y); t.z = silu_f(t.z); t.w = silu_f(t.w); }
-              if (p.round_tf32) { t.x = round_tf32(t.x); t.y = round_tf32(t.y); t.z = round_tf32(t.z); t.w = round_tf32(t.w); }
-              *reinterpret_cast<float4*>(orow + n0 + c + j) = t;
             }
-          } else {
+          }
+          uint32_t r[32];
+          tmem_ld32(t_base + c, r);
+#pragma unroll
+          for (int k = 0; k < 8; ++k)
+            stg[lane * 8 + (k ^ (lane & 7))] = make_float4(__uint_as_float(r[4 * k]), __uint_as_float(r[4 * k + 1]),
+                                                           __uint_as_float(r[4 * k + 2]), __uint_as_float(r[4 * k + 3]));
+          __syncwarp();
+          const int n = n0 + c + 4 * ck;
+          float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (p.bias) bias4 = __ldg(reinterpret_cast<const float4*>(p.bias + n));
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int rl = 4 * j + sub;
+            float4 v = stg[rl * 8 + (ck ^ (rl & 7))];
+            if (obase[j] >= 0) {
+              const long long base = obase[j];
+              const int b = tb * p.TB + ((q * 32 + rl) >> (p.lTW + p.lTH));
+              v.x = v.x * p.alpha + bias4.x; v.y = v.y * p.alpha + bias4.y; v.z = v.z * p.alpha + bias4.z; v.w = v.w * p.alpha + bias4.w;
+              if (p.rowvec) {
+                const float4 e = __ldg(reinterpret_cast<const float4*>(p.rowvec + (long long)b * p.rowvec_sb + n));
+                v.x += e.x; v.y += e.y; v.z += e.z; v.w += e.w;
+              }
+              if (p.act == FRIDO_ACT_GEGLU) {
+                float2 t = make_float2(v.x * gelu_erf(v.y), v.z * gelu_erf(v.w));
+                const long long o = base + (n >> 1);
+                if (p.res) { t.x += rres[j].x; t.y += rres[j].y; }
+                if (p.round_tf32) { t.x = round_tf32(t.x); t.y = round_tf32(t.y); }
+                *reinterpret_cast<float2*>(p.out + o) = t;
+              } else {
+                const long long o = base + n;
+                if (p.res) { v.x += rres[j].x; v.y += rres[j].y; v.z += rres[j].z; v.w += rres[j].w; }
+                if (p.act == FRIDO_ACT_RELU) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+                else if (p.act == FRIDO_ACT_SILU) { v.x = silu_f(v.x); v.y = silu_f(v.y); v.z = silu_f(v.z); v.w = silu_f(v.w); }
+                if (p.round_tf32) { v.x = round_tf32(v.x); v.y = round_tf32(v.y); v.z = round_tf32(v.z); v.w = round_tf32(v.w); }
+                *reinterpret_cast<float4*>(p.out + o) = v;
+              }
+            }
+          }
+          __syncwarp();
+        }
+      } else {
+        const int ox = tx * p.TW + (row & (p.TW - 1));
+        const int oy = ty * p.TH + ((row >> p.lTW) & (p.TH - 1));
+        const int b = tb * p.TB + (row >> (p.lTW + p.lTH));
+        const bool valid = ox < p.Wout && oy < p.Hout && b < p.B;
+        const long long pix = (long long)oy * p.Wout + ox;
+        float* __restrict__ orow = p.out + (long long)b * p.o_sb + pix * p.o_sp;
+        const float* __restrict__ rrow = p.res ? p.res + (long long)b * p.o_sb + pix * p.o_sp : nullptr;
+        const float* __restrict__ rv = p.rowvec ? p.rowvec + (long long)b * p.rowvec_sb : nullptr;
+        for (int c = 0; c < p.BN; c += 32) {
+          uint32_t r[32];
+          tmem_ld32(t_base + c, r);
+          if (valid) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
-              const long long o = (long long)(n0 + c + j) * p.o_sn;
-              float t = v[j];
+              const int n = n0 + c + j;
+              float t = __uint_as_float(r[j]) * p.alpha;
+              if (p.bias) t += __ldg(p.bias + n);
+              if (rv) t += __ldg(rv + n);
+              const long long o = (long long)n * p.o_sn;
               if (rrow) t += rrow[o];
               if (p.act == FRIDO_ACT_RELU) t = fmaxf(t, 0.f);
               else if (p.act == FRIDO_ACT_SILU) t = silu_f(t);
@@ -398,7 +445,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
     // ===================== splitter (warps 6..9), BF16x3: fp32 A tile -> bf16 hi / lo tiles =====================
     // source: 128 rows x 128 B, SWIZZLE_128B (16-B chunk c of row r sits at chunk c ^ (r & 7));
     // destination: 128 rows x 64 B, SWIZZLE_64B (16-B chunk q of row r sits at chunk q ^ ((r >> 1) & 3)).
-    const int t = threadIdx.x - 192;  // 0..127
+    const int t = threadIdx.x - 192;  // 0..TC_SPLIT_THREADS-1
     int stage = 0;
     uint32_t phase = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -406,8 +453,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
         mbar_wait(full_bar(stage), phase);
         uint8_t* sbase = smem_raw + (smem_base - smem_u32(smem_raw)) + (size_t)stage * stage_bytes;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int item = t + 128 * j;   // (row, out-chunk) pairs: 128 x 4
+        for (int j = 0; j < 512 / TC_SPLIT_THREADS; ++j) {
+          const int item = t + TC_SPLIT_THREADS * j;   // (row, out-chunk) pairs: 128 x 4
           const int r = item >> 2, q = item & 3;
           const float4 v0 = *reinterpret_cast<const float4*>(sbase + r * 128 + (((2 * q) ^ (r & 7)) << 4));
           const float4 v1 = *reinterpret_cast<const float4*>(sbase + r * 128 + (((2 * q + 1) ^ (r & 7)) << 4));
@@ -430,7 +477,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
   } else if (X3) {
     // ===================== splitter (warps 6..9, 3xTF32 only) =====================
     // In place: v -> hi = rna_tf32(v); lo = v - hi goes to the twin buffer at the same (swizzled) offset.
-    const int t = threadIdx.x - 192;  // 0..127
+    const int t = threadIdx.x - 192;
     int stage = 0;
     uint32_t phase = 0;
     const int a_vec = TC_A_BYTES / 16, w_vec = (int)(b_bytes / 16);
@@ -443,14 +490,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
         float4* w_hi = reinterpret_cast<float4*>(sbase + off_w);
         float4* w_lo = reinterpret_cast<float4*>(sbase + off_wlo);
 #pragma unroll 4
-        for (int i = t; i < a_vec; i += 128) {
+        for (int i = t; i < a_vec; i += TC_SPLIT_THREADS) {
           const float4 v = a_hi[i];
           const float4 h = make_float4(round_tf32(v.x), round_tf32(v.y), round_tf32(v.z), round_tf32(v.w));
           a_hi[i] = h;
           a_lo[i] = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
         }
 #pragma unroll 4
-        for (int i = t; i < w_vec; i += 128) {
+        for (int i = t; i < w_vec; i += TC_SPLIT_THREADS) {
           const float4 v = w_hi[i];
           const float4 h = make_float4(round_tf32(v.x), round_tf32(v.y), round_tf32(v.z), round_tf32(v.w));
           w_hi[i] = h;
@@ -549,6 +596,8 @@ int conv2d_tc(const FridoConvParams* p, cudaStream_t s) {
   if (w_ld % 4 || p->w_sb % 4) return set_error(FRIDO_E_ARG, "conv2d_tc: weight strides must be multiples of 16 bytes");
   if (p->act == FRIDO_ACT_GEGLU && p->o_sn != 1) return set_error(FRIDO_E_ARG, "conv2d_tc: GEGLU needs a dense output");
   if (p->o_sn == 1 && (p->o_sp % 4 || p->o_sb % 4)) return set_error(FRIDO_E_ARG, "conv2d_tc: output rows must be 16-byte aligned");
+  if (p->o_sn == 1 && ((p->bias && !a16(p->bias)) || (p->rowvec && (!a16(p->rowvec) || p->rowvec_sb % 4))))
+    return set_error(FRIDO_E_ARG, "conv2d_tc: bias / rowvec must be 16-byte aligned");
 
   TcParams t;
   t.B = p->B; t.Hout = p->Hout; t.Wout = p->Wout; t.Cout = p->Cout;
@@ -556,6 +605,8 @@ int conv2d_tc(const FridoConvParams* p, cudaStream_t s) {
   t.TW = next_pow2(p->Wout) < TC_BM ? next_pow2(p->Wout) : TC_BM;
   t.TH = next_pow2(p->Hout) < TC_BM / t.TW ? next_pow2(p->Hout) : TC_BM / t.TW;
   t.TB = TC_BM / (t.TW * t.TH);
+  t.lTW = 0; while ((1 << t.lTW) < t.TW) ++t.lTW;
+  t.lTH = 0; while ((1 << t.lTH) < t.TH) ++t.lTH;
   t.tiles_x = (p->Wout + t.TW - 1) / t.TW;
   t.tiles_y = (p->Hout + t.TH - 1) / t.TH;
   t.tiles_b = (p->B + t.TB - 1) / t.TB;
@@ -564,10 +615,22 @@ int conv2d_tc(const FridoConvParams* p, cudaStream_t s) {
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  // Tile width: minimise waves x per-stage time.  Per stage the tensor pipe needs (#MMA per stage) * BN/2 cycles and the
+  // operand splitter / TMA issue put a floor under it, so narrow tiles only pay when they remove whole waves.
+  const int mode = p->engine == 3 ? 2 : (p->engine == 2 ? 1 : 0);
+  const int mma_per_stage[3] = {4, 12, 6};
+  const int floor_clk[3] = {260, 1000, 450};
   int bn = 64;
+  double best_cost = 1e30;
   const int cands[4] = {256, 192, 128, 64};
-  for (int i = 0; i < 4; ++i)
-    if (p->Cout % cands[i] == 0 && (int64_t)m_tiles * (p->Cout / cands[i]) >= sms) { bn = cands[i]; break; }
+  for (int i = 0; i < 4; ++i) {
+    if (p->Cout % cands[i]) continue;
+    const int64_t tiles = (int64_t)m_tiles * (p->Cout / cands[i]);
+    const int64_t waves = (tiles + sms - 1) / sms;
+    const int clk = mma_per_stage[mode] * cands[i] / 2;
+    const double cost = (double)waves * (clk > floor_clk[mode] ? clk : floor_clk[mode]);
+    if (cost < best_cost) { best_cost = cost; bn = cands[i]; }
+  }
   t.BN = bn;
   t.tiles_n = p->Cout / bn;
   t.w_batched = p->w_sb != 0;

@@ -167,7 +167,7 @@ class UNetPlan:
         self.ts = torch.zeros(B, dtype=torch.int64, device=dev)
         self.ctx = torch.zeros(B, Lc, net.context_dim, **f32)
         self.eps = torch.zeros(B, self.e_s, H, W, **f32)
-        self.Lp = (Lc + 31) // 32 * 32
+        self.Lp = (Lc + 63) // 64 * 64  # padded key count: zero keys, so cross-attention can run on the tensor-core engine
         self.prologue = Program(dev, f"unet.s{stage}.prologue")
         self.step = Program(dev, f"unet.s{stage}.step")
         self._gn_slots = []
@@ -309,7 +309,9 @@ class UNetPlan:
         # scores: pad columns [Nk, Nkp) stay zero forever (zero-initialised, never written)
         sc = torch.zeros(B, N, Nkp, dtype=torch.float32, device=self.dev) if Nkp != Nk else S.buf(B, N, Nkp)
         S.hold(sc)
-        S.conv(q_src, k_t, sc, B=B, Hin=1, Win=N, Hout=1, Wout=N, Cout=Nk, w_sb=k_sb, w_ld=k_ld, w_off=k_off,
+        # cross-attention: computing the (zero) padded key columns too makes C_out a multiple of 64 -> tensor-core eligible
+        n_cols = Nkp if (Nkp != Nk and S.tc_code and N >= 128) else Nk
+        S.conv(q_src, k_t, sc, B=B, Hin=1, Win=N, Hout=1, Wout=N, Cout=n_cols, w_sb=k_sb, w_ld=k_ld, w_off=k_off,
                o_sb=N * Nkp, o_sp=Nkp, tag=tag + ".qk^T")
         S.softmax(sc, rows=B * N, n=Nk, ld=Nkp, scale=scale, round_tf32=S.R, tag=tag + ".softmax")
         o = S.buf(B, N, C)
