@@ -30,7 +30,7 @@ class ConvParams(C.Structure):
         ("w", c_p), ("w_sb", c_l), ("w_ld", c_l), ("w_lo", c_p), ("Cout", c_i),
         ("bias", c_p), ("rowvec", c_p), ("rowvec_sb", c_l), ("res", c_p),
         ("alpha", c_f), ("act", c_i), ("out", c_p),
-        ("o_sb", c_l), ("o_sp", c_l), ("o_sn", c_l), ("round_tf32", c_i), ("engine", c_i),
+        ("o_sb", c_l), ("o_sp", c_l), ("o_sn", c_l), ("round_tf32", c_i), ("chan_sums", c_p), ("engine", c_i),
     ]
 
 
@@ -41,7 +41,7 @@ class GnStatsParams(C.Structure):
 
 class NormActParams(C.Structure):
     _fields_ = [("a0", c_p), ("a1", c_p), ("c0", c_i), ("c1", c_i), ("B", c_i), ("HW", c_i), ("groups", c_i),
-                ("sums", c_p), ("eps", c_f), ("gamma", c_p), ("beta", c_p), ("gb", c_p), ("silu", c_i),
+                ("sums", c_p), ("eps", c_f), ("csum0", c_p), ("csum1", c_p), ("gamma", c_p), ("beta", c_p), ("gb", c_p), ("silu", c_i),
                 ("round_tf32", c_i), ("out", c_p)]
 
 

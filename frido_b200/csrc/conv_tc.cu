@@ -31,7 +31,8 @@ constexpr int TC_MAX_BN = 256;
 constexpr int TC_A_BYTES = TC_BM * TC_BK * 4;       // 16 KB
 constexpr int TC_SMEM_BUDGET = 200 * 1024;          // operand ring
 constexpr int TC_STG_BYTES = 4 * 4096;              // epilogue transpose staging, 4 KB per epilogue warp
-constexpr int TC_SMEM_BYTES = TC_SMEM_BUDGET + TC_STG_BYTES + 256 /*barriers*/ + 1024 /*align slack*/;  // < 227 KB
+constexpr int TC_CSUM_BYTES = 4 * 256 * 2 * 4;          // per-tile channel sum / sum-of-squares accumulators [img<=4][BN<=256][2]
+constexpr int TC_SMEM_BYTES = TC_SMEM_BUDGET + TC_STG_BYTES + TC_CSUM_BYTES + 256 /*barriers*/ + 1024 /*align slack*/;  // < 227 KB
 constexpr int TC_THREADS = 192;                     // TMA, MMA, 4 epilogue warps
 constexpr int TC_SPLIT_WARPS = 8;
 constexpr int TC_SPLIT_THREADS = TC_SPLIT_WARPS * 32;
@@ -54,6 +55,7 @@ struct TcParams {
   int act;
   float* out; long long o_sb, o_sp, o_sn;
   int round_tf32;
+  double* csum;         // optional [B][Cout][2] per-channel sum / sum of squares of the stored outputs (GroupNorm fusion)
 };
 
 // ---------------------------------------------------------------- PTX wrappers
@@ -196,7 +198,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
   const uint32_t off_alo = BF ? (uint32_t)TC_A_BYTES + TC_A_BYTES / 2 : (uint32_t)TC_A_BYTES;
   const uint32_t off_w = (X3 || BF) ? 2u * TC_A_BYTES : (uint32_t)TC_A_BYTES;
   const uint32_t off_wlo = off_w + b_bytes;
-  const uint32_t bar_base = smem_base + TC_SMEM_BUDGET + TC_STG_BYTES;
+  const uint32_t bar_base = smem_base + TC_SMEM_BUDGET + TC_STG_BYTES + TC_CSUM_BYTES;
   // barrier layout: full[6] | empty[6] | split[6] | tmem_full[2] | tmem_empty[2] | tmem_ptr
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (TC_MAX_STAGES + s); };
@@ -329,6 +331,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
     const int q = warp & 3;            // TMEM lane quarter this warp may access
     const int row = q * 32 + lane;     // tile row owned by this thread
     float4* stg = reinterpret_cast<float4*>(smem_raw + (smem_base - smem_u32(smem_raw)) + TC_SMEM_BUDGET) + q * 256;
+    float* cacc = reinterpret_cast<float*>(smem_raw + (smem_base - smem_u32(smem_raw)) + TC_SMEM_BUDGET + TC_STG_BYTES);
+    const int et = threadIdx.x - 64;   // 0..127 among the epilogue warps
+    const int img_q = (q * 32) >> (p.lTW + p.lTH);  // image slot of this warp's rows inside the tile (all 32 rows share it)
     const int sub = lane >> 3, ck = lane & 7;
     int acc = 0;
     uint32_t acc_phase = 0;
@@ -354,7 +359,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
           obase[j] = (ox < p.Wout && oy < p.Hout && b < p.B) ? (long long)b * p.o_sb + ((long long)oy * p.Wout + ox) * p.o_sp : -1;
         }
         const bool geglu = p.act == FRIDO_ACT_GEGLU;
+        if (p.csum) {
+          for (int i = et; i < p.TB * p.BN * 2; i += 128) cacc[i] = 0.f;
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+        }
         for (int c = 0; c < p.BN; c += 32) {
+          float cs[4] = {0.f, 0.f, 0.f, 0.f}, cq[4] = {0.f, 0.f, 0.f, 0.f};
           // residual loads of this chunk are issued first so their latency overlaps the TMEM load + transpose
           float4 rres[8];
           if (p.res) {
@@ -403,10 +413,36 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
                 else if (p.act == FRIDO_ACT_SILU) { v.x = silu_f(v.x); v.y = silu_f(v.y); v.z = silu_f(v.z); v.w = silu_f(v.w); }
                 if (p.round_tf32) { v.x = round_tf32(v.x); v.y = round_tf32(v.y); v.z = round_tf32(v.z); v.w = round_tf32(v.w); }
                 *reinterpret_cast<float4*>(p.out + o) = v;
+                cs[0] += v.x; cs[1] += v.y; cs[2] += v.z; cs[3] += v.w;
+                cq[0] += v.x * v.x; cq[1] += v.y * v.y; cq[2] += v.z * v.z; cq[3] += v.w * v.w;
               }
             }
           }
+          if (p.csum) {  // reduce over the 4 row-subsets held by lanes {ck, ck+8, ck+16, ck+24}, then one shared atomic per column
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              cs[e] += __shfl_xor_sync(0xffffffffu, cs[e], 8);  cs[e] += __shfl_xor_sync(0xffffffffu, cs[e], 16);
+              cq[e] += __shfl_xor_sync(0xffffffffu, cq[e], 8);  cq[e] += __shfl_xor_sync(0xffffffffu, cq[e], 16);
+            }
+            if (sub == 0) {
+              float* a = cacc + ((img_q * p.BN) + c + 4 * ck) * 2;
+#pragma unroll
+              for (int e = 0; e < 4; ++e) { atomicAdd(a + 2 * e, cs[e]); atomicAdd(a + 2 * e + 1, cq[e]); }
+            }
+          }
           __syncwarp();
+        }
+        if (p.csum) {
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          for (int i = et; i < p.TB * p.BN; i += 128) {
+            const int im = i / p.BN, col = i - im * p.BN;
+            const int b = tb * p.TB + im;
+            if (b < p.B) {
+              double* d = p.csum + ((long long)b * p.Cout + n0 + col) * 2;
+              atomicAdd(d, (double)cacc[2 * i]);
+              atomicAdd(d + 1, (double)cacc[2 * i + 1]);
+            }
+          }
         }
       } else {
         const int ox = tx * p.TW + (row & (p.TW - 1));
@@ -637,6 +673,9 @@ int conv2d_tc(const FridoConvParams* p, cudaStream_t s) {
   t.bias = p->bias; t.rowvec = p->rowvec; t.rowvec_sb = p->rowvec_sb; t.res = p->res;
   t.alpha = p->alpha; t.act = p->act; t.out = p->out; t.o_sb = p->o_sb; t.o_sp = p->o_sp; t.o_sn = p->o_sn;
   t.round_tf32 = p->round_tf32;
+  t.csum = p->chan_sums;
+  if (p->chan_sums && (p->o_sn != 1 || p->act == FRIDO_ACT_GEGLU || t.TW * t.TH < 32 || t.TB > 4))
+    return set_error(FRIDO_E_ARG, "conv2d_tc: chan_sums needs a dense NHWC output, no GEGLU and >= 32 pixels per image");
 
   CUtensorMap ma0, ma1, mw, mwlo;
   if (!make_map4(&ma0, p->a0, p->c0, p->Win, p->Hin, p->B, p->a0_sx, p->a0_sy, p->a0_sb, t.TW, t.TH, t.TB, (uint32_t)p->stride))

@@ -89,10 +89,20 @@ __global__ void __launch_bounds__(256) norm_act_kernel(const FridoNormActParams 
   const int cg = C / p.groups;
   const int b = blockIdx.y;
   if (threadIdx.x < p.groups) {
-    const double* sm = p.sums + ((int64_t)b * p.groups + threadIdx.x) * 2;
+    double s0, s1;
+    if (p.csum0) {  // group sums from the producers' per-channel sums (the group may straddle the two sources)
+      s0 = 0.0; s1 = 0.0;
+      for (int c = threadIdx.x * cg; c < (threadIdx.x + 1) * cg; ++c) {
+        const double* cs = (c < p.c0) ? p.csum0 + ((int64_t)b * p.c0 + c) * 2 : p.csum1 + ((int64_t)b * p.c1 + (c - p.c0)) * 2;
+        s0 += cs[0]; s1 += cs[1];
+      }
+    } else {
+      const double* sm = p.sums + ((int64_t)b * p.groups + threadIdx.x) * 2;
+      s0 = sm[0]; s1 = sm[1];
+    }
     const double cnt = (double)cg * (double)p.HW;
-    const double mean = sm[0] / cnt;
-    double var = sm[1] / cnt - mean * mean;
+    const double mean = s0 / cnt;
+    double var = s1 / cnt - mean * mean;
     if (var < 0.0) var = 0.0;
     s_mean[threadIdx.x] = (float)mean;
     s_rstd[threadIdx.x] = (float)(1.0 / sqrt(var + (double)p.eps));
@@ -310,7 +320,8 @@ extern "C" int frido_gn_stats(const FridoGnStatsParams* p, void* stream) {
 }
 
 extern "C" int frido_norm_act(const FridoNormActParams* p, void* stream) {
-  if (!p || !p->a0 || !p->sums || !p->out || !p->gamma || !p->beta) return set_error(FRIDO_E_ARG, "norm_act: null pointer");
+  if (!p || !p->a0 || (!p->sums && !p->csum0) || !p->out || !p->gamma || !p->beta) return set_error(FRIDO_E_ARG, "norm_act: null pointer");
+  if (p->csum0 && p->c1 > 0 && !p->csum1) return set_error(FRIDO_E_ARG, "norm_act: csum1 missing for the second source");
   const int C = p->c0 + p->c1;
   if (p->groups <= 0 || p->groups > 64 || C % p->groups || (C & 3) || (p->c0 & 3))
     return set_error(FRIDO_E_ARG, "norm_act: unsupported channel count");

@@ -115,7 +115,9 @@ class Program:
 
     def conv(self, a0, w, out, *, B, Hin, Win, Hout, Wout, Cout, ksize=1, stride=1, pad=0, ups=1, a1=None,
              bias=None, rowvec=None, rowvec_sb=0, res=None, alpha=1.0, act=L.ACT_NONE, o_sb=None, o_sp=None, o_sn=1,
-             w_sb=0, w_ld=0, w_off=0, out_off=0, round_tf32=0, engine=None, tag="conv"):
+             w_sb=0, w_ld=0, w_off=0, out_off=0, round_tf32=0, engine=None, csum=None, tag="conv"):
+        """Returns True when `csum` (per-channel GroupNorm sums of the output, [B,Cout,2] fp64) was attached to the op:
+        only the tcgen05 engines accumulate it, for dense NHWC outputs with >= 32 pixels per image."""
         if engine is None:
             engine = self.tc_code if (self.tc_code and self._tc_ok(a0, a1, B, Hin, Win, Hout, Wout, Cout, ksize, stride, pad, ups, w,
                                                                w_sb, w_ld, w_off, act, o_sb, o_sp, o_sn, out, out_off, res)) else 0
@@ -147,6 +149,12 @@ class Program:
         p.o_sb = Hout * Wout * p.o_sp if o_sb is None else o_sb
         p.o_sn = o_sn
         p.round_tf32, p.engine = round_tf32, engine
+        tw = min(128, 1 << max(Wout - 1, 0).bit_length())
+        th = min(128 // tw, 1 << max(Hout - 1, 0).bit_length())
+        csum_ok = csum is not None and engine in (1, 2, 3) and o_sn == 1 and act != L.ACT_GEGLU and tw * th >= 32
+        if csum_ok:
+            p.chan_sums = csum.data_ptr()
+            self.hold(csum)
         self.hold(a0.t, None if a1 is None else a1.t, w, out, bias, rowvec, res)
         fl = 2 * B * Hout * Wout * Cout * ksize * ksize * (a0.C + (a1.C if a1 is not None else 0))
         self.flops += fl
@@ -154,6 +162,7 @@ class Program:
             self.tc_flops += fl
             self.mma_weights.append(w)
         self._add(L.OP_CONV, p, tag)
+        return csum_ok
 
     @staticmethod
     def _tc_ok(a0, a1, B, Hin, Win, Hout, Wout, Cout, ksize, stride, pad, ups, w, w_sb, w_ld, w_off, act, o_sb, o_sp, o_sn,
@@ -222,10 +231,12 @@ class Program:
         self._add(L.OP_GN_STATS, p, tag)
 
     def norm_act(self, a0, c0, sums, gamma, beta, out, *, B, HW, eps, a1=None, c1=0, gb=None, silu=1, groups=32,
-                 round_tf32=0, tag="norm_act"):
+                 round_tf32=0, csum0=None, csum1=None, tag="norm_act"):
         p = L.NormActParams()
         p.a0, p.a1, p.c0, p.c1, p.B, p.HW, p.groups = _ptr(a0), _ptr(a1), c0, c1, B, HW, groups
-        p.sums, p.eps, p.gamma, p.beta, p.gb = sums.data_ptr(), eps, gamma.data_ptr(), beta.data_ptr(), _ptr(gb)
+        p.sums, p.eps, p.gamma, p.beta, p.gb = _ptr(sums), eps, gamma.data_ptr(), beta.data_ptr(), _ptr(gb)
+        p.csum0, p.csum1 = _ptr(csum0), _ptr(csum1)
+        self.hold(csum0, csum1)
         p.silu, p.round_tf32, p.out = silu, round_tf32, out.data_ptr()
         self.hold(a0, a1, sums, gamma, beta, gb, out)
         self._add(L.OP_NORM_ACT, p, tag)

@@ -210,6 +210,21 @@ class UNetPlan:
         return self._packed(lambda: p.detach().clone())
 
     # ---- helpers ---------------------------------------------------------
+    def _csum_new(self, C):
+        """Carve a [B,C,2] fp64 block for producer-side GroupNorm sums out of the per-step zeroed pool."""
+        n = self.B * C * 2
+        if self._csum_used + n > self._csum_pool.numel():
+            return None
+        t = self._csum_pool[self._csum_used:self._csum_used + n].view(self.B, C, 2)
+        self._csum_used += n
+        return t
+
+    def _conv_stats(self, prog, a0, w, out, Cout, **kw):
+        """conv whose output feeds a GroupNorm: ask the epilogue for the per-channel sums; remember them by tensor."""
+        cs = self._csum_new(Cout) if prog is self.step else None
+        if prog.conv(a0, w, out, Cout=Cout, csum=cs, **kw):
+            self._csum[id(out)] = cs
+
     def _gn_slot(self, prog):
         t = self._sums_all[len(self._gn_slots)]
         self._gn_slots.append(t)
@@ -220,16 +235,22 @@ class UNetPlan:
         B = self.B
         hw = h * w
         C = sum(cs)
-        sums = self._gn_slot(prog)
         a1 = xs[1] if len(xs) > 1 else None
         c1 = cs[1] if len(xs) > 1 else 0
-        prog.gn_stats(xs[0], cs[0], sums, B=B, HW=hw, a1=a1, c1=c1)
+        cs0 = self._csum.get(id(xs[0]))
+        cs1 = self._csum.get(id(a1)) if a1 is not None else None
+        fused = cs0 is not None and (a1 is None or cs1 is not None)
+        sums = None
+        if not fused:  # producer could not provide the statistics (SIMT-engine producer): separate reduction pass
+            cs0 = cs1 = None
+            sums = self._gn_slot(prog)
+            prog.gn_stats(xs[0], cs[0], sums, B=B, HW=hw, a1=a1, c1=c1)
         is_spade = isinstance(norm, M.SPADE)
         g = norm.param_free_norm if is_spade else norm
         gb = self._spade_site(norm, C, h, w) if (is_spade and self.c_cond) else None
         out = prog.buf(B, hw, C)
         prog.norm_act(xs[0], cs[0], sums, self._vec(g.weight), self._vec(g.bias), out, B=B, HW=hw, eps=eps, a1=a1,
-                      c1=c1, gb=gb, silu=silu, round_tf32=prog.R, tag=site)
+                      c1=c1, gb=gb, silu=silu, round_tf32=prog.R, csum0=cs0, csum1=cs1, tag=site)
         return out
 
     def _spade_site(self, sp, C, h, w):
@@ -259,9 +280,9 @@ class UNetPlan:
         t1 = self._norm(S, xs, cs, h, w, rb.in_layers[0], 1e-5, 1, "res.norm1")
         h1 = S.buf(B, hw, cout)
         off = self._emb_off[id(rb)]
-        S.conv(Src.nhwc(t1, h, w), self._conv_w(rb.in_layers[2]), h1, B=B, Hin=h, Win=w, Hout=h, Wout=w, Cout=cout,
-               ksize=3, pad=1, bias=self._vec(rb.in_layers[2].bias), rowvec=self.emb_all[:, off:], rowvec_sb=self.emb_total,
-               tag="res.conv1")
+        self._conv_stats(S, Src.nhwc(t1, h, w), self._conv_w(rb.in_layers[2]), h1, cout, B=B, Hin=h, Win=w, Hout=h, Wout=w,
+                         ksize=3, pad=1, bias=self._vec(rb.in_layers[2].bias), rowvec=self.emb_all[:, off:],
+                         rowvec_sb=self.emb_total, tag="res.conv1")
         S.release(t1)
         t2 = self._norm(S, [h1], [cout], h, w, rb.out_layers[0], 1e-5, 1, "res.norm2")
         S.release(h1)
@@ -275,8 +296,8 @@ class UNetPlan:
             assert len(xs) == 1
             res, sk = xs[0], None
         out = S.buf(B, hw, cout)
-        S.conv(Src.nhwc(t2, h, w), self._conv_w(rb.out_layers[3]), out, B=B, Hin=h, Win=w, Hout=h, Wout=w, Cout=cout,
-               ksize=3, pad=1, bias=self._vec(rb.out_layers[3].bias), res=res, tag="res.conv2")
+        self._conv_stats(S, Src.nhwc(t2, h, w), self._conv_w(rb.out_layers[3]), out, cout, B=B, Hin=h, Win=w, Hout=h, Wout=w,
+                         ksize=3, pad=1, bias=self._vec(rb.out_layers[3].bias), res=res, tag="res.conv2")
         S.release(t2)
         if sk is not None:
             S.release(sk)
@@ -385,8 +406,9 @@ class UNetPlan:
             S.release(ff); S.release(h2)
             hcur = h3
         out = S.buf(B, N, C)
-        S.linear(hcur, self._packed(lambda: st.proj_out.weight.detach().view(C, C).clone()), out, M=B * N, K=C, N=C,
-                 bias=self._vec(st.proj_out.bias), res=x, tag="st.proj_out")
+        # same GEMM as a 1x1 conv over [B,h,w,C] (so the epilogue can attribute rows to images for the GroupNorm sums)
+        self._conv_stats(S, Src.nhwc(hcur, h, w), self._packed(lambda: st.proj_out.weight.detach().view(C, C).clone()), out, C,
+                         B=B, Hin=h, Win=w, Hout=h, Wout=w, bias=self._vec(st.proj_out.bias), res=x, tag="st.proj_out")
         S.release(hcur)
         return out
 
@@ -403,8 +425,8 @@ class UNetPlan:
             elif isinstance(layer, M.Downsample):
                 ho, wo = (h + 1) // 2, (w + 1) // 2
                 x = S.buf(B, ho * wo, cs[0])
-                S.conv(Src.nhwc(xs[0], h, w), self._conv_w(layer.op), x, B=B, Hin=h, Win=w, Hout=ho, Wout=wo, Cout=cs[0],
-                       ksize=3, stride=2, pad=1, bias=self._vec(layer.op.bias), tag="down")
+                self._conv_stats(S, Src.nhwc(xs[0], h, w), self._conv_w(layer.op), x, cs[0], B=B, Hin=h, Win=w, Hout=ho, Wout=wo,
+                                 ksize=3, stride=2, pad=1, bias=self._vec(layer.op.bias), tag="down")
                 xs, h, w = [x], ho, wo
             elif isinstance(layer, M.Upsample):
                 x = S.buf(B, 4 * h * w, cs[0])
@@ -412,8 +434,8 @@ class UNetPlan:
                     # tensor-core path: materialise the nearest x2 copy (TF32-rounded), then a plain 3x3 conv
                     up = S.buf(B, 4 * h * w, cs[0])
                     S.upsample2x(xs[0], up, B=B, H=h, W=w, Cdim=cs[0], round_tf32=S.R)
-                    S.conv(Src.nhwc(up, 2 * h, 2 * w), self._conv_w(layer.conv), x, B=B, Hin=2 * h, Win=2 * w, Hout=2 * h,
-                           Wout=2 * w, Cout=cs[0], ksize=3, pad=1, bias=self._vec(layer.conv.bias), tag="up")
+                    self._conv_stats(S, Src.nhwc(up, 2 * h, 2 * w), self._conv_w(layer.conv), x, cs[0], B=B, Hin=2 * h,
+                                     Win=2 * w, Hout=2 * h, Wout=2 * w, ksize=3, pad=1, bias=self._vec(layer.conv.bias), tag="up")
                     S.release(up)
                 else:
                     S.conv(Src.nhwc(xs[0], h, w), self._conv_w(layer.conv), x, B=B, Hin=h, Win=w, Hout=2 * h, Wout=2 * w,
@@ -433,6 +455,12 @@ class UNetPlan:
         n_norm = sum(1 for m in net.modules() if isinstance(m, (nn.GroupNorm,)))
         self._sums_all = torch.zeros(n_norm + 2, B, 32, 2, dtype=torch.float64, device=self.dev)
         S.zero(self._sums_all, tag="gn.zero")
+        # producer-side GroupNorm statistics: per-channel (sum, sumsq) blocks written by conv epilogues, zeroed per step
+        tot_c = sum(m.num_channels for m in net.modules() if isinstance(m, nn.GroupNorm))
+        self._csum_pool = torch.zeros(B * tot_c * 2 + 16, dtype=torch.float64, device=self.dev)
+        self._csum_used = 0
+        self._csum = {}
+        S.zero(self._csum_pool, tag="gn.zero")
         # --- embedding (a7) ---
         te = S.buf(B, mc)
         S.time_embed(self.ts, te, B=B, dim=mc)

@@ -71,6 +71,8 @@ typedef struct FridoConvParams {
   float* out;
   int64_t o_sb, o_sp, o_sn; /* out[b*o_sb + p*o_sp + n*o_sn], p = oy*Wout + ox */
   int32_t round_tf32;       /* round stored values to TF32 (rna) */
+  double* chan_sums;        /* optional (tcgen05 engines only): [B][Cout][2] += per-channel (sum, sum of squares) of the
+                               stored outputs, i.e. the GroupNorm statistics of the tensor being produced; zero on entry */
   int32_t engine;           /* 0 = SIMT fp32; 1 = tcgen05 TF32; 2 = tcgen05 3xTF32 (error-compensated, ~2^-21 products);
                                3 = tcgen05 BF16x3 (error-compensated, ~2^-16 products, pre-split weights, 2x the TF32
                                issue rate); 1-3 take aligned shapes only (see csrc/conv_tc.cu) */
@@ -97,7 +99,9 @@ int frido_gn_stats(const FridoGnStatsParams* p, void* stream);
 typedef struct FridoNormActParams {
   const float* a0; const float* a1; int32_t c0, c1;
   int32_t B, HW, groups;
-  const double* sums; float eps;
+  const double* sums; float eps;          /* per-(image,group) sums from frido_gn_stats, or NULL when csum0 is given */
+  const double* csum0; const double* csum1; /* alternative: per-channel sums [B][c0][2] / [B][c1][2] accumulated by the
+                                               producing conv (FridoConvParams.chan_sums) */
   const float* gamma; const float* beta;  /* [C] */
   const float* gb;                        /* [B,HW,2C] SPADE (gamma|beta) or NULL */
   int32_t silu;

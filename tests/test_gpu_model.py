@@ -200,3 +200,40 @@ def test_full_size_decoder(dev, golden_dir, engine):
         assert torch.equal(torch.tensor(a), b)
     err = (img.cpu() - g["dec_img"]).abs().max().item()
     assert err < OUT_TOL, err
+
+
+@pytest.mark.parametrize("name,B", [("t2i_clip", 2), ("sg2i_vg", 2)])
+def test_f16f8_configs_vs_oracle(dev, name, B):
+    """BASELINE configs 3/4 (latent 8x32x32, 4x4 bottom level, 8192x4 codebooks, context 1x768 / 180x640): full-size
+    models with synthetic weights, product path vs the CPU oracle on the same state dict — eps for both stages, one
+    PLMS/DDIM step through the sampler with 2 steps, CFG 1.5, and a decode with bit-exact VQ indices."""
+    import frido_b200 as fb
+    from frido_b200 import configs
+    from oracle import torch_oracle as O
+    model, cfg = configs.build(name, dev)
+    sd = {k: v.detach().float().cpu() for k, v in model.state_dict().items()}
+    split = list(model.split_embed_dim_list)
+    C, H, W = cfg["latent"]
+    Lc, D = cfg["ctx"]
+    g = torch.Generator().manual_seed(3)
+    ctx = torch.randn(B, Lc, D, generator=g)
+    uc = torch.randn(B, Lc, D, generator=g)
+    for s in range(2):
+        x = torch.randn(B, sum(split[: s + 1]), H, W, generator=g)
+        ts = torch.full((B,), 491, dtype=torch.long)
+        e = model.apply_model(x.to(dev), ts.to(dev), ctx.to(dev), stage=s)
+        ref = O.unet_forward(sd, x, ts, ctx, s, split)
+        assert (e.cpu() - ref).abs().max() < 1e-3, (name, s)
+    x0 = torch.randn(B, C, H, W, generator=g)
+    kind = cfg["sampler"]
+    smp = (fb.DDIMSampler if kind == "ddim" else fb.PLMSSampler)(model)
+    out, _ = smp.sample(2, B, (C, H, W), conditioning=ctx.to(dev), num_stage=2, eta=0.0, verbose=False, init_noise=x0.to(dev),
+                        unconditional_guidance_scale=1.5, unconditional_conditioning=uc.to(dev))
+    ref = O.sample(sd, split, ctx, x0, 2, sampler=kind, uc=uc, cfg_scale=1.5)
+    assert (out.cpu() - ref).abs().max() < 1e-3, name
+    z = torch.randn(1, C, 8, 8, generator=g) * 1.5
+    img, codes = model.decode_first_stage(z.to(dev), return_code=True)
+    img_ref, codes_ref = O.decode_first_stage(sd, z, split, model.scale_factor.cpu().tolist())
+    for a, b in zip(codes, codes_ref):
+        assert torch.equal(torch.tensor(a), b)
+    assert (img.cpu() - img_ref).abs().max() < 1e-3
