@@ -15,7 +15,7 @@ c_i = C.c_int32
 c_l = C.c_int64
 c_p = C.c_void_p
 
-ACT_NONE, ACT_RELU, ACT_SILU, ACT_GEGLU = 0, 1, 2, 3
+ACT_NONE, ACT_RELU, ACT_SILU, ACT_GEGLU, ACT_GEGLU_FAST = 0, 1, 2, 3, 4
 (OP_CONV, OP_GN_STATS, OP_NORM_ACT, OP_LAYERNORM, OP_SOFTMAX, OP_TIME_EMBED, OP_STEP_BEGIN, OP_UPDATE, OP_SNAP, OP_VQ,
  OP_ZERO, OP_UPSAMPLE) = range(1, 13)
 
@@ -30,7 +30,7 @@ class ConvParams(C.Structure):
         ("w", c_p), ("w_sb", c_l), ("w_ld", c_l), ("w_lo", c_p), ("Cout", c_i),
         ("bias", c_p), ("rowvec", c_p), ("rowvec_sb", c_l), ("res", c_p),
         ("alpha", c_f), ("act", c_i), ("out", c_p),
-        ("o_sb", c_l), ("o_sp", c_l), ("o_sn", c_l), ("round_tf32", c_i), ("chan_sums", c_p), ("engine", c_i),
+        ("o_sb", c_l), ("o_sp", c_l), ("o_sn", c_l), ("round_tf32", c_i), ("out_hi", c_p), ("out_lo", c_p), ("chan_sums", c_p), ("engine", c_i),
     ]
 
 

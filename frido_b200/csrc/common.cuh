@@ -32,9 +32,29 @@ __device__ __forceinline__ float round_tf32(float x) {
   return __uint_as_float(r);
 }
 
+// bf16 hi/lo split of one value: hi = bf16_rn(v), lo = bf16_rn(v - hi)
+__device__ __forceinline__ void split_bf16(float v, uint16_t& hi, uint16_t& lo) {
+  uint32_t h, l;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(h) : "f"(0.f), "f"(v));
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(l) : "f"(0.f), "f"(v - __uint_as_float(h << 16)));
+  hi = (uint16_t)h; lo = (uint16_t)l;
+}
+
 __device__ __forceinline__ float silu_f(float v) { return v / (1.0f + __expf(-v)); }
 // exact-erf GELU (attention.py:44 F.gelu default)
 __device__ __forceinline__ float gelu_erf(float v) { return 0.5f * v * (1.0f + erff(v * 0.70710678118654752440f)); }
+// Same function for the tensor-core GEGLU epilogue, where 2 erf per output make the epilogue the bottleneck:
+// erf by Abramowitz-Stegun 7.1.26 (|abs err| <= 1.5e-7, i.e. fp32 rounding level) = 1 rcp + 1 ex2 + 7 FMA, branch-free.
+__device__ __forceinline__ float gelu_erf_fast(float v) {
+  const float x = fabsf(v) * 0.70710678118654752440f;
+  const float t = __fdividef(1.0f, fmaf(0.3275911f, x, 1.0f));
+  float poly = fmaf(1.061405429f, t, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  const float e = 1.0f - poly * t * __expf(-x * x);   // erf(|v|/sqrt2)
+  return 0.5f * v * (1.0f + copysignf(e, v));
+}
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

@@ -185,7 +185,14 @@ __global__ void __launch_bounds__(NT) conv_simt_kernel(const FridoConvParams p) 
           if (res) t += res[o];
           if (p.act == FRIDO_ACT_RELU) t = fmaxf(t, 0.f);
           else if (p.act == FRIDO_ACT_SILU) t = silu_f(t);
-          out[o] = p.round_tf32 ? round_tf32(t) : t;
+          t = p.round_tf32 ? round_tf32(t) : t;
+          out[o] = t;
+          if (p.out_hi) {
+            uint16_t hh, ll;
+            split_bf16(t, hh, ll);
+            const int64_t oo = (int64_t)b * p.o_sb + o;
+            ((uint16_t*)p.out_hi)[oo] = hh; ((uint16_t*)p.out_lo)[oo] = ll;
+          }
         }
       }
     }
@@ -272,7 +279,9 @@ int conv2d_simt(const FridoConvParams* p, cudaStream_t s) {
   if (p->a1)
     vecA = vecA && p->a1_sc == 1 && aligned16(p->a1) && p->a1_sb % 4 == 0 && p->a1_sy % 4 == 0 && p->a1_sx % 4 == 0;
   const bool vecW = (Ktot % 4 == 0) && aligned16(p->w) && (p->w_sb % 4 == 0) && (p->w_ld % 4 == 0);
-  if (vecA && p->Cout <= SC_MAXCOUT && p->act != FRIDO_ACT_GEGLU && (size_t)p->Cout * Ktot * 4 <= 96 * 1024 && Ktot % 4 == 0) {
+  if ((p->out_hi != nullptr) != (p->out_lo != nullptr) || (p->out_hi && p->act == FRIDO_ACT_GEGLU))
+    return set_error(FRIDO_E_ARG, "conv2d: out_hi/out_lo must come together and not with GEGLU");
+  if (vecA && !p->out_hi && p->Cout <= SC_MAXCOUT && p->act != FRIDO_ACT_GEGLU && (size_t)p->Cout * Ktot * 4 <= 96 * 1024 && Ktot % 4 == 0) {
     const size_t smem = (size_t)p->Cout * Ktot * 4;
     static bool attr = false;
     if (!attr) {

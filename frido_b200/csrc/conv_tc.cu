@@ -33,10 +33,11 @@ constexpr int TC_SMEM_BUDGET = 200 * 1024;          // operand ring
 constexpr int TC_STG_BYTES = 4 * 4096;              // epilogue transpose staging, 4 KB per epilogue warp
 constexpr int TC_CSUM_BYTES = 4 * 256 * 2 * 4;          // per-tile channel sum / sum-of-squares accumulators [img<=4][BN<=256][2]
 constexpr int TC_SMEM_BYTES = TC_SMEM_BUDGET + TC_STG_BYTES + TC_CSUM_BYTES + 256 /*barriers*/ + 1024 /*align slack*/;  // < 227 KB
-constexpr int TC_THREADS = 192;                     // TMA, MMA, 4 epilogue warps
-constexpr int TC_SPLIT_WARPS = 8;
+constexpr int TC_EPI_WARPS = 8;
+constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;   // TMA, MMA, 8 epilogue warps
+constexpr int TC_SPLIT_WARPS = 4;
 constexpr int TC_SPLIT_THREADS = TC_SPLIT_WARPS * 32;
-constexpr int TC_THREADS_X3 = 192 + TC_SPLIT_THREADS;  // + splitter warps (error-compensated modes)
+constexpr int TC_THREADS_X3 = TC_THREADS + TC_SPLIT_THREADS;  // + splitter warps (error-compensated modes)
 
 struct TcParams {
   int B, Hout, Wout, Cout;
@@ -55,6 +56,7 @@ struct TcParams {
   int act;
   float* out; long long o_sb, o_sp, o_sn;
   int round_tf32;
+  uint16_t* out_hi; uint16_t* out_lo;  // optional bf16 pair copy of the outputs
   double* csum;         // optional [B][Cout][2] per-channel sum / sum of squares of the stored outputs (GroupNorm fusion)
 };
 
@@ -176,6 +178,16 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
 // ----------------------------------------------------------------------------
 // MODE 0: single-pass TF32.
 // MODE 1: error-compensated 3xTF32: every operand tile is split in shared memory into hi = rna_tf32(v) and
@@ -232,7 +244,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), 4);  // one arrive per epilogue warp
+      mbar_init(tempty_bar(a), TC_EPI_WARPS);  // one arrive per epilogue warp
     }
     fence_barrier_init();
   }
@@ -322,19 +334,29 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
-  } else if (warp < 6) {
-    // ===================== epilogue (warps 2..5) =====================
-    // tcgen05.ld gives thread = accumulator row.  For NHWC outputs (o_sn == 1) each 32x32 chunk is transposed
-    // through a 4 KB per-warp shared staging tile so that every global access instruction covers 4 rows x 128
-    // contiguous bytes (bias / timestep row / residual / activation are applied in that coalesced arrangement).
+  } else if (warp < 2 + TC_EPI_WARPS) {
+    // ===================== epilogue (warps 2..9) =====================
+    // Eight warps: warp w reads TMEM lane quarter (w & 3) and the column half ((w - 2) >> 2) of the accumulator, in
+    // chunks of 16 columns.  tcgen05.ld gives thread = accumulator row; for NHWC outputs (o_sn == 1) each 32x16 chunk
+    // is transposed through a 2 KB per-warp swizzled staging tile so that every global instruction covers 8 rows x
+    // 64 contiguous bytes, and bias / timestep row / residual / activation are applied in that arrangement.
     // Transposed outputs (V^T: o_sp == 1) are already coalesced across lanes and go out directly.
+    const int ew = warp - 2;
     const int q = warp & 3;            // TMEM lane quarter this warp may access
-    const int row = q * 32 + lane;     // tile row owned by this thread
-    float4* stg = reinterpret_cast<float4*>(smem_raw + (smem_base - smem_u32(smem_raw)) + TC_SMEM_BUDGET) + q * 256;
+    const int half = ew >> 2;
+    const int row = q * 32 + lane;     // tile row owned by this thread (direct path)
+    float4* stg = reinterpret_cast<float4*>(smem_raw + (smem_base - smem_u32(smem_raw)) + TC_SMEM_BUDGET) + ew * 128;
     float* cacc = reinterpret_cast<float*>(smem_raw + (smem_base - smem_u32(smem_raw)) + TC_SMEM_BUDGET + TC_STG_BYTES);
-    const int et = threadIdx.x - 64;   // 0..127 among the epilogue warps
+    const int et = threadIdx.x - 64;   // 0..255 among the epilogue warps
     const int img_q = (q * 32) >> (p.lTW + p.lTH);  // image slot of this warp's rows inside the tile (all 32 rows share it)
-    const int sub = lane >> 3, ck = lane & 7;
+    const int sub = lane >> 2, c4 = lane & 3;
+    const int hcols = p.BN >> 1;
+    const int col_lo = half * hcols;
+    const bool geglu = p.act == FRIDO_ACT_GEGLU || p.act == FRIDO_ACT_GEGLU_FAST;
+    const bool has_res = p.res != nullptr, has_rv = p.rowvec != nullptr, has_bias = p.bias != nullptr;
+    const bool has_cs = p.csum != nullptr, has_pair = p.out_hi != nullptr, rnd = p.round_tf32 != 0;
+    const float alpha = p.alpha;
+    const int act = p.act;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -343,102 +365,108 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
       const int tx = mt % p.tiles_x; mt /= p.tiles_x;
       const int ty = mt % p.tiles_y;
       const int tb = mt / p.tiles_y;
-      const int n0 = nt * p.BN;
+      const int n0 = nt * p.BN + col_lo;
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
-      const uint32_t t_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * TC_MAX_BN);
+      const uint32_t t_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * TC_MAX_BN + col_lo);
       if (p.o_sn == 1) {
-        // per-lane output rows of the coalesced arrangement (8 rows: rl = 4j + sub) are the same for every chunk
-        long long obase[8];
+        // the 4 output rows this lane serves in the coalesced arrangement (rl = 8j + sub) are the same for every chunk
+        long long obase[4];
+        int bimg[4];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const int rr = q * 32 + 4 * j + sub;
+        for (int j = 0; j < 4; ++j) {
+          const int rr = q * 32 + 8 * j + sub;
           const int ox = tx * p.TW + (rr & (p.TW - 1));
           const int oy = ty * p.TH + ((rr >> p.lTW) & (p.TH - 1));
           const int b = tb * p.TB + (rr >> (p.lTW + p.lTH));
+          bimg[j] = b;
           obase[j] = (ox < p.Wout && oy < p.Hout && b < p.B) ? (long long)b * p.o_sb + ((long long)oy * p.Wout + ox) * p.o_sp : -1;
         }
-        const bool geglu = p.act == FRIDO_ACT_GEGLU;
-        if (p.csum) {
-          for (int i = et; i < p.TB * p.BN * 2; i += 128) cacc[i] = 0.f;
-          asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (has_cs) {
+          for (int i = et; i < p.TB * p.BN * 2; i += 32 * TC_EPI_WARPS) cacc[i] = 0.f;
+          asm volatile("bar.sync 1, 256;" ::: "memory");
         }
-        for (int c = 0; c < p.BN; c += 32) {
-          float cs[4] = {0.f, 0.f, 0.f, 0.f}, cq[4] = {0.f, 0.f, 0.f, 0.f};
-          // residual loads of this chunk are issued first so their latency overlaps the TMEM load + transpose
-          float4 rres[8];
-          if (p.res) {
-            const int nn = n0 + c + 4 * ck;
+        for (int c = 0; c < hcols; c += 16) {
+          const int n = n0 + c + 4 * c4;
+          // residual loads of this chunk go out first: their latency overlaps the TMEM load + transpose
+          float4 rres[4];
+          if (has_res) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
+            for (int j = 0; j < 4; ++j) {
               rres[j] = make_float4(0.f, 0.f, 0.f, 0.f);
               if (obase[j] >= 0) {
-                if (geglu) { const float2 t2 = *reinterpret_cast<const float2*>(p.res + obase[j] + (nn >> 1)); rres[j].x = t2.x; rres[j].y = t2.y; }
-                else rres[j] = *reinterpret_cast<const float4*>(p.res + obase[j] + nn);
+                if (geglu) { const float2 t2 = *reinterpret_cast<const float2*>(p.res + obase[j] + (n >> 1)); rres[j].x = t2.x; rres[j].y = t2.y; }
+                else rres[j] = *reinterpret_cast<const float4*>(p.res + obase[j] + n);
               }
             }
           }
-          uint32_t r[32];
-          tmem_ld32(t_base + c, r);
-#pragma unroll
-          for (int k = 0; k < 8; ++k)
-            stg[lane * 8 + (k ^ (lane & 7))] = make_float4(__uint_as_float(r[4 * k]), __uint_as_float(r[4 * k + 1]),
-                                                           __uint_as_float(r[4 * k + 2]), __uint_as_float(r[4 * k + 3]));
-          __syncwarp();
-          const int n = n0 + c + 4 * ck;
           float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (p.bias) bias4 = __ldg(reinterpret_cast<const float4*>(p.bias + n));
+          if (has_bias) bias4 = __ldg(reinterpret_cast<const float4*>(p.bias + n));
+          uint32_t r[16];
+          tmem_ld16(t_base + c, r);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const int rl = 4 * j + sub;
-            float4 v = stg[rl * 8 + (ck ^ (rl & 7))];
+          for (int k = 0; k < 4; ++k)
+            stg[lane * 4 + (k ^ ((lane >> 1) & 3))] = make_float4(__uint_as_float(r[4 * k]), __uint_as_float(r[4 * k + 1]),
+                                                                  __uint_as_float(r[4 * k + 2]), __uint_as_float(r[4 * k + 3]));
+          __syncwarp();
+          float cs[4] = {0.f, 0.f, 0.f, 0.f}, cq[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int rl = 8 * j + sub;
+            float4 v = stg[rl * 4 + (c4 ^ ((rl >> 1) & 3))];
             if (obase[j] >= 0) {
-              const long long base = obase[j];
-              const int b = tb * p.TB + ((q * 32 + rl) >> (p.lTW + p.lTH));
-              v.x = v.x * p.alpha + bias4.x; v.y = v.y * p.alpha + bias4.y; v.z = v.z * p.alpha + bias4.z; v.w = v.w * p.alpha + bias4.w;
-              if (p.rowvec) {
-                const float4 e = __ldg(reinterpret_cast<const float4*>(p.rowvec + (long long)b * p.rowvec_sb + n));
+              v.x = fmaf(v.x, alpha, bias4.x); v.y = fmaf(v.y, alpha, bias4.y); v.z = fmaf(v.z, alpha, bias4.z); v.w = fmaf(v.w, alpha, bias4.w);
+              if (has_rv) {
+                const float4 e = __ldg(reinterpret_cast<const float4*>(p.rowvec + (long long)bimg[j] * p.rowvec_sb + n));
                 v.x += e.x; v.y += e.y; v.z += e.z; v.w += e.w;
               }
-              if (p.act == FRIDO_ACT_GEGLU) {
-                float2 t = make_float2(v.x * gelu_erf(v.y), v.z * gelu_erf(v.w));
-                const long long o = base + (n >> 1);
-                if (p.res) { t.x += rres[j].x; t.y += rres[j].y; }
-                if (p.round_tf32) { t.x = round_tf32(t.x); t.y = round_tf32(t.y); }
-                *reinterpret_cast<float2*>(p.out + o) = t;
+              if (geglu) {
+                float2 t = act == FRIDO_ACT_GEGLU ? make_float2(v.x * gelu_erf(v.y), v.z * gelu_erf(v.w))
+                                                  : make_float2(v.x * gelu_erf_fast(v.y), v.z * gelu_erf_fast(v.w));
+                if (has_res) { t.x += rres[j].x; t.y += rres[j].y; }
+                if (rnd) { t.x = round_tf32(t.x); t.y = round_tf32(t.y); }
+                *reinterpret_cast<float2*>(p.out + obase[j] + (n >> 1)) = t;
               } else {
-                const long long o = base + n;
-                if (p.res) { v.x += rres[j].x; v.y += rres[j].y; v.z += rres[j].z; v.w += rres[j].w; }
-                if (p.act == FRIDO_ACT_RELU) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
-                else if (p.act == FRIDO_ACT_SILU) { v.x = silu_f(v.x); v.y = silu_f(v.y); v.z = silu_f(v.z); v.w = silu_f(v.w); }
-                if (p.round_tf32) { v.x = round_tf32(v.x); v.y = round_tf32(v.y); v.z = round_tf32(v.z); v.w = round_tf32(v.w); }
+                if (has_res) { v.x += rres[j].x; v.y += rres[j].y; v.z += rres[j].z; v.w += rres[j].w; }
+                if (act == FRIDO_ACT_RELU) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+                else if (act == FRIDO_ACT_SILU) { v.x = silu_f(v.x); v.y = silu_f(v.y); v.z = silu_f(v.z); v.w = silu_f(v.w); }
+                if (rnd) { v.x = round_tf32(v.x); v.y = round_tf32(v.y); v.z = round_tf32(v.z); v.w = round_tf32(v.w); }
+                const long long o = obase[j] + n;
                 *reinterpret_cast<float4*>(p.out + o) = v;
-                cs[0] += v.x; cs[1] += v.y; cs[2] += v.z; cs[3] += v.w;
-                cq[0] += v.x * v.x; cq[1] += v.y * v.y; cq[2] += v.z * v.z; cq[3] += v.w * v.w;
+                if (has_pair) {
+                  uint16_t h0, h1, h2, h3, l0, l1, l2, l3;
+                  split_bf16(v.x, h0, l0); split_bf16(v.y, h1, l1); split_bf16(v.z, h2, l2); split_bf16(v.w, h3, l3);
+                  *reinterpret_cast<uint2*>(p.out_hi + o) = make_uint2((uint32_t)h0 | ((uint32_t)h1 << 16), (uint32_t)h2 | ((uint32_t)h3 << 16));
+                  *reinterpret_cast<uint2*>(p.out_lo + o) = make_uint2((uint32_t)l0 | ((uint32_t)l1 << 16), (uint32_t)l2 | ((uint32_t)l3 << 16));
+                }
+                if (has_cs) {
+                  cs[0] += v.x; cs[1] += v.y; cs[2] += v.z; cs[3] += v.w;
+                  cq[0] += v.x * v.x; cq[1] += v.y * v.y; cq[2] += v.z * v.z; cq[3] += v.w * v.w;
+                }
               }
             }
           }
-          if (p.csum) {  // reduce over the 4 row-subsets held by lanes {ck, ck+8, ck+16, ck+24}, then one shared atomic per column
+          if (has_cs) {  // reduce over the 8 row-subsets (lanes with equal c4), then one shared atomic per column
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-              cs[e] += __shfl_xor_sync(0xffffffffu, cs[e], 8);  cs[e] += __shfl_xor_sync(0xffffffffu, cs[e], 16);
-              cq[e] += __shfl_xor_sync(0xffffffffu, cq[e], 8);  cq[e] += __shfl_xor_sync(0xffffffffu, cq[e], 16);
+              cs[e] += __shfl_xor_sync(0xffffffffu, cs[e], 4); cs[e] += __shfl_xor_sync(0xffffffffu, cs[e], 8); cs[e] += __shfl_xor_sync(0xffffffffu, cs[e], 16);
+              cq[e] += __shfl_xor_sync(0xffffffffu, cq[e], 4); cq[e] += __shfl_xor_sync(0xffffffffu, cq[e], 8); cq[e] += __shfl_xor_sync(0xffffffffu, cq[e], 16);
             }
             if (sub == 0) {
-              float* a = cacc + ((img_q * p.BN) + c + 4 * ck) * 2;
+              float* a = cacc + ((img_q * p.BN) + col_lo + c + 4 * c4) * 2;
 #pragma unroll
               for (int e = 0; e < 4; ++e) { atomicAdd(a + 2 * e, cs[e]); atomicAdd(a + 2 * e + 1, cq[e]); }
             }
           }
           __syncwarp();
         }
-        if (p.csum) {
-          asm volatile("bar.sync 1, 128;" ::: "memory");
-          for (int i = et; i < p.TB * p.BN; i += 128) {
+        if (has_cs) {
+          asm volatile("bar.sync 1, 256;" ::: "memory");
+          for (int i = et; i < p.TB * p.BN; i += 32 * TC_EPI_WARPS) {
             const int im = i / p.BN, col = i - im * p.BN;
             const int b = tb * p.TB + im;
             if (b < p.B) {
-              double* d = p.csum + ((long long)b * p.Cout + n0 + col) * 2;
+              double* d = p.csum + ((long long)b * p.Cout + nt * p.BN + col) * 2;
               atomicAdd(d, (double)cacc[2 * i]);
               atomicAdd(d + 1, (double)cacc[2 * i + 1]);
             }
@@ -450,24 +478,29 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
         const int b = tb * p.TB + (row >> (p.lTW + p.lTH));
         const bool valid = ox < p.Wout && oy < p.Hout && b < p.B;
         const long long pix = (long long)oy * p.Wout + ox;
-        float* __restrict__ orow = p.out + (long long)b * p.o_sb + pix * p.o_sp;
-        const float* __restrict__ rrow = p.res ? p.res + (long long)b * p.o_sb + pix * p.o_sp : nullptr;
-        const float* __restrict__ rv = p.rowvec ? p.rowvec + (long long)b * p.rowvec_sb : nullptr;
-        for (int c = 0; c < p.BN; c += 32) {
-          uint32_t r[32];
-          tmem_ld32(t_base + c, r);
+        const long long rowoff = (long long)b * p.o_sb + pix * p.o_sp;
+        const float* __restrict__ rv = has_rv ? p.rowvec + (long long)b * p.rowvec_sb : nullptr;
+        for (int c = 0; c < hcols; c += 16) {
+          uint32_t r[16];
+          tmem_ld16(t_base + c, r);
           if (valid) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
+            for (int j = 0; j < 16; ++j) {
               const int n = n0 + c + j;
-              float t = __uint_as_float(r[j]) * p.alpha;
-              if (p.bias) t += __ldg(p.bias + n);
+              float t = __uint_as_float(r[j]) * alpha;
+              if (has_bias) t += __ldg(p.bias + n);
               if (rv) t += __ldg(rv + n);
-              const long long o = (long long)n * p.o_sn;
-              if (rrow) t += rrow[o];
-              if (p.act == FRIDO_ACT_RELU) t = fmaxf(t, 0.f);
-              else if (p.act == FRIDO_ACT_SILU) t = silu_f(t);
-              orow[o] = p.round_tf32 ? round_tf32(t) : t;
+              const long long o = rowoff + (long long)n * p.o_sn;
+              if (has_res) t += p.res[o];
+              if (act == FRIDO_ACT_RELU) t = fmaxf(t, 0.f);
+              else if (act == FRIDO_ACT_SILU) t = silu_f(t);
+              t = rnd ? round_tf32(t) : t;
+              if (p.out) p.out[o] = t;
+              if (has_pair) {
+                uint16_t hh, ll;
+                split_bf16(t, hh, ll);
+                p.out_hi[o] = hh; p.out_lo[o] = ll;
+              }
             }
           }
         }
@@ -481,7 +514,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
     // ===================== splitter (warps 6..9), BF16x3: fp32 A tile -> bf16 hi / lo tiles =====================
     // source: 128 rows x 128 B, SWIZZLE_128B (16-B chunk c of row r sits at chunk c ^ (r & 7));
     // destination: 128 rows x 64 B, SWIZZLE_64B (16-B chunk q of row r sits at chunk q ^ ((r >> 1) & 3)).
-    const int t = threadIdx.x - 192;  // 0..TC_SPLIT_THREADS-1
+    const int t = threadIdx.x - TC_THREADS;  // 0..TC_SPLIT_THREADS-1
     int stage = 0;
     uint32_t phase = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -513,7 +546,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
   } else if (X3) {
     // ===================== splitter (warps 6..9, 3xTF32 only) =====================
     // In place: v -> hi = rna_tf32(v); lo = v - hi goes to the twin buffer at the same (swizzled) offset.
-    const int t = threadIdx.x - 192;
+    const int t = threadIdx.x - TC_THREADS;
     int stage = 0;
     uint32_t phase = 0;
     const int a_vec = TC_A_BYTES / 16, w_vec = (int)(b_bytes / 16);
@@ -607,7 +640,7 @@ static bool make_map3(CUtensorMap* m, const void* base, uint64_t K, uint64_t N, 
 static bool a16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 int conv2d_tc(const FridoConvParams* p, cudaStream_t s) {
-  if (!p->a0 || !p->w || !p->out) return set_error(FRIDO_E_ARG, "conv2d_tc: null pointer");
+  if (!p->a0 || !p->w || (!p->out && !(p->out_hi && p->o_sn != 1))) return set_error(FRIDO_E_ARG, "conv2d_tc: null pointer");
   if (p->ups != 1) return set_error(FRIDO_E_ARG, "conv2d_tc: ups must be 1 (materialise the upsample first)");
   if (p->stride != 1 && !(p->stride == 2 && p->ksize == 3)) return set_error(FRIDO_E_ARG, "conv2d_tc: stride must be 1, or 2 for 3x3");
   if (p->ksize != 1 && p->ksize != 3) return set_error(FRIDO_E_ARG, "conv2d_tc: ksize must be 1 or 3");
@@ -618,7 +651,7 @@ int conv2d_tc(const FridoConvParams* p, cudaStream_t s) {
   if (p->a0_sc != 1 || (p->a1 && p->a1_sc != 1)) return set_error(FRIDO_E_ARG, "conv2d_tc: channel stride must be 1");
   if (p->Hout != (p->Hin + p->stride - 1) / p->stride || p->Wout != (p->Win + p->stride - 1) / p->stride)
     return set_error(FRIDO_E_ARG, "conv2d_tc: output size must be ceil(in/stride)");
-  if (!a16(p->a0) || !a16(p->w) || (p->a1 && !a16(p->a1)) || !a16(p->out) || (p->res && !a16(p->res)))
+  if (!a16(p->a0) || !a16(p->w) || (p->a1 && !a16(p->a1)) || (p->out && !a16(p->out)) || (p->res && !a16(p->res)))
     return set_error(FRIDO_E_ARG, "conv2d_tc: pointers must be 16-byte aligned");
   if (p->a0_sx % 4 || p->a0_sy % 4 || p->a0_sb % 4 || (p->a1 && (p->a1_sx % 4 || p->a1_sy % 4 || p->a1_sb % 4)))
     return set_error(FRIDO_E_ARG, "conv2d_tc: strides must be multiples of 16 bytes");
@@ -630,7 +663,7 @@ int conv2d_tc(const FridoConvParams* p, cudaStream_t s) {
   if (bf && (w_ld % 8 || p->w_sb % 8 || !a16(p->w_lo)))
     return set_error(FRIDO_E_ARG, "conv2d_tc: bf16 weight strides must be multiples of 16 bytes");
   if (w_ld % 4 || p->w_sb % 4) return set_error(FRIDO_E_ARG, "conv2d_tc: weight strides must be multiples of 16 bytes");
-  if (p->act == FRIDO_ACT_GEGLU && p->o_sn != 1) return set_error(FRIDO_E_ARG, "conv2d_tc: GEGLU needs a dense output");
+  if ((p->act == FRIDO_ACT_GEGLU || p->act == FRIDO_ACT_GEGLU_FAST) && p->o_sn != 1) return set_error(FRIDO_E_ARG, "conv2d_tc: GEGLU needs a dense output");
   if (p->o_sn == 1 && (p->o_sp % 4 || p->o_sb % 4)) return set_error(FRIDO_E_ARG, "conv2d_tc: output rows must be 16-byte aligned");
   if (p->o_sn == 1 && ((p->bias && !a16(p->bias)) || (p->rowvec && (!a16(p->rowvec) || p->rowvec_sb % 4))))
     return set_error(FRIDO_E_ARG, "conv2d_tc: bias / rowvec must be 16-byte aligned");
@@ -674,7 +707,10 @@ int conv2d_tc(const FridoConvParams* p, cudaStream_t s) {
   t.alpha = p->alpha; t.act = p->act; t.out = p->out; t.o_sb = p->o_sb; t.o_sp = p->o_sp; t.o_sn = p->o_sn;
   t.round_tf32 = p->round_tf32;
   t.csum = p->chan_sums;
-  if (p->chan_sums && (p->o_sn != 1 || p->act == FRIDO_ACT_GEGLU || t.TW * t.TH < 32 || t.TB > 4))
+  t.out_hi = (uint16_t*)p->out_hi; t.out_lo = (uint16_t*)p->out_lo;
+  if ((p->out_hi != nullptr) != (p->out_lo != nullptr) || (p->out_hi && (p->act == FRIDO_ACT_GEGLU || p->act == FRIDO_ACT_GEGLU_FAST)))
+    return set_error(FRIDO_E_ARG, "conv2d_tc: out_hi/out_lo must come together and not with GEGLU");
+  if (p->chan_sums && (p->o_sn != 1 || (p->act == FRIDO_ACT_GEGLU || p->act == FRIDO_ACT_GEGLU_FAST) || t.TW * t.TH < 32 || t.TB > 4))
     return set_error(FRIDO_E_ARG, "conv2d_tc: chan_sums needs a dense NHWC output, no GEGLU and >= 32 pixels per image");
 
   CUtensorMap ma0, ma1, mw, mwlo;

@@ -115,14 +115,19 @@ class Program:
 
     def conv(self, a0, w, out, *, B, Hin, Win, Hout, Wout, Cout, ksize=1, stride=1, pad=0, ups=1, a1=None,
              bias=None, rowvec=None, rowvec_sb=0, res=None, alpha=1.0, act=L.ACT_NONE, o_sb=None, o_sp=None, o_sn=1,
-             w_sb=0, w_ld=0, w_off=0, out_off=0, round_tf32=0, engine=None, csum=None, tag="conv"):
+             w_sb=0, w_ld=0, w_off=0, out_off=0, round_tf32=0, engine=None, csum=None, out_pair=None, w_pair=None,
+             tag="conv"):
         """Returns True when `csum` (per-channel GroupNorm sums of the output, [B,Cout,2] fp64) was attached to the op:
         only the tcgen05 engines accumulate it, for dense NHWC outputs with >= 32 pixels per image."""
         if engine is None:
             engine = self.tc_code if (self.tc_code and self._tc_ok(a0, a1, B, Hin, Win, Hout, Wout, Cout, ksize, stride, pad, ups, w,
                                                                w_sb, w_ld, w_off, act, o_sb, o_sp, o_sn, out, out_off, res)) else 0
-        if engine == 3 and w_sb:
-            engine = 2  # per-image "weights" are activations (attention): no pre-split copy exists -> 3xTF32
+        if engine != 0 and act == L.ACT_GEGLU and os.environ.get("FRIDO_EXACT_ERF", "0") != "1":
+            act = L.ACT_GEGLU_FAST  # tensor-core epilogue: erf by A&S 7.1.26 (|err| < 5e-7), see csrc/common.cuh
+        if engine == 0 and act == L.ACT_GEGLU_FAST:
+            act = L.ACT_GEGLU
+        if engine == 3 and w_sb and w_pair is None:
+            engine = 2  # per-image "weights" are activations (attention) without a bf16 pair copy -> 3xTF32
         p = L.ConvParams()
         p.a0, p.c0 = a0.ptr, a0.C
         p.a0_sb, p.a0_sy, p.a0_sx, p.a0_sc = a0.sb, a0.sy, a0.sx, a0.sc
@@ -132,7 +137,10 @@ class Program:
         p.B, p.Hin, p.Win, p.ups = B, Hin, Win, ups
         p.ksize, p.stride, p.pad, p.Hout, p.Wout = ksize, stride, pad, Hout, Wout
         p.w, p.w_sb, p.w_ld, p.Cout = w.data_ptr() + 4 * w_off, w_sb, w_ld, Cout
-        if engine == 3:
+        if engine == 3 and w_pair is not None:  # operand already stored as a bf16 hi/lo pair by its producer's epilogue
+            p.w, p.w_lo = w_pair[0].data_ptr() + 2 * w_off, w_pair[1].data_ptr() + 2 * w_off
+            self.hold(w_pair[0], w_pair[1])
+        elif engine == 3:
             ent = self._split_ids.get(id(w))
             if ent is None:
                 ent = (w, torch.empty(w.shape, dtype=torch.bfloat16, device=w.device),
@@ -143,15 +151,18 @@ class Program:
             self.hold(ent[1], ent[2])
         p.bias, p.rowvec, p.rowvec_sb, p.res = _ptr(bias), _ptr(rowvec), rowvec_sb, _ptr(res)
         p.alpha, p.act = alpha, act
-        n_out = Cout // 2 if act == L.ACT_GEGLU else Cout
+        n_out = Cout // 2 if act in (L.ACT_GEGLU, L.ACT_GEGLU_FAST) else Cout
         p.out = out.data_ptr() + 4 * out_off
         p.o_sp = n_out if o_sp is None else o_sp
         p.o_sb = Hout * Wout * p.o_sp if o_sb is None else o_sb
         p.o_sn = o_sn
         p.round_tf32, p.engine = round_tf32, engine
+        if out_pair is not None:
+            p.out_hi, p.out_lo = out_pair[0].data_ptr() + 2 * out_off, out_pair[1].data_ptr() + 2 * out_off
+            self.hold(out_pair[0], out_pair[1])
         tw = min(128, 1 << max(Wout - 1, 0).bit_length())
         th = min(128 // tw, 1 << max(Hout - 1, 0).bit_length())
-        csum_ok = csum is not None and engine in (1, 2, 3) and o_sn == 1 and act != L.ACT_GEGLU and tw * th >= 32
+        csum_ok = csum is not None and engine in (1, 2, 3) and o_sn == 1 and act not in (L.ACT_GEGLU, L.ACT_GEGLU_FAST) and tw * th >= 32
         if csum_ok:
             p.chan_sums = csum.data_ptr()
             self.hold(csum)
@@ -193,10 +204,10 @@ class Program:
             th = min(128 // tw, 1 << (Hout - 1).bit_length())
             if tw * th != 128:
                 return False
-        n_out = Cout // 2 if act == L.ACT_GEGLU else Cout
+        n_out = Cout // 2 if act in (L.ACT_GEGLU, L.ACT_GEGLU_FAST) else Cout
         o_sp_ = n_out if o_sp is None else o_sp
         o_sb_ = Hout * Wout * o_sp_ if o_sb is None else o_sb
-        if act == L.ACT_GEGLU and o_sn != 1:
+        if act in (L.ACT_GEGLU, L.ACT_GEGLU_FAST) and o_sn != 1:
             return False
         if o_sn == 1 and (o_sp_ % 4 or o_sb_ % 4):
             return False
@@ -211,12 +222,12 @@ class Program:
         self._add(L.OP_UPSAMPLE, p, tag)
 
     def linear(self, a, w, out, *, M, K, N, bias=None, res=None, act=L.ACT_NONE, a_ld=None, a_off=0, out_ld=None,
-               rowvec=None, round_tf32=0, engine=None, tag="linear"):
+               rowvec=None, round_tf32=0, engine=None, out_pair=None, tag="linear"):
         """out[M,N] = act(a[M,K] @ w[N,K]^T + bias (+rowvec) (+res))  — rows are 'pixels' of one image."""
         a_ld = K if a_ld is None else a_ld
         src = Src(a, K, 0, 0, a_ld, 1, a_off)
         self.conv(src, w, out, B=1, Hin=1, Win=M, Hout=1, Wout=M, Cout=N, bias=bias, res=res, act=act,
-                  rowvec=rowvec, o_sp=out_ld, round_tf32=round_tf32, engine=engine, tag=tag)
+                  rowvec=rowvec, o_sp=out_ld, round_tf32=round_tf32, engine=engine, out_pair=out_pair, tag=tag)
 
     def zero(self, t, tag="zero"):
         p = L.ZeroParams()

@@ -310,16 +310,21 @@ class UNetPlan:
         if ctx_kv is None:  # self-attention: fused q|k projection, V written transposed
             wqk = self._packed(lambda: torch.cat([ca.to_q.weight.detach(), ca.to_k.weight.detach()], 0))
             qk = S.buf(B, N, 2 * C)
-            S.linear(x, wqk, qk, M=B * N, K=C, N=2 * C, round_tf32=S.R, tag=tag + ".qk")
+            # BF16x3: K and V^T later act as the W operand of QK^T / PV, so their producers also emit the bf16 hi/lo pair
+            pair = S.tc_code == 3 and N >= 128
+            qk_pair = (S.buf(B, N, 2 * C, dtype=torch.bfloat16), S.buf(B, N, 2 * C, dtype=torch.bfloat16)) if pair else None
+            S.linear(x, wqk, qk, M=B * N, K=C, N=2 * C, round_tf32=S.R, out_pair=qk_pair, tag=tag + ".qk")
             vT = S.buf(B, C, N)
+            vT_pair = (S.buf(B, C, N, dtype=torch.bfloat16), S.buf(B, C, N, dtype=torch.bfloat16)) if pair else None
             S.conv(Src(x, C, N * C, 0, C, 1), self._vec(ca.to_v.weight), vT, B=B, Hin=1, Win=N, Hout=1, Wout=N, Cout=C,
-                   o_sb=C * N, o_sp=1, o_sn=N, round_tf32=S.R, tag=tag + ".vT")
+                   o_sb=C * N, o_sp=1, o_sn=N, round_tf32=S.R, out_pair=vT_pair, tag=tag + ".vT")
             Nk, Nkp = N, N
             q_src = Src(qk, C, N * 2 * C, 0, 2 * C, 1)
             k_t, k_off, k_sb, k_ld = qk, C, N * 2 * C, 2 * C
             v_t, v_sb = vT, C * N
+            k_pair, v_pair = qk_pair, vT_pair
         else:
-            kc, vTc = ctx_kv
+            kc, vTc, k_pair, v_pair = ctx_kv
             q = S.buf(B, N, C)
             S.linear(x, self._vec(ca.to_q.weight), q, M=B * N, K=C, N=C, round_tf32=S.R, tag=tag + ".q")
             Nk, Nkp = self.Lc, self.Lp
@@ -333,16 +338,19 @@ class UNetPlan:
         # cross-attention: computing the (zero) padded key columns too makes C_out a multiple of 64 -> tensor-core eligible
         n_cols = Nkp if (Nkp != Nk and S.tc_code and N >= 128) else Nk
         S.conv(q_src, k_t, sc, B=B, Hin=1, Win=N, Hout=1, Wout=N, Cout=n_cols, w_sb=k_sb, w_ld=k_ld, w_off=k_off,
-               o_sb=N * Nkp, o_sp=Nkp, tag=tag + ".qk^T")
+               o_sb=N * Nkp, o_sp=Nkp, w_pair=k_pair, tag=tag + ".qk^T")
         S.softmax(sc, rows=B * N, n=Nk, ld=Nkp, scale=scale, round_tf32=S.R, tag=tag + ".softmax")
         o = S.buf(B, N, C)
         # K runs over the padded key count when that makes the tensor-core engine eligible (pad columns are zero)
         Kpv = Nkp if Nkp % 32 == 0 else Nk
         S.conv(Src(sc, Kpv, N * Nkp, 0, Nkp, 1), v_t, o, B=B, Hin=1, Win=N, Hout=1, Wout=N, Cout=C, w_sb=v_sb, w_ld=Nkp,
-               round_tf32=S.R, tag=tag + ".pv")
+               round_tf32=S.R, w_pair=v_pair, tag=tag + ".pv")
         S.release(qk)
         if ctx_kv is None:
             S.release(vT)
+            if qk_pair is not None:
+                for t_ in qk_pair + vT_pair:
+                    S.release(t_)
         if Nkp == Nk:
             S.release(sc)
         return o
@@ -353,11 +361,15 @@ class UNetPlan:
         D = self.net.context_dim
         kc = torch.zeros(B, Lp, C, dtype=torch.float32, device=self.dev)
         vT = torch.zeros(B, C, Lp, dtype=torch.float32, device=self.dev)
+        k_pair = v_pair = None
+        if self.step.tc_code == 3:  # bf16 hi/lo copies (zero pad rows/columns stay zero)
+            k_pair = tuple(torch.zeros(B, Lp, C, dtype=torch.bfloat16, device=self.dev) for _ in range(2))
+            v_pair = tuple(torch.zeros(B, C, Lp, dtype=torch.bfloat16, device=self.dev) for _ in range(2))
         P.conv(Src(self.ctx, D, Lc * D, 0, D, 1), self._vec(ca.to_k.weight), kc, B=B, Hin=1, Win=Lc, Hout=1, Wout=Lc,
-               Cout=C, o_sb=Lp * C, o_sp=C, round_tf32=P.R, tag="ctx.k")
+               Cout=C, o_sb=Lp * C, o_sp=C, round_tf32=P.R, out_pair=k_pair, tag="ctx.k")
         P.conv(Src(self.ctx, D, Lc * D, 0, D, 1), self._vec(ca.to_v.weight), vT, B=B, Hin=1, Win=Lc, Hout=1, Wout=Lc,
-               Cout=C, o_sb=C * Lp, o_sp=1, o_sn=Lp, round_tf32=P.R, tag="ctx.vT")
-        return kc, vT
+               Cout=C, o_sb=C * Lp, o_sp=1, o_sn=Lp, round_tf32=P.R, out_pair=v_pair, tag="ctx.vT")
+        return kc, vT, k_pair, v_pair
 
     def _transformer(self, st, x, C, h, w):
         S, B = self.step, self.B

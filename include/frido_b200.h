@@ -33,6 +33,7 @@ extern "C" {
 #define FRIDO_ACT_RELU 1
 #define FRIDO_ACT_SILU 2
 #define FRIDO_ACT_GEGLU 3 /* columns (2j,2j+1) = (value,gate) -> out[j] = value*gelu_erf(gate) */
+#define FRIDO_ACT_GEGLU_FAST 4 /* same with erf by Abramowitz-Stegun 7.1.26 (|err| < 5e-7); tcgen05 engines only */
 
 /* ---------------------------------------------------------------------------
  * Implicit-GEMM convolution / linear / batched matmul.
@@ -71,6 +72,9 @@ typedef struct FridoConvParams {
   float* out;
   int64_t o_sb, o_sp, o_sn; /* out[b*o_sb + p*o_sp + n*o_sn], p = oy*Wout + ox */
   int32_t round_tf32;       /* round stored values to TF32 (rna) */
+  void* out_hi; void* out_lo; /* optional: also store the outputs as a bf16 pair (hi = bf16(v), lo = bf16(v - hi)), indexed like
+                               `out`; this is how activations that later act as the W operand of a BF16x3 matmul
+                               (attention K and V^T) get their pre-split copy.  Not with GEGLU. */
   double* chan_sums;        /* optional (tcgen05 engines only): [B][Cout][2] += per-channel (sum, sum of squares) of the
                                stored outputs, i.e. the GroupNorm statistics of the tensor being produced; zero on entry */
   int32_t engine;           /* 0 = SIMT fp32; 1 = tcgen05 TF32; 2 = tcgen05 3xTF32 (error-compensated, ~2^-21 products);
