@@ -33,9 +33,13 @@ def gather_images(img, n_global=None, group=None):
         out = torch.empty((world * img.shape[0],) + tuple(img.shape[1:]), dtype=img.dtype, device=img.device)
         dist.all_gather_into_tensor(out, img.contiguous(), group=group)
         return out
-    parts = [torch.empty((hi - lo,) + tuple(img.shape[1:]), dtype=img.dtype, device=img.device) for lo, hi in sizes]
-    dist.all_gather(parts, img.contiguous(), group=group)
-    return torch.cat(parts, 0)
+    # ragged shards: collectives need equal sizes -> pad to the largest shard, gather, trim
+    mx = max(hi - lo for lo, hi in sizes)
+    padded = torch.zeros((mx,) + tuple(img.shape[1:]), dtype=img.dtype, device=img.device)
+    padded[: img.shape[0]] = img
+    out = torch.empty((world * mx,) + tuple(img.shape[1:]), dtype=img.dtype, device=img.device)
+    dist.all_gather_into_tensor(out, padded, group=group)
+    return torch.cat([out[r * mx: r * mx + (hi - lo)] for r, (lo, hi) in enumerate(sizes)], 0)
 
 
 @torch.no_grad()

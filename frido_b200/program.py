@@ -116,7 +116,7 @@ class Program:
     def conv(self, a0, w, out, *, B, Hin, Win, Hout, Wout, Cout, ksize=1, stride=1, pad=0, ups=1, a1=None,
              bias=None, rowvec=None, rowvec_sb=0, res=None, alpha=1.0, act=L.ACT_NONE, o_sb=None, o_sp=None, o_sn=1,
              w_sb=0, w_ld=0, w_off=0, out_off=0, round_tf32=0, engine=None, csum=None, out_pair=None, w_pair=None,
-             tag="conv"):
+             alg_flops=None, tag="conv"):
         """Returns True when `csum` (per-channel GroupNorm sums of the output, [B,Cout,2] fp64) was attached to the op:
         only the tcgen05 engines accumulate it, for dense NHWC outputs with >= 32 pixels per image."""
         if engine is None:
@@ -167,7 +167,8 @@ class Program:
             p.chan_sums = csum.data_ptr()
             self.hold(csum)
         self.hold(a0.t, None if a1 is None else a1.t, w, out, bias, rowvec, res)
-        fl = 2 * B * Hout * Wout * Cout * ksize * ksize * (a0.C + (a1.C if a1 is not None else 0))
+        # algorithmic FLOPs: zero-padded rows/columns added only to fit the tensor-core tile are not counted
+        fl = alg_flops if alg_flops is not None else 2 * B * Hout * Wout * Cout * ksize * ksize * (a0.C + (a1.C if a1 is not None else 0))
         self.flops += fl
         if engine in (1, 2, 3):
             self.tc_flops += fl

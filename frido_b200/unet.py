@@ -338,13 +338,13 @@ class UNetPlan:
         # cross-attention: computing the (zero) padded key columns too makes C_out a multiple of 64 -> tensor-core eligible
         n_cols = Nkp if (Nkp != Nk and S.tc_code and N >= 128) else Nk
         S.conv(q_src, k_t, sc, B=B, Hin=1, Win=N, Hout=1, Wout=N, Cout=n_cols, w_sb=k_sb, w_ld=k_ld, w_off=k_off,
-               o_sb=N * Nkp, o_sp=Nkp, w_pair=k_pair, tag=tag + ".qk^T")
+               o_sb=N * Nkp, o_sp=Nkp, w_pair=k_pair, alg_flops=2 * B * N * Nk * C, tag=tag + ".qk^T")
         S.softmax(sc, rows=B * N, n=Nk, ld=Nkp, scale=scale, round_tf32=S.R, tag=tag + ".softmax")
         o = S.buf(B, N, C)
         # K runs over the padded key count when that makes the tensor-core engine eligible (pad columns are zero)
         Kpv = Nkp if Nkp % 32 == 0 else Nk
         S.conv(Src(sc, Kpv, N * Nkp, 0, Nkp, 1), v_t, o, B=B, Hin=1, Win=N, Hout=1, Wout=N, Cout=C, w_sb=v_sb, w_ld=Nkp,
-               round_tf32=S.R, w_pair=v_pair, tag=tag + ".pv")
+               round_tf32=S.R, w_pair=v_pair, alg_flops=2 * B * N * Nk * C, tag=tag + ".pv")
         S.release(qk)
         if ctx_kv is None:
             S.release(vT)
