@@ -307,7 +307,11 @@ def run_reference(args):
     line = {"impl": "reference", "metric": "images/sec DDIM-200 256x256 layout-to-image (sampling + decode)", "value": v,
             "unit": "images/sec", "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": len(vals), "warmup": min(args.warmup, 1),
             "ms_per_step": round(1e3 * B / v, 1), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-            "data": "synthetic", "config": {"workload": f"{args.config}: latent {C}x{H}x{W}, bounded CPU sample extrapolated to the full step count"},
+            "data": "synthetic (same weights / shapes as the GPU arm)",
+            "config": {"workload": f"{args.config}: latent {C}x{H}x{W}, context {cfg['ctx'][0]}x{cfg['ctx'][1]}, {cfg['sampler'].upper()}-{cfg['steps']} x "
+                                   f"{len(model.split_embed_dim_list)} stages + MS-VQGAN decode, batch {B} per GPU (BASELINE configs[1])",
+                       "batch_per_gpu": B, "sampler_steps": cfg["steps"], "engine": "reference algorithm on host CPU (oracle port)",
+                       "sample": "each step = 1 UNet eval per stage + 1 decode, extrapolated linearly to the full step count"},
             "cpu_baseline": dict(vals[-1], value=v),
             "e2e": {"value": v, "unit": "images/sec", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     print(json.dumps(line), flush=True)
