@@ -7,8 +7,9 @@ All device arithmetic is in libfrido_b200.so (hand-written CUDA, C ABI in
 include/frido_b200.h); there is no CPU or PyTorch compute fallback.
 """
 from ._lib import FridoError, lib  # noqa: F401
+from .cond import BERTEmbedder  # noqa: F401
 from .diffusion import DiffusionWrapper, FridoDiffusion, LitEma, instantiate_from_config  # noqa: F401
-from .first_stage import VQModelInterface  # noqa: F401
+from .first_stage import VQModelInterface, images_to_uint8  # noqa: F401
 from .samplers import DDIMSampler, PLMSSampler  # noqa: F401
 from .unet import PyUNetModel  # noqa: F401
 

@@ -15,9 +15,9 @@ c_i = C.c_int32
 c_l = C.c_int64
 c_p = C.c_void_p
 
-ACT_NONE, ACT_RELU, ACT_SILU, ACT_GEGLU, ACT_GEGLU_FAST = 0, 1, 2, 3, 4
+ACT_NONE, ACT_RELU, ACT_SILU, ACT_GEGLU, ACT_GEGLU_FAST, ACT_GELU = 0, 1, 2, 3, 4, 5
 (OP_CONV, OP_GN_STATS, OP_NORM_ACT, OP_LAYERNORM, OP_SOFTMAX, OP_TIME_EMBED, OP_STEP_BEGIN, OP_UPDATE, OP_SNAP, OP_VQ,
- OP_ZERO, OP_UPSAMPLE) = range(1, 13)
+ OP_ZERO, OP_UPSAMPLE, OP_EMBED, OP_MHA) = range(1, 15)
 
 
 class ConvParams(C.Structure):
@@ -90,11 +90,23 @@ class UpsampleParams(C.Structure):
     _fields_ = [("x", c_p), ("B", c_i), ("H", c_i), ("W", c_i), ("C", c_i), ("round_tf32", c_i), ("out", c_p)]
 
 
+class EmbedParams(C.Structure):
+    _fields_ = [("tokens", c_p), ("B", c_i), ("L", c_i), ("D", c_i), ("vocab", c_i), ("tok_emb", c_p), ("pos_emb", c_p), ("out", c_p)]
+
+
+class MhaParams(C.Structure):
+    _fields_ = [("qkv", c_p), ("B", c_i), ("L", c_i), ("H", c_i), ("Dh", c_i), ("scale", c_f), ("out", c_p)]
+
+
+class ToU8Params(C.Structure):
+    _fields_ = [("x", c_p), ("B", c_i), ("C", c_i), ("HW", c_i), ("mode", c_i), ("out", c_p)]
+
+
 class _OpU(C.Union):
     _fields_ = [("conv", ConvParams), ("gn_stats", GnStatsParams), ("norm_act", NormActParams),
                 ("layernorm", LayerNormParams), ("softmax", SoftmaxParams), ("time_embed", TimeEmbedParams),
                 ("step_begin", StepBeginParams), ("update", UpdateParams), ("snap", SnapParams), ("vq", VqParams),
-                ("zero", ZeroParams), ("upsample", UpsampleParams)]
+                ("zero", ZeroParams), ("upsample", UpsampleParams), ("embed", EmbedParams), ("mha", MhaParams)]
 
 
 class Op(C.Structure):
@@ -103,12 +115,12 @@ class Op(C.Structure):
 
 _KIND_FIELD = {OP_CONV: "conv", OP_GN_STATS: "gn_stats", OP_NORM_ACT: "norm_act", OP_LAYERNORM: "layernorm",
                OP_SOFTMAX: "softmax", OP_TIME_EMBED: "time_embed", OP_STEP_BEGIN: "step_begin", OP_UPDATE: "update",
-               OP_SNAP: "snap", OP_VQ: "vq", OP_ZERO: "zero", OP_UPSAMPLE: "upsample"}
+               OP_SNAP: "snap", OP_VQ: "vq", OP_ZERO: "zero", OP_UPSAMPLE: "upsample", OP_EMBED: "embed", OP_MHA: "mha"}
 
 EXPORTS = [
     "frido_conv2d", "frido_gn_stats", "frido_norm_act", "frido_layernorm", "frido_softmax", "frido_time_embed",
     "frido_step_begin", "frido_sampler_update", "frido_stage_snap", "frido_vq_lookup", "frido_zero",
-    "frido_round_tf32", "frido_split_bf16", "frido_upsample2x", "frido_run_program", "frido_abi_version", "frido_sizeof_op", "frido_last_error",
+    "frido_round_tf32", "frido_split_bf16", "frido_upsample2x", "frido_to_uint8", "frido_embed_tokens", "frido_mha_small", "frido_run_program", "frido_abi_version", "frido_sizeof_op", "frido_last_error",
     "frido_launch_count", "frido_check_device",
 ]
 
@@ -141,7 +153,7 @@ def lib():
     L.frido_split_bf16.argtypes = [c_p, c_p, c_p, c_l, c_p]
     for name in ("frido_conv2d", "frido_gn_stats", "frido_norm_act", "frido_layernorm", "frido_softmax",
                  "frido_time_embed", "frido_step_begin", "frido_sampler_update", "frido_stage_snap", "frido_vq_lookup",
-                 "frido_upsample2x"):
+                 "frido_upsample2x", "frido_to_uint8", "frido_embed_tokens", "frido_mha_small"):
         getattr(L, name).argtypes = [c_p, c_p]
     if L.frido_sizeof_op() != C.sizeof(Op):
         raise FridoError(f"ABI mismatch: sizeof(FridoOp) C={L.frido_sizeof_op()} python={C.sizeof(Op)}")

@@ -185,6 +185,7 @@ __global__ void __launch_bounds__(NT) conv_simt_kernel(const FridoConvParams p) 
           if (res) t += res[o];
           if (p.act == FRIDO_ACT_RELU) t = fmaxf(t, 0.f);
           else if (p.act == FRIDO_ACT_SILU) t = silu_f(t);
+          else if (p.act == FRIDO_ACT_GELU) t = gelu_erf(t);
           t = p.round_tf32 ? round_tf32(t) : t;
           out[o] = t;
           if (p.out_hi) {
@@ -258,6 +259,7 @@ __global__ void __launch_bounds__(128) conv_smallcout_kernel(const FridoConvPara
       if (res) t += res[(int64_t)n * p.o_sn];
       if (p.act == FRIDO_ACT_RELU) t = fmaxf(t, 0.f);
       else if (p.act == FRIDO_ACT_SILU) t = silu_f(t);
+          else if (p.act == FRIDO_ACT_GELU) t = gelu_erf(t);
       out[(int64_t)n * p.o_sn] = p.round_tf32 ? round_tf32(t) : t;
     }
 }

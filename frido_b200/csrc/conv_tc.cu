@@ -430,6 +430,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
                 if (has_res) { v.x += rres[j].x; v.y += rres[j].y; v.z += rres[j].z; v.w += rres[j].w; }
                 if (act == FRIDO_ACT_RELU) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
                 else if (act == FRIDO_ACT_SILU) { v.x = silu_f(v.x); v.y = silu_f(v.y); v.z = silu_f(v.z); v.w = silu_f(v.w); }
+                else if (act == FRIDO_ACT_GELU) { v.x = gelu_erf(v.x); v.y = gelu_erf(v.y); v.z = gelu_erf(v.z); v.w = gelu_erf(v.w); }
                 if (rnd) { v.x = round_tf32(v.x); v.y = round_tf32(v.y); v.z = round_tf32(v.z); v.w = round_tf32(v.w); }
                 const long long o = obase[j] + n;
                 *reinterpret_cast<float4*>(p.out + o) = v;
@@ -494,6 +495,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
               if (has_res) t += p.res[o];
               if (act == FRIDO_ACT_RELU) t = fmaxf(t, 0.f);
               else if (act == FRIDO_ACT_SILU) t = silu_f(t);
+              else if (act == FRIDO_ACT_GELU) t = gelu_erf(t);
               t = rnd ? round_tf32(t) : t;
               if (p.out) p.out[o] = t;
               if (has_pair) {

@@ -294,9 +294,94 @@ __global__ void __launch_bounds__(256) upsample2x_kernel(const FridoUpsamplePara
   }
 }
 
+// token + position embedding gather (condition encoder)
+__global__ void __launch_bounds__(256) embed_kernel(const FridoEmbedParams p) {
+  const int Q = p.D >> 2;
+  const int64_t total = (int64_t)p.B * p.L * Q;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int q = (int)(e % Q);
+    const int64_t bl = e / Q;
+    const int l = (int)(bl % p.L);
+    int64_t tok = p.tokens[bl];
+    tok = tok < 0 ? 0 : (tok >= p.vocab ? p.vocab - 1 : tok);
+    const float4 a = __ldg(reinterpret_cast<const float4*>(p.tok_emb + tok * p.D) + q);
+    const float4 b = __ldg(reinterpret_cast<const float4*>(p.pos_emb + (int64_t)l * p.D) + q);
+    reinterpret_cast<float4*>(p.out + bl * p.D)[q] = make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+  }
+}
+
+// short-sequence multi-head attention: one CTA per (b, h); K, V in shared memory; one warp per query row
+__global__ void __launch_bounds__(256) mha_small_kernel(const FridoMhaParams p) {
+  extern __shared__ float sm[];
+  const int L = p.L, Dh = p.Dh, HD = p.H * p.Dh;
+  float* ks = sm;                 // [L][Dh+1]
+  float* vs = sm + (size_t)L * (Dh + 1);  // [L][Dh]
+  float* ps = vs + (size_t)L * Dh;        // [8 warps][L] probabilities
+  const int b = blockIdx.x / p.H, h = blockIdx.x % p.H;
+  const float* base = p.qkv + (int64_t)b * L * 3 * HD + h * Dh;
+  for (int i = threadIdx.x; i < L * Dh; i += blockDim.x) {
+    const int j = i / Dh, d = i - j * Dh;
+    ks[j * (Dh + 1) + d] = base[(int64_t)j * 3 * HD + HD + d];
+    vs[j * Dh + d] = base[(int64_t)j * 3 * HD + 2 * HD + d];
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* pw = ps + warp * L;
+  for (int i = warp; i < L; i += 8) {
+    const float* qrow = base + (int64_t)i * 3 * HD;
+    float m = -INFINITY;
+    for (int j = lane; j < L; j += 32) {
+      float s = 0.f;
+      for (int d = 0; d < Dh; ++d) s = fmaf(__ldg(qrow + d), ks[j * (Dh + 1) + d], s);
+      s *= p.scale;
+      pw[j] = s;
+      m = fmaxf(m, s);
+    }
+    m = warp_max(m);
+    float sum = 0.f;
+    for (int j = lane; j < L; j += 32) {
+      const float e = __expf(pw[j] - m);
+      pw[j] = e;
+      sum += e;
+    }
+    sum = warp_sum(sum);
+    __syncwarp();
+    const float inv = 1.0f / sum;
+    for (int d = lane; d < Dh; d += 32) {
+      float o = 0.f;
+      for (int j = 0; j < L; ++j) o = fmaf(pw[j], vs[j * Dh + d], o);
+      p.out[((int64_t)b * L + i) * HD + h * Dh + d] = o * inv;
+    }
+    __syncwarp();
+  }
+}
+
 }  // namespace frido
 
 using namespace frido;
+
+extern "C" int frido_embed_tokens(const FridoEmbedParams* p, void* stream) {
+  if (!p || !p->tokens || !p->tok_emb || !p->pos_emb || !p->out || (p->D & 3) || p->vocab <= 0)
+    return set_error(FRIDO_E_ARG, "embed_tokens: bad argument");
+  const int64_t total = (int64_t)p->B * p->L * (p->D >> 2);
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  embed_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(*p);
+  return check_launch("embed_tokens");
+}
+
+extern "C" int frido_mha_small(const FridoMhaParams* p, void* stream) {
+  if (!p || !p->qkv || !p->out || p->B <= 0 || p->L <= 0 || p->H <= 0 || p->Dh <= 0) return set_error(FRIDO_E_ARG, "mha_small: bad argument");
+  const size_t smem = ((size_t)p->L * (p->Dh + 1) + (size_t)p->L * p->Dh + 8 * (size_t)p->L) * sizeof(float);
+  if (smem > 200 * 1024) return set_error(FRIDO_E_ARG, "mha_small: sequence too long for shared memory");
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(mha_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    attr = true;
+  }
+  mha_small_kernel<<<p->B * p->H, 256, smem, (cudaStream_t)stream>>>(*p);
+  return check_launch("mha_small");
+}
 
 extern "C" int frido_upsample2x(const FridoUpsampleParams* p, void* stream) {
   if (!p || !p->x || !p->out || (p->C & 3)) return set_error(FRIDO_E_ARG, "upsample2x: bad argument");

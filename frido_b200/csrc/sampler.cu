@@ -197,9 +197,39 @@ __global__ void split_bf16_kernel(const float* __restrict__ src, uint16_t* __res
   }
 }
 
+__global__ void to_uint8_kernel(const FridoToU8Params p) {
+  const int64_t total = (int64_t)p.B * p.HW * p.C;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(e % p.C);
+    const int64_t r = e / p.C;
+    const int hw = (int)(r % p.HW);
+    const int b = (int)(r / p.HW);
+    const float x = p.x[((int64_t)b * p.C + c) * p.HW + hw];
+    float t;
+    if (p.mode == 0) {
+      t = __fmul_rn(__fadd_rn(x, 1.0f), 127.5f);
+      t = fminf(fmaxf(t, 0.f), 255.f);
+    } else {
+      const float cl = fminf(fmaxf(x, -1.f), 1.f);
+      t = __fmul_rn(255.0f, __fdiv_rn(__fadd_rn(cl, 1.0f), 2.0f));
+    }
+    p.out[e] = (uint8_t)(int)t;  // truncation, as torch .to(uint8) / numpy astype(uint8) on non-negative values
+  }
+}
+
 }  // namespace frido
 
 using namespace frido;
+
+extern "C" int frido_to_uint8(const FridoToU8Params* p, void* stream) {
+  if (!p || !p->x || !p->out || p->B <= 0 || p->C <= 0 || p->HW <= 0 || (p->mode != 0 && p->mode != 1))
+    return set_error(FRIDO_E_ARG, "to_uint8: bad argument");
+  const int64_t total = (int64_t)p->B * p->HW * p->C;
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  to_uint8_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(*p);
+  return check_launch("to_uint8");
+}
 
 extern "C" int frido_split_bf16(const float* src, void* hi, void* lo, int64_t n, void* stream) {
   if (!src || !hi || !lo || n < 0) return set_error(FRIDO_E_ARG, "split_bf16: bad argument");

@@ -17,6 +17,7 @@ import torch
 from torch import nn
 
 from . import _lib as L
+from .cond import BERTEmbedder
 from .first_stage import VQModelInterface
 from .unet import PyUNetModel
 
@@ -27,6 +28,8 @@ _TARGETS = {
     "ldm.modules.diffusionmodules.openaimodel.UNetModel": PyUNetModel,
     "ldm.modules.diffusionmodules.pyunet.PyUNetModel": PyUNetModel,
     "taming.models.msvqgan.VQModelInterface": VQModelInterface,
+    "frido.modules.encoders.modules.BERTEmbedder": BERTEmbedder,
+    "ldm.modules.encoders.modules.BERTEmbedder": BERTEmbedder,
 }
 
 

@@ -21,6 +21,23 @@ from .program import round_tf32_
 from .unet import _pack_conv
 
 
+@torch.no_grad()
+def images_to_uint8(img, mode="np"):
+    """Decoded images [B,C,H,W] fp32 -> uint8 NHWC on the device, byte-identical to the reference's
+    `custom_to_np` (mode "np", scripts/sample_diffusion.py:115-121) or `custom_to_pil` (mode "pil", :103-108)."""
+    import ctypes as C
+    if not img.is_cuda:
+        raise L.FridoError("images_to_uint8 runs on a CUDA device only (no CPU path)")
+    img = img.contiguous().float()
+    B, Cc, H, W = img.shape
+    out = torch.empty(B, H, W, Cc, dtype=torch.uint8, device=img.device)
+    p = L.ToU8Params()
+    p.x, p.B, p.C, p.HW, p.mode, p.out = img.data_ptr(), B, Cc, H * W, {"np": 0, "pil": 1}[mode], out.data_ptr()
+    s = torch.cuda.current_stream(img.device).cuda_stream
+    L.check(L.lib().frido_to_uint8(C.byref(p), C.c_void_p(s)), "to_uint8")
+    return out
+
+
 class VQModelInterface(nn.Module):
     def __init__(self, embed_dim, edconfig=None, ddconfig=None, lossconfig=None, n_embed=None, channel_range=[],
                  fusion="concat", ckpt_path=None, ignore_keys=[], image_key="image", colorize_nlabels=None, monitor=None,

@@ -216,6 +216,20 @@ class Program:
             return False
         return True
 
+    def embed_tokens(self, tokens, tok_emb, pos_emb, out, *, B, Lseq, D, tag="embed"):
+        p = L.EmbedParams()
+        p.tokens, p.B, p.L, p.D, p.vocab = tokens.data_ptr(), B, Lseq, D, tok_emb.shape[0]
+        p.tok_emb, p.pos_emb, p.out = tok_emb.data_ptr(), pos_emb.data_ptr(), out.data_ptr()
+        self.hold(tokens, tok_emb, pos_emb, out)
+        self._add(L.OP_EMBED, p, tag)
+
+    def mha_small(self, qkv, out, *, B, Lseq, H, Dh, scale, tag="mha"):
+        p = L.MhaParams()
+        p.qkv, p.B, p.L, p.H, p.Dh, p.scale, p.out = qkv.data_ptr(), B, Lseq, H, Dh, scale, out.data_ptr()
+        self.hold(qkv, out)
+        self.flops += 4 * B * H * Lseq * Lseq * Dh
+        self._add(L.OP_MHA, p, tag)
+
     def upsample2x(self, x, out, *, B, H, W, Cdim, round_tf32=0, tag="upsample2x"):
         p = L.UpsampleParams()
         p.x, p.B, p.H, p.W, p.C, p.round_tf32, p.out = x.data_ptr(), B, H, W, Cdim, round_tf32, out.data_ptr()

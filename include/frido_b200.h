@@ -33,6 +33,7 @@ extern "C" {
 #define FRIDO_ACT_RELU 1
 #define FRIDO_ACT_SILU 2
 #define FRIDO_ACT_GEGLU 3 /* columns (2j,2j+1) = (value,gate) -> out[j] = value*gelu_erf(gate) */
+#define FRIDO_ACT_GELU 5  /* exact-erf GELU (x_transformer.py:199-202 FeedForward of the condition encoder) */
 #define FRIDO_ACT_GEGLU_FAST 4 /* same with erf by Abramowitz-Stegun 7.1.26 (|err| < 5e-7); tcgen05 engines only */
 
 /* ---------------------------------------------------------------------------
@@ -200,6 +201,28 @@ int frido_vq_lookup(const FridoVqParams* p, void* stream);
 typedef struct FridoUpsampleParams { const float* x; int32_t B, H, W, C; int32_t round_tf32; float* out; } FridoUpsampleParams;
 int frido_upsample2x(const FridoUpsampleParams* p, void* stream);
 
+/* Condition encoder (BERTEmbedder = x-transformer encoder, frido/modules/x_transformer.py).
+ * Token + absolute position embedding (x_transformer.py:34-36,608-609): out[b,l,:] = tok_emb[tokens[b,l]] + pos_emb[l]. */
+typedef struct FridoEmbedParams {
+  const int64_t* tokens; int32_t B, L, D; int32_t vocab; const float* tok_emb; const float* pos_emb; float* out;
+} FridoEmbedParams;
+int frido_embed_tokens(const FridoEmbedParams* p, void* stream);
+
+/* Multi-head self-attention for short sequences (x_transformer.py:268-366, no mask, no memory): qkv [B,L,3*H*Dh] holds
+ * q | k | v (each H*Dh wide, head-major); out[b,l,h*Dh+d] = sum_j softmax_j(scale * q.k_j) v_j.  One CTA per (b,h),
+ * K and V staged in shared memory; L*Dh*8 bytes must fit in 200 KB. */
+typedef struct FridoMhaParams {
+  const float* qkv; int32_t B, L, H, Dh; float scale; float* out;
+} FridoMhaParams;
+int frido_mha_small(const FridoMhaParams* p, void* stream);
+
+/* Output formatting of the sampling script, fused into one pass: fp32 NCHW image in [-1,1] -> uint8 NHWC.
+ *   mode 0 = custom_to_np  (scripts/sample_diffusion.py:115-121): ((x + 1) * 127.5).clamp(0, 255) -> uint8 (truncate)
+ *   mode 1 = custom_to_pil (scripts/sample_diffusion.py:103-108): 255 * ((clamp(x,-1,1) + 1) / 2)  -> uint8 (truncate)
+ * Same fp32 operation order as the reference, so the bytes are identical. */
+typedef struct FridoToU8Params { const float* x; int32_t B, C, HW; int32_t mode; uint8_t* out; } FridoToU8Params;
+int frido_to_uint8(const FridoToU8Params* p, void* stream);
+
 /* Fill `n` bytes with zero (graph-capturable helper for the GN sums). */
 int frido_zero(void* ptr, int64_t nbytes, void* stream);
 
@@ -217,7 +240,8 @@ int frido_round_tf32(const float* src, float* dst, int64_t n, void* stream);
 enum FridoOpKind {
   FRIDO_OP_CONV = 1, FRIDO_OP_GN_STATS = 2, FRIDO_OP_NORM_ACT = 3, FRIDO_OP_LAYERNORM = 4,
   FRIDO_OP_SOFTMAX = 5, FRIDO_OP_TIME_EMBED = 6, FRIDO_OP_STEP_BEGIN = 7, FRIDO_OP_UPDATE = 8,
-  FRIDO_OP_SNAP = 9, FRIDO_OP_VQ = 10, FRIDO_OP_ZERO = 11, FRIDO_OP_UPSAMPLE = 12
+  FRIDO_OP_SNAP = 9, FRIDO_OP_VQ = 10, FRIDO_OP_ZERO = 11, FRIDO_OP_UPSAMPLE = 12,
+  FRIDO_OP_EMBED = 13, FRIDO_OP_MHA = 14
 };
 typedef struct FridoZeroParams { void* ptr; int64_t nbytes; } FridoZeroParams;
 typedef struct FridoOp {
@@ -227,7 +251,7 @@ typedef struct FridoOp {
     FridoConvParams conv; FridoGnStatsParams gn_stats; FridoNormActParams norm_act;
     FridoLayerNormParams layernorm; FridoSoftmaxParams softmax; FridoTimeEmbedParams time_embed;
     FridoStepBeginParams step_begin; FridoUpdateParams update; FridoSnapParams snap; FridoVqParams vq;
-    FridoZeroParams zero; FridoUpsampleParams upsample;
+    FridoZeroParams zero; FridoUpsampleParams upsample; FridoEmbedParams embed; FridoMhaParams mha;
   } u;
 } FridoOp;
 /* Launches ops[0..n) in order on `stream`; returns 0 or (-(1000+i)) if op i failed. */

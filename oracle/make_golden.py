@@ -194,10 +194,28 @@ def case_sched(base):
     print("sched done")
 
 
+def case_bert(base):
+    """BERTEmbedder of the layout2img config (32 layers, 640-d, vocab 30522, max_seq_len 96), tokens [2, 26]."""
+    ref_loader.activate()
+    from frido.modules.encoders.modules import BERTEmbedder
+    g = {}
+    for tag, kw, Lseq in (("full", dict(n_embed=640, n_layer=32, max_seq_len=96, use_tokenizer=False, device="cpu"), 26),
+                          ("small", dict(n_embed=64, n_layer=2, vocab_size=100, max_seq_len=16, use_tokenizer=False, device="cpu"), 7)):
+        enc = BERTEmbedder(**kw).eval()
+        man = synth.manifest_of(enc, "cond_stage_model.")
+        synth.fill_module_(enc, 7, "cond_stage_model.")
+        vocab = kw.get("vocab_size", 30522)
+        tokens = torch.from_numpy(np.random.default_rng(3).integers(0, min(vocab, 1024), size=(2, Lseq)))
+        z = enc.encode(tokens)
+        g[tag] = dict(kwargs=kw, manifest=man, seed=7, tokens=tokens, z=z.clone())
+    torch.save(g, os.path.join(OUT, "bert.pt"))
+    print("bert done", {k: tuple(v["z"].shape) for k, v in g.items()})
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     base = ref_loader.load_config("configs/frido/layout2i/frido_f8f4_coco_seg.yaml")
-    which = sys.argv[1:] or ["sched", "tiny2", "tiny3", "l2i32"]
+    which = sys.argv[1:] or ["sched", "tiny2", "tiny3", "l2i32", "bert"]
     if "sched" in which:
         case_sched(base)
     if "tiny2" in which:
@@ -206,6 +224,8 @@ def main():
         case_tiny(base, 3, "tiny3")
     if "l2i32" in which:
         case_unet_l2i32(base)
+    if "bert" in which:
+        case_bert(base)
 
 
 if __name__ == "__main__":

@@ -433,3 +433,29 @@ def decode_first_stage(sd, z, embed_dim, scale_factor, pre="first_stage_model.")
     quant = torch.cat(quants[::-1], dim=1)  # msvqgan.py:392-393 (fine -> coarse)
     quant = _conv(quant, sd, pre + "post_quant_conv", padding=0)
     return decoder_forward(sd, quant, pre + "decoder."), codes
+
+
+# --------------------------------------------------------------------------
+# f1 ("next" row): BERTEmbedder = x-transformer encoder  (encoders/modules.py:85-114; x_transformer.py:215-366,481-538,598-625)
+# --------------------------------------------------------------------------
+
+
+def bert_embedder(sd, tokens, pre="cond_stage_model.transformer.", heads=8):
+    x = sd[pre + "token_emb.weight"][tokens] + sd[pre + "pos_emb.emb.weight"][: tokens.shape[1]][None]  # :608-609
+    i = 0
+    while _has(sd, f"{pre}attn_layers.layers.{i}.0.weight"):
+        p = f"{pre}attn_layers.layers.{i}"
+        h = _ln(x, sd, p + ".0")  # pre-norm :506-507
+        if _has(sd, p + ".1.to_q.weight"):
+            q, k, v = (F.linear(h, sd[f"{p}.1.to_{n}.weight"]) for n in "qkv")
+            b, n, inner = q.shape
+            dh = inner // heads
+            q, k, v = (t.view(b, n, heads, dh).transpose(1, 2) for t in (q, k, v))
+            dots = torch.einsum("bhid,bhjd->bhij", q, k) * dh**-0.5  # :318
+            out = torch.einsum("bhij,bhjd->bhid", dots.softmax(dim=-1), v)
+            out = out.transpose(1, 2).reshape(b, n, inner)
+            x = _linear(out, sd, p + ".1.to_out") + x
+        else:
+            x = _linear(F.gelu(_linear(h, sd, p + ".1.net.0.0")), sd, p + ".1.net.2") + x  # FeedForward :194-212
+        i += 1
+    return _ln(x, sd, pre + "norm")  # :622

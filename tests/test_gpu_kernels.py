@@ -345,3 +345,19 @@ def test_errors_are_loud(dev):
     P.gn_stats(x, 30, sums, B=1, HW=16)  # 30 channels: not divisible into 32 groups
     with pytest.raises(L.FridoError):
         P.run()
+
+
+@pytest.mark.parametrize("mode", ["np", "pil"])
+def test_images_to_uint8_bit_exact(dev, mode):
+    """output formatting identical to custom_to_np / custom_to_pil (scripts/sample_diffusion.py:103-121)."""
+    import frido_b200 as fb
+    g = torch.Generator().manual_seed(4)
+    x = torch.randn(3, 3, 37, 41, generator=g) * 0.8
+    x[0, 0, 0, :8] = torch.tensor([-1.0, 1.0, -1.5, 1.5, 0.0, 0.999999, -0.999999, 0.5])
+    if mode == "np":
+        ref = ((x + 1) * 127.5).clamp(0, 255).to(torch.uint8).permute(0, 2, 3, 1).contiguous()
+    else:
+        y = (torch.clamp(x, -1.0, 1.0) + 1.0) / 2.0
+        ref = torch.from_numpy((255 * y.permute(0, 2, 3, 1).numpy()).astype(np.uint8))
+    got = fb.images_to_uint8(x.to(dev), mode).cpu()
+    assert torch.equal(got, ref)

@@ -237,3 +237,120 @@ def test_f16f8_configs_vs_oracle(dev, name, B):
     for a, b in zip(codes, codes_ref):
         assert torch.equal(torch.tensor(a), b)
     assert (img.cpu() - img_ref).abs().max() < 1e-3
+
+
+@pytest.mark.parametrize("B,H,W", [(3, 8, 16), (1, 16, 16), (5, 8, 8), (2, 12, 20)])
+def test_edge_shapes_vs_oracle(dev, golden_dir, B, H, W, monkeypatch):
+    """Ragged / odd cases through the tensor-core path: odd batch (partly empty 128-row tiles), batch 1, non-square and
+    non-power-of-two latents (masked tile rows, TMA zero fill on both borders), vs the CPU oracle on the same weights."""
+    from oracle import synth
+    from oracle import torch_oracle as O
+    monkeypatch.setenv("FRIDO_ENGINE", "bf16x3")
+    g = _load(golden_dir, "tiny2.pt")
+    model = _build_tiny(g, dev)
+    sd = synth.synth_state_dict(g["manifest"], g["seed"])
+    gen = torch.Generator().manual_seed(B * 100 + H)
+    ctx = torch.randn(B, 7, 24, generator=gen)
+    for s in range(2):
+        x = torch.randn(B, 3 * (s + 1), H, W, generator=gen)
+        ts = torch.randint(1, 999, (B,), generator=gen)  # per-sample timesteps (apply_model allows them)
+        e = model.apply_model(x.to(dev), ts.to(dev), ctx.to(dev), stage=s)
+        ref = O.unet_forward(sd, x, ts, ctx, s, g["split"])
+        assert (e.cpu() - ref).abs().max() < 1e-3, (s, (e.cpu() - ref).abs().max().item())
+    z = torch.randn(B, 6, H // 2 * 2, W // 2 * 2, generator=gen)
+    img, codes = model.decode_first_stage(z.to(dev), return_code=True)
+    img_ref, codes_ref = O.decode_first_stage(sd, z, g["split"], g["scale_factor"].tolist())
+    for a, b in zip(codes, codes_ref):
+        assert torch.equal(torch.tensor(a), b)
+    assert (img.cpu() - img_ref).abs().max() < 1e-3
+
+
+@pytest.mark.slow
+def test_config5_three_scale_512_vs_oracle(dev):
+    """BASELINE config 5 (3-scale, latent 9x128x128, context 92x640; not shipped by the reference): the
+    finest stage of the full-size UNet at a 64x64 crop of the latent, B=1, and a 3-codebook decode, vs the oracle."""
+    import frido_b200 as fb
+    from frido_b200 import configs
+    from oracle import torch_oracle as O
+    model, cfg = configs.build("l2i_512", dev)
+    sd = {k: v.detach().float().cpu() for k, v in model.state_dict().items()}
+    split = list(model.split_embed_dim_list)
+    assert split == [3, 3, 3]
+    g = torch.Generator().manual_seed(9)
+    ctx = torch.randn(1, 92, 640, generator=g)
+    x = torch.randn(1, 9, 64, 64, generator=g)
+    ts = torch.full((1,), 733, dtype=torch.long)
+    e = model.apply_model(x.to(dev), ts.to(dev), ctx.to(dev), stage=2)
+    ref = O.unet_forward(sd, x, ts, ctx, 2, split)
+    assert (e.cpu() - ref).abs().max() < 1e-3
+    # 3-stage DDIM with both inter-stage snaps (n = 2 then 1), 2 steps per stage, small latent
+    x0 = torch.randn(1, 9, 16, 16, generator=g)
+    out, _ = fb.DDIMSampler(model).sample(2, 1, (9, 16, 16), conditioning=ctx.to(dev), num_stage=3, eta=0.0, verbose=False,
+                                          init_noise=x0.to(dev))
+    ref = O.sample(sd, split, ctx, x0, 2)
+    assert (out.cpu() - ref).abs().max() < 1e-3
+    z = torch.randn(1, 9, 16, 16, generator=g) * 1.5
+    img, codes = model.decode_first_stage(z.to(dev), return_code=True)
+    img_ref, codes_ref = O.decode_first_stage(sd, z, split, model.scale_factor.cpu().tolist())
+    assert img.shape == (1, 3, 64, 64)
+    for a, b in zip(codes, codes_ref):
+        assert torch.equal(torch.tensor(a), b)
+    assert (img.cpu() - img_ref).abs().max() < 1e-3
+
+
+@pytest.mark.parametrize("tag", ["small", "full"])
+def test_bert_embedder_matches_reference_golden(dev, golden_dir, tag, engine):
+    """SURVEY 8f.1 ("next" row): the condition encoder on the device (tcgen05 GEMMs + short-sequence MHA kernel) against
+    the reference's BERTEmbedder output; state-dict keys identical to the reference's."""
+    import frido_b200 as fb
+    from oracle import synth
+    g = _load(golden_dir, "bert.pt")[tag]
+    kw = dict(g["kwargs"])
+    kw.pop("device", None)
+    enc = fb.BERTEmbedder(**kw)
+    mine = {"cond_stage_model." + k: tuple(v.shape) for k, v in enc.state_dict().items()}
+    assert mine == {n: tuple(s) for n, s in g["manifest"]}
+    synth.fill_module_(enc, g["seed"], "cond_stage_model.")
+    enc = enc.to(dev)
+    z = enc.encode(g["tokens"].to(dev))
+    err = (z.cpu() - g["z"]).abs().max().item()
+    assert err < TOLS[engine][0], err
+
+
+def test_drop_in_flow_tokens_to_image(dev, golden_dir, monkeypatch):
+    """The caller's sequence in scripts/sample_diffusion.py:236-257,175-206 on the native classes: layout tokens ->
+    get_learned_conditioning (BERTEmbedder) -> ema_scope -> DDIMSampler.sample -> decode_first_stage -> uint8 NHWC,
+    against the oracle chained the same way."""
+    import frido_b200 as fb
+    from oracle import synth
+    from oracle import torch_oracle as O
+    monkeypatch.setenv("FRIDO_ENGINE", "bf16x3")
+    g = _load(golden_dir, "tiny2.pt")
+    p = copy.deepcopy(g["cfg"]["params"])
+    p["use_ema"] = True
+    p["cond_stage_trainable"] = True
+    p["first_stage_config"]["params"]["ckpt_path"] = None
+    p["cond_stage_config"] = dict(target="frido.modules.encoders.modules.BERTEmbedder",
+                                  params=dict(n_embed=24, n_layer=2, vocab_size=100, max_seq_len=16, use_tokenizer=False))
+    model = fb.FridoDiffusion(**p)
+    assert isinstance(model.cond_stage_model, fb.BERTEmbedder)
+    synth.fill_module_(model, 5)
+    model.model_ema = fb.LitEma(model.model)
+    model.scale_factor.copy_(g["scale_factor"])
+    model = model.to(dev)
+    sd = {k: v.detach().float().cpu() for k, v in model.state_dict().items()}
+    tokens = torch.randint(0, 100, (2, 9), generator=torch.Generator().manual_seed(1))
+    c = model.get_learned_conditioning(tokens.to(dev))
+    c_ref = O.bert_embedder(sd, tokens)
+    assert (c.cpu() - c_ref).abs().max() < 1e-3
+    x0 = torch.randn(2, 6, 8, 8, generator=torch.Generator().manual_seed(2))
+    with model.ema_scope():
+        z, _ = fb.DDIMSampler(model).sample(4, 2, (6, 8, 8), conditioning=c, num_stage=2, eta=0.0, verbose=False,
+                                            init_noise=x0.to(dev), log_every_t=20)
+    img = model.decode_first_stage(z)
+    z_ref = O.sample(sd, g["split"], c_ref, x0, 4)
+    assert (z.cpu() - z_ref).abs().max() < 1e-3
+    img_ref, _ = O.decode_first_stage(sd, z.cpu(), g["split"], g["scale_factor"].tolist())
+    assert (img.cpu() - img_ref).abs().max() < 1e-3
+    u8 = fb.images_to_uint8(img, "np")
+    assert u8.shape == (2, 16, 16, 3) and u8.dtype == torch.uint8

@@ -99,3 +99,12 @@ def test_full_size_l2i_unet_step_and_decoder(golden_dir):
     for a, b in zip(codes, g["dec_codes"]):
         assert torch.equal(a, b)
     assert (img - g["dec_img"]).abs().max() < 1e-4
+
+
+@pytest.mark.parametrize("tag", ["small", "full"])
+def test_bert_embedder_vs_reference(golden_dir, tag):
+    """the condition encoder restatement against the reference's BERTEmbedder (x-transformer encoder)."""
+    g = _load(golden_dir, "bert.pt")[tag]
+    sd = synth.synth_state_dict(g["manifest"], g["seed"])
+    z = O.bert_embedder(sd, g["tokens"])
+    assert (z - g["z"]).abs().max() < 5e-5
