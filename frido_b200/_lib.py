@@ -17,7 +17,7 @@ c_p = C.c_void_p
 
 ACT_NONE, ACT_RELU, ACT_SILU, ACT_GEGLU, ACT_GEGLU_FAST, ACT_GELU = 0, 1, 2, 3, 4, 5
 (OP_CONV, OP_GN_STATS, OP_NORM_ACT, OP_LAYERNORM, OP_SOFTMAX, OP_TIME_EMBED, OP_STEP_BEGIN, OP_UPDATE, OP_SNAP, OP_VQ,
- OP_ZERO, OP_UPSAMPLE, OP_EMBED, OP_MHA) = range(1, 15)
+ OP_ZERO, OP_UPSAMPLE, OP_EMBED, OP_MHA, OP_CONVT, OP_ASSEMBLE) = range(1, 17)
 
 
 class ConvParams(C.Structure):
@@ -79,7 +79,7 @@ class SnapParams(C.Structure):
 class VqParams(C.Structure):
     _fields_ = [("z", c_p), ("B", c_i), ("C_total", c_i), ("HW", c_i), ("c_start", c_i), ("e_dim", c_i),
                 ("scale_factor", c_f), ("codebook", c_p), ("n_e", c_i), ("out", c_p), ("out_C", c_i),
-                ("out_coff", c_i), ("indices", c_p)]
+                ("out_coff", c_i), ("indices", c_p), ("z_nhwc", c_i)]
 
 
 class ZeroParams(C.Structure):
@@ -98,6 +98,15 @@ class MhaParams(C.Structure):
     _fields_ = [("qkv", c_p), ("B", c_i), ("L", c_i), ("H", c_i), ("Dh", c_i), ("scale", c_f), ("out", c_p)]
 
 
+class ConvT2dParams(C.Structure):
+    _fields_ = [("x", c_p), ("B", c_i), ("H", c_i), ("W", c_i), ("Cin", c_i), ("Cout", c_i), ("w", c_p), ("bias", c_p), ("out", c_p), ("x_ld", c_i)]
+
+
+class AssembleParams(C.Structure):
+    _fields_ = [("h", c_p), ("B", c_i), ("H", c_i), ("W", c_i), ("e", c_i), ("sh", c_i), ("scale", c_f), ("out", c_p),
+                ("C_total", c_i), ("c_off", c_i)]
+
+
 class ToU8Params(C.Structure):
     _fields_ = [("x", c_p), ("B", c_i), ("C", c_i), ("HW", c_i), ("mode", c_i), ("out", c_p)]
 
@@ -106,7 +115,8 @@ class _OpU(C.Union):
     _fields_ = [("conv", ConvParams), ("gn_stats", GnStatsParams), ("norm_act", NormActParams),
                 ("layernorm", LayerNormParams), ("softmax", SoftmaxParams), ("time_embed", TimeEmbedParams),
                 ("step_begin", StepBeginParams), ("update", UpdateParams), ("snap", SnapParams), ("vq", VqParams),
-                ("zero", ZeroParams), ("upsample", UpsampleParams), ("embed", EmbedParams), ("mha", MhaParams)]
+                ("zero", ZeroParams), ("upsample", UpsampleParams), ("embed", EmbedParams), ("mha", MhaParams), ("convt", ConvT2dParams),
+                ("assemble", AssembleParams)]
 
 
 class Op(C.Structure):
@@ -115,12 +125,12 @@ class Op(C.Structure):
 
 _KIND_FIELD = {OP_CONV: "conv", OP_GN_STATS: "gn_stats", OP_NORM_ACT: "norm_act", OP_LAYERNORM: "layernorm",
                OP_SOFTMAX: "softmax", OP_TIME_EMBED: "time_embed", OP_STEP_BEGIN: "step_begin", OP_UPDATE: "update",
-               OP_SNAP: "snap", OP_VQ: "vq", OP_ZERO: "zero", OP_UPSAMPLE: "upsample", OP_EMBED: "embed", OP_MHA: "mha"}
+               OP_SNAP: "snap", OP_VQ: "vq", OP_ZERO: "zero", OP_UPSAMPLE: "upsample", OP_EMBED: "embed", OP_MHA: "mha", OP_CONVT: "convt", OP_ASSEMBLE: "assemble"}
 
 EXPORTS = [
     "frido_conv2d", "frido_gn_stats", "frido_norm_act", "frido_layernorm", "frido_softmax", "frido_time_embed",
     "frido_step_begin", "frido_sampler_update", "frido_stage_snap", "frido_vq_lookup", "frido_zero",
-    "frido_round_tf32", "frido_split_bf16", "frido_upsample2x", "frido_to_uint8", "frido_embed_tokens", "frido_mha_small", "frido_run_program", "frido_abi_version", "frido_sizeof_op", "frido_last_error",
+    "frido_round_tf32", "frido_split_bf16", "frido_upsample2x", "frido_to_uint8", "frido_embed_tokens", "frido_mha_small", "frido_conv_transpose2d", "frido_assemble_latent", "frido_run_program", "frido_abi_version", "frido_sizeof_op", "frido_last_error",
     "frido_launch_count", "frido_check_device",
 ]
 
@@ -153,7 +163,8 @@ def lib():
     L.frido_split_bf16.argtypes = [c_p, c_p, c_p, c_l, c_p]
     for name in ("frido_conv2d", "frido_gn_stats", "frido_norm_act", "frido_layernorm", "frido_softmax",
                  "frido_time_embed", "frido_step_begin", "frido_sampler_update", "frido_stage_snap", "frido_vq_lookup",
-                 "frido_upsample2x", "frido_to_uint8", "frido_embed_tokens", "frido_mha_small"):
+                 "frido_upsample2x", "frido_to_uint8", "frido_embed_tokens", "frido_mha_small",
+                 "frido_conv_transpose2d", "frido_assemble_latent"):
         getattr(L, name).argtypes = [c_p, c_p]
     if L.frido_sizeof_op() != C.sizeof(Op):
         raise FridoError(f"ABI mismatch: sizeof(FridoOp) C={L.frido_sizeof_op()} python={C.sizeof(Op)}")

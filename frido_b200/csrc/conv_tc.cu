@@ -646,12 +646,16 @@ int conv2d_tc(const FridoConvParams* p, cudaStream_t s) {
   if (p->ups != 1) return set_error(FRIDO_E_ARG, "conv2d_tc: ups must be 1 (materialise the upsample first)");
   if (p->stride != 1 && !(p->stride == 2 && p->ksize == 3)) return set_error(FRIDO_E_ARG, "conv2d_tc: stride must be 1, or 2 for 3x3");
   if (p->ksize != 1 && p->ksize != 3) return set_error(FRIDO_E_ARG, "conv2d_tc: ksize must be 1 or 3");
-  if (p->pad != p->ksize / 2) return set_error(FRIDO_E_ARG, "conv2d_tc: pad must be ksize/2");
+  // pad = ksize/2, or 0 for the encoder's asymmetric stride-2 conv (taming model.py:68-72: pad right/bottom by 1 = TMA zero fill)
+  if (p->pad != p->ksize / 2 && !(p->pad == 0 && p->stride == 2 && p->ksize == 3))
+    return set_error(FRIDO_E_ARG, "conv2d_tc: pad must be ksize/2 (or 0 for 3x3 stride 2)");
   if (p->c0 % TC_BK || p->c1 % TC_BK || p->c0 <= 0) return set_error(FRIDO_E_ARG, "conv2d_tc: channels must be multiples of 32");
   if ((p->c1 > 0) != (p->a1 != nullptr)) return set_error(FRIDO_E_ARG, "conv2d_tc: a1/c1 mismatch");
   if (p->Cout % 64) return set_error(FRIDO_E_ARG, "conv2d_tc: Cout must be a multiple of 64");
   if (p->a0_sc != 1 || (p->a1 && p->a1_sc != 1)) return set_error(FRIDO_E_ARG, "conv2d_tc: channel stride must be 1");
-  if (p->Hout != (p->Hin + p->stride - 1) / p->stride || p->Wout != (p->Win + p->stride - 1) / p->stride)
+  if (p->pad == 0 && p->ksize == 3) {
+    if (p->Hout != (p->Hin - 2) / 2 + 1 || p->Wout != (p->Win - 2) / 2 + 1) return set_error(FRIDO_E_ARG, "conv2d_tc: bad output size");
+  } else if (p->Hout != (p->Hin + p->stride - 1) / p->stride || p->Wout != (p->Win + p->stride - 1) / p->stride)
     return set_error(FRIDO_E_ARG, "conv2d_tc: output size must be ceil(in/stride)");
   if (!a16(p->a0) || !a16(p->w) || (p->a1 && !a16(p->a1)) || (p->out && !a16(p->out)) || (p->res && !a16(p->res)))
     return set_error(FRIDO_E_ARG, "conv2d_tc: pointers must be 16-byte aligned");

@@ -161,7 +161,8 @@ __global__ void __launch_bounds__(256) vq_kernel(const FridoVqParams p) {
   const float inv = __fdiv_rn(1.0f, p.scale_factor);  // frido.py:836 `1. / self.scale_factor[i]`
   float zz = 0.f;
   for (int d = 0; d < p.e_dim; ++d) {
-    z[d] = __fmul_rn(p.z[((int64_t)b * p.C_total + p.c_start + d) * p.HW + hw], inv);
+    const float zin = p.z_nhwc ? p.z[pos * p.C_total + p.c_start + d] : p.z[((int64_t)b * p.C_total + p.c_start + d) * p.HW + hw];
+    z[d] = __fmul_rn(zin, inv);
     zz = __fadd_rn(zz, __fmul_rn(z[d], z[d]));
   }
   float best = INFINITY;
@@ -197,6 +198,50 @@ __global__ void split_bf16_kernel(const float* __restrict__ src, uint16_t* __res
   }
 }
 
+// ConvTranspose2d(k=4, s=2, p=1): out[oy,ox] += x[iy,ix] * w[ky,kx] with oy = 2*iy - 1 + ky  (tiny channel counts)
+__global__ void convt_kernel(const FridoConvT2dParams p) {
+  const int Ho = 2 * p.H, Wo = 2 * p.W;
+  const int64_t total = (int64_t)p.B * Ho * Wo * p.Cout;
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= total) return;
+  const int co = (int)(e % p.Cout);
+  int64_t r = e / p.Cout;
+  const int ox = (int)(r % Wo); r /= Wo;
+  const int oy = (int)(r % Ho);
+  const int b = (int)(r / Ho);
+  float acc = p.bias ? p.bias[co] : 0.f;
+  const int ld = p.x_ld ? p.x_ld : p.Cin;
+  // torch accumulates over ci, then ky, kx in its col2im GEMM; plain fp32 FMA chain here (parity ~1e-7)
+  for (int ky = 0; ky < 4; ++ky) {
+    const int ty = oy + 1 - ky;
+    if (ty < 0 || (ty & 1)) continue;
+    const int iy = ty >> 1;
+    if (iy >= p.H) continue;
+    for (int kx = 0; kx < 4; ++kx) {
+      const int tx = ox + 1 - kx;
+      if (tx < 0 || (tx & 1)) continue;
+      const int ix = tx >> 1;
+      if (ix >= p.W) continue;
+      const float* xin = p.x + (((int64_t)b * p.H + iy) * p.W + ix) * ld;
+      for (int ci = 0; ci < p.Cin; ++ci) acc = fmaf(xin[ci], p.w[((ci * p.Cout + co) * 4 + ky) * 4 + kx], acc);
+    }
+  }
+  p.out[e] = acc;
+}
+
+__global__ void assemble_kernel(const FridoAssembleParams p) {
+  const int64_t total = (int64_t)p.B * p.e * p.H * p.W;
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= total) return;
+  const int x = (int)(t % p.W);
+  const int y = (int)((t / p.W) % p.H);
+  const int d = (int)((t / ((int64_t)p.W * p.H)) % p.e);
+  const int b = (int)(t / ((int64_t)p.W * p.H * p.e));
+  const int hs = p.H >> p.sh, ws = p.W >> p.sh;
+  const float v = p.h[(((int64_t)b * hs + (y >> p.sh)) * ws + (x >> p.sh)) * p.e + d];
+  p.out[(((int64_t)b * p.C_total + p.c_off + d) * p.H + y) * p.W + x] = __fmul_rn(v, p.scale);
+}
+
 __global__ void to_uint8_kernel(const FridoToU8Params p) {
   const int64_t total = (int64_t)p.B * p.HW * p.C;
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
@@ -220,6 +265,21 @@ __global__ void to_uint8_kernel(const FridoToU8Params p) {
 }  // namespace frido
 
 using namespace frido;
+
+extern "C" int frido_conv_transpose2d(const FridoConvT2dParams* p, void* stream) {
+  if (!p || !p->x || !p->w || !p->out || p->B <= 0 || p->Cin <= 0 || p->Cout <= 0) return set_error(FRIDO_E_ARG, "conv_transpose2d: bad argument");
+  const int64_t total = (int64_t)p->B * 4 * p->H * p->W * p->Cout;
+  convt_kernel<<<(unsigned)((total + 127) / 128), 128, 0, (cudaStream_t)stream>>>(*p);
+  return check_launch("conv_transpose2d");
+}
+
+extern "C" int frido_assemble_latent(const FridoAssembleParams* p, void* stream) {
+  if (!p || !p->h || !p->out || p->sh < 0 || (p->H & ((1 << p->sh) - 1)) || (p->W & ((1 << p->sh) - 1)))
+    return set_error(FRIDO_E_ARG, "assemble_latent: bad argument");
+  const int64_t total = (int64_t)p->B * p->e * p->H * p->W;
+  assemble_kernel<<<(unsigned)((total + 127) / 128), 128, 0, (cudaStream_t)stream>>>(*p);
+  return check_launch("assemble_latent");
+}
 
 extern "C" int frido_to_uint8(const FridoToU8Params* p, void* stream) {
   if (!p || !p->x || !p->out || p->B <= 0 || p->C <= 0 || p->HW <= 0 || (p->mode != 0 && p->mode != 1))

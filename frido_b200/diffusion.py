@@ -289,12 +289,84 @@ class FridoDiffusion(nn.Module):
         1/scale_factor (frido.py:832-838) is folded into the VQ kernel."""
         if predict_cids:
             raise NotImplementedError("predict_cids is not used by any shipped config")
+        return self.first_stage_model.decode(z_in, return_code=return_code, scale_factor=self._scale_factors())
+
+    def _scale_factors(self):
         n = len(self.first_stage_model.embed_dim)
         if not self.adopted_scale_factor:
-            sf = [float(self.scale_factor)] * n
-        else:
-            sf = [float(v) for v in self.scale_factor.detach().cpu().tolist()]
-        return self.first_stage_model.decode(z_in, return_code=return_code, scale_factor=sf)
+            return [float(self.scale_factor)] * n
+        return [float(v) for v in self.scale_factor.detach().cpu().tolist()]
+
+    @torch.no_grad()
+    def encode_first_stage(self, x):
+        """frido.py:960-1006 (the non-split branch: `first_stage_model.encode(x)`), SURVEY.md §8f.3."""
+        if hasattr(self, "split_input_params"):
+            raise NotImplementedError("patch-distributed VQ (split_input_params) is not used by any shipped config")
+        if self.use_prob:
+            raise NotImplementedError("use_prob / encode_prob is not used by any shipped config")
+        return self.first_stage_model.encode(x)
+
+    @torch.no_grad()
+    def get_first_stage_encoding(self, encoder_posterior):
+        """frido.py:646-662: per-scale (or global) scale_factor multiply of the encoder output."""
+        if not isinstance(encoder_posterior, torch.Tensor):
+            raise NotImplementedError(f"encoder_posterior of type '{type(encoder_posterior)}' not yet implemented")
+        z = encoder_posterior
+        if not self.adopted_scale_factor:
+            return self.scale_factor * z
+        start = 0
+        for i, e in enumerate(self.first_stage_model.embed_dim):
+            if start + e <= z.size(1):
+                z[:, start:start + e, :, :] *= self.scale_factor[i]  # in place, like the reference
+                start += e
+        return z.clone()
+
+    @torch.no_grad()
+    def encode_to_latent(self, x):
+        """encode_first_stage + get_first_stage_encoding in one program (the scale multiply rides the last kernel)."""
+        return self.first_stage_model.encode(x, scale_factor=self._scale_factors())
+
+    @torch.no_grad()
+    def get_input(self, batch, k, return_first_stage_outputs=False, force_c_encode=False, cond_key=None,
+                  return_original_cond=False, bs=None):
+        """frido.py:766-817 (and DDPM.get_input :372-380): batch dict -> [z, c, (x, xrec), (xc)]."""
+        def base(key):
+            x = batch[key]
+            if len(x.shape) == 3:
+                x = x[..., None]
+            if key != "objects_bbox":
+                x = x.permute(0, 3, 1, 2)  # 'b h w c -> b c h w'
+            return x.contiguous().float()
+
+        x = base(k)
+        if bs is not None:
+            x = x[:bs]
+        x = x.to(self.device)
+        z = self.encode_to_latent(x)
+        c = xc = None
+        if self.model.conditioning_key is not None:
+            cond_key = self.cond_stage_key if cond_key is None else cond_key
+            if cond_key != self.first_stage_key:
+                if cond_key in ("caption", "coordinates_bbox"):
+                    xc = batch[cond_key]
+                elif cond_key in ("objects", "class_label"):
+                    xc = batch
+                else:
+                    xc = base(cond_key).to(self.device)
+            else:
+                xc = x
+            if not self.cond_stage_trainable or force_c_encode:
+                c = self.get_learned_conditioning(xc if isinstance(xc, (dict, list)) else xc.to(self.device))
+            else:
+                c = xc
+            if bs is not None:
+                c = c[:bs]
+        out = [z, c]
+        if return_first_stage_outputs:
+            out.extend([x, self.decode_first_stage(z)])
+        if return_original_cond:
+            out.append(xc)
+        return out
 
     def get_img_ids(self, batch):
         return batch.get("file_name")

@@ -178,6 +178,54 @@ class TDecoder(_NoForward):
         self.conv_out = nn.Conv2d(block_in, out_ch, 3, padding=1)
 
 
+class TDownsample(_NoForward):
+    """taming Downsample (model.py:57-78): 3x3 stride-2 conv after a right/bottom zero pad."""
+
+    def __init__(self, ch):
+        super().__init__()
+        self.conv = nn.Conv2d(ch, ch, 3, stride=2, padding=0)
+
+
+class MSEncoder(_NoForward):
+    """taming MSEncoder (model.py:435-510): weights only.  One mid/norm/conv_out head per scale, finest first."""
+
+    def __init__(self, *, ch, ch_mult=(1, 2, 4, 8), num_res_blocks, attn_resolutions, in_channels, resolution, z_channels,
+                 double_z=True, multiscale=3, **ignored):
+        super().__init__()
+        self.ch, self.num_resolutions, self.num_res_blocks = ch, len(ch_mult), num_res_blocks
+        self.resolution, self.in_channels, self.multiscale = resolution, in_channels, multiscale
+        self.conv_in = nn.Conv2d(in_channels, ch, 3, padding=1)
+        curr_res = resolution
+        in_ch_mult = (1,) + tuple(ch_mult)
+        self.down = nn.ModuleList()
+        for i_level in range(self.num_resolutions):
+            block, attn = nn.ModuleList(), nn.ModuleList()
+            block_in, block_out = ch * in_ch_mult[i_level], ch * ch_mult[i_level]
+            for _ in range(num_res_blocks):
+                block.append(TResnetBlock(block_in, block_out))
+                block_in = block_out
+                if curr_res in attn_resolutions:
+                    attn.append(TAttnBlock(block_in))
+            down = nn.Module()
+            down.block, down.attn = block, attn
+            if i_level != self.num_resolutions - 1:
+                down.downsample = TDownsample(block_in)
+                curr_res = curr_res // 2
+            self.down.append(down)
+        in_ch_mult = in_ch_mult[-multiscale:]
+        assert len(z_channels) == multiscale, "Error using multiscale encoder, but the z gets wrong dim."
+        self.mid_ms, self.norm_out_ms, self.conv_out_ms = nn.ModuleList(), nn.ModuleList(), nn.ModuleList()
+        for i in range(multiscale):
+            block_in = ch * in_ch_mult[i]
+            mid = nn.Module()
+            mid.block_1 = TResnetBlock(block_in, block_in)
+            mid.attn_1 = TAttnBlock(block_in)
+            mid.block_2 = TResnetBlock(block_in, block_in)
+            self.mid_ms.append(mid)
+            self.norm_out_ms.append(gn(block_in, 1e-6))
+            self.conv_out_ms.append(nn.Conv2d(block_in, 2 * z_channels[i] if double_z else z_channels[i], 3, padding=1))
+
+
 class VectorQuantizer(_NoForward):
     def __init__(self, n_e, e_dim, init_normal=False):
         super().__init__()

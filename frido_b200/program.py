@@ -180,11 +180,13 @@ class Program:
     def _tc_ok(a0, a1, B, Hin, Win, Hout, Wout, Cout, ksize, stride, pad, ups, w, w_sb, w_ld, w_off, act, o_sb, o_sp, o_sn,
                out, out_off, res):
         """Shape contract of conv2d_tc (csrc/conv_tc.cu); everything else runs on the SIMT engine."""
-        if ups != 1 or ksize not in (1, 3) or pad != ksize // 2:
+        asym = ksize == 3 and stride == 2 and pad == 0  # encoder Downsample (taming model.py:68-72)
+        if ups != 1 or ksize not in (1, 3) or (pad != ksize // 2 and not asym):
             return False
         if not (stride == 1 or (stride == 2 and ksize == 3 and os.environ.get('FRIDO_TC_STRIDE2', '1') == '1')):
             return False
-        if (Hout, Wout) != ((Hin + stride - 1) // stride, (Win + stride - 1) // stride):
+        want = ((Hin - 2) // 2 + 1, (Win - 2) // 2 + 1) if asym else ((Hin + stride - 1) // stride, (Win + stride - 1) // stride)
+        if (Hout, Wout) != want:
             return False
         if stride == 2 and (2 * min(128, 1 << (Wout - 1).bit_length()) > 256):
             return False
@@ -316,11 +318,25 @@ class Program:
         self.hold(x)
         self._add(L.OP_SNAP, p, tag)
 
-    def vq(self, z, codebook, out, indices, *, B, C_total, HW, c_start, e_dim, scale_factor, out_C, out_coff, tag="vq"):
+    def conv_transpose2d(self, x, w, bias, out, *, B, H, W, Cin, Cout, x_ld=0, x_off=0, tag="conv_transpose2d"):
+        p = L.ConvT2dParams()
+        p.x, p.B, p.H, p.W, p.Cin, p.Cout = x.data_ptr() + 4 * x_off, B, H, W, Cin, Cout
+        p.w, p.bias, p.out, p.x_ld = w.data_ptr(), _ptr(bias), out.data_ptr(), x_ld
+        self.hold(x, w, bias, out)
+        self.flops += 2 * B * H * W * 16 * Cin * Cout
+        self._add(L.OP_CONVT, p, tag)
+
+    def assemble_latent(self, h, out, *, B, H, W, e, sh, scale, C_total, c_off, tag="assemble_latent"):
+        p = L.AssembleParams()
+        p.h, p.B, p.H, p.W, p.e, p.sh, p.scale, p.out, p.C_total, p.c_off = h.data_ptr(), B, H, W, e, sh, scale, out.data_ptr(), C_total, c_off
+        self.hold(h, out)
+        self._add(L.OP_ASSEMBLE, p, tag)
+
+    def vq(self, z, codebook, out, indices, *, B, C_total, HW, c_start, e_dim, scale_factor, out_C, out_coff, z_nhwc=0, tag="vq"):
         p = L.VqParams()
         p.z, p.B, p.C_total, p.HW, p.c_start, p.e_dim = z.data_ptr(), B, C_total, HW, c_start, e_dim
         p.scale_factor, p.codebook, p.n_e = scale_factor, codebook.data_ptr(), codebook.shape[0]
-        p.out, p.out_C, p.out_coff, p.indices = out.data_ptr(), out_C, out_coff, indices.data_ptr()
+        p.out, p.out_C, p.out_coff, p.indices, p.z_nhwc = out.data_ptr(), out_C, out_coff, indices.data_ptr(), z_nhwc
         self.hold(z, codebook, out, indices)
         self._add(L.OP_VQ, p, tag)
 

@@ -186,13 +186,14 @@ int frido_stage_snap(const FridoSnapParams* p, void* stream);
  * (first minimum) -> z + (e_idx - z), written NHWC at channel offset out_coff of
  * a [B,HW,out_C] tensor (msvqgan.py:392-393 reverses the group order). */
 typedef struct FridoVqParams {
-  const float* z;            /* NCHW [B, C_total, H, W] */
+  const float* z;            /* NCHW [B, C_total, H, W]  (z_nhwc = 0)  or NHWC [B, HW, C_total] (z_nhwc = 1) */
   int32_t B, C_total, HW, c_start, e_dim;
   float scale_factor;
   const float* codebook;     /* [n_e][e_dim] */
   int32_t n_e;
   float* out; int32_t out_C, out_coff;
   int64_t* indices;          /* [B*HW] */
+  int32_t z_nhwc;            /* input layout, see `z` (the encoder's top-down path quantises NHWC conv outputs) */
 } FridoVqParams;
 int frido_vq_lookup(const FridoVqParams* p, void* stream);
 
@@ -215,6 +216,22 @@ typedef struct FridoMhaParams {
   const float* qkv; int32_t B, L, H, Dh; float scale; float* out;
 } FridoMhaParams;
 int frido_mha_small(const FridoMhaParams* p, void* stream);
+
+/* MS-VQGAN encode side.
+ * nn.ConvTranspose2d(Cin, Cout, 4, stride=2, padding=1) on NHWC (msvqgan.py:82-84): out [B,2H,2W,Cout] dense;
+ * w is the PyTorch layout [Cin][Cout][4][4]. */
+typedef struct FridoConvT2dParams {
+  const float* x; int32_t B, H, W, Cin, Cout; const float* w; const float* bias; float* out;
+  int32_t x_ld;              /* floats between consecutive input pixels (>= Cin; 0 = Cin): lets x be a channel slice */
+} FridoConvT2dParams;
+int frido_conv_transpose2d(const FridoConvT2dParams* p, void* stream);
+
+/* Assemble one scale into the latent (msvqgan.py:355-372 + frido.py:646-662): nearest-upsample an NHWC map
+ * [B,H>>sh,W>>sh,e] by 2^sh, multiply by `scale`, write channels [c_off, c_off+e) of the NCHW latent [B,C_total,H,W]. */
+typedef struct FridoAssembleParams {
+  const float* h; int32_t B, H, W, e, sh; float scale; float* out; int32_t C_total, c_off;
+} FridoAssembleParams;
+int frido_assemble_latent(const FridoAssembleParams* p, void* stream);
 
 /* Output formatting of the sampling script, fused into one pass: fp32 NCHW image in [-1,1] -> uint8 NHWC.
  *   mode 0 = custom_to_np  (scripts/sample_diffusion.py:115-121): ((x + 1) * 127.5).clamp(0, 255) -> uint8 (truncate)
@@ -241,7 +258,7 @@ enum FridoOpKind {
   FRIDO_OP_CONV = 1, FRIDO_OP_GN_STATS = 2, FRIDO_OP_NORM_ACT = 3, FRIDO_OP_LAYERNORM = 4,
   FRIDO_OP_SOFTMAX = 5, FRIDO_OP_TIME_EMBED = 6, FRIDO_OP_STEP_BEGIN = 7, FRIDO_OP_UPDATE = 8,
   FRIDO_OP_SNAP = 9, FRIDO_OP_VQ = 10, FRIDO_OP_ZERO = 11, FRIDO_OP_UPSAMPLE = 12,
-  FRIDO_OP_EMBED = 13, FRIDO_OP_MHA = 14
+  FRIDO_OP_EMBED = 13, FRIDO_OP_MHA = 14, FRIDO_OP_CONVT = 15, FRIDO_OP_ASSEMBLE = 16
 };
 typedef struct FridoZeroParams { void* ptr; int64_t nbytes; } FridoZeroParams;
 typedef struct FridoOp {
@@ -252,6 +269,7 @@ typedef struct FridoOp {
     FridoLayerNormParams layernorm; FridoSoftmaxParams softmax; FridoTimeEmbedParams time_embed;
     FridoStepBeginParams step_begin; FridoUpdateParams update; FridoSnapParams snap; FridoVqParams vq;
     FridoZeroParams zero; FridoUpsampleParams upsample; FridoEmbedParams embed; FridoMhaParams mha;
+    FridoConvT2dParams convt; FridoAssembleParams assemble;
   } u;
 } FridoOp;
 /* Launches ops[0..n) in order on `stream`; returns 0 or (-(1000+i)) if op i failed. */

@@ -194,6 +194,50 @@ def case_sched(base):
     print("sched done")
 
 
+def _encode_ref(model, x):
+    """Reference encode_first_stage -> get_first_stage_encoding, plus the code indices each scale's quantiser picked."""
+    fs = model.first_stage_model
+    picked, hooks = [], []
+    for q in fs.ms_quantize:
+        hooks.append(q.register_forward_hook(lambda m, i, o: picked.append(o[2][2].reshape(-1).clone())))
+    try:
+        h = model.encode_first_stage(x)
+    finally:
+        for hk in hooks:
+            hk.remove()
+    n = len(fs.ms_quantize)
+    z = model.get_first_stage_encoding(h.clone())
+    return h.clone(), z.clone(), picked[-n:]  # encode_first_stage runs encode twice (frido.py:1000-1006); keep the last pass
+
+
+def case_encode(base):
+    """8f.3: MS-VQGAN encode side.  tiny2 / tiny3 (same configs, seeds and weights as tiny2.pt / tiny3.pt) on a
+    [2,3,32,32] image, and the full-size f8f4 first stage of config 2 on a [1,3,64,64] image."""
+    g = {}
+    for ns, tag in ((2, "tiny2"), (3, "tiny3")):
+        cfg = tiny_cfg(base, ns)
+        model = ref_loader.build_model(cfg)
+        prep(model, seed=3)
+        model.scale_factor.copy_(torch.tensor([0.8, 1.3, 1.1][:ns]))
+        x = synth.synth_input("img", (2, 3, 32, 32), 7)
+        h, z, codes = _encode_ref(model, x)
+        g[tag] = dict(x=x, h=h, z=z, codes=codes)
+        # get_input on a 'b h w c' batch dict (frido.py:766-817), cond_stage "__is_unconditional__" + crossattn key
+        print(tag, "encode", tuple(h.shape), [tuple(c.shape) for c in codes])
+    m = copy.deepcopy(base["model"])
+    model = ref_loader.build_model(m)
+    fs = model.first_stage_model
+    man = [(n, s) for n, s in synth.manifest_of(fs, "first_stage_model.") if ".loss." not in n]
+    synth.fill_module_(fs, 0, "first_stage_model.")
+    model.scale_factor.copy_(torch.tensor([0.8, 1.3]))
+    x = synth.synth_input("img", (1, 3, 64, 64), 8)
+    h, z, codes = _encode_ref(model, x)
+    g["l2i"] = dict(x=x, h=h, z=z, codes=codes, manifest=man, seed=0, scale_factor=model.scale_factor.clone(),
+                    fs_params={k: v for k, v in m["params"]["first_stage_config"]["params"].items() if k != "lossconfig"})
+    print("l2i encode", tuple(h.shape))
+    torch.save(g, os.path.join(OUT, "enc.pt"))
+
+
 def case_bert(base):
     """BERTEmbedder of the layout2img config (32 layers, 640-d, vocab 30522, max_seq_len 96), tokens [2, 26]."""
     ref_loader.activate()
@@ -215,7 +259,7 @@ def case_bert(base):
 def main():
     os.makedirs(OUT, exist_ok=True)
     base = ref_loader.load_config("configs/frido/layout2i/frido_f8f4_coco_seg.yaml")
-    which = sys.argv[1:] or ["sched", "tiny2", "tiny3", "l2i32", "bert"]
+    which = sys.argv[1:] or ["sched", "tiny2", "tiny3", "l2i32", "bert", "enc"]
     if "sched" in which:
         case_sched(base)
     if "tiny2" in which:
@@ -226,6 +270,8 @@ def main():
         case_unet_l2i32(base)
     if "bert" in which:
         case_bert(base)
+    if "enc" in which:
+        case_encode(base)
 
 
 if __name__ == "__main__":

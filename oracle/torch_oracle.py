@@ -436,6 +436,74 @@ def decode_first_stage(sd, z, embed_dim, scale_factor, pre="first_stage_model.")
 
 
 # --------------------------------------------------------------------------
+# f3 ("next" row): MSEncoder + VQModelInterface.encode + get_first_stage_encoding
+#   (taming model.py:57-78,435-546; msvqgan.py:326-374; frido.py:646-662,960-1006)
+# --------------------------------------------------------------------------
+
+
+def ms_encoder_forward(sd, x, multiscale, pre="first_stage_model.encoder."):
+    """model.py:512-546: returns the per-scale heads, finest first."""
+    h = _conv(x, sd, pre + "conv_in")
+    n_lvl = _count(sd, re.escape(pre) + r"down\.(\d+)\.")
+    taps = []
+    for lvl in range(n_lvl):
+        j = 0
+        while _has(sd, f"{pre}down.{lvl}.block.{j}.conv1.weight"):
+            h = _t_resblock(h, sd, f"{pre}down.{lvl}.block.{j}")
+            if _has(sd, f"{pre}down.{lvl}.attn.{j}.q.weight"):
+                h = _t_attn(h, sd, f"{pre}down.{lvl}.attn.{j}")
+            j += 1
+        taps.append(h)  # hs_ms: output of the last block of the level (:523-524)
+        if lvl != n_lvl - 1:
+            h = _conv(F.pad(h, (0, 1, 0, 1)), sd, f"{pre}down.{lvl}.downsample.conv", stride=2, padding=0)  # :68-72
+    outs = []
+    for i in range(multiscale):
+        h = taps[-(multiscale - i)]
+        h = _t_resblock(h, sd, f"{pre}mid_ms.{i}.block_1")
+        h = _t_attn(h, sd, f"{pre}mid_ms.{i}.attn_1")
+        h = _t_resblock(h, sd, f"{pre}mid_ms.{i}.block_2")
+        h = F.silu(_gn(h, sd, f"{pre}norm_out_ms.{i}", 1e-6))
+        outs.append(_conv(h, sd, f"{pre}conv_out_ms.{i}"))
+    return outs
+
+
+def encode_first_stage(sd, x, embed_dim, pre="first_stage_model."):
+    """msvqgan.py:326-374.  Returns (latent [B,sum(e),H,W] coarse-first, per-scale codes)."""
+    S = len(embed_dim)
+    h_ms = ms_encoder_forward(sd, x, S, pre + "encoder.")[::-1]
+    prev_h, h_out, codes = [], [], []
+    for ii in range(S):
+        if prev_h:
+            for j in range(ii):
+                prev_h[j] = F.conv_transpose2d(prev_h[j], sd[f"{pre}upsample.{ii - 1}.weight"], sd[f"{pre}upsample.{ii - 1}.bias"],
+                                               stride=2, padding=1)
+                prev_h[j] = _conv(prev_h[j], sd, f"{pre}shared_post_quant_conv.{ii - 1}", padding=0)
+            quant = decoder_forward(sd, torch.cat((*prev_h[:ii], h_ms[ii]), dim=1), f"{pre}shared_decoder.{ii - 1}.")
+        else:
+            quant = h_ms[ii]
+        h = _conv(quant, sd, f"{pre}ms_quant_conv.{ii}", padding=0)
+        h_out.append(h)
+        q, idx = vq_lookup(h, sd[f"{pre}ms_quantize.{ii}.embedding.weight"])
+        codes.append(idx.reshape(x.shape[0], -1))
+        prev_h.append(q)
+    h_out = h_out[::-1]
+    for i in range(S):
+        for _ in range(i):
+            h_out[i] = F.interpolate(h_out[i], scale_factor=2)
+    return torch.cat(h_out[::-1], dim=1), codes
+
+
+def first_stage_encoding(z, embed_dim, scale_factor):
+    """frido.py:646-662 (adopted_scale_factor branch)."""
+    z = z.clone()
+    start = 0
+    for i, e in enumerate(embed_dim):
+        z[:, start : start + e] *= scale_factor[i]
+        start += e
+    return z
+
+
+# --------------------------------------------------------------------------
 # f1 ("next" row): BERTEmbedder = x-transformer encoder  (encoders/modules.py:85-114; x_transformer.py:215-366,481-538,598-625)
 # --------------------------------------------------------------------------
 

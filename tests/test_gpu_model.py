@@ -354,3 +354,67 @@ def test_drop_in_flow_tokens_to_image(dev, golden_dir, monkeypatch):
     assert (img.cpu() - img_ref).abs().max() < 1e-3
     u8 = fb.images_to_uint8(img, "np")
     assert u8.shape == (2, 16, 16, 3) and u8.dtype == torch.uint8
+
+
+@pytest.mark.parametrize("tag", ["tiny2", "tiny3", "l2i"])
+def test_encode_first_stage_matches_reference_golden(dev, golden_dir, tag, engine):
+    """SURVEY 8f.3 ("next" row): MS-VQGAN encode side — bottom-up MSEncoder, coarse->fine top-down pass through the VQ,
+    ConvTranspose2d, shared decoders — against the UNMODIFIED reference's encode_first_stage / get_first_stage_encoding
+    outputs; code indices of every scale bit-exact."""
+    import frido_b200 as fb
+    from oracle import synth
+    OUT_TOL = TOLS[engine][1]
+    g = _load(golden_dir, "enc.pt")[tag]
+    if tag == "l2i":
+        p = copy.deepcopy(g["fs_params"])
+        p["ckpt_path"] = None
+        fs = fb.VQModelInterface(**p)
+        synth.fill_module_(fs, g["seed"], "first_stage_model.")
+        fs = fs.to(dev)
+        sf = g["scale_factor"].tolist()
+        h, codes = fs.encode(g["x"].to(dev), return_code=True)
+        z = fs.encode(g["x"].to(dev), scale_factor=sf)
+    else:
+        model = _build_tiny(_load(golden_dir, f"{tag}.pt"), dev)
+        x = g["x"].to(dev)
+        h, codes = model.first_stage_model.encode(x, return_code=True)
+        h2 = model.encode_first_stage(x)
+        assert torch.equal(h, h2)
+        z = model.get_first_stage_encoding(h2)
+        assert torch.equal(z, model.encode_to_latent(x))  # fused scale multiply == the reference's separate one
+        # get_input on a 'b h w c' batch (frido.py:766-817) with a precomputed-free unconditional cond stage
+        model.model.conditioning_key = None
+        zz, c = model.get_input({"image": x.permute(0, 2, 3, 1).contiguous()}, "image")
+        assert c is None and torch.equal(zz, z)
+    if engine == "tc":
+        # single-pass TF32 (opt-in, not parity-valid): a near-tie code flip at a coarse scale changes everything finer,
+        # so only the coarsest group (no quantiser upstream) is compared, and the codes statistically
+        e0 = g["codes"][0].numel() and h.shape[1] // len(codes)
+        assert (h.cpu()[:, :e0] - g["h"][:, :e0]).abs().max().item() < OUT_TOL
+        assert (codes[0].reshape(-1).cpu() != g["codes"][0].reshape(-1)).float().mean().item() < 0.05
+        return
+    for a, b in zip(codes, g["codes"]):
+        assert torch.equal(a.reshape(-1).cpu(), b.reshape(-1))
+    assert (h.cpu() - g["h"]).abs().max().item() < OUT_TOL
+    assert (z.cpu() - g["z"]).abs().max().item() < OUT_TOL
+
+
+def test_encode_decode_round_trip_full_size(dev):
+    """Config 2 first stage at full size (256^2 image, B=2): encode -> decode runs through both programs; against the CPU
+    oracle on the encode side (the 256^2 attention-free bottom-up path + 64x64-token shared decoder)."""
+    import frido_b200 as fb
+    from frido_b200 import configs
+    from oracle import torch_oracle as O
+    model, cfg = configs.build("l2i_coco", dev)
+    fs = model.first_stage_model
+    g = torch.Generator().manual_seed(5)
+    x = torch.rand(1, 3, 256, 256, generator=g) * 2 - 1
+    z, codes = fs.encode(x.to(dev), return_code=True)
+    assert z.shape == (1, 6, 64, 64)
+    sd = {"first_stage_model." + k: v.detach().float().cpu() for k, v in fs.state_dict().items()}
+    zo, co = O.encode_first_stage(sd, x, list(fs.embed_dim))
+    assert (z.cpu() - zo).abs().max().item() < 1e-3
+    for a, b in zip(codes, co):
+        assert (a.reshape(-1).cpu() != b.reshape(-1)).float().mean().item() < 2e-3  # near-tie flips only
+    img = model.decode_first_stage(model.encode_to_latent(x.to(dev)))
+    assert img.shape == (1, 3, 256, 256) and torch.isfinite(img).all()

@@ -108,3 +108,22 @@ def test_bert_embedder_vs_reference(golden_dir, tag):
     sd = synth.synth_state_dict(g["manifest"], g["seed"])
     z = O.bert_embedder(sd, g["tokens"])
     assert (z - g["z"]).abs().max() < 5e-5
+
+
+@pytest.mark.parametrize("tag", ["tiny2", "tiny3", "l2i"])
+def test_encode_first_stage_vs_reference(golden_dir, tag):
+    """MSEncoder + VQModelInterface.encode + get_first_stage_encoding against the reference's outputs
+    (pre-quantisation latent, scale-factor multiply, and the code indices every scale's quantiser picked)."""
+    g = _load(golden_dir, "enc.pt")[tag]
+    if tag == "l2i":
+        man, seed, sf, ed = g["manifest"], g["seed"], g["scale_factor"], g["fs_params"]["embed_dim"]
+    else:
+        t = _load(golden_dir, f"{tag}.pt")
+        man, seed, sf, ed = t["manifest"], t["seed"], t["scale_factor"], t["split"]
+    sd = synth.synth_state_dict([(n, s) for n, s in man if n.startswith("first_stage_model.")], seed)
+    h, codes = O.encode_first_stage(sd, g["x"], list(ed))
+    for a, b in zip(codes, g["codes"]):
+        assert torch.equal(a.reshape(-1), b.reshape(-1))
+    assert (h - g["h"]).abs().max() < TOL
+    z = O.first_stage_encoding(h, list(ed), sf)
+    assert (z - g["z"]).abs().max() < TOL
