@@ -19,6 +19,7 @@
 // * accumulators are double-buffered in TMEM (2 x 256 columns): the epilogue of
 //   tile i overlaps the main loop of tile i+1.
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -35,6 +36,9 @@ constexpr int TC_CSUM_BYTES = 4 * 256 * 2 * 4;          // per-tile channel sum 
 constexpr int TC_SMEM_BYTES = TC_SMEM_BUDGET + TC_STG_BYTES + TC_CSUM_BYTES + 256 /*barriers*/ + 1024 /*align slack*/;  // < 227 KB
 constexpr int TC_EPI_WARPS = 8;
 constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;   // TMA, MMA, 8 epilogue warps
+constexpr int TC_BF_ACC_STRIDE = 192;  // BF16x3: accumulators at TMEM columns 0 / 192 (BN <= 192) ...
+constexpr int TC_BF_A_COL = 384;       // ... and the split A operand ring behind them: 32 columns (hi 16 | lo 16) per stage
+constexpr int TC_BF_MAX_STAGES = 4;    // (512 - 384) / 32
 constexpr int TC_SPLIT_WARPS = 4;
 constexpr int TC_SPLIT_THREADS = TC_SPLIT_WARPS * 32;
 constexpr int TC_THREADS_X3 = TC_THREADS + TC_SPLIT_THREADS;  // + splitter warps (error-compensated modes)
@@ -140,6 +144,25 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// A operand from tensor memory (lane = row, 2 bf16 of K per 32-bit column), B from shared memory
+__device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]),
+      "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo_elem, float hi_elem) {
   uint32_t r;
   asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi_elem), "f"(lo_elem));  // first source -> upper half
@@ -192,9 +215,13 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
 // MODE 0: single-pass TF32.
 // MODE 1: error-compensated 3xTF32: every operand tile is split in shared memory into hi = rna_tf32(v) and
 //         lo = v - hi by four extra warps, and each K-step issues hi*hi + lo*hi + hi*lo (products ~2^-21).
-// MODE 2: error-compensated BF16x3 at twice the TF32 issue rate: the fp32 A tile is split in shared memory into
-//         bf16 hi/lo tiles (SWIZZLE_64B), the weights arrive PRE-SPLIT from HBM as two bf16 matrices (two TMA maps);
-//         hi*hi + lo*hi + hi*lo with fp32 accumulation (products ~2^-16).
+// MODE 2: error-compensated BF16x3 at twice the TF32 issue rate: the fp32 A tile (TMA, shared memory) is split by four
+//         warps into bf16 hi/lo halves that go straight into TENSOR MEMORY (tcgen05.st) and feed the MMA as its TMEM
+//         A operand; the weights arrive PRE-SPLIT from HBM as two bf16 matrices (two TMA maps, SWIZZLE_64B);
+//         hi*hi + lo*hi + hi*lo with fp32 accumulation (products ~2^-16).  Shared-memory bandwidth (128 B/clk/SM) is
+//         what bounds this kernel: per 32-wide K step it carries the TMA writes (16 KB A + 128*BN B of W), the
+//         splitter's read of A (16 KB) and the tensor core's reads of W (3 MMAs x 2 x 32*BN B); keeping the split A
+//         tiles out of shared memory removes 16 KB of writes and 32 KB of MMA operand reads per step.
 template <int MODE>
 __global__ void __launch_bounds__(MODE ? TC_THREADS_X3 : TC_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
@@ -203,13 +230,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
   constexpr bool BF = MODE == 2;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // SWIZZLE_128B atoms need 1024 B alignment
-  // stage layout  MODE 0: A | W      MODE 1: A_hi | A_lo | W_hi | W_lo      MODE 2: A_raw(fp32) | A_hi | A_lo | W_hi | W_lo (bf16)
+  // stage layout  MODE 0: A | W      MODE 1: A_hi | A_lo | W_hi | W_lo      MODE 2: A_raw(fp32) | W_hi | W_lo (bf16)
   const uint32_t b_bytes = BF ? (uint32_t)p.BN * TC_BK * 2 : (uint32_t)p.BN * TC_BK * 4;
-  const uint32_t stage_bytes = BF ? (2u * TC_A_BYTES + 2u * b_bytes) : (TC_A_BYTES + b_bytes) * (X3 ? 2u : 1u);
-  const uint32_t off_ahi = BF ? (uint32_t)TC_A_BYTES : 0u;
-  const uint32_t off_alo = BF ? (uint32_t)TC_A_BYTES + TC_A_BYTES / 2 : (uint32_t)TC_A_BYTES;
-  const uint32_t off_w = (X3 || BF) ? 2u * TC_A_BYTES : (uint32_t)TC_A_BYTES;
+  const uint32_t stage_bytes = BF ? (TC_A_BYTES + 2u * b_bytes) : (TC_A_BYTES + b_bytes) * (X3 ? 2u : 1u);
+  const uint32_t off_alo = (uint32_t)TC_A_BYTES;
+  const uint32_t off_w = X3 ? 2u * TC_A_BYTES : (uint32_t)TC_A_BYTES;
   const uint32_t off_wlo = off_w + b_bytes;
+  const uint32_t acc_stride = BF ? TC_BF_ACC_STRIDE : TC_MAX_BN;
   const uint32_t bar_base = smem_base + TC_SMEM_BUDGET + TC_STG_BYTES + TC_CSUM_BYTES;
   // barrier layout: full[6] | empty[6] | split[6] | tmem_full[2] | tmem_empty[2] | tmem_ptr
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
@@ -299,7 +326,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         mbar_wait(tempty_bar(acc), acc_phase ^ 1);  // epilogue has drained this accumulator
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * TC_MAX_BN);
+        const uint32_t d_tmem = tmem_base + (uint32_t)acc * acc_stride;
         for (int ks = 0; ks < ksteps; ++ks) {
           mbar_wait(MODE ? split_bar(stage) : full_bar(stage), phase);
           tc_fence_after();
@@ -307,12 +334,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
           const uint32_t sb = sa + off_w;
           if (BF) {
 #pragma unroll
-            for (int k = 0; k < TC_BK / 16; ++k) {  // 2 K-steps of 16 bf16 (32 B) inside the 64 B swizzle row
-              const uint64_t ah = umma_desc_sw64(sa + off_ahi + k * 32), al = umma_desc_sw64(sa + off_alo + k * 32);
+            for (int k = 0; k < TC_BK / 16; ++k) {  // 2 K-steps of 16 bf16: 8 TMEM columns of A, 32 B inside the 64 B swizzle row of W
+              const uint32_t ah = tmem_base + (uint32_t)(TC_BF_A_COL + stage * 32 + k * 8), al = ah + 16;
               const uint64_t bh = umma_desc_sw64(sb + k * 32), bl = umma_desc_sw64(sa + off_wlo + k * 32);
-              umma_bf16(d_tmem, ah, bh, idesc, (ks | k) ? 1u : 0u);
-              umma_bf16(d_tmem, al, bh, idesc, 1u);
-              umma_bf16(d_tmem, ah, bl, idesc, 1u);
+              umma_bf16_ts(d_tmem, ah, bh, idesc, (ks | k) ? 1u : 0u);
+              umma_bf16_ts(d_tmem, al, bh, idesc, 1u);
+              umma_bf16_ts(d_tmem, ah, bl, idesc, 1u);
             }
           } else
 #pragma unroll
@@ -368,7 +395,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
       const int n0 = nt * p.BN + col_lo;
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
-      const uint32_t t_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * TC_MAX_BN + col_lo);
+      const uint32_t t_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * acc_stride + (uint32_t)col_lo;
       if (p.o_sn == 1) {
         // the 4 output rows this lane serves in the coalesced arrangement (rl = 8j + sub) are the same for every chunk
         long long obase[4];
@@ -513,33 +540,31 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   } else if (BF) {
-    // ===================== splitter (warps 6..9), BF16x3: fp32 A tile -> bf16 hi / lo tiles =====================
-    // source: 128 rows x 128 B, SWIZZLE_128B (16-B chunk c of row r sits at chunk c ^ (r & 7));
-    // destination: 128 rows x 64 B, SWIZZLE_64B (16-B chunk q of row r sits at chunk q ^ ((r >> 1) & 3)).
-    const int t = threadIdx.x - TC_THREADS;  // 0..TC_SPLIT_THREADS-1
+    // ===================== splitter (warps 10..13), BF16x3: fp32 A tile (smem) -> bf16 hi / lo halves in TMEM ==========
+    // source: 128 rows x 128 B, SWIZZLE_128B (16-B chunk c of row r sits at chunk c ^ (r & 7)).  Thread = row (the warp
+    // owns TMEM lanes 32*(warp & 3) ..+31); destination columns: hi k0..31 -> 16 columns, lo -> the next 16.
+    const int r = (warp & 3) * 32 + lane;
+    const uint32_t a_lane = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)TC_BF_A_COL;
     int stage = 0;
     uint32_t phase = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       for (int ks = 0; ks < ksteps; ++ks) {
         mbar_wait(full_bar(stage), phase);
-        uint8_t* sbase = smem_raw + (smem_base - smem_u32(smem_raw)) + (size_t)stage * stage_bytes;
+        const uint8_t* srow = smem_raw + (smem_base - smem_u32(smem_raw)) + (size_t)stage * stage_bytes + r * 128;
+        uint32_t hi[16], lo[16];
 #pragma unroll
-        for (int j = 0; j < 512 / TC_SPLIT_THREADS; ++j) {
-          const int item = t + TC_SPLIT_THREADS * j;   // (row, out-chunk) pairs: 128 x 4
-          const int r = item >> 2, q = item & 3;
-          const float4 v0 = *reinterpret_cast<const float4*>(sbase + r * 128 + (((2 * q) ^ (r & 7)) << 4));
-          const float4 v1 = *reinterpret_cast<const float4*>(sbase + r * 128 + (((2 * q + 1) ^ (r & 7)) << 4));
-          uint4 h, l;
-          h.x = pack_bf16x2(v0.x, v0.y); h.y = pack_bf16x2(v0.z, v0.w); h.z = pack_bf16x2(v1.x, v1.y); h.w = pack_bf16x2(v1.z, v1.w);
-          l.x = pack_bf16x2(v0.x - bf16_lo_to_f32(h.x), v0.y - bf16_hi_to_f32(h.x));
-          l.y = pack_bf16x2(v0.z - bf16_lo_to_f32(h.y), v0.w - bf16_hi_to_f32(h.y));
-          l.z = pack_bf16x2(v1.x - bf16_lo_to_f32(h.z), v1.y - bf16_hi_to_f32(h.z));
-          l.w = pack_bf16x2(v1.z - bf16_lo_to_f32(h.w), v1.w - bf16_hi_to_f32(h.w));
-          const uint32_t o = (uint32_t)r * 64 + ((q ^ ((r >> 1) & 3)) << 4);
-          *reinterpret_cast<uint4*>(sbase + off_ahi + o) = h;
-          *reinterpret_cast<uint4*>(sbase + off_alo + o) = l;
+        for (int c = 0; c < 8; ++c) {
+          const float4 v = *reinterpret_cast<const float4*>(srow + ((c ^ (r & 7)) << 4));
+          const uint32_t h0 = pack_bf16x2(v.x, v.y), h1 = pack_bf16x2(v.z, v.w);
+          hi[2 * c] = h0; hi[2 * c + 1] = h1;
+          lo[2 * c] = pack_bf16x2(v.x - bf16_lo_to_f32(h0), v.y - bf16_hi_to_f32(h0));
+          lo[2 * c + 1] = pack_bf16x2(v.z - bf16_lo_to_f32(h1), v.w - bf16_hi_to_f32(h1));
         }
-        fence_proxy_async();
+        tc_fence_after();  // the MMAs that last read this TMEM slot retired before the TMA refilled the stage
+        tmem_st16(a_lane + (uint32_t)(stage * 32), hi);
+        tmem_st16(a_lane + (uint32_t)(stage * 32 + 16), lo);
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(split_bar(stage));
         if (++stage == NS) { stage = 0; phase ^= 1; }
@@ -700,11 +725,19 @@ int conv2d_tc(const FridoConvParams* p, cudaStream_t s) {
   const int cands[4] = {256, 192, 128, 64};
   for (int i = 0; i < 4; ++i) {
     if (p->Cout % cands[i]) continue;
+    if (mode == 2 && cands[i] > TC_BF_ACC_STRIDE) continue;  // BF16x3 keeps the A operand ring in TMEM next to 2 x 192 accumulator columns
     const int64_t tiles = (int64_t)m_tiles * (p->Cout / cands[i]);
     const int64_t waves = (tiles + sms - 1) / sms;
-    const int clk = mma_per_stage[mode] * cands[i] / 2;
-    const double cost = (double)waves * (clk > floor_clk[mode] ? clk : floor_clk[mode]);
+    int clk = mma_per_stage[mode] * cands[i] / 2;
+    if (clk < floor_clk[mode]) clk = floor_clk[mode];
+    // BF16x3 is bound by shared-memory bandwidth (128 B/clk): TMA writes 16 KB + 128*BN, splitter reads 16 KB, MMAs read 192*BN
+    if (mode == 2) clk = 256 + 5 * cands[i] / 2;
+    const double cost = (double)waves * clk;
     if (cost < best_cost) { best_cost = cost; bn = cands[i]; }
+  }
+  if (const char* f = getenv("FRIDO_TC_FORCE_BN")) {  // profiling aid only (tools/prof/conv_bench.py)
+    const int v = atoi(f);
+    if (v >= 32 && v <= (mode == 2 ? TC_BF_ACC_STRIDE : TC_MAX_BN) && v % 32 == 0 && p->Cout % v == 0) bn = v;
   }
   t.BN = bn;
   t.tiles_n = p->Cout / bn;
@@ -746,9 +779,10 @@ int conv2d_tc(const FridoConvParams* p, cudaStream_t s) {
     attr = true;
   }
   const bool x3 = p->engine == 2;
-  const int stage_bytes = bf ? (2 * TC_A_BYTES + 2 * bn * TC_BK * 2) : (TC_A_BYTES + bn * TC_BK * 4) * (x3 ? 2 : 1);
+  const int stage_bytes = bf ? (TC_A_BYTES + 2 * bn * TC_BK * 2) : (TC_A_BYTES + bn * TC_BK * 4) * (x3 ? 2 : 1);
   t.stages = TC_SMEM_BUDGET / stage_bytes;
   if (t.stages > TC_MAX_STAGES) t.stages = TC_MAX_STAGES;
+  if (bf && t.stages > TC_BF_MAX_STAGES) t.stages = TC_BF_MAX_STAGES;
   const int total = m_tiles * t.tiles_n;
   const int grid = total < sms ? total : sms;
   if (bf) conv_tc_kernel<2><<<grid, TC_THREADS_X3, TC_SMEM_BYTES, s>>>(ma0, ma1, mw, mwlo, t);
