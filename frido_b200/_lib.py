@@ -17,7 +17,7 @@ c_p = C.c_void_p
 
 ACT_NONE, ACT_RELU, ACT_SILU, ACT_GEGLU, ACT_GEGLU_FAST, ACT_GELU = 0, 1, 2, 3, 4, 5
 (OP_CONV, OP_GN_STATS, OP_NORM_ACT, OP_LAYERNORM, OP_SOFTMAX, OP_TIME_EMBED, OP_STEP_BEGIN, OP_UPDATE, OP_SNAP, OP_VQ,
- OP_ZERO, OP_UPSAMPLE, OP_EMBED, OP_MHA, OP_CONVT, OP_ASSEMBLE) = range(1, 17)
+ OP_ZERO, OP_UPSAMPLE, OP_EMBED, OP_MHA, OP_CONVT, OP_ASSEMBLE, OP_ATTN) = range(1, 18)
 
 
 class ConvParams(C.Structure):
@@ -30,7 +30,8 @@ class ConvParams(C.Structure):
         ("w", c_p), ("w_sb", c_l), ("w_ld", c_l), ("w_lo", c_p), ("Cout", c_i),
         ("bias", c_p), ("rowvec", c_p), ("rowvec_sb", c_l), ("res", c_p),
         ("alpha", c_f), ("act", c_i), ("out", c_p),
-        ("o_sb", c_l), ("o_sp", c_l), ("o_sn", c_l), ("round_tf32", c_i), ("out_hi", c_p), ("out_lo", c_p), ("chan_sums", c_p), ("engine", c_i),
+        ("o_sb", c_l), ("o_sp", c_l), ("o_sn", c_l), ("round_tf32", c_i), ("out_hi", c_p), ("out_lo", c_p), ("chan_sums", c_p),
+        ("sk_ws", c_p), ("sk_ws_bytes", c_l), ("engine", c_i),
     ]
 
 
@@ -98,6 +99,12 @@ class MhaParams(C.Structure):
     _fields_ = [("qkv", c_p), ("B", c_i), ("L", c_i), ("H", c_i), ("Dh", c_i), ("scale", c_f), ("out", c_p)]
 
 
+class AttnParams(C.Structure):
+    _fields_ = [("q", c_p), ("q_sb", c_l), ("q_ld", c_l), ("k", c_p), ("k_sb", c_l), ("k_ld", c_l), ("v", c_p), ("v_sb", c_l), ("v_ld", c_l),
+                ("B", c_i), ("N", c_i), ("Nk", c_i), ("C", c_i), ("scale", c_f), ("out", c_p), ("o_sb", c_l), ("o_ld", c_l),
+                ("ln_gamma", c_p), ("ln_beta", c_p), ("ln_eps", c_f), ("bias", c_p), ("res", c_p), ("r_sb", c_l), ("r_ld", c_l)]
+
+
 class ConvT2dParams(C.Structure):
     _fields_ = [("x", c_p), ("B", c_i), ("H", c_i), ("W", c_i), ("Cin", c_i), ("Cout", c_i), ("w", c_p), ("bias", c_p), ("out", c_p), ("x_ld", c_i)]
 
@@ -116,7 +123,7 @@ class _OpU(C.Union):
                 ("layernorm", LayerNormParams), ("softmax", SoftmaxParams), ("time_embed", TimeEmbedParams),
                 ("step_begin", StepBeginParams), ("update", UpdateParams), ("snap", SnapParams), ("vq", VqParams),
                 ("zero", ZeroParams), ("upsample", UpsampleParams), ("embed", EmbedParams), ("mha", MhaParams), ("convt", ConvT2dParams),
-                ("assemble", AssembleParams)]
+                ("assemble", AssembleParams), ("attn", AttnParams)]
 
 
 class Op(C.Structure):
@@ -125,14 +132,17 @@ class Op(C.Structure):
 
 _KIND_FIELD = {OP_CONV: "conv", OP_GN_STATS: "gn_stats", OP_NORM_ACT: "norm_act", OP_LAYERNORM: "layernorm",
                OP_SOFTMAX: "softmax", OP_TIME_EMBED: "time_embed", OP_STEP_BEGIN: "step_begin", OP_UPDATE: "update",
-               OP_SNAP: "snap", OP_VQ: "vq", OP_ZERO: "zero", OP_UPSAMPLE: "upsample", OP_EMBED: "embed", OP_MHA: "mha", OP_CONVT: "convt", OP_ASSEMBLE: "assemble"}
+               OP_SNAP: "snap", OP_VQ: "vq", OP_ZERO: "zero", OP_UPSAMPLE: "upsample", OP_EMBED: "embed", OP_MHA: "mha", OP_CONVT: "convt", OP_ASSEMBLE: "assemble", OP_ATTN: "attn"}
 
 EXPORTS = [
     "frido_conv2d", "frido_gn_stats", "frido_norm_act", "frido_layernorm", "frido_softmax", "frido_time_embed",
     "frido_step_begin", "frido_sampler_update", "frido_stage_snap", "frido_vq_lookup", "frido_zero",
-    "frido_round_tf32", "frido_split_bf16", "frido_upsample2x", "frido_to_uint8", "frido_embed_tokens", "frido_mha_small", "frido_conv_transpose2d", "frido_assemble_latent", "frido_run_program", "frido_abi_version", "frido_sizeof_op", "frido_last_error",
+    "frido_round_tf32", "frido_split_bf16", "frido_upsample2x", "frido_to_uint8", "frido_embed_tokens", "frido_mha_small", "frido_attn_small", "frido_conv_transpose2d", "frido_assemble_latent", "frido_run_program", "frido_abi_version", "frido_sizeof_op", "frido_last_error",
     "frido_launch_count", "frido_check_device",
 ]
+
+SK_WS_BYTES = 40 << 20
+ABI_VERSION = 2
 
 _lib = None
 
@@ -163,9 +173,11 @@ def lib():
     L.frido_split_bf16.argtypes = [c_p, c_p, c_p, c_l, c_p]
     for name in ("frido_conv2d", "frido_gn_stats", "frido_norm_act", "frido_layernorm", "frido_softmax",
                  "frido_time_embed", "frido_step_begin", "frido_sampler_update", "frido_stage_snap", "frido_vq_lookup",
-                 "frido_upsample2x", "frido_to_uint8", "frido_embed_tokens", "frido_mha_small",
+                 "frido_upsample2x", "frido_to_uint8", "frido_embed_tokens", "frido_mha_small", "frido_attn_small",
                  "frido_conv_transpose2d", "frido_assemble_latent"):
         getattr(L, name).argtypes = [c_p, c_p]
+    if L.frido_abi_version() != ABI_VERSION:
+        raise FridoError(f"ABI mismatch: library version {L.frido_abi_version()}, binding {ABI_VERSION} (rebuild: make -C frido_b200/csrc)")
     if L.frido_sizeof_op() != C.sizeof(Op):
         raise FridoError(f"ABI mismatch: sizeof(FridoOp) C={L.frido_sizeof_op()} python={C.sizeof(Op)}")
     _lib = L

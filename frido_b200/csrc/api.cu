@@ -4,6 +4,7 @@
 namespace frido {
 char g_last_error[512] = "";
 long long g_launch_count = 0;
+bool g_prev_kernel = false;
 }  // namespace frido
 
 using namespace frido;
@@ -17,6 +18,7 @@ extern "C" int frido_conv2d(const FridoConvParams* p, void* stream) {
 extern "C" int frido_zero(void* ptr, int64_t nbytes, void* stream) {
   if (!ptr || nbytes < 0) return set_error(FRIDO_E_ARG, "zero: bad argument");
   ++g_launch_count;
+  g_prev_kernel = false;  // a memset node: the next kernel takes a plain (full) dependency
   cudaError_t e = cudaMemsetAsync(ptr, 0, (size_t)nbytes, (cudaStream_t)stream);
   if (e != cudaSuccess) return set_error(FRIDO_E_LAUNCH, cudaGetErrorString(e));
   return FRIDO_OK;
@@ -24,6 +26,7 @@ extern "C" int frido_zero(void* ptr, int64_t nbytes, void* stream) {
 
 extern "C" int frido_run_program(const FridoOp* ops, int32_t n, void* stream) {
   if (!ops || n < 0) return set_error(FRIDO_E_ARG, "run_program: bad argument");
+  g_prev_kernel = false;  // whatever ran before this program is not ours: first kernel launches with a full dependency
   for (int i = 0; i < n; ++i) {
     const FridoOp& op = ops[i];
     int rc;
@@ -39,6 +42,7 @@ extern "C" int frido_run_program(const FridoOp* ops, int32_t n, void* stream) {
       case FRIDO_OP_SNAP: rc = frido_stage_snap(&op.u.snap, stream); break;
       case FRIDO_OP_VQ: rc = frido_vq_lookup(&op.u.vq, stream); break;
       case FRIDO_OP_EMBED: rc = frido_embed_tokens(&op.u.embed, stream); break;
+      case FRIDO_OP_ATTN: rc = frido_attn_small(&op.u.attn, stream); break;
       case FRIDO_OP_MHA: rc = frido_mha_small(&op.u.mha, stream); break;
       case FRIDO_OP_CONVT: rc = frido_conv_transpose2d(&op.u.convt, stream); break;
       case FRIDO_OP_ASSEMBLE: rc = frido_assemble_latent(&op.u.assemble, stream); break;

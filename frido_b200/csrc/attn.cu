@@ -1,0 +1,273 @@
+// Fused single-head attention for SHORT key sequences (fp32 SIMT, flash-style online softmax):
+//   q'        = LayerNorm(q[b,n,:])                       (optional, attention.py:203-205 / :323-325)
+//   out[b,n,:] = softmax_j(scale * q' . k[b,j,:]) @ v[b,j,:] + bias + res[b,n,:]      (bias / res optional)
+// Replaces einsum -> *scale -> softmax -> einsum of CrossAttention.forward (attention.py:178-191) where the tensor-core
+// engine has nothing to chew on: the cross-attention to a 26-token layout condition (QK^T is a [N x 26] product, PV a
+// K=26 product) and the self-attention of the 8x8 level (64 tokens per image).  The scores never leave the SM.
+// With k = K Wq and v = V Wo^T folded on the host side (both step-invariant for the condition) and the LayerNorm, output
+// bias and residual fused here, the whole cross-attention sub-block x + to_out(attn(LN(x), ctx)) is this one kernel:
+// one read of x, one write of the result.
+//
+// One warp owns R query rows; the C channels are spread over the lanes as float4 quads (lane, lane+32, ...), so q and the
+// output accumulator live in registers.  Keys/values are staged in shared memory in chunks of KC <= 32 keys, shared by
+// the 8 warps of the CTA.  Scores: every lane forms its partial dot products for a block of 32 (key,row) pairs, and one
+// transposing butterfly (31 shuffles instead of 32 x 5) leaves pair L fully reduced in lane L; running (max, sum) per row
+// rescale the accumulator between chunks.
+#include "common.cuh"
+
+namespace frido {
+
+constexpr int ATTN_WARPS = 8;
+constexpr int ATTN_SMEM_MAX = 200 * 1024;
+
+// reduce-scatter over the warp: on return v[0] of lane L holds the sum over all lanes of the caller's v[L]
+__device__ __forceinline__ void warp_transpose_sum(float (&v)[32], int lane) {
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) {
+    const bool up = (lane & o) != 0;
+#pragma unroll
+    for (int i = 0; i < o; ++i) {
+      const float send = up ? v[i] : v[i + o];
+      const float keep = up ? v[i + o] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+    }
+  }
+}
+
+// reductions over the lanes that share (lane % R): xor offsets R, 2R, ..., 16
+template <int R>
+__device__ __forceinline__ float row_max(float v) {
+#pragma unroll
+  for (int o = 16; o >= R; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+template <int R>
+__device__ __forceinline__ float row_sum(float v) {
+#pragma unroll
+  for (int o = 16; o >= R; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// SINGLE: all keys fit one chunk (Nk <= KC): straight-line code, q is dead before the accumulator comes alive.
+template <int NJ, int R, bool SINGLE>
+__global__ void __launch_bounds__(ATTN_WARPS * 32, SINGLE ? 2 : 1) attn_small_kernel(const FridoAttnParams p, int KC) {
+  constexpr int KB = 32 / R;  // keys per reduction block (32 (key,row) pairs)
+  constexpr int NB = R;       // blocks per chunk (KC <= 32)
+  extern __shared__ float4 attn_sm[];
+  const int Q = p.C >> 2;
+  float4* Ks = attn_sm;
+  float4* Vs = attn_sm + (size_t)KC * Q;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.y;
+  const int row0 = (blockIdx.x * ATTN_WARPS + warp) * R;
+  pdl_trigger();
+  pdl_wait();
+
+  float4 q[R][NJ], o[R][NJ];
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    const int n = row0 + r;
+    const float4* qp = reinterpret_cast<const float4*>(p.q + (int64_t)b * p.q_sb + (int64_t)(n < p.N ? n : 0) * p.q_ld);
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+      const int quad = lane + 32 * j;
+      q[r][j] = (quad < Q && n < p.N) ? __ldg(qp + quad) : make_float4(0.f, 0.f, 0.f, 0.f);
+      o[r][j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+  if (p.ln_gamma) {  // LayerNorm of the query rows, two-pass variance like layernorm_kernel (norm.cu)
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      float s = 0.f;
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) s += (q[r][j].x + q[r][j].y) + (q[r][j].z + q[r][j].w);  // lanes beyond Q hold zeros
+      const float mean = warp_sum(s) / (float)p.C;
+      float ss = 0.f;
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) {
+        if (lane + 32 * j < Q) {
+          const float a = q[r][j].x - mean, c = q[r][j].y - mean, d = q[r][j].z - mean, e = q[r][j].w - mean;
+          ss += (a * a + c * c) + (d * d + e * e);
+        }
+      }
+      const float rstd = rsqrtf(warp_sum(ss) / (float)p.C + p.ln_eps);
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) {
+        const int quad = lane + 32 * j;
+        if (quad < Q) {
+          const float4 g = __ldg(reinterpret_cast<const float4*>(p.ln_gamma) + quad);
+          const float4 be = __ldg(reinterpret_cast<const float4*>(p.ln_beta) + quad);
+          q[r][j].x = (q[r][j].x - mean) * rstd * g.x + be.x;
+          q[r][j].y = (q[r][j].y - mean) * rstd * g.y + be.y;
+          q[r][j].z = (q[r][j].z - mean) * rstd * g.z + be.z;
+          q[r][j].w = (q[r][j].w - mean) * rstd * g.w + be.w;
+        }
+      }
+    }
+  }
+  const float* kb = p.k + (int64_t)b * p.k_sb;
+  const float* vb = p.v + (int64_t)b * p.v_sb;
+  float m_run = -INFINITY, l_run = 0.f;  // of row lane % R
+
+  int j0 = 0;
+  do {
+    const int kc = min(KC, p.Nk - j0);
+    if (!SINGLE) __syncthreads();  // every warp is done with the previous chunk
+    for (int kk = warp; kk < kc; kk += ATTN_WARPS) {
+      const float4* ks = reinterpret_cast<const float4*>(kb + (int64_t)(j0 + kk) * p.k_ld);
+      const float4* vs = reinterpret_cast<const float4*>(vb + (int64_t)(j0 + kk) * p.v_ld);
+      for (int quad = lane; quad < Q; quad += 32) {
+        Ks[kk * Q + quad] = __ldg(ks + quad);
+        Vs[kk * Q + quad] = __ldg(vs + quad);
+      }
+    }
+    __syncthreads();
+    // ---- scores: block blk covers keys [blk*KB, blk*KB + KB); lane L ends up with pair (key blk*KB + L/R, row L%R)
+    float sv[NB];
+#pragma unroll
+    for (int blk = 0; blk < NB; ++blk) {
+      sv[blk] = -INFINITY;
+      if (blk * KB < kc) {
+        float part[32];
+#pragma unroll
+        for (int kl = 0; kl < KB; ++kl) {
+          const int kk = blk * KB + kl;
+#pragma unroll
+          for (int r = 0; r < R; ++r) part[kl * R + r] = 0.f;
+          if (kk < kc) {
+#pragma unroll
+            for (int j = 0; j < NJ; ++j) {
+              const int quad = lane + 32 * j;
+              if (quad < Q) {
+                const float4 kv = Ks[kk * Q + quad];
+#pragma unroll
+                for (int r = 0; r < R; ++r)
+                  part[kl * R + r] = fmaf(q[r][j].x, kv.x, fmaf(q[r][j].y, kv.y, fmaf(q[r][j].z, kv.z, fmaf(q[r][j].w, kv.w, part[kl * R + r]))));
+              }
+            }
+          }
+        }
+        warp_transpose_sum(part, lane);
+        if (blk * KB + lane / R < kc) sv[blk] = part[0] * p.scale;
+      }
+    }
+    // ---- softmax state of row lane % R (replicated over the lanes that share it)
+    float mloc = sv[0];
+#pragma unroll
+    for (int blk = 1; blk < NB; ++blk) mloc = fmaxf(mloc, sv[blk]);
+    const float m_new = fmaxf(m_run, row_max<R>(mloc));
+    float pv[NB], psum = 0.f;
+#pragma unroll
+    for (int blk = 0; blk < NB; ++blk) {
+      pv[blk] = __expf(sv[blk] - m_new);  // exp(-inf) = 0 for pairs beyond kc
+      psum += pv[blk];
+    }
+    const float corr = __expf(m_run - m_new);  // first chunk: exp(-inf) = 0
+    l_run = l_run * corr + row_sum<R>(psum);
+    m_run = m_new;
+    if (!SINGLE) {
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        const float cr = __shfl_sync(0xffffffffu, corr, r);
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) { o[r][j].x *= cr; o[r][j].y *= cr; o[r][j].z *= cr; o[r][j].w *= cr; }
+      }
+    }
+    // ---- accumulate P V
+#pragma unroll
+    for (int blk = 0; blk < NB; ++blk) {
+#pragma unroll
+      for (int kl = 0; kl < KB; ++kl) {
+        const int kk = blk * KB + kl;
+        if (kk < kc) {
+          float pk[R];
+#pragma unroll
+          for (int r = 0; r < R; ++r) pk[r] = __shfl_sync(0xffffffffu, pv[blk], kl * R + r);
+#pragma unroll
+          for (int j = 0; j < NJ; ++j) {
+            const int quad = lane + 32 * j;
+            if (quad < Q) {
+              const float4 vv = Vs[kk * Q + quad];
+#pragma unroll
+              for (int r = 0; r < R; ++r) {
+                o[r][j].x = fmaf(pk[r], vv.x, o[r][j].x); o[r][j].y = fmaf(pk[r], vv.y, o[r][j].y);
+                o[r][j].z = fmaf(pk[r], vv.z, o[r][j].z); o[r][j].w = fmaf(pk[r], vv.w, o[r][j].w);
+              }
+            }
+          }
+        }
+      }
+    }
+  } while (!SINGLE && (j0 += KC) < p.Nk);
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    const int n = row0 + r;
+    const float inv = 1.0f / __shfl_sync(0xffffffffu, l_run, r);
+    if (n < p.N) {
+      float4* op = reinterpret_cast<float4*>(p.out + (int64_t)b * p.o_sb + (int64_t)n * p.o_ld);
+      const float4* rp = p.res ? reinterpret_cast<const float4*>(p.res + (int64_t)b * p.r_sb + (int64_t)n * p.r_ld) : nullptr;
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) {
+        const int quad = lane + 32 * j;
+        if (quad < Q) {
+          float4 v = make_float4(o[r][j].x * inv, o[r][j].y * inv, o[r][j].z * inv, o[r][j].w * inv);
+          if (p.bias) {
+            const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bias) + quad);
+            v.x += bb.x; v.y += bb.y; v.z += bb.z; v.w += bb.w;
+          }
+          if (rp) {
+            const float4 rr = __ldg(rp + quad);
+            v.x += rr.x; v.y += rr.y; v.z += rr.z; v.w += rr.w;
+          }
+          op[quad] = v;
+        }
+      }
+    }
+  }
+}
+
+template <int NJ, int R, bool SINGLE>
+static int launch_attn2(const FridoAttnParams* p, int KC, cudaStream_t s) {
+  static bool attr = false;
+  if (!attr) {
+    if (cudaFuncSetAttribute(attn_small_kernel<NJ, R, SINGLE>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATTN_SMEM_MAX) != cudaSuccess)
+      return set_error(FRIDO_E_LAUNCH, "attn_small: cannot opt in to dynamic shared memory");
+    attr = true;
+  }
+  const size_t smem = (size_t)2 * KC * p->C * sizeof(float);
+  dim3 grid((p->N + ATTN_WARPS * R - 1) / (ATTN_WARPS * R), p->B);
+  launch_pdl(attn_small_kernel<NJ, R, SINGLE>, grid, dim3(ATTN_WARPS * 32), smem, s, *p, KC);
+  return check_launch("attn_small");
+}
+
+template <int NJ, int R>
+static int launch_attn(const FridoAttnParams* p, int KC, cudaStream_t s) {
+  return p->Nk <= KC ? launch_attn2<NJ, R, true>(p, KC, s) : launch_attn2<NJ, R, false>(p, KC, s);
+}
+
+}  // namespace frido
+
+using namespace frido;
+
+extern "C" int frido_attn_small(const FridoAttnParams* p, void* stream) {
+  if (!p || !p->q || !p->k || !p->v || !p->out || p->B <= 0 || p->N <= 0 || p->Nk <= 0 || p->C <= 0)
+    return set_error(FRIDO_E_ARG, "attn_small: bad argument");
+  if ((p->C & 3) || p->C > 1024) return set_error(FRIDO_E_ARG, "attn_small: C must be a multiple of 4, at most 1024");
+  if ((p->ln_gamma != nullptr) != (p->ln_beta != nullptr)) return set_error(FRIDO_E_ARG, "attn_small: ln_gamma / ln_beta come together");
+  const int64_t strides[10] = {p->q_sb, p->q_ld, p->k_sb, p->k_ld, p->v_sb, p->v_ld, p->o_sb, p->o_ld, p->r_sb, p->r_ld};
+  for (int i = 0; i < 10; ++i)
+    if (strides[i] & 3) return set_error(FRIDO_E_ARG, "attn_small: strides must be multiples of 4 floats");
+  const void* ptrs[8] = {p->q, p->k, p->v, p->out, p->ln_gamma, p->ln_beta, p->bias, p->res};
+  for (int i = 0; i < 8; ++i)
+    if (reinterpret_cast<uintptr_t>(ptrs[i]) & 15) return set_error(FRIDO_E_ARG, "attn_small: pointers must be 16-byte aligned");
+  int KC = ATTN_SMEM_MAX / (8 * p->C);  // K and V chunk, fp32
+  if (KC > 32) KC = 32;
+  if (KC > p->Nk) KC = p->Nk;
+  if (KC < 1) return set_error(FRIDO_E_ARG, "attn_small: C too large for shared memory");
+  const int nj = ((p->C >> 2) + 31) / 32;
+  cudaStream_t s = (cudaStream_t)stream;
+  // rows per warp by register budget: q and the accumulator take 8 * NJ * R registers
+  if (nj <= 3) return launch_attn<3, 4>(p, KC, s);
+  if (nj <= 5) return launch_attn<5, 2>(p, KC, s);
+  return launch_attn<8, 1>(p, KC, s);
+}

@@ -3,8 +3,15 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
+
+#include <utility>
 
 #include "../../include/frido_b200.h"
+
+#ifndef FRIDO_PDL_DEFAULT
+#define FRIDO_PDL_DEFAULT false
+#endif
 
 namespace frido {
 
@@ -16,8 +23,34 @@ inline int set_error(int code, const char* msg) {
   return code;
 }
 
+// Programmatic dependent launch (PDL): a kernel launched with the attribute may start while its predecessor on the stream
+// is still draining; it must execute pdl_wait() before it touches global memory the predecessor may write (or still
+// read).  The hot kernels call pdl_trigger() at their top, so the successor's launch latency and set-up (barrier init,
+// TMEM allocation, tensor-map prefetch) overlap the predecessor's tail.  Only kernel -> kernel edges inside one op
+// program use it (g_prev_kernel); FRIDO_PDL=0 turns it off.
+extern bool g_prev_kernel;
+inline bool pdl_enabled() {
+  static const bool on = [] { const char* e = getenv("FRIDO_PDL"); return e ? atoi(e) != 0 : FRIDO_PDL_DEFAULT; }();
+  return on;
+}
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+inline void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = (pdl_enabled() && g_prev_kernel) ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);  // errors surface in check_launch
+}
+
 inline int check_launch(const char* what) {
   ++g_launch_count;
+  g_prev_kernel = true;
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
     snprintf(g_last_error, sizeof(g_last_error), "%s: %s", what, cudaGetErrorString(e));

@@ -62,6 +62,41 @@ struct TcParams {
   int round_tf32;
   uint16_t* out_hi; uint16_t* out_lo;  // optional bf16 pair copy of the outputs
   double* csum;         // optional [B][Cout][2] per-channel sum / sum of squares of the stored outputs (GroupNorm fusion)
+  // stream-K (under-filled launches): the (tile, k-step) iteration space is cut into equal contiguous ranges, one per CTA;
+  // a range that covers only part of a tile's K loop parks its partial accumulator in sk_ws and the LAST contributor to
+  // arrive (sk_cnt[tile]) sums the partials in CTA order (deterministic) and runs the normal epilogue.
+  int sk;               // 1 = stream-K schedule, 0 = one whole tile per CTA at a time
+  int sk_per;           // iterations (k-steps) per CTA
+  float4* sk_ws;        // [2 * grid][BN/16][4][128] float4 partial-accumulator slots
+  int* sk_cnt;          // [tiles] arrival counters, zero between launches
+};
+
+// Work iterator shared by all warp roles: yields (tile, [k0, k1)) segments in the same order everywhere.
+struct SegIter {
+  int sk, ksteps, total_tiles, stride, cur, end;
+  __device__ __forceinline__ SegIter(const TcParams& p, int ksteps_, int total_tiles_)
+      : sk(p.sk), ksteps(ksteps_), total_tiles(total_tiles_), stride((int)gridDim.x) {
+    if (sk) {
+      cur = (int)blockIdx.x * p.sk_per;
+      end = min(cur + p.sk_per, total_tiles_ * ksteps_);
+    } else {
+      cur = (int)blockIdx.x;
+      end = 0;
+    }
+  }
+  __device__ __forceinline__ bool next(int& tile, int& k0, int& k1) {
+    if (!sk) {
+      if (cur >= total_tiles) return false;
+      tile = cur; k0 = 0; k1 = ksteps; cur += stride;
+      return true;
+    }
+    if (cur >= end) return false;
+    tile = cur / ksteps;
+    k0 = cur - tile * ksteps;
+    k1 = min(ksteps, k0 + (end - cur));
+    cur += k1 - k0;
+    return true;
+  }
 };
 
 // ---------------------------------------------------------------- PTX wrappers
@@ -250,6 +285,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  pdl_trigger();
 
   const int Cin = p.c0 + p.c1;
   const int kchunks = Cin / TC_BK;
@@ -283,13 +319,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  pdl_wait();  // set-up above overlapped the predecessor's tail; from here on we touch its outputs
 
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      SegIter it(p, ksteps, total_tiles);
+      int tile, k0, k1;
+      while (it.next(tile, k0, k1)) {
         const int nt = tile % p.tiles_n;
         int mt = tile / p.tiles_n;
         const int tx = mt % p.tiles_x; mt /= p.tiles_x;
@@ -297,7 +336,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
         const int tb = mt / p.tiles_y;
         const int ox0 = tx * p.TW, oy0 = ty * p.TH, b0 = tb * p.TB;
         const int n0 = nt * p.BN;
-        for (int ks = 0; ks < ksteps; ++ks) {
+        for (int ks = k0; ks < k1; ++ks) {
           const int tap = ks / kchunks;
           const int kc = ks - tap * kchunks;
           const int dy = tap / p.ksize, dx = tap - dy * p.ksize;
@@ -323,11 +362,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      SegIter it(p, ksteps, total_tiles);
+      int tile, k0, k1;
+      while (it.next(tile, k0, k1)) {
         mbar_wait(tempty_bar(acc), acc_phase ^ 1);  // epilogue has drained this accumulator
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)acc * acc_stride;
-        for (int ks = 0; ks < ksteps; ++ks) {
+        for (int ks = k0; ks < k1; ++ks) {
           mbar_wait(MODE ? split_bar(stage) : full_bar(stage), phase);
           tc_fence_after();
           const uint32_t sa = smem_base + stage * stage_bytes;
@@ -337,7 +378,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
             for (int k = 0; k < TC_BK / 16; ++k) {  // 2 K-steps of 16 bf16: 8 TMEM columns of A, 32 B inside the 64 B swizzle row of W
               const uint32_t ah = tmem_base + (uint32_t)(TC_BF_A_COL + stage * 32 + k * 8), al = ah + 16;
               const uint64_t bh = umma_desc_sw64(sb + k * 32), bl = umma_desc_sw64(sa + off_wlo + k * 32);
-              umma_bf16_ts(d_tmem, ah, bh, idesc, (ks | k) ? 1u : 0u);
+              umma_bf16_ts(d_tmem, ah, bh, idesc, ((ks - k0) | k) ? 1u : 0u);
               umma_bf16_ts(d_tmem, al, bh, idesc, 1u);
               umma_bf16_ts(d_tmem, ah, bl, idesc, 1u);
             }
@@ -346,7 +387,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
           for (int k = 0; k < TC_BK / 8; ++k) {
             const uint64_t ad = umma_desc_sw128(sa + k * 32);
             const uint64_t bd = umma_desc_sw128(sb + k * 32);
-            umma_tf32(d_tmem, ad, bd, idesc, (ks | k) ? 1u : 0u);
+            umma_tf32(d_tmem, ad, bd, idesc, ((ks - k0) | k) ? 1u : 0u);
             if (X3) {
               const uint64_t al = umma_desc_sw128(sa + off_alo + k * 32);
               const uint64_t bl = umma_desc_sw128(sa + off_wlo + k * 32);
@@ -386,7 +427,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
     const int act = p.act;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    volatile uint32_t* sk_flag = reinterpret_cast<volatile uint32_t*>(smem_raw + (bar_base + 8u * 23 - smem_u32(smem_raw)));
+    SegIter it(p, ksteps, total_tiles);
+    int tile, k0, k1;
+    bool first_seg = true;
+    while (it.next(tile, k0, k1)) {
       const int nt = tile % p.tiles_n;
       int mt = tile / p.tiles_n;
       const int tx = mt % p.tiles_x; mt /= p.tiles_x;
@@ -396,6 +441,63 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
       const uint32_t t_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * acc_stride + (uint32_t)col_lo;
+      // ---- stream-K: a segment that covers only part of the K loop parks its partial sums; the last contributor of the
+      // tile to arrive adds them up in CTA order and runs the epilogue below from the workspace instead of TMEM
+      bool from_ws = false;
+      int c_first = 0, c_last = 0;
+      if (k1 - k0 != ksteps) {
+        float4* slot = p.sk_ws + (size_t)(2 * blockIdx.x + (first_seg ? 0 : 1)) * (size_t)(32 * p.BN);
+        for (int c = 0; c < hcols; c += 16) {
+          uint32_t r[16];
+          tmem_ld16(t_base + c, r);
+          const int ch = (col_lo + c) >> 4;
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            slot[(ch * 4 + k) * 128 + row] = make_float4(__uint_as_float(r[4 * k]), __uint_as_float(r[4 * k + 1]),
+                                                         __uint_as_float(r[4 * k + 2]), __uint_as_float(r[4 * k + 3]));
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty_bar(acc));  // the accumulator is free again
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        first_seg = false;
+        c_first = (tile * ksteps) / p.sk_per;
+        c_last = ((tile + 1) * ksteps - 1) / p.sk_per;
+        __threadfence();
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (et == 0) {
+          const int old = atomicAdd(p.sk_cnt + tile, 1);
+          const bool last = old == c_last - c_first;
+          if (last) p.sk_cnt[tile] = 0;  // every contributor has arrived: leave the counter ready for the next launch
+          *sk_flag = last ? 1u : 0u;
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (*sk_flag == 0u) continue;
+        __threadfence();
+        from_ws = true;
+      }
+      first_seg = false;
+      auto fetch16 = [&](int c, uint32_t (&r)[16]) {
+        if (!from_ws) { tmem_ld16(t_base + c, r); return; }
+        float4 a[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) a[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+        const int ch = (col_lo + c) >> 4;
+        for (int cc = c_first; cc <= c_last; ++cc) {
+          const int sl = 2 * cc + ((cc * p.sk_per) / ksteps == tile ? 0 : 1);
+          const float4* src = p.sk_ws + (size_t)sl * (size_t)(32 * p.BN) + (ch * 4) * 128 + row;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const float4 v = __ldcg(src + k * 128);
+            a[k].x += v.x; a[k].y += v.y; a[k].z += v.z; a[k].w += v.w;
+          }
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          r[4 * k] = __float_as_uint(a[k].x); r[4 * k + 1] = __float_as_uint(a[k].y);
+          r[4 * k + 2] = __float_as_uint(a[k].z); r[4 * k + 3] = __float_as_uint(a[k].w);
+        }
+      };
       if (p.o_sn == 1) {
         // the 4 output rows this lane serves in the coalesced arrangement (rl = 8j + sub) are the same for every chunk
         long long obase[4];
@@ -430,7 +532,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
           float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
           if (has_bias) bias4 = __ldg(reinterpret_cast<const float4*>(p.bias + n));
           uint32_t r[16];
-          tmem_ld16(t_base + c, r);
+          fetch16(c, r);
 #pragma unroll
           for (int k = 0; k < 4; ++k)
             stg[lane * 4 + (k ^ ((lane >> 1) & 3))] = make_float4(__uint_as_float(r[4 * k]), __uint_as_float(r[4 * k + 1]),
@@ -510,7 +612,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
         const float* __restrict__ rv = has_rv ? p.rowvec + (long long)b * p.rowvec_sb : nullptr;
         for (int c = 0; c < hcols; c += 16) {
           uint32_t r[16];
-          tmem_ld16(t_base + c, r);
+          fetch16(c, r);
           if (valid) {
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
@@ -534,10 +636,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
           }
         }
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar(acc));
-      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      if (!from_ws) {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty_bar(acc));
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
     }
   } else if (BF) {
     // ===================== splitter (warps 10..13), BF16x3: fp32 A tile (smem) -> bf16 hi / lo halves in TMEM ==========
@@ -547,8 +651,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
     const uint32_t a_lane = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)TC_BF_A_COL;
     int stage = 0;
     uint32_t phase = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      for (int ks = 0; ks < ksteps; ++ks) {
+    SegIter it(p, ksteps, total_tiles);
+    int tile, k0, k1;
+    while (it.next(tile, k0, k1)) {
+      for (int ks = k0; ks < k1; ++ks) {
         mbar_wait(full_bar(stage), phase);
         const uint8_t* srow = smem_raw + (smem_base - smem_u32(smem_raw)) + (size_t)stage * stage_bytes + r * 128;
         uint32_t hi[16], lo[16];
@@ -577,8 +683,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
     int stage = 0;
     uint32_t phase = 0;
     const int a_vec = TC_A_BYTES / 16, w_vec = (int)(b_bytes / 16);
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      for (int ks = 0; ks < ksteps; ++ks) {
+    SegIter it(p, ksteps, total_tiles);
+    int tile, k0, k1;
+    while (it.next(tile, k0, k1)) {
+      for (int ks = k0; ks < k1; ++ks) {
         mbar_wait(full_bar(stage), phase);
         uint8_t* sbase = smem_raw + (smem_base - smem_u32(smem_raw)) + (size_t)stage * stage_bytes;
         float4* a_hi = reinterpret_cast<float4*>(sbase);
@@ -739,6 +847,50 @@ int conv2d_tc(const FridoConvParams* p, cudaStream_t s) {
     const int v = atoi(f);
     if (v >= 32 && v <= (mode == 2 ? TC_BF_ACC_STRIDE : TC_MAX_BN) && v % 32 == 0 && p->Cout % v == 0) bn = v;
   }
+  // Stream-K for launches that cannot fill the machine with whole tiles (8x8 / 16x16 levels, long K): compare the
+  // data-parallel schedule chosen above with an even split of all (tile, k-step) iterations over the SMs, in clocks.
+  t.sk = 0; t.sk_per = 0; t.sk_ws = nullptr; t.sk_cnt = nullptr;
+  int sk_grid = 0;
+  {
+    const int ksteps = p->ksize * p->ksize * (Cin / TC_BK);
+    const char* sk_e = getenv("FRIDO_SK");  // 0 = off, 1 = cost model (default), 2 = whenever legal (tests)
+    const int sk_env = sk_e ? atoi(sk_e) : 1;
+    auto stage_clk = [&](int n) {
+      int clk = mma_per_stage[mode] * n / 2;
+      if (clk < floor_clk[mode]) clk = floor_clk[mode];
+      if (mode == 2) clk = 256 + 5 * n / 2;
+      return clk;
+    };
+    const int64_t dp_tiles = (int64_t)m_tiles * (p->Cout / bn);
+    const double dp_cost = (double)((dp_tiles + sms - 1) / sms) * ksteps * stage_clk(bn);
+    double best = sk_env == 2 ? 1e30 : 0.9 * dp_cost;
+    const bool forced_bn = getenv("FRIDO_TC_FORCE_BN") != nullptr;
+    if (sk_env && p->sk_ws && (reinterpret_cast<uintptr_t>(p->sk_ws) & 15) == 0 && ksteps >= 8) {
+      for (int i = 0; i < 4; ++i) {
+        const int n = cands[i];
+        if (p->Cout % n || (mode == 2 && n > TC_BF_ACC_STRIDE) || (forced_bn && n != bn)) continue;
+        const int64_t tiles = (int64_t)m_tiles * (p->Cout / n);
+        const int64_t iters = tiles * ksteps;
+        if (tiles > 1024 || iters > (1 << 28)) continue;
+        int64_t g = iters / 4 < sms ? iters / 4 : sms;   // at least 4 k-steps per CTA
+        if (g < 1) g = 1;
+        int64_t per = (iters + g - 1) / g;
+        const int64_t min_per = (ksteps + 5) / 6;         // at most 7 contributors per tile
+        if (per < min_per) per = min_per;
+        g = (iters + per - 1) / per;
+        if (per % ksteps == 0 && sk_env != 2) continue;   // whole tiles only: that is the data-parallel schedule
+        const int64_t need = 4096 + 2 * g * 128 * n * 4;
+        if (need > p->sk_ws_bytes) continue;
+        const int contrib = (int)((ksteps + per - 1) / per) + 1;
+        const double cost = (double)per * stage_clk(n) + 3000.0 + 8.0 * n * (1 + contrib);
+        if (cost < best) { best = cost; bn = n; t.sk = 1; t.sk_per = (int)per; sk_grid = (int)g; }
+      }
+    }
+    if (t.sk) {
+      t.sk_cnt = reinterpret_cast<int*>(p->sk_ws);
+      t.sk_ws = reinterpret_cast<float4*>(reinterpret_cast<char*>(p->sk_ws) + 4096);
+    }
+  }
   t.BN = bn;
   t.tiles_n = p->Cout / bn;
   t.w_batched = p->w_sb != 0;
@@ -784,10 +936,10 @@ int conv2d_tc(const FridoConvParams* p, cudaStream_t s) {
   if (t.stages > TC_MAX_STAGES) t.stages = TC_MAX_STAGES;
   if (bf && t.stages > TC_BF_MAX_STAGES) t.stages = TC_BF_MAX_STAGES;
   const int total = m_tiles * t.tiles_n;
-  const int grid = total < sms ? total : sms;
-  if (bf) conv_tc_kernel<2><<<grid, TC_THREADS_X3, TC_SMEM_BYTES, s>>>(ma0, ma1, mw, mwlo, t);
-  else if (x3) conv_tc_kernel<1><<<grid, TC_THREADS_X3, TC_SMEM_BYTES, s>>>(ma0, ma1, mw, mwlo, t);
-  else conv_tc_kernel<0><<<grid, TC_THREADS, TC_SMEM_BYTES, s>>>(ma0, ma1, mw, mwlo, t);
+  const int grid = t.sk ? sk_grid : (total < sms ? total : sms);
+  if (bf) launch_pdl(conv_tc_kernel<2>, dim3(grid), dim3(TC_THREADS_X3), TC_SMEM_BYTES, s, ma0, ma1, mw, mwlo, t);
+  else if (x3) launch_pdl(conv_tc_kernel<1>, dim3(grid), dim3(TC_THREADS_X3), TC_SMEM_BYTES, s, ma0, ma1, mw, mwlo, t);
+  else launch_pdl(conv_tc_kernel<0>, dim3(grid), dim3(TC_THREADS), TC_SMEM_BYTES, s, ma0, ma1, mw, mwlo, t);
   return check_launch(bf ? "conv2d_tc(bf16x3)" : x3 ? "conv2d_tc(3xTF32)" : "conv2d_tc");
 }
 

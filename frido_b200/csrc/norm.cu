@@ -81,66 +81,98 @@ static int gn_chunk(int B, int HW) {
 
 // ----------------------------------------------------------------------------
 // normalise + affine (+SPADE) (+SiLU)
+// Thread layout: tid -> (pixel lane pl, quad column ql); a thread keeps its channel quad for the whole CTA chunk, so
+// gamma / beta / mean / rstd are loop invariants in registers and the pixel loop is pure streaming: 1 (or 3 with SPADE)
+// float4 loads and one float4 store per iteration, four pixels in flight per thread.  Channels beyond 4*Qe are covered
+// by nj passes (quad = ql + j*Qe).
 // ----------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) norm_act_kernel(const FridoNormActParams p, int pix_per_cta) {
+constexpr int NA_MAX_THREADS = 384;
+constexpr int NA_UNROLL = 4;
+
+__global__ void __launch_bounds__(NA_MAX_THREADS) norm_act_kernel(const FridoNormActParams p, int pix_per_cta, int Qe, int PL, int nj) {
   __shared__ float s_mean[64], s_rstd[64];
+  pdl_trigger();
+  pdl_wait();
   const int C = p.c0 + p.c1;
   const int Q = C >> 2;
   const int cg = C / p.groups;
   const int b = blockIdx.y;
-  if (threadIdx.x < p.groups) {
-    double s0, s1;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nw = blockDim.x >> 5;
+  for (int g = warp; g < p.groups; g += nw) {  // one warp per group: lanes stride over the group's channels
+    double s0 = 0.0, s1 = 0.0;
     if (p.csum0) {  // group sums from the producers' per-channel sums (the group may straddle the two sources)
-      s0 = 0.0; s1 = 0.0;
-      for (int c = threadIdx.x * cg; c < (threadIdx.x + 1) * cg; ++c) {
+      for (int c = g * cg + lane; c < (g + 1) * cg; c += 32) {
         const double* cs = (c < p.c0) ? p.csum0 + ((int64_t)b * p.c0 + c) * 2 : p.csum1 + ((int64_t)b * p.c1 + (c - p.c0)) * 2;
         s0 += cs[0]; s1 += cs[1];
       }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) { s0 += __shfl_xor_sync(0xffffffffu, s0, o); s1 += __shfl_xor_sync(0xffffffffu, s1, o); }
     } else {
-      const double* sm = p.sums + ((int64_t)b * p.groups + threadIdx.x) * 2;
+      const double* sm = p.sums + ((int64_t)b * p.groups + g) * 2;
       s0 = sm[0]; s1 = sm[1];
     }
-    const double cnt = (double)cg * (double)p.HW;
-    const double mean = s0 / cnt;
-    double var = s1 / cnt - mean * mean;
-    if (var < 0.0) var = 0.0;
-    s_mean[threadIdx.x] = (float)mean;
-    s_rstd[threadIdx.x] = (float)(1.0 / sqrt(var + (double)p.eps));
+    if (lane == 0) {
+      const double cnt = (double)cg * (double)p.HW;
+      const double mean = s0 / cnt;
+      double var = s1 / cnt - mean * mean;
+      if (var < 0.0) var = 0.0;
+      s_mean[g] = (float)mean;
+      s_rstd[g] = (float)(1.0 / sqrt(var + (double)p.eps));
+    }
   }
   __syncthreads();
+  if (tid >= Qe * PL) return;
+  const int pl = tid / Qe, ql = tid - pl * Qe;
   const int pix0 = blockIdx.x * pix_per_cta;
   const int pix1 = min(pix0 + pix_per_cta, p.HW);
-  const int64_t n = (int64_t)(pix1 - pix0) * Q;
-  const float* a0 = p.a0 + (int64_t)b * p.HW * p.c0;
-  const float* a1 = p.a1 ? p.a1 + (int64_t)b * p.HW * p.c1 : nullptr;
   const float* gb = p.gb ? p.gb + (int64_t)b * p.HW * 2 * C : nullptr;
   float* out = p.out + (int64_t)b * p.HW * C;
-  for (int64_t e = threadIdx.x; e < n; e += blockDim.x) {
-    const int pix = pix0 + (int)(e / Q);
-    const int c = ((int)(e % Q)) << 2;
-    const float4 xv = (c < p.c0) ? __ldg(reinterpret_cast<const float4*>(a0 + (int64_t)pix * p.c0 + c))
-                                 : __ldg(reinterpret_cast<const float4*>(a1 + (int64_t)pix * p.c1 + (c - p.c0)));
+  const bool silu = p.silu != 0, rnd = p.round_tf32 != 0;
+  for (int j = 0; j < nj; ++j) {
+    const int quad = ql + j * Qe;
+    if (quad >= Q) break;
+    const int c = quad << 2;
+    const bool first = c < p.c0;
+    const int cs = first ? p.c0 : p.c1;  // row stride of the source this quad lives in
+    const float* src = first ? p.a0 + (int64_t)b * p.HW * p.c0 + c : p.a1 + (int64_t)b * p.HW * p.c1 + (c - p.c0);
     const float4 gm = __ldg(reinterpret_cast<const float4*>(p.gamma + c));
     const float4 bt = __ldg(reinterpret_cast<const float4*>(p.beta + c));
-    float x[4] = {xv.x, xv.y, xv.z, xv.w};
     const float g4[4] = {gm.x, gm.y, gm.z, gm.w};
     const float b4[4] = {bt.x, bt.y, bt.z, bt.w};
-    float sg[4] = {0, 0, 0, 0}, sb[4] = {0, 0, 0, 0};
-    if (gb) {
-      const float4 a = __ldg(reinterpret_cast<const float4*>(gb + (int64_t)pix * 2 * C + c));
-      const float4 d = __ldg(reinterpret_cast<const float4*>(gb + (int64_t)pix * 2 * C + C + c));
-      sg[0] = a.x; sg[1] = a.y; sg[2] = a.z; sg[3] = a.w;
-      sb[0] = d.x; sb[1] = d.y; sb[2] = d.z; sb[3] = d.w;
-    }
+    float mean[4], rstd[4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int g = (c + j) / cg;
-      float y = (x[j] - s_mean[g]) * s_rstd[g] * g4[j] + b4[j];
-      if (gb) y = y * (1.0f + sg[j]) + sb[j];
-      if (p.silu) y = silu_f(y);
-      x[j] = p.round_tf32 ? round_tf32(y) : y;
+    for (int e = 0; e < 4; ++e) { const int g = (c + e) / cg; mean[e] = s_mean[g]; rstd[e] = s_rstd[g]; }
+    for (int pix = pix0 + pl; pix < pix1; pix += PL * NA_UNROLL) {
+      float4 xv[NA_UNROLL], ga[NA_UNROLL], be[NA_UNROLL];
+#pragma unroll
+      for (int u = 0; u < NA_UNROLL; ++u) {
+        const int px = pix + u * PL;
+        if (px < pix1) {
+          xv[u] = __ldg(reinterpret_cast<const float4*>(src + (int64_t)px * cs));
+          if (gb) {
+            ga[u] = __ldg(reinterpret_cast<const float4*>(gb + (int64_t)px * 2 * C + c));
+            be[u] = __ldg(reinterpret_cast<const float4*>(gb + (int64_t)px * 2 * C + C + c));
+          }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < NA_UNROLL; ++u) {
+        const int px = pix + u * PL;
+        if (px < pix1) {
+          float x[4] = {xv[u].x, xv[u].y, xv[u].z, xv[u].w};
+          const float sg[4] = {ga[u].x, ga[u].y, ga[u].z, ga[u].w};
+          const float sb[4] = {be[u].x, be[u].y, be[u].z, be[u].w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            float y = (x[e] - mean[e]) * rstd[e] * g4[e] + b4[e];
+            if (gb) y = y * (1.0f + sg[e]) + sb[e];
+            if (silu) y = silu_f(y);
+            x[e] = rnd ? round_tf32(y) : y;
+          }
+          *reinterpret_cast<float4*>(out + (int64_t)px * C + c) = make_float4(x[0], x[1], x[2], x[3]);
+        }
+      }
     }
-    *reinterpret_cast<float4*>(out + (int64_t)pix * C + c) = make_float4(x[0], x[1], x[2], x[3]);
   }
 }
 
@@ -151,6 +183,8 @@ constexpr int LN_MAXQ = 8;
 __global__ void __launch_bounds__(256) layernorm_kernel(const FridoLayerNormParams p) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
+  pdl_trigger();
+  pdl_wait();
   if (warp >= p.rows) return;
   const int Q = p.C >> 2;
   const float* x = p.x + (int64_t)warp * p.C;
@@ -199,6 +233,8 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const FridoLayerNormPara
 __global__ void __launch_bounds__(256) softmax_warp_kernel(const FridoSoftmaxParams p) {
   const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
+  pdl_trigger();
+  pdl_wait();
   if (row >= p.rows) return;
   const float* s = p.s + row * p.ld;
   float* o = p.out + row * p.ld;
@@ -282,6 +318,8 @@ __global__ void time_embed_kernel(const FridoTimeEmbedParams p) {
 __global__ void __launch_bounds__(256) upsample2x_kernel(const FridoUpsampleParams p) {
   const int Q = p.C >> 2;
   const int64_t total = (int64_t)p.B * 4 * p.H * p.W * Q;
+  pdl_trigger();
+  pdl_wait();
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
     const int q = (int)(e % Q);
     int64_t r = e / Q;
@@ -388,7 +426,7 @@ extern "C" int frido_upsample2x(const FridoUpsampleParams* p, void* stream) {
   const int64_t total = (int64_t)p->B * 4 * p->H * p->W * (p->C >> 2);
   int blocks = (int)((total + 255) / 256);
   if (blocks > 148 * 16) blocks = 148 * 16;
-  upsample2x_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(*p);
+  launch_pdl(upsample2x_kernel, dim3(blocks), dim3(256), 0, (cudaStream_t)stream, *p);
   return check_launch("upsample2x");
 }
 
@@ -413,7 +451,15 @@ extern "C" int frido_norm_act(const FridoNormActParams* p, void* stream) {
   if ((p->c1 > 0) != (p->a1 != nullptr)) return set_error(FRIDO_E_ARG, "norm_act: a1/c1 mismatch");
   const int ppc = gn_chunk(p->B, p->HW);
   dim3 grid((p->HW + ppc - 1) / ppc, p->B);
-  norm_act_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(*p, ppc);
+  const int Q = C >> 2;
+  const int nj = (Q + 255) / 256;
+  const int Qe = (Q + nj - 1) / nj;
+  int PL = (256 + Qe / 2) / Qe;  // pixel lanes: about 256 threads per CTA
+  if (PL < 1) PL = 1;
+  if (PL > ppc) PL = ppc;
+  while (PL > 1 && Qe * PL > NA_MAX_THREADS) --PL;
+  const int threads = (Qe * PL + 31) / 32 * 32;
+  launch_pdl(norm_act_kernel, grid, dim3(threads), 0, (cudaStream_t)stream, *p, ppc, Qe, PL, nj);
   return check_launch("norm_act");
 }
 
@@ -421,7 +467,7 @@ extern "C" int frido_layernorm(const FridoLayerNormParams* p, void* stream) {
   if (!p || !p->x || !p->out || !p->gamma || !p->beta) return set_error(FRIDO_E_ARG, "layernorm: null pointer");
   if ((p->C & 3) || p->C > LN_MAXQ * 128 || p->rows <= 0) return set_error(FRIDO_E_ARG, "layernorm: unsupported C");
   const int64_t blocks = (p->rows + 7) / 8;
-  layernorm_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(*p);
+  launch_pdl(layernorm_kernel, dim3((unsigned)blocks), dim3(256), 0, (cudaStream_t)stream, *p);
   return check_launch("layernorm");
 }
 
@@ -429,7 +475,7 @@ extern "C" int frido_softmax(const FridoSoftmaxParams* p, void* stream) {
   if (!p || !p->s || !p->out || p->rows <= 0 || p->n <= 0) return set_error(FRIDO_E_ARG, "softmax: bad argument");
   if (p->n <= 1024) {
     const int64_t blocks = (p->rows + 7) / 8;
-    softmax_warp_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(*p);
+    launch_pdl(softmax_warp_kernel, dim3((unsigned)blocks), dim3(256), 0, (cudaStream_t)stream, *p);
   } else {
     if ((p->ld & 3) || (reinterpret_cast<uintptr_t>(p->s) & 15) || (reinterpret_cast<uintptr_t>(p->out) & 15))
       return set_error(FRIDO_E_ARG, "softmax: wide rows need 16B-aligned rows");

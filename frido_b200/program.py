@@ -30,6 +30,21 @@ def default_engine():
     return e
 
 
+_SK_WS = {}
+
+
+def sk_workspace(device):
+    """One zero-initialised stream-K workspace per device (FridoConvParams.sk_ws): launches on a stream execute in order and
+    every launch leaves its arrival counters at zero, so all programs of a device share it."""
+    device = torch.device(device)
+    key = (device.type, device.index if device.index is not None else torch.cuda.current_device())
+    ws = _SK_WS.get(key)
+    if ws is None:
+        ws = torch.zeros(L.SK_WS_BYTES, dtype=torch.uint8, device=device)
+        _SK_WS[key] = ws
+    return ws
+
+
 def round_tf32_(t):
     """In-place round-to-nearest (ties away) to TF32 of a device tensor: MMA operands are rounded once
     by their producer so the tensor core's mantissa truncation never bites."""
@@ -157,6 +172,10 @@ class Program:
         p.o_sb = Hout * Wout * p.o_sp if o_sb is None else o_sb
         p.o_sn = o_sn
         p.round_tf32, p.engine = round_tf32, engine
+        if engine in (1, 2, 3) and out.is_cuda:
+            ws = sk_workspace(self.device)
+            p.sk_ws, p.sk_ws_bytes = ws.data_ptr(), ws.numel()
+            self.hold(ws)
         if out_pair is not None:
             p.out_hi, p.out_lo = out_pair[0].data_ptr() + 2 * out_off, out_pair[1].data_ptr() + 2 * out_off
             self.hold(out_pair[0], out_pair[1])
@@ -231,6 +250,26 @@ class Program:
         self.hold(qkv, out)
         self.flops += 4 * B * H * Lseq * Lseq * Dh
         self._add(L.OP_MHA, p, tag)
+
+    def attn_small(self, q, k, v, out, *, B, N, Nk, Cdim, scale, q_off=0, q_sb, q_ld, k_off=0, k_sb, k_ld, v_off=0, v_sb, v_ld,
+                   ln=None, ln_eps=1e-5, bias=None, res=None, tag="attn_small"):
+        """Fused softmax(scale LN(q) k^T) v + bias + res for short key sequences (csrc/attn.cu); offsets/strides in
+        floats; ln = (gamma, beta) applies a LayerNorm to the query rows first; res is a dense [B,N,C] tensor."""
+        p = L.AttnParams()
+        p.q, p.q_sb, p.q_ld = q.data_ptr() + 4 * q_off, q_sb, q_ld
+        p.k, p.k_sb, p.k_ld = k.data_ptr() + 4 * k_off, k_sb, k_ld
+        p.v, p.v_sb, p.v_ld = v.data_ptr() + 4 * v_off, v_sb, v_ld
+        p.B, p.N, p.Nk, p.C, p.scale = B, N, Nk, Cdim, scale
+        p.out, p.o_sb, p.o_ld = out.data_ptr(), N * Cdim, Cdim
+        if ln is not None:
+            p.ln_gamma, p.ln_beta, p.ln_eps = ln[0].data_ptr(), ln[1].data_ptr(), ln_eps
+            self.hold(ln[0], ln[1])
+        p.bias = _ptr(bias)
+        if res is not None:
+            p.res, p.r_sb, p.r_ld = res.data_ptr(), N * Cdim, Cdim
+        self.hold(q, k, v, out, bias, res)
+        self.flops += 4 * B * N * Nk * Cdim
+        self._add(L.OP_ATTN, p, tag)
 
     def upsample2x(self, x, out, *, B, H, W, Cdim, round_tf32=0, tag="upsample2x"):
         p = L.UpsampleParams()

@@ -307,6 +307,16 @@ class UNetPlan:
         """x: LayerNorm-ed tokens [B,N,C]; returns attention output before to_out."""
         S, B = self.step, self.B
         scale = float(C) ** -0.5
+        if ctx_kv is None and self._small_attn(N, C):
+            # fewer than 128 tokens per image (8x8 level): one q|k|v GEMM + the fused short-sequence attention kernel
+            wqkv = self._packed(lambda: torch.cat([ca.to_q.weight.detach(), ca.to_k.weight.detach(), ca.to_v.weight.detach()], 0))
+            qkv = S.buf(B, N, 3 * C)
+            S.linear(x, wqkv, qkv, M=B * N, K=C, N=3 * C, tag=tag + ".qkv")
+            o = S.buf(B, N, C)
+            S.attn_small(qkv, qkv, qkv, o, B=B, N=N, Nk=N, Cdim=C, scale=scale, q_sb=N * 3 * C, q_ld=3 * C, k_off=C,
+                         k_sb=N * 3 * C, k_ld=3 * C, v_off=2 * C, v_sb=N * 3 * C, v_ld=3 * C, tag=tag + ".fused")
+            S.release(qkv)
+            return o
         if ctx_kv is None:  # self-attention: fused q|k projection, V written transposed
             wqk = self._packed(lambda: torch.cat([ca.to_q.weight.detach(), ca.to_k.weight.detach()], 0))
             qk = S.buf(B, N, 2 * C)
@@ -355,6 +365,28 @@ class UNetPlan:
             S.release(sc)
         return o
 
+    def _small_attn(self, Nk, C):
+        """Key sequences too short for a 128-row tensor-core tile go to the fused SIMT attention kernel (csrc/attn.cu)."""
+        import os
+        return Nk <= 64 and C <= 1024 and C % 4 == 0 and os.environ.get("FRIDO_ATTN_SMALL", "1") == "1"
+
+    def _ctx_folded(self, ca, C):
+        """Prologue, short condition: the score and output operands of the fused cross-attention kernel with the
+        step-invariant projections folded in (attention.py:172-191 re-associated):
+          sim = (x Wq^T)(ctx Wk^T)^T = x ((ctx Wk^T) Wq)^T        -> k' = (ctx Wk^T) Wq    [B,Lc,C]
+          to_out(P (ctx Wv^T)) = P ((ctx Wv^T) Wo^T) + b_o        -> v' = (ctx Wv^T) Wo^T  [B,Lc,C]"""
+        P, B, Lc = self.prologue, self.B, self.Lc
+        D = self.net.context_dim
+        kf = torch.empty(B, Lc, C, dtype=torch.float32, device=self.dev)  # live across steps: not pooled
+        vf = torch.empty(B, Lc, C, dtype=torch.float32, device=self.dev)
+        kc = P.buf(B, Lc, C)
+        P.linear(self.ctx, self._vec(ca.to_k.weight), kc, M=B * Lc, K=D, N=C, tag="ctx.k")
+        P.linear(kc, self._packed(lambda: ca.to_q.weight.detach().t().contiguous()), kf, M=B * Lc, K=C, N=C, tag="ctx.k.Wq")
+        P.linear(self.ctx, self._vec(ca.to_v.weight), kc, M=B * Lc, K=D, N=C, tag="ctx.v")
+        P.linear(kc, self._vec(ca.to_out[0].weight), vf, M=B * Lc, K=C, N=C, tag="ctx.v.Wo")
+        P.release(kc)
+        return kf, vf
+
     def _ctx_kv(self, ca, C):
         """Prologue: K = ctx Wk^T [B,Lp,C] (rows >= Lc zero), V^T [B,C,Lp] (attention.py:175-176)."""
         P, B, Lc, Lp = self.prologue, self.B, self.Lc, self.Lp
@@ -388,14 +420,25 @@ class UNetPlan:
             S.linear(o, self._vec(blk.attn1.to_out[0].weight), h1, M=B * N, K=C, N=C, bias=self._vec(blk.attn1.to_out[0].bias),
                      res=hcur, tag="attn1.out")
             S.release(o); S.release(hcur)
-            ln = S.buf(B, N, C)
-            S.layernorm(h1, self._vec(blk.norm2.weight), self._vec(blk.norm2.bias), ln, rows=B * N, Cdim=C, round_tf32=S.R)
-            o = self._attention(ln, C, N, blk.attn2, self._ctx_kv(blk.attn2, C), "attn2")
-            S.release(ln)
-            h2 = S.buf(B, N, C)
-            S.linear(o, self._vec(blk.attn2.to_out[0].weight), h2, M=B * N, K=C, N=C, bias=self._vec(blk.attn2.to_out[0].bias),
-                     res=h1, tag="attn2.out")
-            S.release(o); S.release(h1)
+            if self._small_attn(self.Lc, C):
+                # h2 = h1 + to_out(attn2(LN(h1), ctx)) in one launch: LayerNorm, 26-key attention against the folded
+                # operands, output bias and residual (attention.py:324)
+                kf, vf = self._ctx_folded(blk.attn2, C)
+                h2 = S.buf(B, N, C)
+                S.attn_small(h1, kf, vf, h2, B=B, N=N, Nk=self.Lc, Cdim=C, scale=float(C) ** -0.5, q_sb=N * C, q_ld=C,
+                             k_sb=self.Lc * C, k_ld=C, v_sb=self.Lc * C, v_ld=C,
+                             ln=(self._vec(blk.norm2.weight), self._vec(blk.norm2.bias)),
+                             bias=self._vec(blk.attn2.to_out[0].bias), res=h1, tag="attn2.block")
+                S.release(h1)
+            else:
+                ln = S.buf(B, N, C)
+                S.layernorm(h1, self._vec(blk.norm2.weight), self._vec(blk.norm2.bias), ln, rows=B * N, Cdim=C, round_tf32=S.R)
+                o = self._attention(ln, C, N, blk.attn2, self._ctx_kv(blk.attn2, C), "attn2")
+                S.release(ln)
+                h2 = S.buf(B, N, C)
+                S.linear(o, self._vec(blk.attn2.to_out[0].weight), h2, M=B * N, K=C, N=C,
+                         bias=self._vec(blk.attn2.to_out[0].bias), res=h1, tag="attn2.out")
+                S.release(o); S.release(h1)
             ln = S.buf(B, N, C)
             S.layernorm(h2, self._vec(blk.norm3.weight), self._vec(blk.norm3.bias), ln, rows=B * N, Cdim=C, round_tf32=S.R)
             proj = blk.ff.net[0].proj

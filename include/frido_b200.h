@@ -21,7 +21,8 @@
 extern "C" {
 #endif
 
-#define FRIDO_ABI_VERSION 1
+#define FRIDO_ABI_VERSION 2
+#define FRIDO_SK_WS_BYTES (40ll << 20)
 
 #define FRIDO_OK 0
 #define FRIDO_E_ARG (-1)     /* bad argument / unsupported shape */
@@ -78,6 +79,10 @@ typedef struct FridoConvParams {
                                (attention K and V^T) get their pre-split copy.  Not with GEGLU. */
   double* chan_sums;        /* optional (tcgen05 engines only): [B][Cout][2] += per-channel (sum, sum of squares) of the
                                stored outputs, i.e. the GroupNorm statistics of the tensor being produced; zero on entry */
+  void* sk_ws;              /* optional (tcgen05 engines only) stream-K workspace: launches with too few output tiles for
+                               the 148 SMs split their K loops across CTAs and combine the partial sums here (in a fixed
+                               order: results stay deterministic).  Zero it once; launches on one stream may share it. */
+  int64_t sk_ws_bytes;      /* 40 MiB covers every shape (FRIDO_SK_WS_BYTES) */
   int32_t engine;           /* 0 = SIMT fp32; 1 = tcgen05 TF32; 2 = tcgen05 3xTF32 (error-compensated, ~2^-21 products);
                                3 = tcgen05 BF16x3 (error-compensated, ~2^-16 products, pre-split weights, 2x the TF32
                                issue rate); 1-3 take aligned shapes only (see csrc/conv_tc.cu) */
@@ -217,6 +222,26 @@ typedef struct FridoMhaParams {
 } FridoMhaParams;
 int frido_mha_small(const FridoMhaParams* p, void* stream);
 
+/* Fused single-head attention for short key sequences (attention.py:178-191: einsum -> *scale -> softmax -> einsum):
+ *   q' = LayerNorm(q[b,n,:]) if ln_gamma else q[b,n,:]                                  (attention.py:323-325)
+ *   out[b,n,:] = softmax_j(scale * q'.k[b,j,:]) @ v[b,j,:] + bias + res[b,n,:],  j < Nk, fp32 throughout, scores on chip.
+ * Used for the cross-attention to a short condition (26 layout tokens) and for self-attention with < 128 tokens per
+ * image (the 8x8 level), where the tcgen05 engine has no 128-row tile to work on.  For the cross-attention the host
+ * folds the step-invariant projections into the operands (k = (ctx Wk^T) Wq, v = (ctx Wv^T) Wo^T), so that with the
+ * LayerNorm, to_out bias and residual fused here  x + to_out(attn(LN(x), ctx))  (attention.py:324) is this one launch.
+ * Row strides in floats; C <= 1024. */
+typedef struct FridoAttnParams {
+  const float* q; int64_t q_sb, q_ld;
+  const float* k; int64_t k_sb, k_ld;
+  const float* v; int64_t v_sb, v_ld;
+  int32_t B, N, Nk, C; float scale;
+  float* out; int64_t o_sb, o_ld;
+  const float* ln_gamma; const float* ln_beta; float ln_eps; /* optional LayerNorm of the query rows ([C] each) */
+  const float* bias;                                          /* optional [C] added to every output row */
+  const float* res; int64_t r_sb, r_ld;                       /* optional residual, addressed like out */
+} FridoAttnParams;
+int frido_attn_small(const FridoAttnParams* p, void* stream);
+
 /* MS-VQGAN encode side.
  * nn.ConvTranspose2d(Cin, Cout, 4, stride=2, padding=1) on NHWC (msvqgan.py:82-84): out [B,2H,2W,Cout] dense;
  * w is the PyTorch layout [Cin][Cout][4][4]. */
@@ -258,7 +283,7 @@ enum FridoOpKind {
   FRIDO_OP_CONV = 1, FRIDO_OP_GN_STATS = 2, FRIDO_OP_NORM_ACT = 3, FRIDO_OP_LAYERNORM = 4,
   FRIDO_OP_SOFTMAX = 5, FRIDO_OP_TIME_EMBED = 6, FRIDO_OP_STEP_BEGIN = 7, FRIDO_OP_UPDATE = 8,
   FRIDO_OP_SNAP = 9, FRIDO_OP_VQ = 10, FRIDO_OP_ZERO = 11, FRIDO_OP_UPSAMPLE = 12,
-  FRIDO_OP_EMBED = 13, FRIDO_OP_MHA = 14, FRIDO_OP_CONVT = 15, FRIDO_OP_ASSEMBLE = 16
+  FRIDO_OP_EMBED = 13, FRIDO_OP_MHA = 14, FRIDO_OP_CONVT = 15, FRIDO_OP_ASSEMBLE = 16, FRIDO_OP_ATTN = 17
 };
 typedef struct FridoZeroParams { void* ptr; int64_t nbytes; } FridoZeroParams;
 typedef struct FridoOp {
@@ -269,7 +294,7 @@ typedef struct FridoOp {
     FridoLayerNormParams layernorm; FridoSoftmaxParams softmax; FridoTimeEmbedParams time_embed;
     FridoStepBeginParams step_begin; FridoUpdateParams update; FridoSnapParams snap; FridoVqParams vq;
     FridoZeroParams zero; FridoUpsampleParams upsample; FridoEmbedParams embed; FridoMhaParams mha;
-    FridoConvT2dParams convt; FridoAssembleParams assemble;
+    FridoConvT2dParams convt; FridoAssembleParams assemble; FridoAttnParams attn;
   } u;
 } FridoOp;
 /* Launches ops[0..n) in order on `stream`; returns 0 or (-(1000+i)) if op i failed. */

@@ -197,6 +197,59 @@ def test_layernorm(dev, C):
     assert (out.cpu() - F.layer_norm(x, (C,), gm, bt, 1e-5)).abs().max() < 2e-5
 
 
+ATTN_CASES = [
+    # B, N, Nk, C, packed qkv, fused LayerNorm + bias + residual
+    (2, 1024, 26, 384, False, True),    # cross-attention sub-block, 26 layout tokens, 32x32 level (4 rows per warp)
+    (16, 256, 26, 576, False, True),    # 16x16 level (2 rows per warp)
+    (2, 64, 26, 960, False, True),      # 8x8 level: K/V chunk of 26 keys fills shared memory
+    (2, 1024, 26, 384, False, False),
+    (3, 64, 64, 960, True, False),      # self-attention of the 8x8 level: 3 key chunks, online softmax rescale
+    (2, 16, 16, 960, True, False),      # 4x4 level of the f16f8 configs
+    (1, 37, 5, 24, False, True),        # ragged rows, tiny C (parity fixtures)
+    (2, 50, 50, 132, True, False),      # C/4 not a multiple of 32, keys not a multiple of the chunk
+    (2, 50, 45, 132, False, True),
+    (1, 9, 1, 768, False, False),       # a single key (CLIP pooled condition): softmax == 1
+    (1, 40, 64, 384, False, True),      # 64 keys with 4 rows per warp: two chunks
+]
+
+
+@pytest.mark.parametrize("case", ATTN_CASES)
+def test_attn_small_matches_torch(dev, case):
+    """CrossAttention.forward core (attention.py:178-191): einsum * scale -> softmax -> einsum, optionally with the
+    block's LayerNorm in front and the to_out bias + residual behind (attention.py:324); fp64 reference."""
+    B, N, Nk, C, packed, fused = case
+    g = torch.Generator().manual_seed(B * 1000 + N + Nk + C)
+    scale = C ** -0.5
+    P = _prog(dev)
+    out = torch.empty(B, N, C, device=dev)
+    kw, ln_w, ln_b, bias = {}, None, None, None
+    if packed:
+        assert N == Nk and not fused
+        qkv = torch.randn(B, N, 3 * C, generator=g) * 2
+        q, k, v = qkv[..., :C], qkv[..., C:2 * C], qkv[..., 2 * C:]
+        d = qkv.to(dev)
+        P.attn_small(d, d, d, out, B=B, N=N, Nk=Nk, Cdim=C, scale=scale, q_sb=N * 3 * C, q_ld=3 * C, k_off=C, k_sb=N * 3 * C,
+                     k_ld=3 * C, v_off=2 * C, v_sb=N * 3 * C, v_ld=3 * C)
+    else:
+        q = torch.randn(B, N, C, generator=g) * 2 + 0.3
+        k = torch.randn(B, Nk, C, generator=g) * 2
+        v = torch.randn(B, Nk, C, generator=g)
+        qd = q.to(dev)
+        if fused:
+            ln_w, ln_b, bias = torch.randn(C, generator=g), torch.randn(C, generator=g), torch.randn(C, generator=g)
+            kw = dict(ln=(ln_w.to(dev), ln_b.to(dev)), bias=bias.to(dev), res=qd)
+        P.attn_small(qd, k.to(dev), v.to(dev), out, B=B, N=N, Nk=Nk, Cdim=C, scale=scale, q_sb=N * C, q_ld=C,
+                     k_sb=Nk * C, k_ld=C, v_sb=Nk * C, v_ld=C, **kw)
+    P.run()
+    torch.cuda.synchronize()
+    qq = F.layer_norm(q.double(), (C,), ln_w.double(), ln_b.double(), 1e-5) if fused else q.double()
+    sim = torch.einsum("bid,bjd->bij", qq, k.double()) * scale
+    ref = torch.einsum("bij,bjd->bid", sim.softmax(-1), v.double())
+    if fused:
+        ref = ref + bias.double() + q.double()
+    assert (out.cpu().double() - ref).abs().max() < 3e-5
+
+
 @pytest.mark.parametrize("n,ld", [(5, 32), (26, 32), (64, 64), (1024, 1024), (4096, 4096), (1500, 1504)])
 def test_softmax(dev, n, ld):
     g = torch.Generator().manual_seed(n)

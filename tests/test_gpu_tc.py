@@ -52,9 +52,22 @@ CASES = [
 ]
 
 
+@pytest.fixture(params=["auto", "force", "off"])
+def sk_mode(request):
+    """Stream-K schedule of conv2d_tc: cost model / whenever legal / never (FRIDO_SK, read at every launch)."""
+    import os
+    old = os.environ.get("FRIDO_SK")
+    os.environ["FRIDO_SK"] = {"auto": "1", "force": "2", "off": "0"}[request.param]
+    yield request.param
+    if old is None:
+        os.environ.pop("FRIDO_SK", None)
+    else:
+        os.environ["FRIDO_SK"] = old
+
+
 @pytest.mark.parametrize("eng", [1, 2, 3])
 @pytest.mark.parametrize("case", CASES)
-def test_conv_tc_matches_torch(dev, case, eng):
+def test_conv_tc_matches_torch(dev, case, eng, sk_mode):
     from frido_b200 import _lib as L
     from frido_b200.program import Program, Src
     B, C0, C1, Cout, H, W, k = case
@@ -81,6 +94,10 @@ def test_conv_tc_matches_torch(dev, case, eng):
     _run(P, dev)
     got = out.view(B, H, W, Cout).permute(0, 3, 1, 2).cpu()
     got2 = out2.view(B, H, W, Cout).permute(0, 3, 1, 2).cpu()
+    if sk_mode != "off":  # replay: the stream-K arrival counters must be back at zero, and the fixed summation order
+        P.run()           # of the partial sums makes the result bit-reproducible
+        torch.cuda.synchronize(dev)
+        assert torch.equal(out2.view(B, H, W, Cout).permute(0, 3, 1, 2).cpu(), got2)
     e1, e2 = (got - ref).abs().max().item(), (got2 - ref2).abs().max().item()
     print(f"case {case} engine {eng}: err {e1:.3e} {e2:.3e} (ref absmax {ref.abs().max():.2f})")
     tol = TOL if eng == 1 else tol3(Cin * k * k, ref.abs().max().item()) + (1e-4 if eng == 3 else 0.0)  # bf16x3 products ~2^-16

@@ -45,3 +45,19 @@ print('--- slowest convs')
 for t, r in sorted(rows, reverse=True)[:25]:
     print(r)
 print('--- least efficient big convs')
+rows_eff = [(fl_t, r) for fl_t, r in ((float(r.split()[-2]), r) for _, r in rows) if True]
+# --- the same step as one captured CUDA graph (what the sampler replays): ms per replay
+plan.step.capture()
+torch.cuda.synchronize()
+reps = int(os.environ.get('PREPS', '30'))
+a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+for _ in range(3):
+    plan.step.replay()
+a.record(stream)
+for _ in range(reps):
+    plan.step.replay()
+b.record(stream)
+torch.cuda.synchronize()
+print(f"GRAPH stage {stage} B {B}: {a.elapsed_time(b) / reps:.3f} ms per step replay ({len(ops)} ops; env "
+      f"FRIDO_SK={os.environ.get('FRIDO_SK', '1')} FRIDO_ATTN_SMALL={os.environ.get('FRIDO_ATTN_SMALL', '1')} "
+      f"FRIDO_PDL={os.environ.get('FRIDO_PDL', '-')})")
