@@ -48,7 +48,7 @@ class NormActParams(C.Structure):
 
 class LayerNormParams(C.Structure):
     _fields_ = [("x", c_p), ("rows", c_l), ("C", c_i), ("eps", c_f), ("gamma", c_p), ("beta", c_p),
-                ("round_tf32", c_i), ("out", c_p)]
+                ("round_tf32", c_i), ("out", c_p), ("out_hi", c_p), ("out_lo", c_p)]
 
 
 class SoftmaxParams(C.Structure):

@@ -20,6 +20,14 @@ namespace frido {
 constexpr int ATTN_WARPS = 8;
 constexpr int ATTN_SMEM_MAX = 200 * 1024;
 
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit_wait_all() {
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+}
+
 // reduce-scatter over the warp: on return v[0] of lane L holds the sum over all lanes of the caller's v[L]
 __device__ __forceinline__ void warp_transpose_sum(float (&v)[32], int lane) {
 #pragma unroll
@@ -63,6 +71,22 @@ __global__ void __launch_bounds__(ATTN_WARPS * 32, SINGLE ? 2 : 1) attn_small_ke
   pdl_trigger();
   pdl_wait();
 
+  const float* kb = p.k + (int64_t)b * p.k_sb;
+  const float* vb = p.v + (int64_t)b * p.v_sb;
+  // K/V chunk -> shared memory with cp.async: every thread fires all of its 16-byte copies without waiting, so the
+  // staging runs at L2 bandwidth instead of one load latency per float4 (and overlaps the q load / LayerNorm below)
+  auto stage = [&](int j0, int kc) {
+    for (int kk = warp; kk < kc; kk += ATTN_WARPS) {
+      const float4* ks = reinterpret_cast<const float4*>(kb + (int64_t)(j0 + kk) * p.k_ld);
+      const float4* vs = reinterpret_cast<const float4*>(vb + (int64_t)(j0 + kk) * p.v_ld);
+      for (int quad = lane; quad < Q; quad += 32) {
+        cp_async16(Ks + kk * Q + quad, ks + quad);
+        cp_async16(Vs + kk * Q + quad, vs + quad);
+      }
+    }
+  };
+  stage(0, min(KC, p.Nk));
+
   float4 q[R][NJ], o[R][NJ];
 #pragma unroll
   for (int r = 0; r < R; ++r) {
@@ -105,22 +129,16 @@ __global__ void __launch_bounds__(ATTN_WARPS * 32, SINGLE ? 2 : 1) attn_small_ke
       }
     }
   }
-  const float* kb = p.k + (int64_t)b * p.k_sb;
-  const float* vb = p.v + (int64_t)b * p.v_sb;
   float m_run = -INFINITY, l_run = 0.f;  // of row lane % R
 
   int j0 = 0;
   do {
     const int kc = min(KC, p.Nk - j0);
-    if (!SINGLE) __syncthreads();  // every warp is done with the previous chunk
-    for (int kk = warp; kk < kc; kk += ATTN_WARPS) {
-      const float4* ks = reinterpret_cast<const float4*>(kb + (int64_t)(j0 + kk) * p.k_ld);
-      const float4* vs = reinterpret_cast<const float4*>(vb + (int64_t)(j0 + kk) * p.v_ld);
-      for (int quad = lane; quad < Q; quad += 32) {
-        Ks[kk * Q + quad] = __ldg(ks + quad);
-        Vs[kk * Q + quad] = __ldg(vs + quad);
-      }
+    if (!SINGLE && j0 > 0) {
+      __syncthreads();  // every warp is done with the previous chunk
+      stage(j0, kc);
     }
+    cp_async_commit_wait_all();
     __syncthreads();
     // ---- scores: block blk covers keys [blk*KB, blk*KB + KB); lane L ends up with pair (key blk*KB + L/R, row L%R)
     float sv[NB];

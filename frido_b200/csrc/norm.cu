@@ -223,6 +223,14 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const FridoLayerNormPara
       o.w = (v[j].w - mean) * rstd * g.w + b.w;
       if (p.round_tf32) { o.x = round_tf32(o.x); o.y = round_tf32(o.y); o.z = round_tf32(o.z); o.w = round_tf32(o.w); }
       reinterpret_cast<float4*>(out)[q] = o;
+      if (p.out_hi) {
+        uint16_t h0, h1, h2, h3, l0, l1, l2, l3;
+        split_bf16(o.x, h0, l0); split_bf16(o.y, h1, l1); split_bf16(o.z, h2, l2); split_bf16(o.w, h3, l3);
+        reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(p.out_hi) + (int64_t)warp * p.C)[q] =
+            make_uint2((uint32_t)h0 | ((uint32_t)h1 << 16), (uint32_t)h2 | ((uint32_t)h3 << 16));
+        reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(p.out_lo) + (int64_t)warp * p.C)[q] =
+            make_uint2((uint32_t)l0 | ((uint32_t)l1 << 16), (uint32_t)l2 | ((uint32_t)l3 << 16));
+      }
     }
   }
 }
@@ -466,6 +474,7 @@ extern "C" int frido_norm_act(const FridoNormActParams* p, void* stream) {
 extern "C" int frido_layernorm(const FridoLayerNormParams* p, void* stream) {
   if (!p || !p->x || !p->out || !p->gamma || !p->beta) return set_error(FRIDO_E_ARG, "layernorm: null pointer");
   if ((p->C & 3) || p->C > LN_MAXQ * 128 || p->rows <= 0) return set_error(FRIDO_E_ARG, "layernorm: unsupported C");
+  if ((p->out_hi != nullptr) != (p->out_lo != nullptr)) return set_error(FRIDO_E_ARG, "layernorm: out_hi / out_lo come together");
   const int64_t blocks = (p->rows + 7) / 8;
   launch_pdl(layernorm_kernel, dim3((unsigned)blocks), dim3(256), 0, (cudaStream_t)stream, *p);
   return check_launch("layernorm");

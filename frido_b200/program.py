@@ -308,10 +308,13 @@ class Program:
         self.hold(a0, a1, sums, gamma, beta, gb, out)
         self._add(L.OP_NORM_ACT, p, tag)
 
-    def layernorm(self, x, gamma, beta, out, *, rows, Cdim, eps=1e-5, round_tf32=0, tag="layernorm"):
+    def layernorm(self, x, gamma, beta, out, *, rows, Cdim, eps=1e-5, round_tf32=0, out_pair=None, tag="layernorm"):
         p = L.LayerNormParams()
         p.x, p.rows, p.C, p.eps, p.gamma, p.beta = x.data_ptr(), rows, Cdim, eps, gamma.data_ptr(), beta.data_ptr()
         p.round_tf32, p.out = round_tf32, out.data_ptr()
+        if out_pair is not None:
+            p.out_hi, p.out_lo = out_pair[0].data_ptr(), out_pair[1].data_ptr()
+            self.hold(out_pair[0], out_pair[1])
         self.hold(x, gamma, beta, out)
         self._add(L.OP_LAYERNORM, p, tag)
 

@@ -365,6 +365,59 @@ class UNetPlan:
             S.release(sc)
         return o
 
+    @staticmethod
+    def _fold_self_attn():
+        import os
+        return os.environ.get("FRIDO_ATTN_FOLD", "1") == "1"
+
+    def _self_attention_folded(self, hcur, blk, C, N):
+        """h1 = hcur + to_out(attn1(LN(hcur))) (attention.py:323) with the weight products folded at pack time
+        (attention.py:172-191 re-associated; x = LN(hcur)):
+          sim = (x Wq^T)(x Wk^T)^T = (x (Wk^T Wq)^T) x^T        -> one C x C projection, the keys are x itself
+          to_out(P (x Wv^T)) = P (x (Wo Wv)^T) + b_o            -> the values carry to_out; bias + residual ride on PV
+        which removes the to_out GEMM and the key projection from every step."""
+        S, B = self.step, self.B
+        ca = blk.attn1
+        scale = float(C) ** -0.5
+        def fold_a():  # [C,C] weight of x -> x (Wk^T Wq)^T, product taken in fp64
+            return (ca.to_k.weight.detach().double().t() @ ca.to_q.weight.detach().double()).float().contiguous()
+
+        def fold_v():  # [C,C] weight of x -> x (Wo Wv)^T
+            return (ca.to_out[0].weight.detach().double() @ ca.to_v.weight.detach().double()).float().contiguous()
+
+        b_o = self._vec(ca.to_out[0].bias)
+        ln = S.buf(B, N, C)
+        h1 = S.buf(B, N, C)
+        if self._small_attn(N, C):  # fewer than 128 tokens per image (8x8 level): fused SIMT attention kernel
+            S.layernorm(hcur, self._vec(blk.norm1.weight), self._vec(blk.norm1.bias), ln, rows=B * N, Cdim=C)
+            w_av = self._packed(lambda: torch.cat([fold_a(), fold_v()], 0).contiguous())
+            qv = S.buf(B, N, 2 * C)
+            S.linear(ln, w_av, qv, M=B * N, K=C, N=2 * C, tag="attn1.qv")
+            S.attn_small(qv, ln, qv, h1, B=B, N=N, Nk=N, Cdim=C, scale=scale, q_sb=N * 2 * C, q_ld=2 * C, k_sb=N * C, k_ld=C,
+                         v_off=C, v_sb=N * 2 * C, v_ld=2 * C, bias=b_o, res=hcur, tag="attn1.fused")
+            S.release(qv); S.release(ln)
+            return h1
+        pair = S.tc_code == 3
+        bf = dict(dtype=torch.bfloat16)
+        ln_pair = (S.buf(B, N, C, **bf), S.buf(B, N, C, **bf)) if pair else None
+        S.layernorm(hcur, self._vec(blk.norm1.weight), self._vec(blk.norm1.bias), ln, rows=B * N, Cdim=C, round_tf32=S.R,
+                    out_pair=ln_pair)
+        t = S.buf(B, N, C)
+        S.linear(ln, self._packed(fold_a), t, M=B * N, K=C, N=C, round_tf32=S.R, tag="attn1.q")
+        vT = S.buf(B, C, N)
+        vT_pair = (S.buf(B, C, N, **bf), S.buf(B, C, N, **bf)) if pair else None
+        S.conv(Src(ln, C, N * C, 0, C, 1), self._packed(fold_v), vT, B=B, Hin=1, Win=N, Hout=1, Wout=N, Cout=C, o_sb=C * N, o_sp=1, o_sn=N,
+               round_tf32=S.R, out_pair=vT_pair, tag="attn1.vT")
+        sc = S.buf(B, N, N)
+        S.conv(Src(t, C, N * C, 0, C, 1), ln, sc, B=B, Hin=1, Win=N, Hout=1, Wout=N, Cout=N, w_sb=N * C, w_ld=C,
+               o_sb=N * N, o_sp=N, w_pair=ln_pair, tag="attn1.qk^T")
+        S.softmax(sc, rows=B * N, n=N, ld=N, scale=scale, round_tf32=S.R, tag="attn1.softmax")
+        S.conv(Src(sc, N, N * N, 0, N, 1), vT, h1, B=B, Hin=1, Win=N, Hout=1, Wout=N, Cout=C, w_sb=C * N, w_ld=N,
+               w_pair=vT_pair, bias=b_o, res=hcur, tag="attn1.pv")
+        for t_ in (t, vT, sc, ln) + (ln_pair + vT_pair if pair else ()):
+            S.release(t_)
+        return h1
+
     def _small_attn(self, Nk, C):
         """Key sequences too short for a 128-row tensor-core tile go to the fused SIMT attention kernel (csrc/attn.cu)."""
         import os
@@ -412,14 +465,18 @@ class UNetPlan:
                  bias=self._vec(st.proj_in.bias), tag="st.proj_in")
         S.release(t)
         for blk in st.transformer_blocks:
-            ln = S.buf(B, N, C)
-            S.layernorm(hcur, self._vec(blk.norm1.weight), self._vec(blk.norm1.bias), ln, rows=B * N, Cdim=C, round_tf32=S.R)
-            o = self._attention(ln, C, N, blk.attn1, None, "attn1")
-            S.release(ln)
-            h1 = S.buf(B, N, C)
-            S.linear(o, self._vec(blk.attn1.to_out[0].weight), h1, M=B * N, K=C, N=C, bias=self._vec(blk.attn1.to_out[0].bias),
-                     res=hcur, tag="attn1.out")
-            S.release(o); S.release(hcur)
+            if self._fold_self_attn():
+                h1 = self._self_attention_folded(hcur, blk, C, N)
+            else:
+                ln = S.buf(B, N, C)
+                S.layernorm(hcur, self._vec(blk.norm1.weight), self._vec(blk.norm1.bias), ln, rows=B * N, Cdim=C, round_tf32=S.R)
+                o = self._attention(ln, C, N, blk.attn1, None, "attn1")
+                S.release(ln)
+                h1 = S.buf(B, N, C)
+                S.linear(o, self._vec(blk.attn1.to_out[0].weight), h1, M=B * N, K=C, N=C,
+                         bias=self._vec(blk.attn1.to_out[0].bias), res=hcur, tag="attn1.out")
+                S.release(o)
+            S.release(hcur)
             if self._small_attn(self.Lc, C):
                 # h2 = h1 + to_out(attn2(LN(h1), ctx)) in one launch: LayerNorm, 26-key attention against the folded
                 # operands, output bias and residual (attention.py:324)

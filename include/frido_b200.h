@@ -124,6 +124,8 @@ int frido_norm_act(const FridoNormActParams* p, void* stream);
 typedef struct FridoLayerNormParams {
   const float* x; int64_t rows; int32_t C; float eps;
   const float* gamma; const float* beta; int32_t round_tf32; float* out;
+  void* out_hi; void* out_lo; /* optional bf16 pair copy of the output (see FridoConvParams.out_hi): the LayerNorm output is
+                                 the K operand of the folded self-attention score matmul */
 } FridoLayerNormParams;
 int frido_layernorm(const FridoLayerNormParams* p, void* stream);
 

@@ -34,6 +34,15 @@ for i, op in enumerate(ops):
         fl = 2 * c.B * c.Hout * c.Wout * c.Cout * c.ksize * c.ksize * (c.c0 + c.c1)
         key = f"{tags[i]} e{c.engine}"
         rows.append((t, f"{tags[i]:16s} eng{c.engine} B{c.B} {c.Hout}x{c.Wout} cin{c.c0}+{c.c1} cout{c.Cout} k{c.ksize} s{c.stride}  {t*1e3:8.1f} us  {fl/t/1e9:8.1f} TF/s"))
+    elif op.kind == L.OP_ATTN:
+        a = op.u.attn
+        fl = 4 * a.B * a.N * a.Nk * a.C; key = tags[i]
+        rows.append((t, f"{tags[i]:16s} attn B{a.B} N{a.N} Nk{a.Nk} C{a.C} ln{int(bool(a.ln_gamma))}  {t*1e3:8.1f} us  {fl/t/1e9:8.1f} TF/s"))
+    elif op.kind == L.OP_NORM_ACT:
+        a = op.u.norm_act
+        by = 4 * a.B * a.HW * (a.c0 + a.c1) * (4 if a.gb else 2)
+        fl = 0; key = tags[i]
+        rows.append((t, f"{tags[i]:16s} norm B{a.B} HW{a.HW} C{a.c0}+{a.c1} spade{int(bool(a.gb))}  {t*1e3:8.1f} us  {by/t/1e6:8.1f} GB/s"))
     else:
         fl = 0; key = tags[i] if op.kind != L.OP_GN_STATS else 'gn_stats'
     agg[key][0] += t; agg[key][1] += fl; agg[key][2] += 1
@@ -42,7 +51,7 @@ print(f"stage {stage} B {B}: total eager per-op sum {tot:.2f} ms over {len(ops)}
 for k, (t, fl, n) in sorted(agg.items(), key=lambda kv: -kv[1][0]):
     print(f"{k:24s} n={n:3d} {t:8.3f} ms {100*t/tot:5.1f}%  {fl/t/1e9 if t else 0:8.1f} TF/s")
 print('--- slowest convs')
-for t, r in sorted(rows, reverse=True)[:25]:
+for t, r in sorted(rows, reverse=True)[:60]:
     print(r)
 print('--- least efficient big convs')
 rows_eff = [(fl_t, r) for fl_t, r in ((float(r.split()[-2]), r) for _, r in rows) if True]
