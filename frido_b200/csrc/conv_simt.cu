@@ -264,6 +264,72 @@ __global__ void __launch_bounds__(128) conv_smallcout_kernel(const FridoConvPara
     }
 }
 
+// Same job for the common case (3x3, stride 1, one dense NHWC source: the UNet and decoder output heads), tiled: a CTA owns
+// 8 x 16 output pixels, stages their 10 x 18 input halo tile in shared memory with cp.async (zero fill outside the
+// image) and then every thread reads its 9 x Cin window from there instead of re-fetching it through L1 with 768-byte
+// lane strides.  Pixel stride in shared memory is Cin + 4 floats, so the float4 reads of a warp are conflict-free.
+constexpr int SCT_TH = 8, SCT_TW = 16;
+__global__ void __launch_bounds__(SCT_TH * SCT_TW) conv_smallcout_tiled_kernel(const FridoConvParams p) {
+  extern __shared__ float4 sct_sm[];
+  const int Cin = p.c0;
+  const int Q = Cin >> 2, QS = Q + 1;       // quads per pixel, padded stride
+  const int Ktot = 9 * Cin;
+  float4* xs = sct_sm;                                                  // [(TH+2)*(TW+2)][QS]
+  float* wsm = reinterpret_cast<float*>(sct_sm + (SCT_TH + 2) * (SCT_TW + 2) * QS);  // [Cout][Ktot]
+  const int b = blockIdx.z;
+  const int oy0 = blockIdx.y * SCT_TH, ox0 = blockIdx.x * SCT_TW;
+  const float* a0 = p.a0 + (int64_t)b * p.a0_sb;
+  const int64_t wld = p.w_ld ? p.w_ld : Ktot;
+  for (int i = threadIdx.x; i < (SCT_TH + 2) * (SCT_TW + 2) * Q; i += blockDim.x) {
+    const int pix = i / Q, quad = i - pix * Q;
+    const int ly = pix / (SCT_TW + 2), lx = pix - ly * (SCT_TW + 2);
+    const int iy = oy0 + ly - 1, ix = ox0 + lx - 1;
+    const bool in = iy >= 0 && iy < p.Hin && ix >= 0 && ix < p.Win;
+    const float* src = a0 + (in ? (int64_t)iy * p.a0_sy + (int64_t)ix * p.a0_sx + 4 * quad : 0);
+    const uint32_t dst = (uint32_t)__cvta_generic_to_shared(xs + pix * QS + quad);
+    const int nbytes = in ? 16 : 0;  // src-size 0: the 16 destination bytes are zero-filled (conv padding)
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(nbytes) : "memory");
+  }
+  for (int i = threadIdx.x; i < p.Cout * Ktot; i += blockDim.x) wsm[i] = p.w[(int64_t)b * p.w_sb + (int64_t)(i / Ktot) * wld + (i % Ktot)];
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncthreads();
+  const int ty = threadIdx.x / SCT_TW, tx = threadIdx.x - ty * SCT_TW;
+  const int oy = oy0 + ty, ox = ox0 + tx;
+  float acc[SC_MAXCOUT] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int tap = 0; tap < 9; ++tap) {
+    const int dy = tap / 3, dx = tap - dy * 3;
+    const float4* xr = xs + ((ty + dy) * (SCT_TW + 2) + tx + dx) * QS;
+    const float* wt = wsm + tap * Cin;
+    for (int c4 = 0; c4 < Q; ++c4) {
+      const float4 v = xr[c4];
+#pragma unroll
+      for (int n = 0; n < SC_MAXCOUT; ++n)
+        if (n < p.Cout) {
+          const float4 w = *reinterpret_cast<const float4*>(wt + n * Ktot + 4 * c4);
+          acc[n] = fmaf(v.x, w.x, fmaf(v.y, w.y, fmaf(v.z, w.z, fmaf(v.w, w.w, acc[n]))));
+        }
+    }
+  }
+  if (oy >= p.Hout || ox >= p.Wout) return;
+  const int pix = oy * p.Wout + ox;
+  float* out = p.out + (int64_t)b * p.o_sb + (int64_t)pix * p.o_sp;
+  const float* res = p.res ? p.res + (int64_t)b * p.o_sb + (int64_t)pix * p.o_sp : nullptr;
+#pragma unroll
+  for (int n = 0; n < SC_MAXCOUT; ++n)
+    if (n < p.Cout) {
+      float t = acc[n] * p.alpha;
+      if (p.bias) t += __ldg(p.bias + n);
+      if (p.rowvec) t += __ldg(p.rowvec + (int64_t)b * p.rowvec_sb + n);
+      if (res) t += res[(int64_t)n * p.o_sn];
+      if (p.act == FRIDO_ACT_RELU) t = fmaxf(t, 0.f);
+      else if (p.act == FRIDO_ACT_SILU) t = silu_f(t);
+      else if (p.act == FRIDO_ACT_GELU) t = gelu_erf(t);
+      out[(int64_t)n * p.o_sn] = p.round_tf32 ? round_tf32(t) : t;
+    }
+}
+
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 int conv2d_simt(const FridoConvParams* p, cudaStream_t s) {
@@ -288,7 +354,15 @@ int conv2d_simt(const FridoConvParams* p, cudaStream_t s) {
     static bool attr = false;
     if (!attr) {
       cudaFuncSetAttribute(conv_smallcout_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+      cudaFuncSetAttribute(conv_smallcout_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
       attr = true;
+    }
+    const size_t smem_t = (size_t)(SCT_TH + 2) * (SCT_TW + 2) * (Cin / 4 + 1) * 16 + smem;
+    if (p->ksize == 3 && p->stride == 1 && p->pad == 1 && p->ups == 1 && !p->a1 && p->Hout == p->Hin && p->Wout == p->Win &&
+        smem_t <= 200 * 1024 && p->Hout * p->Wout >= 256) {
+      dim3 g((p->Wout + SCT_TW - 1) / SCT_TW, (p->Hout + SCT_TH - 1) / SCT_TH, p->B);
+      conv_smallcout_tiled_kernel<<<g, SCT_TH * SCT_TW, smem_t, s>>>(*p);
+      return check_launch("conv2d_smallcout_tiled");
     }
     dim3 g((p->Hout * p->Wout + 127) / 128, p->B);
     conv_smallcout_kernel<<<g, 128, smem, s>>>(*p);

@@ -261,7 +261,7 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
 // pair copy), so the per-chunk loop carries no dead branches.  Measured with ncu on a K=384 GEMM: the generic epilogue
 // executes ~300 instructions per 32x16 chunk at ~12 clocks each (instruction-cache misses and branch resolution on the
 // uniform feature tests) and, at 22 k clocks per tile, outlasts the 12 k-step main loop it is supposed to hide behind.
-enum { EPI_GENERIC = 0, EPI_BIAS = 1, EPI_BIAS_RES = 2, EPI_BIAS_RV_CS = 3, EPI_BIAS_RES_CS = 4, EPI_BIAS_GEGLU = 5, EPI_BIAS_CS = 6, EPI_COUNT = 7 };
+enum { EPI_GENERIC = 0, EPI_BIAS = 1, EPI_BIAS_RES = 2, EPI_BIAS_RV_CS = 3, EPI_BIAS_RES_CS = 4, EPI_BIAS_GEGLU = 5, EPI_BIAS_CS = 6, EPI_BIAS_PAIR = 7, EPI_COUNT = 8 };
 
 template <int MODE, int EPI>
 __global__ void __launch_bounds__(MODE ? TC_THREADS_X3 : TC_THREADS, 1)
@@ -432,7 +432,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
     const bool has_rv = GEN ? (p.rowvec != nullptr) : (EPI == EPI_BIAS_RV_CS);
     const bool has_bias = p.bias != nullptr;
     const bool has_cs = GEN ? (p.csum != nullptr) : (EPI == EPI_BIAS_RV_CS || EPI == EPI_BIAS_RES_CS || EPI == EPI_BIAS_CS);
-    const bool has_pair = GEN ? (p.out_hi != nullptr) : false;
+    const bool has_pair = GEN ? (p.out_hi != nullptr) : (EPI == EPI_BIAS_PAIR);
     const bool rnd = GEN ? (p.round_tf32 != 0) : false;
     const float alpha = GEN ? p.alpha : 1.0f;
     const int act = GEN ? p.act : (EPI == EPI_BIAS_GEGLU ? FRIDO_ACT_GEGLU_FAST : FRIDO_ACT_NONE);
@@ -875,7 +875,7 @@ int conv2d_tc(const FridoConvParams* p, cudaStream_t s) {
     };
     const int64_t dp_tiles = (int64_t)m_tiles * (p->Cout / bn);
     const double dp_cost = (double)((dp_tiles + sms - 1) / sms) * ksteps * stage_clk(bn);
-    double best = sk_env == 2 ? 1e30 : 0.9 * dp_cost;
+    double best = sk_env == 2 ? 1e30 : 0.95 * dp_cost;
     const bool forced_bn = getenv("FRIDO_TC_FORCE_BN") != nullptr;
     if (sk_env && p->sk_ws && (reinterpret_cast<uintptr_t>(p->sk_ws) & 15) == 0 && ksteps >= 8) {
       for (int i = 0; i < 4; ++i) {
@@ -937,7 +937,8 @@ int conv2d_tc(const FridoConvParams* p, cudaStream_t s) {
   using KernelFn = void (*)(CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, TcParams);
   static const KernelFn bf_kernels[EPI_COUNT] = {conv_tc_kernel<2, EPI_GENERIC>, conv_tc_kernel<2, EPI_BIAS>, conv_tc_kernel<2, EPI_BIAS_RES>,
                                                 conv_tc_kernel<2, EPI_BIAS_RV_CS>, conv_tc_kernel<2, EPI_BIAS_RES_CS>,
-                                                conv_tc_kernel<2, EPI_BIAS_GEGLU>, conv_tc_kernel<2, EPI_BIAS_CS>};
+                                                conv_tc_kernel<2, EPI_BIAS_GEGLU>, conv_tc_kernel<2, EPI_BIAS_CS>,
+                                                conv_tc_kernel<2, EPI_BIAS_PAIR>};
   static bool attr = false;
   if (!attr) {
     bool ok = cudaFuncSetAttribute(conv_tc_kernel<0, EPI_GENERIC>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES) == cudaSuccess &&
@@ -952,7 +953,9 @@ int conv2d_tc(const FridoConvParams* p, cudaStream_t s) {
   {
     const char* e = getenv("FRIDO_EPI_SPEC");  // 0 = always the generic epilogue (A/B aid)
     const bool spec = !e || atoi(e) != 0;
-    if (bf && spec && p->o_sn == 1 && p->alpha == 1.0f && !p->round_tf32 && !p->out_hi) {
+    if (bf && spec && p->o_sn == 1 && p->alpha == 1.0f && !p->round_tf32 && p->out_hi) {
+      if (p->out && p->act == FRIDO_ACT_NONE && !p->res && !p->rowvec && !p->chan_sums) epi = EPI_BIAS_PAIR;
+    } else if (bf && spec && p->o_sn == 1 && p->alpha == 1.0f && !p->round_tf32) {
       const bool res = p->res != nullptr, rv = p->rowvec != nullptr, cs = p->chan_sums != nullptr;
       if (p->act == FRIDO_ACT_NONE) {
         if (!res && !rv && !cs) epi = EPI_BIAS;

@@ -404,15 +404,18 @@ class UNetPlan:
                     out_pair=ln_pair)
         t = S.buf(B, N, C)
         S.linear(ln, self._packed(fold_a), t, M=B * N, K=C, N=C, round_tf32=S.R, tag="attn1.q")
-        vT = S.buf(B, C, N)
-        vT_pair = (S.buf(B, C, N, **bf), S.buf(B, C, N, **bf)) if pair else None
-        S.conv(Src(ln, C, N * C, 0, C, 1), self._packed(fold_v), vT, B=B, Hin=1, Win=N, Hout=1, Wout=N, Cout=C, o_sb=C * N, o_sp=1, o_sn=N,
-               round_tf32=S.R, out_pair=vT_pair, tag="attn1.vT")
+        # V'^T for all images at once, [C, B*N]: the folded value weights (Wo Wv) are the A operand (C rows) and the
+        # tokens x play the weight matrix ([B*N rows][K=C], bf16 pair from the LayerNorm) - a dense row-major store
+        # instead of a transposing epilogue.  Image b's V'^T is the column block [b*N, (b+1)*N).
+        vT = S.buf(C, B * N)
+        vT_pair = (S.buf(C, B * N, **bf), S.buf(C, B * N, **bf)) if pair else None
+        S.conv(Src(self._packed(fold_v), C, 0, 0, C, 1), ln, vT, B=1, Hin=1, Win=C, Hout=1, Wout=C, Cout=B * N, w_ld=C,
+               round_tf32=S.R, out_pair=vT_pair, w_pair=ln_pair, tag="attn1.vT")
         sc = S.buf(B, N, N)
         S.conv(Src(t, C, N * C, 0, C, 1), ln, sc, B=B, Hin=1, Win=N, Hout=1, Wout=N, Cout=N, w_sb=N * C, w_ld=C,
                o_sb=N * N, o_sp=N, w_pair=ln_pair, tag="attn1.qk^T")
         S.softmax(sc, rows=B * N, n=N, ld=N, scale=scale, round_tf32=S.R, tag="attn1.softmax")
-        S.conv(Src(sc, N, N * N, 0, N, 1), vT, h1, B=B, Hin=1, Win=N, Hout=1, Wout=N, Cout=C, w_sb=C * N, w_ld=N,
+        S.conv(Src(sc, N, N * N, 0, N, 1), vT, h1, B=B, Hin=1, Win=N, Hout=1, Wout=N, Cout=C, w_sb=N, w_ld=B * N,
                w_pair=vT_pair, bias=b_o, res=hcur, tag="attn1.pv")
         for t_ in (t, vT, sc, ln) + (ln_pair + vT_pair if pair else ()):
             S.release(t_)

@@ -45,6 +45,8 @@ CONV_CASES = [
     (2, 3, 32, 8, 8, 3, 1, 1),       # Cin = 3 (pre_input_blocks)
     (2, 32, 3, 8, 8, 3, 1, 1),       # Cout = 3 (out head)
     (1, 6, 6, 8, 8, 1, 1, 1),        # post_quant_conv
+    (2, 64, 3, 32, 32, 3, 1, 1),     # out head at >= 256 pixels: shared-memory tiled small-Cout kernel
+    (1, 32, 3, 19, 21, 3, 1, 1),     # same, ragged (partial tiles, zero-filled halo)
 ]
 
 
