@@ -102,7 +102,8 @@ class MhaParams(C.Structure):
 class AttnParams(C.Structure):
     _fields_ = [("q", c_p), ("q_sb", c_l), ("q_ld", c_l), ("k", c_p), ("k_sb", c_l), ("k_ld", c_l), ("v", c_p), ("v_sb", c_l), ("v_ld", c_l),
                 ("B", c_i), ("N", c_i), ("Nk", c_i), ("C", c_i), ("scale", c_f), ("out", c_p), ("o_sb", c_l), ("o_ld", c_l),
-                ("ln_gamma", c_p), ("ln_beta", c_p), ("ln_eps", c_f), ("bias", c_p), ("res", c_p), ("r_sb", c_l), ("r_ld", c_l)]
+                ("ln_gamma", c_p), ("ln_beta", c_p), ("ln_eps", c_f), ("bias", c_p), ("res", c_p), ("r_sb", c_l), ("r_ld", c_l),
+                ("ln2_gamma", c_p), ("ln2_beta", c_p), ("ln2_eps", c_f), ("out2", c_p)]
 
 
 class ConvT2dParams(C.Structure):

@@ -221,23 +221,50 @@ __global__ void __launch_bounds__(ATTN_WARPS * 32, SINGLE ? 2 : 1) attn_small_ke
   for (int r = 0; r < R; ++r) {
     const int n = row0 + r;
     const float inv = 1.0f / __shfl_sync(0xffffffffu, l_run, r);
-    if (n < p.N) {
-      float4* op = reinterpret_cast<float4*>(p.out + (int64_t)b * p.o_sb + (int64_t)n * p.o_ld);
-      const float4* rp = p.res ? reinterpret_cast<const float4*>(p.res + (int64_t)b * p.r_sb + (int64_t)n * p.r_ld) : nullptr;
+    const bool live = n < p.N;
+    float4* op = reinterpret_cast<float4*>(p.out + (int64_t)b * p.o_sb + (int64_t)(live ? n : 0) * p.o_ld);
+    const float4* rp = p.res ? reinterpret_cast<const float4*>(p.res + (int64_t)b * p.r_sb + (int64_t)(live ? n : 0) * p.r_ld) : nullptr;
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+      const int quad = lane + 32 * j;
+      float4 v = make_float4(o[r][j].x * inv, o[r][j].y * inv, o[r][j].z * inv, o[r][j].w * inv);
+      if (quad < Q && live) {
+        if (p.bias) {
+          const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bias) + quad);
+          v.x += bb.x; v.y += bb.y; v.z += bb.z; v.w += bb.w;
+        }
+        if (rp) {
+          const float4 rr = __ldg(rp + quad);
+          v.x += rr.x; v.y += rr.y; v.z += rr.z; v.w += rr.w;
+        }
+        op[quad] = v;
+        s += (v.x + v.y) + (v.z + v.w);
+      } else {
+        v = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      o[r][j] = v;
+    }
+    if (p.ln2_gamma) {  // LayerNorm of the row just produced (the block's next norm, attention.py:325), second output
+      const float mean = warp_sum(s) / (float)p.C;
+      float ss = 0.f;
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) {
+        if (lane + 32 * j < Q) {
+          const float a = o[r][j].x - mean, c = o[r][j].y - mean, d = o[r][j].z - mean, e = o[r][j].w - mean;
+          ss += (a * a + c * c) + (d * d + e * e);
+        }
+      }
+      const float rstd = rsqrtf(warp_sum(ss) / (float)p.C + p.ln2_eps);
+      float4* o2 = reinterpret_cast<float4*>(p.out2 + (int64_t)b * p.o_sb + (int64_t)(live ? n : 0) * p.o_ld);
 #pragma unroll
       for (int j = 0; j < NJ; ++j) {
         const int quad = lane + 32 * j;
-        if (quad < Q) {
-          float4 v = make_float4(o[r][j].x * inv, o[r][j].y * inv, o[r][j].z * inv, o[r][j].w * inv);
-          if (p.bias) {
-            const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bias) + quad);
-            v.x += bb.x; v.y += bb.y; v.z += bb.z; v.w += bb.w;
-          }
-          if (rp) {
-            const float4 rr = __ldg(rp + quad);
-            v.x += rr.x; v.y += rr.y; v.z += rr.z; v.w += rr.w;
-          }
-          op[quad] = v;
+        if (quad < Q && live) {
+          const float4 g = __ldg(reinterpret_cast<const float4*>(p.ln2_gamma) + quad);
+          const float4 be = __ldg(reinterpret_cast<const float4*>(p.ln2_beta) + quad);
+          o2[quad] = make_float4((o[r][j].x - mean) * rstd * g.x + be.x, (o[r][j].y - mean) * rstd * g.y + be.y,
+                                 (o[r][j].z - mean) * rstd * g.z + be.z, (o[r][j].w - mean) * rstd * g.w + be.w);
         }
       }
     }
@@ -272,11 +299,13 @@ extern "C" int frido_attn_small(const FridoAttnParams* p, void* stream) {
     return set_error(FRIDO_E_ARG, "attn_small: bad argument");
   if ((p->C & 3) || p->C > 1024) return set_error(FRIDO_E_ARG, "attn_small: C must be a multiple of 4, at most 1024");
   if ((p->ln_gamma != nullptr) != (p->ln_beta != nullptr)) return set_error(FRIDO_E_ARG, "attn_small: ln_gamma / ln_beta come together");
+  if ((p->ln2_gamma != nullptr) != (p->ln2_beta != nullptr) || (p->ln2_gamma != nullptr) != (p->out2 != nullptr))
+    return set_error(FRIDO_E_ARG, "attn_small: ln2_gamma / ln2_beta / out2 come together");
   const int64_t strides[10] = {p->q_sb, p->q_ld, p->k_sb, p->k_ld, p->v_sb, p->v_ld, p->o_sb, p->o_ld, p->r_sb, p->r_ld};
   for (int i = 0; i < 10; ++i)
     if (strides[i] & 3) return set_error(FRIDO_E_ARG, "attn_small: strides must be multiples of 4 floats");
-  const void* ptrs[8] = {p->q, p->k, p->v, p->out, p->ln_gamma, p->ln_beta, p->bias, p->res};
-  for (int i = 0; i < 8; ++i)
+  const void* ptrs[11] = {p->q, p->k, p->v, p->out, p->ln_gamma, p->ln_beta, p->bias, p->res, p->ln2_gamma, p->ln2_beta, p->out2};
+  for (int i = 0; i < 11; ++i)
     if (reinterpret_cast<uintptr_t>(ptrs[i]) & 15) return set_error(FRIDO_E_ARG, "attn_small: pointers must be 16-byte aligned");
   int KC = ATTN_SMEM_MAX / (8 * p->C);  // K and V chunk, fp32
   if (KC > 32) KC = 32;

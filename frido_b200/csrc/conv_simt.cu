@@ -268,8 +268,10 @@ __global__ void __launch_bounds__(128) conv_smallcout_kernel(const FridoConvPara
 // 8 x 16 output pixels, stages their 10 x 18 input halo tile in shared memory with cp.async (zero fill outside the
 // image) and then every thread reads its 9 x Cin window from there instead of re-fetching it through L1 with 768-byte
 // lane strides.  Pixel stride in shared memory is Cin + 4 floats, so the float4 reads of a warp are conflict-free.
-constexpr int SCT_TH = 8, SCT_TW = 16;
-__global__ void __launch_bounds__(SCT_TH * SCT_TW) conv_smallcout_tiled_kernel(const FridoConvParams p) {
+// Four threads share a pixel (a quarter of the input channels each, partial sums combined through shared memory): with
+// 160 KB of staging only one CTA fits an SM, so the 512 threads are what hides the shared-memory latency.
+constexpr int SCT_TH = 8, SCT_TW = 16, SCT_PARTS = 4;
+__global__ void __launch_bounds__(SCT_TH * SCT_TW * SCT_PARTS) conv_smallcout_tiled_kernel(const FridoConvParams p) {
   extern __shared__ float4 sct_sm[];
   const int Cin = p.c0;
   const int Q = Cin >> 2, QS = Q + 1;       // quads per pixel, padded stride
@@ -294,15 +296,17 @@ __global__ void __launch_bounds__(SCT_TH * SCT_TW) conv_smallcout_tiled_kernel(c
   asm volatile("cp.async.commit_group;" ::: "memory");
   asm volatile("cp.async.wait_group 0;" ::: "memory");
   __syncthreads();
-  const int ty = threadIdx.x / SCT_TW, tx = threadIdx.x - ty * SCT_TW;
+  const int part = threadIdx.x / (SCT_TH * SCT_TW), tp = threadIdx.x - part * (SCT_TH * SCT_TW);
+  const int ty = tp / SCT_TW, tx = tp - ty * SCT_TW;
   const int oy = oy0 + ty, ox = ox0 + tx;
+  const int c_lo = part * Q / SCT_PARTS, c_hi = (part + 1) * Q / SCT_PARTS;
   float acc[SC_MAXCOUT] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
   for (int tap = 0; tap < 9; ++tap) {
     const int dy = tap / 3, dx = tap - dy * 3;
     const float4* xr = xs + ((ty + dy) * (SCT_TW + 2) + tx + dx) * QS;
     const float* wt = wsm + tap * Cin;
-    for (int c4 = 0; c4 < Q; ++c4) {
+    for (int c4 = c_lo; c4 < c_hi; ++c4) {
       const float4 v = xr[c4];
 #pragma unroll
       for (int n = 0; n < SC_MAXCOUT; ++n)
@@ -312,14 +316,23 @@ __global__ void __launch_bounds__(SCT_TH * SCT_TW) conv_smallcout_tiled_kernel(c
         }
     }
   }
-  if (oy >= p.Hout || ox >= p.Wout) return;
+  // combine the channel quarters in a fixed order (the staged input tile is dead by now: reuse its memory)
+  __syncthreads();
+  float* red = reinterpret_cast<float*>(xs);  // [PARTS][SC_MAXCOUT][TH*TW]
+#pragma unroll
+  for (int n = 0; n < SC_MAXCOUT; ++n) red[(part * SC_MAXCOUT + n) * (SCT_TH * SCT_TW) + tp] = acc[n];
+  __syncthreads();
+  if (part != 0 || oy >= p.Hout || ox >= p.Wout) return;
   const int pix = oy * p.Wout + ox;
   float* out = p.out + (int64_t)b * p.o_sb + (int64_t)pix * p.o_sp;
   const float* res = p.res ? p.res + (int64_t)b * p.o_sb + (int64_t)pix * p.o_sp : nullptr;
 #pragma unroll
   for (int n = 0; n < SC_MAXCOUT; ++n)
     if (n < p.Cout) {
-      float t = acc[n] * p.alpha;
+      float t = 0.f;
+#pragma unroll
+      for (int q = 0; q < SCT_PARTS; ++q) t += red[(q * SC_MAXCOUT + n) * (SCT_TH * SCT_TW) + tp];
+      t *= p.alpha;
       if (p.bias) t += __ldg(p.bias + n);
       if (p.rowvec) t += __ldg(p.rowvec + (int64_t)b * p.rowvec_sb + n);
       if (res) t += res[(int64_t)n * p.o_sn];
@@ -328,6 +341,53 @@ __global__ void __launch_bounds__(SCT_TH * SCT_TW) conv_smallcout_tiled_kernel(c
       else if (p.act == FRIDO_ACT_GELU) t = gelu_erf(t);
       out[(int64_t)n * p.o_sn] = p.round_tf32 ? round_tf32(t) : t;
     }
+}
+
+// Linear layer with at most 16 rows (the timestep-embedding MLP and the 22 stacked ResBlock embedding projections,
+// pyunet.py:561-565,225-231: M = batch): weight streaming is the whole cost, so one warp owns an output column, reads its
+// weight row once (coalesced float4) and accumulates all rows against the input held in shared memory.
+constexpr int SM_MAXROWS = 16, SM_COLS_PER_WARP = 4;
+__global__ void __launch_bounds__(256) linear_smallm_kernel(const FridoConvParams p) {
+  extern __shared__ float4 lsm_x[];  // [M][K/4]
+  const int M = p.Wout, K = p.c0, Q = K >> 2;
+  for (int i = threadIdx.x; i < M * Q; i += blockDim.x) {
+    const int m = i / Q, q = i - m * Q;
+    lsm_x[i] = __ldg(reinterpret_cast<const float4*>(p.a0 + (int64_t)m * p.a0_sx) + q);
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t wld = p.w_ld ? p.w_ld : K;
+  for (int c = 0; c < SM_COLS_PER_WARP; ++c) {
+    const int n = (blockIdx.x * 8 + warp) * SM_COLS_PER_WARP + c;
+    if (n >= p.Cout) return;
+    const float4* wr = reinterpret_cast<const float4*>(p.w + (int64_t)n * wld);
+    float acc[SM_MAXROWS];
+#pragma unroll
+    for (int m = 0; m < SM_MAXROWS; ++m) acc[m] = 0.f;
+    for (int q = lane; q < Q; q += 32) {
+      const float4 w = __ldg(wr + q);
+#pragma unroll
+      for (int m = 0; m < SM_MAXROWS; ++m)
+        if (m < M) {
+          const float4 x = lsm_x[m * Q + q];
+          acc[m] = fmaf(x.x, w.x, fmaf(x.y, w.y, fmaf(x.z, w.z, fmaf(x.w, w.w, acc[m]))));
+        }
+    }
+#pragma unroll
+    for (int m = 0; m < SM_MAXROWS; ++m)
+      if (m < M) {
+        float t = warp_sum(acc[m]) * p.alpha;
+        if (lane == 0) {
+          if (p.bias) t += __ldg(p.bias + n);
+          if (p.rowvec) t += __ldg(p.rowvec + n);
+          if (p.res) t += p.res[(int64_t)m * p.o_sp + n];
+          if (p.act == FRIDO_ACT_RELU) t = fmaxf(t, 0.f);
+          else if (p.act == FRIDO_ACT_SILU) t = silu_f(t);
+          else if (p.act == FRIDO_ACT_GELU) t = gelu_erf(t);
+          p.out[(int64_t)m * p.o_sp + n] = p.round_tf32 ? round_tf32(t) : t;
+        }
+      }
+  }
 }
 
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
@@ -349,6 +409,18 @@ int conv2d_simt(const FridoConvParams* p, cudaStream_t s) {
   const bool vecW = (Ktot % 4 == 0) && aligned16(p->w) && (p->w_sb % 4 == 0) && (p->w_ld % 4 == 0);
   if ((p->out_hi != nullptr) != (p->out_lo != nullptr) || (p->out_hi && p->act == FRIDO_ACT_GEGLU))
     return set_error(FRIDO_E_ARG, "conv2d: out_hi/out_lo must come together and not with GEGLU");
+  if (vecA && vecW && !p->out_hi && !p->a1 && p->ksize == 1 && p->stride == 1 && p->ups == 1 && p->B == 1 && p->Hout == 1 && p->Hin == 1 &&
+      p->Wout == p->Win && p->Wout <= SM_MAXROWS && p->o_sn == 1 && p->w_sb == 0 && p->act != FRIDO_ACT_GEGLU && p->act != FRIDO_ACT_GEGLU_FAST &&
+      p->Cout >= 64 && (size_t)p->Wout * Cin * 4 <= 96 * 1024) {
+    static bool attr_l = false;
+    if (!attr_l) {
+      cudaFuncSetAttribute(linear_smallm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+      attr_l = true;
+    }
+    const int cols_per_cta = 8 * SM_COLS_PER_WARP;
+    linear_smallm_kernel<<<(p->Cout + cols_per_cta - 1) / cols_per_cta, 256, (size_t)p->Wout * Cin * 4, s>>>(*p);
+    return check_launch("linear_smallm");
+  }
   if (vecA && !p->out_hi && p->Cout <= SC_MAXCOUT && p->act != FRIDO_ACT_GEGLU && (size_t)p->Cout * Ktot * 4 <= 96 * 1024 && Ktot % 4 == 0) {
     const size_t smem = (size_t)p->Cout * Ktot * 4;
     static bool attr = false;
@@ -361,7 +433,7 @@ int conv2d_simt(const FridoConvParams* p, cudaStream_t s) {
     if (p->ksize == 3 && p->stride == 1 && p->pad == 1 && p->ups == 1 && !p->a1 && p->Hout == p->Hin && p->Wout == p->Win &&
         smem_t <= 200 * 1024 && p->Hout * p->Wout >= 256) {
       dim3 g((p->Wout + SCT_TW - 1) / SCT_TW, (p->Hout + SCT_TH - 1) / SCT_TH, p->B);
-      conv_smallcout_tiled_kernel<<<g, SCT_TH * SCT_TW, smem_t, s>>>(*p);
+      conv_smallcout_tiled_kernel<<<g, SCT_TH * SCT_TW * SCT_PARTS, smem_t, s>>>(*p);
       return check_launch("conv2d_smallcout_tiled");
     }
     dim3 g((p->Hout * p->Wout + 127) / 128, p->B);

@@ -252,7 +252,7 @@ class Program:
         self._add(L.OP_MHA, p, tag)
 
     def attn_small(self, q, k, v, out, *, B, N, Nk, Cdim, scale, q_off=0, q_sb, q_ld, k_off=0, k_sb, k_ld, v_off=0, v_sb, v_ld,
-                   ln=None, ln_eps=1e-5, bias=None, res=None, tag="attn_small"):
+                   ln=None, ln_eps=1e-5, bias=None, res=None, ln2=None, ln2_eps=1e-5, out2=None, tag="attn_small"):
         """Fused softmax(scale LN(q) k^T) v + bias + res for short key sequences (csrc/attn.cu); offsets/strides in
         floats; ln = (gamma, beta) applies a LayerNorm to the query rows first; res is a dense [B,N,C] tensor."""
         p = L.AttnParams()
@@ -267,6 +267,9 @@ class Program:
         p.bias = _ptr(bias)
         if res is not None:
             p.res, p.r_sb, p.r_ld = res.data_ptr(), N * Cdim, Cdim
+        if ln2 is not None:  # second output: LayerNorm of the produced rows (the block's next norm)
+            p.ln2_gamma, p.ln2_beta, p.ln2_eps, p.out2 = ln2[0].data_ptr(), ln2[1].data_ptr(), ln2_eps, out2.data_ptr()
+            self.hold(ln2[0], ln2[1], out2)
         self.hold(q, k, v, out, bias, res)
         self.flops += 4 * B * N * Nk * Cdim
         self._add(L.OP_ATTN, p, tag)

@@ -480,15 +480,18 @@ class UNetPlan:
                          bias=self._vec(blk.attn1.to_out[0].bias), res=hcur, tag="attn1.out")
                 S.release(o)
             S.release(hcur)
+            ln3 = None
             if self._small_attn(self.Lc, C):
                 # h2 = h1 + to_out(attn2(LN(h1), ctx)) in one launch: LayerNorm, 26-key attention against the folded
                 # operands, output bias and residual (attention.py:324)
                 kf, vf = self._ctx_folded(blk.attn2, C)
                 h2 = S.buf(B, N, C)
+                ln3 = S.buf(B, N, C)  # LayerNorm(h2) for the feed-forward, produced by the same launch
                 S.attn_small(h1, kf, vf, h2, B=B, N=N, Nk=self.Lc, Cdim=C, scale=float(C) ** -0.5, q_sb=N * C, q_ld=C,
                              k_sb=self.Lc * C, k_ld=C, v_sb=self.Lc * C, v_ld=C,
                              ln=(self._vec(blk.norm2.weight), self._vec(blk.norm2.bias)),
-                             bias=self._vec(blk.attn2.to_out[0].bias), res=h1, tag="attn2.block")
+                             bias=self._vec(blk.attn2.to_out[0].bias), res=h1,
+                             ln2=(self._vec(blk.norm3.weight), self._vec(blk.norm3.bias)), out2=ln3, tag="attn2.block")
                 S.release(h1)
             else:
                 ln = S.buf(B, N, C)
@@ -499,8 +502,11 @@ class UNetPlan:
                 S.linear(o, self._vec(blk.attn2.to_out[0].weight), h2, M=B * N, K=C, N=C,
                          bias=self._vec(blk.attn2.to_out[0].bias), res=h1, tag="attn2.out")
                 S.release(o); S.release(h1)
-            ln = S.buf(B, N, C)
-            S.layernorm(h2, self._vec(blk.norm3.weight), self._vec(blk.norm3.bias), ln, rows=B * N, Cdim=C, round_tf32=S.R)
+            if ln3 is not None:
+                ln = ln3
+            else:
+                ln = S.buf(B, N, C)
+                S.layernorm(h2, self._vec(blk.norm3.weight), self._vec(blk.norm3.bias), ln, rows=B * N, Cdim=C, round_tf32=S.R)
             proj = blk.ff.net[0].proj
             inner = proj.weight.shape[0] // 2
 

@@ -241,6 +241,8 @@ typedef struct FridoAttnParams {
   const float* ln_gamma; const float* ln_beta; float ln_eps; /* optional LayerNorm of the query rows ([C] each) */
   const float* bias;                                          /* optional [C] added to every output row */
   const float* res; int64_t r_sb, r_ld;                       /* optional residual, addressed like out */
+  const float* ln2_gamma; const float* ln2_beta; float ln2_eps; /* optional: also write LayerNorm(out row) ... */
+  float* out2;                                                /* ... here, addressed like out (the block's next norm) */
 } FridoAttnParams;
 int frido_attn_small(const FridoAttnParams* p, void* stream);
 

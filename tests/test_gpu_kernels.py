@@ -199,6 +199,22 @@ def test_layernorm(dev, C):
     assert (out.cpu() - F.layer_norm(x, (C,), gm, bt, 1e-5)).abs().max() < 2e-5
 
 
+@pytest.mark.parametrize("M,K,N", [(16, 768, 832), (3, 192, 768), (1, 768, 14976)])
+def test_linear_small_m(dev, M, K, N):
+    """time_embed / emb_layers (pyunet.py:561-565,225-231): M = batch rows through the weight-streaming kernel."""
+    from frido_b200 import _lib as L
+    g = torch.Generator().manual_seed(M + K + N)
+    x = torch.randn(M, K, generator=g)
+    w = torch.randn(N, K, generator=g) / np.sqrt(K)
+    b, rv = torch.randn(N, generator=g), torch.randn(N, generator=g)
+    P = _prog(dev)
+    out = torch.empty(M, N, device=dev)
+    P.linear(x.to(dev), w.to(dev), out, M=M, K=K, N=N, bias=b.to(dev), rowvec=rv.to(dev), act=L.ACT_SILU)
+    P.run()
+    ref = F.silu(x.double() @ w.double().t() + b.double() + rv.double())
+    assert (out.cpu().double() - ref).abs().max() < 2e-5
+
+
 ATTN_CASES = [
     # B, N, Nk, C, packed qkv, fused LayerNorm + bias + residual
     (2, 1024, 26, 384, False, True),    # cross-attention sub-block, 26 layout tokens, 32x32 level (4 rows per warp)
@@ -239,7 +255,9 @@ def test_attn_small_matches_torch(dev, case):
         qd = q.to(dev)
         if fused:
             ln_w, ln_b, bias = torch.randn(C, generator=g), torch.randn(C, generator=g), torch.randn(C, generator=g)
-            kw = dict(ln=(ln_w.to(dev), ln_b.to(dev)), bias=bias.to(dev), res=qd)
+            ln2_w, ln2_b = torch.randn(C, generator=g), torch.randn(C, generator=g)
+            out2 = torch.empty(B, N, C, device=dev)
+            kw = dict(ln=(ln_w.to(dev), ln_b.to(dev)), bias=bias.to(dev), res=qd, ln2=(ln2_w.to(dev), ln2_b.to(dev)), out2=out2)
         P.attn_small(qd, k.to(dev), v.to(dev), out, B=B, N=N, Nk=Nk, Cdim=C, scale=scale, q_sb=N * C, q_ld=C,
                      k_sb=Nk * C, k_ld=C, v_sb=Nk * C, v_ld=C, **kw)
     P.run()
@@ -249,6 +267,8 @@ def test_attn_small_matches_torch(dev, case):
     ref = torch.einsum("bij,bjd->bid", sim.softmax(-1), v.double())
     if fused:
         ref = ref + bias.double() + q.double()
+        ref2 = F.layer_norm(ref, (C,), ln2_w.double(), ln2_b.double(), 1e-5)  # the block's next LayerNorm, second output
+        assert (out2.cpu().double() - ref2).abs().max() < 5e-5
     assert (out.cpu().double() - ref).abs().max() < 3e-5
 
 
