@@ -34,7 +34,14 @@ inline bool pdl_enabled() {
   return on;
 }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
-__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+#ifndef FRIDO_PDL_TRIGGER
+#define FRIDO_PDL_TRIGGER 1  // 0: no explicit trigger - a dependent launch then starts when this grid completes
+#endif
+__device__ __forceinline__ void pdl_trigger() {
+#if FRIDO_PDL_TRIGGER
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
+}
 
 template <typename... KArgs, typename... Args>
 inline void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {

@@ -397,6 +397,7 @@ int conv2d_simt(const FridoConvParams* p, cudaStream_t s) {
   if (p->B <= 0 || p->Hout <= 0 || p->Wout <= 0 || p->Cout <= 0 || p->c0 <= 0 || p->c1 < 0)
     return set_error(FRIDO_E_ARG, "conv2d: bad shape");
   if ((p->c1 > 0) != (p->a1 != nullptr)) return set_error(FRIDO_E_ARG, "conv2d: a1/c1 mismatch");
+  if (p->x0 || p->x1 || p->cx0 || p->cx1) return set_error(FRIDO_E_ARG, "conv2d: the fused 1x1 side input is a tcgen05-engine feature");
   if (p->ups != 1 && p->ups != 2) return set_error(FRIDO_E_ARG, "conv2d: ups must be 1 or 2");
   if (p->ksize != 1 && p->ksize != 3) return set_error(FRIDO_E_ARG, "conv2d: ksize must be 1 or 3");
   if (p->act == FRIDO_ACT_GEGLU && (p->Cout & 1)) return set_error(FRIDO_E_ARG, "conv2d: GEGLU needs even Cout");

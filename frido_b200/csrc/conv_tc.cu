@@ -46,6 +46,7 @@ constexpr int TC_THREADS_X3 = TC_THREADS + TC_SPLIT_THREADS;  // + splitter warp
 struct TcParams {
   int B, Hout, Wout, Cout;
   int c0, c1;           // channels per source (multiples of 32)
+  int cx0, cx1;         // fused 1x1 side input (ResBlock skip_connection): extra K steps after the taps, from maps x0 | x1
   int ksize, pad, stride;
   int TW, TH, TB;       // tile = TW*TH*TB = 128 pixels (powers of two)
   int lTW, lTH;         // log2
@@ -266,7 +267,8 @@ enum { EPI_GENERIC = 0, EPI_BIAS = 1, EPI_BIAS_RES = 2, EPI_BIAS_RV_CS = 3, EPI_
 template <int MODE, int EPI>
 __global__ void __launch_bounds__(MODE ? TC_THREADS_X3 : TC_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
-               const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_wlo, const TcParams p) {
+               const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_wlo,
+               const __grid_constant__ CUtensorMap map_x0, const __grid_constant__ CUtensorMap map_x1, const TcParams p) {
   constexpr bool X3 = MODE == 1;
   constexpr bool BF = MODE == 2;
   extern __shared__ uint8_t smem_raw[];
@@ -296,7 +298,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
   const int Cin = p.c0 + p.c1;
   const int kchunks = Cin / TC_BK;
   const int taps = p.ksize * p.ksize;
-  const int ksteps = taps * kchunks;
+  const int ksteps_main = taps * kchunks;
+  const int ksteps = ksteps_main + (p.cx0 + p.cx1) / TC_BK;  // + the 1x1 side input's channels
   const int m_tiles = p.tiles_x * p.tiles_y * p.tiles_b;
   const int total_tiles = m_tiles * p.tiles_n;
   const uint32_t stage_tx = TC_A_BYTES + b_bytes * (BF ? 2u : 1u);
@@ -304,6 +307,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&map_a0);
     if (p.c1) prefetch_tmap(&map_a1);
+    if (p.cx0) prefetch_tmap(&map_x0);
+    if (p.cx1) prefetch_tmap(&map_x1);
     prefetch_tmap(&map_w);
     if (BF) prefetch_tmap(&map_wlo);
     for (int s = 0; s < NS; ++s) {
@@ -343,19 +348,26 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
         const int ox0 = tx * p.TW, oy0 = ty * p.TH, b0 = tb * p.TB;
         const int n0 = nt * p.BN;
         for (int ks = k0; ks < k1; ++ks) {
-          const int tap = ks / kchunks;
-          const int kc = ks - tap * kchunks;
-          const int dy = tap / p.ksize, dx = tap - dy * p.ksize;
           mbar_wait(empty_bar(stage), phase ^ 1);
           const uint32_t sa = smem_base + stage * stage_bytes;
           const uint32_t sb = sa + off_w;
           mbar_expect_tx(full_bar(stage), stage_tx);
-          const int ch = kc * TC_BK;
-          const int cx = ox0 * p.stride + dx - p.pad, cy = oy0 * p.stride + dy - p.pad;
-          if (ch < p.c0) tma_load_4d(sa, &map_a0, full_bar(stage), ch, cx, cy, b0);
-          else           tma_load_4d(sa, &map_a1, full_bar(stage), ch - p.c0, cx, cy, b0);
-          tma_load_3d(sb, &map_w, full_bar(stage), tap * Cin + ch, n0, p.w_batched ? b0 : 0);
-          if (BF) tma_load_3d(sa + off_wlo, &map_wlo, full_bar(stage), tap * Cin + ch, n0, p.w_batched ? b0 : 0);
+          if (ks < ksteps_main) {
+            const int tap = ks / kchunks;
+            const int kc = ks - tap * kchunks;
+            const int dy = tap / p.ksize, dx = tap - dy * p.ksize;
+            const int ch = kc * TC_BK;
+            const int cx = ox0 * p.stride + dx - p.pad, cy = oy0 * p.stride + dy - p.pad;
+            if (ch < p.c0) tma_load_4d(sa, &map_a0, full_bar(stage), ch, cx, cy, b0);
+            else           tma_load_4d(sa, &map_a1, full_bar(stage), ch - p.c0, cx, cy, b0);
+          } else {  // side input: the pixel itself (a 1x1 tap), channels of x0 then x1
+            const int ch = (ks - ksteps_main) * TC_BK;
+            if (ch < p.cx0) tma_load_4d(sa, &map_x0, full_bar(stage), ch, ox0 * p.stride, oy0 * p.stride, b0);
+            else            tma_load_4d(sa, &map_x1, full_bar(stage), ch - p.cx0, ox0 * p.stride, oy0 * p.stride, b0);
+          }
+          // weight columns run [tap][channel] then the side input's channels: k-step ks starts at column 32 * ks
+          tma_load_3d(sb, &map_w, full_bar(stage), ks * TC_BK, n0, p.w_batched ? b0 : 0);
+          if (BF) tma_load_3d(sa + off_wlo, &map_wlo, full_bar(stage), ks * TC_BK, n0, p.w_batched ? b0 : 0);
           if (++stage == NS) { stage = 0; phase ^= 1; }
         }
       }
@@ -807,7 +819,13 @@ int conv2d_tc(const FridoConvParams* p, cudaStream_t s) {
   if (p->a0_sx % 4 || p->a0_sy % 4 || p->a0_sb % 4 || (p->a1 && (p->a1_sx % 4 || p->a1_sy % 4 || p->a1_sb % 4)))
     return set_error(FRIDO_E_ARG, "conv2d_tc: strides must be multiples of 16 bytes");
   const int Cin = p->c0 + p->c1;
-  const int64_t Ktot = (int64_t)p->ksize * p->ksize * Cin;
+  if (p->cx0 < 0 || p->cx1 < 0 || p->cx0 % TC_BK || p->cx1 % TC_BK || (p->cx0 > 0) != (p->x0 != nullptr) || (p->cx1 > 0) != (p->x1 != nullptr) ||
+      (p->cx1 > 0 && p->cx0 == 0))
+    return set_error(FRIDO_E_ARG, "conv2d_tc: side input channels must be multiples of 32 and match x0/x1");
+  if (p->cx0 && (p->stride != 1 || p->w_sb || !a16(p->x0) || (p->x1 && !a16(p->x1)) || p->x0_sx % 4 || p->x0_sy % 4 || p->x0_sb % 4 ||
+                 (p->x1 && (p->x1_sx % 4 || p->x1_sy % 4 || p->x1_sb % 4))))
+    return set_error(FRIDO_E_ARG, "conv2d_tc: side input needs stride 1, shared weights and 16-byte aligned strides");
+  const int64_t Ktot = (int64_t)p->ksize * p->ksize * Cin + p->cx0 + p->cx1;
   const int64_t w_ld = p->w_ld ? p->w_ld : Ktot;
   const bool bf = p->engine == 3;
   if (bf && !p->w_lo) return set_error(FRIDO_E_ARG, "conv2d_tc: engine 3 (bf16x3) needs pre-split weights (w = bf16 hi, w_lo = bf16 lo)");
@@ -821,7 +839,7 @@ int conv2d_tc(const FridoConvParams* p, cudaStream_t s) {
 
   TcParams t;
   t.B = p->B; t.Hout = p->Hout; t.Wout = p->Wout; t.Cout = p->Cout;
-  t.c0 = p->c0; t.c1 = p->c1; t.ksize = p->ksize; t.pad = p->pad; t.stride = p->stride;
+  t.c0 = p->c0; t.c1 = p->c1; t.cx0 = p->cx0; t.cx1 = p->cx1; t.ksize = p->ksize; t.pad = p->pad; t.stride = p->stride;
   t.TW = next_pow2(p->Wout) < TC_BM ? next_pow2(p->Wout) : TC_BM;
   t.TH = next_pow2(p->Hout) < TC_BM / t.TW ? next_pow2(p->Hout) : TC_BM / t.TW;
   t.TB = TC_BM / (t.TW * t.TH);
@@ -864,7 +882,7 @@ int conv2d_tc(const FridoConvParams* p, cudaStream_t s) {
   t.sk = 0; t.sk_per = 0; t.sk_ws = nullptr; t.sk_cnt = nullptr;
   int sk_grid = 0;
   {
-    const int ksteps = p->ksize * p->ksize * (Cin / TC_BK);
+    const int ksteps = p->ksize * p->ksize * (Cin / TC_BK) + (p->cx0 + p->cx1) / TC_BK;
     const char* sk_e = getenv("FRIDO_SK");  // 0 = off, 1 = cost model (default), 2 = whenever legal (tests)
     const int sk_env = sk_e ? atoi(sk_e) : 1;
     auto stage_clk = [&](int n) {
@@ -916,7 +934,7 @@ int conv2d_tc(const FridoConvParams* p, cudaStream_t s) {
   if (p->chan_sums && (p->o_sn != 1 || (p->act == FRIDO_ACT_GEGLU || p->act == FRIDO_ACT_GEGLU_FAST) || t.TW * t.TH < 32 || t.TB > 4))
     return set_error(FRIDO_E_ARG, "conv2d_tc: chan_sums needs a dense NHWC output, no GEGLU and >= 32 pixels per image");
 
-  CUtensorMap ma0, ma1, mw, mwlo;
+  CUtensorMap ma0, ma1, mw, mwlo, mx0, mx1;
   if (!make_map4(&ma0, p->a0, p->c0, p->Win, p->Hin, p->B, p->a0_sx, p->a0_sy, p->a0_sb, t.TW, t.TH, t.TB, (uint32_t)p->stride))
     return set_error(FRIDO_E_ARG, "conv2d_tc: cuTensorMapEncodeTiled(a0) failed");
   if (p->a1) {
@@ -925,6 +943,11 @@ int conv2d_tc(const FridoConvParams* p, cudaStream_t s) {
   } else {
     ma1 = ma0;
   }
+  mx0 = ma0; mx1 = ma0;
+  if (p->x0 && !make_map4(&mx0, p->x0, p->cx0, p->Wout, p->Hout, p->B, p->x0_sx, p->x0_sy, p->x0_sb, t.TW, t.TH, t.TB, 1u))
+    return set_error(FRIDO_E_ARG, "conv2d_tc: cuTensorMapEncodeTiled(x0) failed");
+  if (p->x1 && !make_map4(&mx1, p->x1, p->cx1, p->Wout, p->Hout, p->B, p->x1_sx, p->x1_sy, p->x1_sb, t.TW, t.TH, t.TB, 1u))
+    return set_error(FRIDO_E_ARG, "conv2d_tc: cuTensorMapEncodeTiled(x1) failed");
   if (!make_map3(&mw, p->w, Ktot, p->Cout, p->w_sb ? p->B : 1, w_ld, p->w_sb, bn, bf))
     return set_error(FRIDO_E_ARG, "conv2d_tc: cuTensorMapEncodeTiled(w) failed");
   if (bf) {
@@ -934,7 +957,7 @@ int conv2d_tc(const FridoConvParams* p, cudaStream_t s) {
     mwlo = mw;
   }
 
-  using KernelFn = void (*)(CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, TcParams);
+  using KernelFn = void (*)(CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, TcParams);
   static const KernelFn bf_kernels[EPI_COUNT] = {conv_tc_kernel<2, EPI_GENERIC>, conv_tc_kernel<2, EPI_BIAS>, conv_tc_kernel<2, EPI_BIAS_RES>,
                                                 conv_tc_kernel<2, EPI_BIAS_RV_CS>, conv_tc_kernel<2, EPI_BIAS_RES_CS>,
                                                 conv_tc_kernel<2, EPI_BIAS_GEGLU>, conv_tc_kernel<2, EPI_BIAS_CS>,
@@ -975,9 +998,9 @@ int conv2d_tc(const FridoConvParams* p, cudaStream_t s) {
   if (bf && t.stages > TC_BF_MAX_STAGES) t.stages = TC_BF_MAX_STAGES;
   const int total = m_tiles * t.tiles_n;
   const int grid = t.sk ? sk_grid : (total < sms ? total : sms);
-  if (bf) launch_pdl(bf_kernels[epi], dim3(grid), dim3(TC_THREADS_X3), TC_SMEM_BYTES, s, ma0, ma1, mw, mwlo, t);
-  else if (x3) launch_pdl(conv_tc_kernel<1, EPI_GENERIC>, dim3(grid), dim3(TC_THREADS_X3), TC_SMEM_BYTES, s, ma0, ma1, mw, mwlo, t);
-  else launch_pdl(conv_tc_kernel<0, EPI_GENERIC>, dim3(grid), dim3(TC_THREADS), TC_SMEM_BYTES, s, ma0, ma1, mw, mwlo, t);
+  if (bf) launch_pdl(bf_kernels[epi], dim3(grid), dim3(TC_THREADS_X3), TC_SMEM_BYTES, s, ma0, ma1, mw, mwlo, mx0, mx1, t);
+  else if (x3) launch_pdl(conv_tc_kernel<1, EPI_GENERIC>, dim3(grid), dim3(TC_THREADS_X3), TC_SMEM_BYTES, s, ma0, ma1, mw, mwlo, mx0, mx1, t);
+  else launch_pdl(conv_tc_kernel<0, EPI_GENERIC>, dim3(grid), dim3(TC_THREADS), TC_SMEM_BYTES, s, ma0, ma1, mw, mwlo, mx0, mx1, t);
   return check_launch(bf ? "conv2d_tc(bf16x3)" : x3 ? "conv2d_tc(3xTF32)" : "conv2d_tc");
 }
 

@@ -131,12 +131,14 @@ class Program:
     def conv(self, a0, w, out, *, B, Hin, Win, Hout, Wout, Cout, ksize=1, stride=1, pad=0, ups=1, a1=None,
              bias=None, rowvec=None, rowvec_sb=0, res=None, alpha=1.0, act=L.ACT_NONE, o_sb=None, o_sp=None, o_sn=1,
              w_sb=0, w_ld=0, w_off=0, out_off=0, round_tf32=0, engine=None, csum=None, out_pair=None, w_pair=None,
-             alg_flops=None, tag="conv"):
+             alg_flops=None, side=None, tag="conv"):
         """Returns True when `csum` (per-channel GroupNorm sums of the output, [B,Cout,2] fp64) was attached to the op:
         only the tcgen05 engines accumulate it, for dense NHWC outputs with >= 32 pixels per image."""
         if engine is None:
             engine = self.tc_code if (self.tc_code and self._tc_ok(a0, a1, B, Hin, Win, Hout, Wout, Cout, ksize, stride, pad, ups, w,
                                                                w_sb, w_ld, w_off, act, o_sb, o_sp, o_sn, out, out_off, res)) else 0
+        if side is not None and engine == 0:
+            raise L.FridoError("conv: the fused 1x1 side input needs the tcgen05 engine (check Program.tc_eligible first)")
         if engine != 0 and act == L.ACT_GEGLU and os.environ.get("FRIDO_EXACT_ERF", "0") != "1":
             act = L.ACT_GEGLU_FAST  # tensor-core epilogue: erf by A&S 7.1.26 (|err| < 5e-7), see csrc/common.cuh
         if engine == 0 and act == L.ACT_GEGLU_FAST:
@@ -149,6 +151,16 @@ class Program:
         if a1 is not None:
             p.a1, p.c1 = a1.ptr, a1.C
             p.a1_sb, p.a1_sy, p.a1_sx, p.a1_sc = a1.sb, a1.sy, a1.sx, a1.sc
+        c_side = 0
+        if side is not None:  # (x0, x1 or None): 1x1 side input accumulated into the same output (ResBlock skip_connection)
+            x0, x1 = side
+            p.x0, p.cx0, p.x0_sb, p.x0_sy, p.x0_sx = x0.ptr, x0.C, x0.sb, x0.sy, x0.sx
+            c_side = x0.C
+            self.hold(x0.t)
+            if x1 is not None:
+                p.x1, p.cx1, p.x1_sb, p.x1_sy, p.x1_sx = x1.ptr, x1.C, x1.sb, x1.sy, x1.sx
+                c_side += x1.C
+                self.hold(x1.t)
         p.B, p.Hin, p.Win, p.ups = B, Hin, Win, ups
         p.ksize, p.stride, p.pad, p.Hout, p.Wout = ksize, stride, pad, Hout, Wout
         p.w, p.w_sb, p.w_ld, p.Cout = w.data_ptr() + 4 * w_off, w_sb, w_ld, Cout
@@ -187,13 +199,18 @@ class Program:
             self.hold(csum)
         self.hold(a0.t, None if a1 is None else a1.t, w, out, bias, rowvec, res)
         # algorithmic FLOPs: zero-padded rows/columns added only to fit the tensor-core tile are not counted
-        fl = alg_flops if alg_flops is not None else 2 * B * Hout * Wout * Cout * ksize * ksize * (a0.C + (a1.C if a1 is not None else 0))
+        fl = alg_flops if alg_flops is not None else 2 * B * Hout * Wout * Cout * (ksize * ksize * (a0.C + (a1.C if a1 is not None else 0)) + c_side)
         self.flops += fl
         if engine in (1, 2, 3):
             self.tc_flops += fl
             self.mma_weights.append(w)
         self._add(L.OP_CONV, p, tag)
         return csum_ok
+
+    def tc_eligible(self, a0, a1, out, *, B, Hin, Win, Hout, Wout, Cout, ksize, stride=1, pad=0, res=None):
+        """Would conv() run this shape on the tcgen05 engine?  (weights assumed freshly allocated, i.e. aligned)"""
+        return bool(self.tc_code) and self._tc_ok(a0, a1, B, Hin, Win, Hout, Wout, Cout, ksize, stride, pad, 1, out, 0, 0, 0,
+                                                  L.ACT_NONE, None, None, 1, out, 0, res)
 
     @staticmethod
     def _tc_ok(a0, a1, B, Hin, Win, Hout, Wout, Cout, ksize, stride, pad, ups, w, w_sb, w_ld, w_off, act, o_sb, o_sp, o_sn,

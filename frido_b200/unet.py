@@ -14,6 +14,7 @@ of forward is a *program* of libfrido_b200 launches (see UNetPlan):
   * the 22 ResBlock timestep projections run as one GEMM.
 """
 import math
+import os
 
 import torch
 from torch import nn
@@ -287,17 +288,30 @@ class UNetPlan:
         t2 = self._norm(S, [h1], [cout], h, w, rb.out_layers[0], 1e-5, 1, "res.norm2")
         S.release(h1)
         a1 = Src.nhwc(xs[1], h, w) if len(xs) > 1 else None
-        if isinstance(rb.skip_connection, nn.Conv2d):
-            sk = S.buf(B, hw, cout)
-            S.conv(Src.nhwc(xs[0], h, w), self._conv_w(rb.skip_connection), sk, B=B, Hin=h, Win=w, Hout=h, Wout=w,
-                   Cout=cout, a1=a1, bias=self._vec(rb.skip_connection.bias), tag="res.skip")
-            res = sk
-        else:
-            assert len(xs) == 1
-            res, sk = xs[0], None
         out = S.buf(B, hw, cout)
-        self._conv_stats(S, Src.nhwc(t2, h, w), self._conv_w(rb.out_layers[3]), out, cout, B=B, Hin=h, Win=w, Hout=h, Wout=w,
-                         ksize=3, pad=1, bias=self._vec(rb.out_layers[3].bias), res=res, tag="res.conv2")
+        sk = None
+        is_conv = isinstance(rb.skip_connection, nn.Conv2d)
+        if (is_conv and os.environ.get("FRIDO_FUSE_SKIP", "1") == "1" and all(c % 32 == 0 for c in cs) and
+                S.tc_eligible(Src.nhwc(t2, h, w), None, out, B=B, Hin=h, Win=w, Hout=h, Wout=w, Cout=cout, ksize=3, pad=1)):
+            # the 1x1 skip_connection conv (pyunet.py:248,299) rides on conv2's K loop: its input channels are extra
+            # K steps read at the output pixel, its weights extra columns, the biases add up - no separate launch, no
+            # round trip of the skip tensor through HBM
+            sc_, c2_ = rb.skip_connection, rb.out_layers[3]
+            w_cat = self._packed(lambda: torch.cat([_pack_conv(c2_.weight), sc_.weight.detach().reshape(cout, -1)], 1).contiguous())
+            b_cat = self._packed(lambda: (c2_.bias.detach() + sc_.bias.detach()))
+            self._conv_stats(S, Src.nhwc(t2, h, w), w_cat, out, cout, B=B, Hin=h, Win=w, Hout=h, Wout=w, ksize=3, pad=1,
+                             bias=b_cat, side=(Src.nhwc(xs[0], h, w), a1), tag="res.conv2+skip")
+        else:
+            if is_conv:
+                sk = S.buf(B, hw, cout)
+                S.conv(Src.nhwc(xs[0], h, w), self._conv_w(rb.skip_connection), sk, B=B, Hin=h, Win=w, Hout=h, Wout=w,
+                       Cout=cout, a1=a1, bias=self._vec(rb.skip_connection.bias), tag="res.skip")
+                res = sk
+            else:
+                assert len(xs) == 1
+                res = xs[0]
+            self._conv_stats(S, Src.nhwc(t2, h, w), self._conv_w(rb.out_layers[3]), out, cout, B=B, Hin=h, Win=w, Hout=h, Wout=w,
+                             ksize=3, pad=1, bias=self._vec(rb.out_layers[3].bias), res=res, tag="res.conv2")
         S.release(t2)
         if sk is not None:
             S.release(sk)

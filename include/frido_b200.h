@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define FRIDO_ABI_VERSION 2
+#define FRIDO_ABI_VERSION 3
 #define FRIDO_SK_WS_BYTES (40ll << 20)
 
 #define FRIDO_OK 0
@@ -79,6 +79,11 @@ typedef struct FridoConvParams {
                                (attention K and V^T) get their pre-split copy.  Not with GEGLU. */
   double* chan_sums;        /* optional (tcgen05 engines only): [B][Cout][2] += per-channel (sum, sum of squares) of the
                                stored outputs, i.e. the GroupNorm statistics of the tensor being produced; zero on entry */
+  const float* x0;          /* optional (tcgen05 engines only) fused 1x1 side input, e.g. a ResBlock's skip_connection conv */
+  const float* x1;          /*   (pyunet.py:248,299): out += sum_c X[b,p,c] * W[n, ksize*ksize*(c0+c1) + c], X = x0|x1 channel- */
+  int32_t cx0, cx1;         /*   concatenated, sampled at the output pixel (stride 1 only); the weight rows carry the extra */
+  int64_t x0_sb, x0_sy, x0_sx; /* cx0+cx1 columns after the taps.  Element strides: image, row, col (channel stride 1). */
+  int64_t x1_sb, x1_sy, x1_sx;
   void* sk_ws;              /* optional (tcgen05 engines only) stream-K workspace: launches with too few output tiles for
                                the 148 SMs split their K loops across CTAs and combine the partial sums here (in a fixed
                                order: results stay deterministic).  Zero it once; launches on one stream may share it. */

@@ -147,6 +147,33 @@ def test_tc_geglu_and_attention_shapes(dev, eng):
     assert max(errs) < {1: 3e-2, 2: 3e-5, 3: 2e-4}[eng], errs
 
 
+@pytest.mark.parametrize("eng", [2, 3])
+@pytest.mark.parametrize("B,C,Cx0,Cx1,Cout,H,W", [(2, 64, 64, 32, 128, 16, 16), (16, 96, 160, 0, 192, 8, 8), (1, 64, 32, 32, 64, 9, 7)])
+def test_conv_tc_fused_skip(dev, eng, B, C, Cx0, Cx1, Cout, H, W):
+    """ResBlock tail (pyunet.py:299): conv3x3(h) + skip_connection 1x1(cat(x, skip)) as ONE launch - the side input's
+    channels are extra K steps of the implicit GEMM."""
+    from frido_b200.program import Program, Src
+    g = torch.Generator().manual_seed(B + C + Cx0 + H)
+    hx = torch.randn(B, C, H, W, generator=g)
+    x0 = torch.randn(B, Cx0, H, W, generator=g)
+    x1 = torch.randn(B, Cx1, H, W, generator=g) if Cx1 else None
+    w3 = torch.randn(Cout, C, 3, 3, generator=g) / np.sqrt(9 * C)
+    w1 = torch.randn(Cout, Cx0 + Cx1, 1, 1, generator=g) / np.sqrt(Cx0 + Cx1)
+    b3, b1 = torch.randn(Cout, generator=g), torch.randn(Cout, generator=g)
+    xin = torch.cat([x0, x1], 1) if Cx1 else x0
+    ref = F.conv2d(hx.double(), w3.double(), b3.double(), padding=1) + F.conv2d(xin.double(), w1.double(), b1.double())
+    P = Program(dev, "tc_skip")
+    wcat = torch.cat([_pack(w3), w1.view(Cout, -1)], 1).contiguous().to(dev)
+    out = torch.zeros(B, H * W, Cout, device=dev)
+    side = (Src.nhwc(_nhwc(x0).to(dev), H, W), Src.nhwc(_nhwc(x1).to(dev), H, W) if Cx1 else None)
+    P.conv(Src.nhwc(_nhwc(hx).to(dev), H, W), wcat, out, B=B, Hin=H, Win=W, Hout=H, Wout=W, Cout=Cout, ksize=3, pad=1,
+           bias=(b3 + b1).to(dev), side=side, engine=eng)
+    _run(P, dev)
+    err = (out.view(B, H, W, Cout).permute(0, 3, 1, 2).cpu().double() - ref).abs().max().item()
+    print("fused skip err", err)
+    assert err < tol3(9 * C + Cx0 + Cx1, ref.abs().max().item()) + (1e-4 if eng == 3 else 0.0)
+
+
 @pytest.mark.parametrize("B,C,H,W", [(2, 64, 16, 16), (3, 192, 64, 64), (2, 96, 9, 7)])
 def test_conv_tc_stride2(dev, B, C, H, W):
     """Downsample (pyunet.py:152-156): 3x3 stride 2 pad 1 through the TMA traversal stride."""
