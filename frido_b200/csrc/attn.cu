@@ -140,45 +140,49 @@ __global__ void __launch_bounds__(ATTN_WARPS * 32, SINGLE ? 2 : 1) attn_small_ke
     }
     cp_async_commit_wait_all();
     __syncthreads();
-    // ---- scores: block blk covers keys [blk*KB, blk*KB + KB); lane L ends up with pair (key blk*KB + L/R, row L%R)
+    // ---- scores: block blk covers keys [blk*KB, blk*KB + KB); lane L ends up with pair (key blk*KB + L/R, row L%R).
+    // The block loop and the key loop of P V below stay ROLLED: fully unrolled this kernel was 124 KB of straight-line
+    // code that every warp streamed through once, and instruction-cache misses were its largest stall (ncu).
+    const int nblk = (kc + KB - 1) / KB;
     float sv[NB];
 #pragma unroll
-    for (int blk = 0; blk < NB; ++blk) {
-      sv[blk] = -INFINITY;
-      if (blk * KB < kc) {
-        float part[32];
+    for (int i = 0; i < NB; ++i) sv[i] = -INFINITY;
+#pragma unroll 1
+    for (int blk = 0; blk < nblk; ++blk) {
+      float part[32];
 #pragma unroll
-        for (int kl = 0; kl < KB; ++kl) {
-          const int kk = blk * KB + kl;
+      for (int kl = 0; kl < KB; ++kl) {
+        const int kk = min(blk * KB + kl, kc - 1);  // keys beyond kc recompute the last key; masked below
+        const float4* kr = Ks + kk * Q;
 #pragma unroll
-          for (int r = 0; r < R; ++r) part[kl * R + r] = 0.f;
-          if (kk < kc) {
+        for (int r = 0; r < R; ++r) part[kl * R + r] = 0.f;
 #pragma unroll
-            for (int j = 0; j < NJ; ++j) {
-              const int quad = lane + 32 * j;
-              if (quad < Q) {
-                const float4 kv = Ks[kk * Q + quad];
+        for (int j = 0; j < NJ; ++j) {
+          const int quad = lane + 32 * j;
+          if (quad < Q) {
+            const float4 kv = kr[quad];
 #pragma unroll
-                for (int r = 0; r < R; ++r)
-                  part[kl * R + r] = fmaf(q[r][j].x, kv.x, fmaf(q[r][j].y, kv.y, fmaf(q[r][j].z, kv.z, fmaf(q[r][j].w, kv.w, part[kl * R + r]))));
-              }
-            }
+            for (int r = 0; r < R; ++r)
+              part[kl * R + r] = fmaf(q[r][j].x, kv.x, fmaf(q[r][j].y, kv.y, fmaf(q[r][j].z, kv.z, fmaf(q[r][j].w, kv.w, part[kl * R + r]))));
           }
         }
-        warp_transpose_sum(part, lane);
-        if (blk * KB + lane / R < kc) sv[blk] = part[0] * p.scale;
       }
+      warp_transpose_sum(part, lane);
+      const float val = (blk * KB + lane / R < kc) ? part[0] * p.scale : -INFINITY;
+#pragma unroll
+      for (int i = 0; i < NB; ++i)
+        if (i == blk) sv[i] = val;  // predicated moves: sv stays in registers
     }
     // ---- softmax state of row lane % R (replicated over the lanes that share it)
     float mloc = sv[0];
 #pragma unroll
-    for (int blk = 1; blk < NB; ++blk) mloc = fmaxf(mloc, sv[blk]);
+    for (int i = 1; i < NB; ++i) mloc = fmaxf(mloc, sv[i]);
     const float m_new = fmaxf(m_run, row_max<R>(mloc));
     float pv[NB], psum = 0.f;
 #pragma unroll
-    for (int blk = 0; blk < NB; ++blk) {
-      pv[blk] = __expf(sv[blk] - m_new);  // exp(-inf) = 0 for pairs beyond kc
-      psum += pv[blk];
+    for (int i = 0; i < NB; ++i) {
+      pv[i] = __expf(sv[i] - m_new);  // exp(-inf) = 0 for pairs beyond kc
+      psum += pv[i];
     }
     const float corr = __expf(m_run - m_new);  // first chunk: exp(-inf) = 0
     l_run = l_run * corr + row_sum<R>(psum);
@@ -192,25 +196,28 @@ __global__ void __launch_bounds__(ATTN_WARPS * 32, SINGLE ? 2 : 1) attn_small_ke
       }
     }
     // ---- accumulate P V
+#pragma unroll 1
+    for (int blk = 0; blk < nblk; ++blk) {
+      float pvb = pv[0];
 #pragma unroll
-    for (int blk = 0; blk < NB; ++blk) {
+      for (int i = 1; i < NB; ++i)
+        if (i == blk) pvb = pv[i];
+      const int kend = min(KB, kc - blk * KB);
+#pragma unroll 2
+      for (int kl = 0; kl < kend; ++kl) {
+        const float4* vr = Vs + (blk * KB + kl) * Q;
+        float pk[R];
 #pragma unroll
-      for (int kl = 0; kl < KB; ++kl) {
-        const int kk = blk * KB + kl;
-        if (kk < kc) {
-          float pk[R];
+        for (int r = 0; r < R; ++r) pk[r] = __shfl_sync(0xffffffffu, pvb, kl * R + r);
 #pragma unroll
-          for (int r = 0; r < R; ++r) pk[r] = __shfl_sync(0xffffffffu, pv[blk], kl * R + r);
+        for (int j = 0; j < NJ; ++j) {
+          const int quad = lane + 32 * j;
+          if (quad < Q) {
+            const float4 vv = vr[quad];
 #pragma unroll
-          for (int j = 0; j < NJ; ++j) {
-            const int quad = lane + 32 * j;
-            if (quad < Q) {
-              const float4 vv = Vs[kk * Q + quad];
-#pragma unroll
-              for (int r = 0; r < R; ++r) {
-                o[r][j].x = fmaf(pk[r], vv.x, o[r][j].x); o[r][j].y = fmaf(pk[r], vv.y, o[r][j].y);
-                o[r][j].z = fmaf(pk[r], vv.z, o[r][j].z); o[r][j].w = fmaf(pk[r], vv.w, o[r][j].w);
-              }
+            for (int r = 0; r < R; ++r) {
+              o[r][j].x = fmaf(pk[r], vv.x, o[r][j].x); o[r][j].y = fmaf(pk[r], vv.y, o[r][j].y);
+              o[r][j].z = fmaf(pk[r], vv.z, o[r][j].z); o[r][j].w = fmaf(pk[r], vv.w, o[r][j].w);
             }
           }
         }

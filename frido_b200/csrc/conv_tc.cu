@@ -507,13 +507,26 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
 #pragma unroll
         for (int k = 0; k < 4; ++k) a[k] = make_float4(0.f, 0.f, 0.f, 0.f);
         const int ch = (col_lo + c) >> 4;
-        for (int cc = c_first; cc <= c_last; ++cc) {
-          const int sl = 2 * cc + ((cc * p.sk_per) / ksteps == tile ? 0 : 1);
-          const float4* src = p.sk_ws + (size_t)sl * (size_t)(32 * p.BN) + (ch * 4) * 128 + row;
+        // two contributors' partials in flight at a time (L2 latency, not bandwidth, is what this costs); the sums are
+        // still taken in CTA order
+        for (int cb = c_first; cb <= c_last; cb += 2) {
+          float4 v[2][4];
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const float4 v = __ldcg(src + k * 128);
-            a[k].x += v.x; a[k].y += v.y; a[k].z += v.z; a[k].w += v.w;
+          for (int g = 0; g < 2; ++g) {
+            const int cc = cb + g;
+            if (cc <= c_last) {
+              const int sl = 2 * cc + ((cc * p.sk_per) / ksteps == tile ? 0 : 1);
+              const float4* src = p.sk_ws + (size_t)sl * (size_t)(32 * p.BN) + (ch * 4) * 128 + row;
+#pragma unroll
+              for (int k = 0; k < 4; ++k) v[g][k] = __ldcg(src + k * 128);
+            }
+          }
+#pragma unroll
+          for (int g = 0; g < 2; ++g) {
+            if (cb + g <= c_last) {
+#pragma unroll
+              for (int k = 0; k < 4; ++k) { a[k].x += v[g][k].x; a[k].y += v[g][k].y; a[k].z += v[g][k].z; a[k].w += v[g][k].w; }
+            }
           }
         }
 #pragma unroll
