@@ -145,6 +145,17 @@ def time_tc_launches(plan_step, reps=2):
     return best[0], flops, len(tc), best[1]
 
 
+def _traffic():
+    """DRAM bytes per launch of the dominant kernel (dram__bytes_read.sum + dram__bytes_write.sum averaged over the
+    tcgen05 conv launches of one UNet step), taken from the committed ncu pass of this round (profiles/traffic.json);
+    bench.py itself never runs under a profiler."""
+    try:
+        with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "traffic.json")) as f:
+            return json.load(f)["bytes_per_launch"]
+    except Exception:
+        return None
+
+
 def run_ours(args):
     import frido_b200 as fb
     from frido_b200 import configs
@@ -245,8 +256,9 @@ def run_ours(args):
             else f"images/sec {cfg['sampler'].upper()}-{S} ({args.config}, sampling + decode)",
             "value": round(value, 4), "unit": "images/sec", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": round(ms / args.steps, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": {"bf16x3": "bf16x3 (error-compensated: bf16 hi/lo operand split, 3 MMAs per product, fp32 accumulate; "
-                                "attention matmuls tf32x3) - fp32-faithful to ~1e-4 on eps",
+            "dtype": {"bf16x3": "bf16x3 (error-compensated: bf16 hi/lo operand split, 3 MMAs per product, fp32 accumulate, for every "
+                                "conv / linear / attention matmul on the tensor cores; short-sequence attention and norms in fp32 "
+                                "SIMT) - fp32-faithful to ~1e-4 on eps",
                       "tc3": "tf32x3 (error-compensated 3xTF32 operands, fp32 accumulate: fp32-faithful)",
                       "tc": "tf32 (fp32 accumulate)", "simt": "f32"}[eng],
             "data": "synthetic (random-init weights with zero_module tensors re-drawn, N(0,1) context and start noise, eta=0)",
@@ -261,7 +273,7 @@ def run_ours(args):
             "gpu_launches": int(launches_per_step * args.steps),
             "clocks": clk,
             "roofline": {"bound": "tensor", "achieved": round(achieved, 2), "peak": peaks["bf16"], "unit": "TFLOP/s",
-                         "frac": round(achieved / peaks["bf16"], 4), "traffic": None,
+                         "frac": round(achieved / peaks["bf16"], 4), "traffic": _traffic(),
                          "kernel": "frido::conv_tc_kernel" + {"bf16x3": "<2> (BF16x3)", "tc3": "<1> (3xTF32)", "tc": "<0> (TF32)"}.get(eng, ""),
                          "note": f"algorithmic FLOPs (1x) of the {tc_n} tcgen05 conv launches of one stage-{ns - 1} UNet step at batch {B} "
                                  f"/ their summed CUDA-event time ({tc_ms:.2f} ms of a {step_ms:.2f} ms eager step); peak = {peaks['source']} "
