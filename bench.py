@@ -141,7 +141,7 @@ def time_tc_launches(plan_step, reps=2):
     flops = 0
     for i in tc:
         c = ops[i].u.conv
-        flops += 2 * c.B * c.Hout * c.Wout * c.Cout * c.ksize * c.ksize * (c.c0 + c.c1)
+        flops += 2 * c.B * c.Hout * c.Wout * c.Cout * (c.ksize * c.ksize * (c.c0 + c.c1) + c.cx0 + c.cx1)
     return best[0], flops, len(tc), best[1]
 
 

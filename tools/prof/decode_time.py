@@ -36,7 +36,7 @@ for i, op in enumerate(ops):
     t = best[i]
     if op.kind == L.OP_CONV:
         c = op.u.conv
-        fl = 2 * c.B * c.Hout * c.Wout * c.Cout * c.ksize * c.ksize * (c.c0 + c.c1)
+        fl = 2 * c.B * c.Hout * c.Wout * c.Cout * (c.ksize * c.ksize * (c.c0 + c.c1) + c.cx0 + c.cx1)
         rows.append((t, f"{tags[i]:18s} eng{c.engine} B{c.B} {c.Hout}x{c.Wout} cin{c.c0}+{c.c1} cout{c.Cout} k{c.ksize} wsb{int(c.w_sb != 0)} {t*1e3:8.1f} us {fl/t/1e9:8.1f} TF/s"))
     else:
         rows.append((t, f"{tags[i]:18s} kind{op.kind} {t*1e3:8.1f} us"))

@@ -17,7 +17,7 @@ for op, tag in zip(plan.step.ops, plan.step.tags):
     d = dict(tag=tag, kind=op.kind)
     if op.kind == L.OP_CONV:
         c = op.u.conv
-        d.update(engine=c.engine, flops=2 * c.B * c.Hout * c.Wout * c.Cout * c.ksize * c.ksize * (c.c0 + c.c1),
+        d.update(engine=c.engine, flops=2 * c.B * c.Hout * c.Wout * c.Cout * (c.ksize * c.ksize * (c.c0 + c.c1) + c.cx0 + c.cx1),
                  shape=f"B{c.B} {c.Hout}x{c.Wout} cin{c.c0}+{c.c1} cout{c.Cout} k{c.ksize} s{c.stride}")
     ops.append(d)
 json.dump(ops, open('/root/repo/gpurun_out/step_ops.json', 'w'))

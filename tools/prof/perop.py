@@ -31,7 +31,7 @@ for i, op in enumerate(ops):
     t = best[i]
     if op.kind == L.OP_CONV:
         c = op.u.conv
-        fl = 2 * c.B * c.Hout * c.Wout * c.Cout * c.ksize * c.ksize * (c.c0 + c.c1)
+        fl = 2 * c.B * c.Hout * c.Wout * c.Cout * (c.ksize * c.ksize * (c.c0 + c.c1) + c.cx0 + c.cx1)
         key = f"{tags[i]} e{c.engine}"
         rows.append((t, f"{tags[i]:16s} eng{c.engine} B{c.B} {c.Hout}x{c.Wout} cin{c.c0}+{c.c1} cout{c.Cout} k{c.ksize} s{c.stride}  {t*1e3:8.1f} us  {fl/t/1e9:8.1f} TF/s"))
     elif op.kind == L.OP_ATTN:
