@@ -552,6 +552,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
           for (int i = et; i < p.TB * p.BN * 2; i += 32 * TC_EPI_WARPS) cacc[i] = 0.f;
           asm volatile("bar.sync 1, 256;" ::: "memory");
         }
+        // the bias slice of a chunk is fetched one chunk ahead: an L2 round trip is longer than a whole chunk (ncu: the first
+        // use of the bias was the epilogue's top stall)
+        float4 bias_nx = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (has_bias) bias_nx = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + 4 * c4));
         for (int c = 0; c < hcols; c += 16) {
           const int n = n0 + c + 4 * c4;
           // residual loads of this chunk go out first: their latency overlaps the TMEM load + transpose
@@ -566,8 +570,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
               }
             }
           }
-          float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (has_bias) bias4 = __ldg(reinterpret_cast<const float4*>(p.bias + n));
+          const float4 bias4 = bias_nx;
+          if (has_bias && c + 16 < hcols) bias_nx = __ldg(reinterpret_cast<const float4*>(p.bias + n + 16));
           uint32_t r[16];
           fetch16(c, r);
 #pragma unroll

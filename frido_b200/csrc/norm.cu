@@ -150,8 +150,10 @@ __global__ void __launch_bounds__(NA_MAX_THREADS) norm_act_kernel(const FridoNor
         if (px < pix1) {
           xv[u] = __ldg(reinterpret_cast<const float4*>(src + (int64_t)px * cs));
           if (gb) {
-            ga[u] = __ldg(reinterpret_cast<const float4*>(gb + (int64_t)px * 2 * C + c));
-            be[u] = __ldg(reinterpret_cast<const float4*>(gb + (int64_t)px * 2 * C + C + c));
+            // the SPADE maps are read once per step and are far larger than L2: streaming (evict-first) loads, so they do
+            // not push the activation just written by the previous conv - and the output the next one reads - out of L2
+            ga[u] = __ldcs(reinterpret_cast<const float4*>(gb + (int64_t)px * 2 * C + c));
+            be[u] = __ldcs(reinterpret_cast<const float4*>(gb + (int64_t)px * 2 * C + C + c));
           }
         }
       }
