@@ -121,7 +121,7 @@ class _SamplerBase(object):
         if dev.type != "cuda":
             raise L.FridoError("sampling runs on a CUDA device only (no CPU path)")
         unet = model.model.diffusion_model
-        unet.invalidate()  # EMA swap may have rewritten the weights in place (sample_diffusion.py:187)
+        unet.invalidate_if_changed()  # EMA swap may have rewritten the weights in place (sample_diffusion.py:187)
         B, C, H, W = shape
         split = list(model.split_embed_dim_list) if getattr(model, "use_split_head", False) else [C]
         if not getattr(model, "use_split_head", False):

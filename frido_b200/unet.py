@@ -109,14 +109,34 @@ class PyUNetModel(nn.Module):
                                   for i in range(len(split))])
         self._plans = {}
         self._pack_version = 0
+        self._fingerprint = None
 
     # ------------------------------------------------------------------
     def invalidate(self):
         """Weights changed under us (EMA swap writes through .data.copy_, ema.py:51,76 —
-        invisible to pointer/version checks): re-pack on next use."""
+        invisible to pointer/version checks): every plan re-packs at its next use (`repack_if_stale`)."""
         self._pack_version += 1
-        for plan in self._plans.values():
-            plan.repack()
+        self._fingerprint = None
+
+    def _weights_fingerprint(self):
+        """L1 and L2 norm of every parameter tensor (two multi-tensor passes over the weights, ~1 ms for 2 GB, one small
+        device->host copy): what `invalidate_if_changed` compares to notice in-place rewrites nobody announced."""
+        ps = [p.detach() for p in self.parameters()]
+        return torch.stack(torch._foreach_norm(ps, 2) + torch._foreach_norm(ps, 1)).double().cpu()
+
+    def invalidate_if_changed(self):
+        """Called at the start of every `sampler.sample()`: the reference lets anyone rewrite the weights in place between
+        calls (`LitEma.copy_to/restore`, frido.py:182-194).  `ema_scope` and `load_state_dict` invalidate explicitly; this
+        catches the rest without paying a full re-pack (2 GB of packing + bf16 splitting per plan) on every call.
+        FRIDO_ALWAYS_REPACK=1 restores the unconditional re-pack."""
+        if os.environ.get("FRIDO_ALWAYS_REPACK", "0") == "1":
+            self.invalidate()
+            return
+        fp = self._weights_fingerprint()
+        old = getattr(self, "_fingerprint", None)
+        if old is None or old.shape != fp.shape or not torch.equal(old, fp):
+            self._pack_version += 1
+        self._fingerprint = fp
 
     def plan(self, stage, B, H, W, L_ctx):
         key = (stage, B, H, W, L_ctx)
