@@ -185,6 +185,72 @@ def test_full_size_l2i_step_and_decoder(dev, golden_dir, engine):
                 assert (p0.cpu() - g[f"step_s{s}_predx0"]).abs().max() < 40 * EPS_TOL  # x0 = (x - s1m*eps)/sqrt(a_t), 1/sqrt(a_996) = 38
 
 
+SWITCHES = ["FRIDO_SK", "FRIDO_ATTN_SMALL", "FRIDO_ATTN_FOLD", "FRIDO_FUSE_SKIP", "FRIDO_EPI_SPEC"]
+
+
+@pytest.mark.parametrize("off", SWITCHES)
+def test_fusion_switches_keep_the_result(dev, golden_dir, off, monkeypatch):
+    """Every scheduling / fusion step of the UNet plan (stream-K, fused short-sequence attention, folded attention weight
+    products, skip_connection fused into conv2, specialised epilogues) can be switched off; the full-size UNet's eps with a
+    switch off must still match the golden vectors of the unmodified reference, and agree with the default plan to fp32
+    re-association level."""
+    import frido_b200 as fb
+    from oracle import synth
+    g = _load(golden_dir, "l2i32.pt")
+
+    def run():
+        unet = fb.PyUNetModel(**g["unet_cfg"])
+        synth.fill_module_(unet, g["seed"], "model.diffusion_model.")
+        unet = unet.to(dev)
+        B = 4  # >= 128 rows at the 8x8 level, so the tensor-core paths (and the fused skip) are the ones exercised
+        ctx = synth.synth_input("ctx", (1, 26, 640), 1).to(dev).expand(B, -1, -1).contiguous()
+        x = synth.synth_input("x1", (1, 6, 32, 32), 2).to(dev).expand(B, -1, -1, -1).contiguous()
+        e = unet(x, torch.full((B,), 996, dtype=torch.long, device=dev), context=ctx, stage=1)
+        tags = set(unet.plan(1, B, 32, 32, 26).step.tags)
+        return e.cpu(), tags
+
+    e_def, tags_def = run()
+    monkeypatch.setenv(off, "0")
+    e_off, tags_off = run()
+    assert (e_def[0] - g["eps_s1_t996"][0]).abs().max() < 1e-3
+    assert (e_off[0] - g["eps_s1_t996"][0]).abs().max() < 1e-3
+    assert (e_def - e_off).abs().max() < 5e-4
+    for b in range(1, 4):  # identical samples in a batch: same result up to the summation grouping of their tiles
+        assert (e_def[b] - e_def[0]).abs().max() < 1e-5
+    if off == "FRIDO_FUSE_SKIP":
+        assert "res.conv2+skip" in tags_def and "res.skip" in tags_off and "res.conv2+skip" not in tags_off
+    if off == "FRIDO_ATTN_FOLD":
+        assert "attn1.out" in tags_off and "attn1.out" not in tags_def
+    if off == "FRIDO_ATTN_SMALL":
+        assert "attn2.block" in tags_def and "attn2.block" not in tags_off
+
+
+def test_silent_in_place_weight_change_is_noticed(dev, golden_dir):
+    """Nobody calls invalidate(): weights rewritten through .data (what LitEma.copy_to does, ema.py:51) between two
+    sampler.sample() calls must still reach the packed copies - the fingerprint guard at the start of sample()."""
+    import frido_b200 as fb
+    from oracle import synth
+    g = _load(golden_dir, "tiny2.pt")
+    model = _build_tiny(g, dev)
+    B = g["B"]
+    ctx = synth.synth_input("ctx", (B, 5, 24), 1).to(dev)
+    sampler = fb.DDIMSampler(model)
+    kw = dict(conditioning=ctx, num_stage=2, eta=0.0, verbose=False, init_noise=g["ddim4_xinit"].to(dev))
+    out1, _ = sampler.sample(4, B, (6, 8, 8), **kw)
+    v0 = model.model.diffusion_model._pack_version
+    out1b, _ = sampler.sample(4, B, (6, 8, 8), **kw)
+    assert model.model.diffusion_model._pack_version == v0 and torch.equal(out1, out1b)  # unchanged weights: no re-pack
+    for q in model.model.diffusion_model.parameters():
+        q.data.mul_(1.01)
+    out2, _ = sampler.sample(4, B, (6, 8, 8), **kw)
+    assert model.model.diffusion_model._pack_version == v0 + 1
+    assert (out2 - out1).abs().max() > 1e-4
+    for q in model.model.diffusion_model.parameters():
+        q.data.div_(1.01)
+    out3, _ = sampler.sample(4, B, (6, 8, 8), **kw)
+    assert (out3.cpu() - g["ddim4_out"]).abs().max() < 1e-3
+
+
 def test_full_size_decoder(dev, golden_dir, engine):
     import frido_b200 as fb
     from oracle import synth

@@ -92,6 +92,32 @@ def test_full_size_unet_keys_and_plan_flops(golden_dir):
     assert p4.step.tc_flops / p4.step.flops > 0.98      # the tcgen05 engine carries the step
 
 
+def test_plan_switches_and_weight_fingerprint(golden_dir, monkeypatch):
+    """Host bookkeeping only (plans are built on CPU tensors, never run there): the fusion switches change the op list the
+    way DESIGN.md says, and the fingerprint guard bumps the pack version exactly when a weight changed in place."""
+    import frido_b200 as fb
+    g = torch.load(os.path.join(golden_dir, "tiny2.pt"), weights_only=False)
+    cfg = dict(g["cfg"]["params"]["unet_config"]["params"])
+    u = fb.PyUNetModel(**cfg)
+    tags = u.plan(0, 2, 8, 8, 5).step.tags
+    assert "attn2.block" in tags and "attn1.fused" in tags and "attn1.out" not in tags and "attn2.out" not in tags
+    monkeypatch.setenv("FRIDO_ATTN_SMALL", "0")
+    monkeypatch.setenv("FRIDO_ATTN_FOLD", "0")
+    u2 = fb.PyUNetModel(**cfg)
+    tags2 = u2.plan(0, 2, 8, 8, 5).step.tags
+    assert "attn2.block" not in tags2 and "attn1.out" in tags2 and "attn2.out" in tags2 and "attn2.qk^T" in tags2
+    v = u._pack_version
+    u.invalidate_if_changed()
+    assert u._pack_version == v + 1          # first call: nothing recorded yet
+    u.invalidate_if_changed()
+    assert u._pack_version == v + 1          # unchanged weights: no re-pack
+    next(u.parameters()).data.mul_(1.5)      # what LitEma.copy_to does: no version counter, no new pointer
+    u.invalidate_if_changed()
+    assert u._pack_version == v + 2
+    u.invalidate()                           # explicit (ema_scope / load_state_dict)
+    assert u._pack_version == v + 3 and u._fingerprint is None
+
+
 def test_schedule_tables_bit_exact_vs_reference(golden_dir):
     from frido_b200 import DDIMSampler, PLMSSampler
     g = torch.load(os.path.join(golden_dir, "sched.pt"), weights_only=False)
