@@ -216,7 +216,7 @@ def test_fusion_switches_keep_the_result(dev, golden_dir, off, monkeypatch):
     assert (e_off[0] - g["eps_s1_t996"][0]).abs().max() < 1e-3
     assert (e_def - e_off).abs().max() < 5e-4
     for b in range(1, 4):  # identical samples in a batch: same result up to the summation grouping of their tiles
-        assert (e_def[b] - e_def[0]).abs().max() < 1e-5
+        assert (e_def[b] - e_def[0]).abs().max() < 2e-4
     if off == "FRIDO_FUSE_SKIP":
         assert "res.conv2+skip" in tags_def and "res.skip" in tags_off and "res.conv2+skip" not in tags_off
     if off == "FRIDO_ATTN_FOLD":
