@@ -910,7 +910,9 @@ int conv2d_tc(const FridoConvParams* p, cudaStream_t s) {
     };
     const int64_t dp_tiles = (int64_t)m_tiles * (p->Cout / bn);
     const double dp_cost = (double)((dp_tiles + sms - 1) / sms) * ksteps * stage_clk(bn);
-    double best = sk_env == 2 ? 1e30 : 0.95 * dp_cost;
+    double thresh = 0.95;
+    if (const char* e = getenv("FRIDO_SK_THRESH")) thresh = atof(e);  // tuning aid
+    double best = sk_env == 2 ? 1e30 : thresh * dp_cost;
     const bool forced_bn = getenv("FRIDO_TC_FORCE_BN") != nullptr;
     if (sk_env && p->sk_ws && (reinterpret_cast<uintptr_t>(p->sk_ws) & 15) == 0 && ksteps >= 8) {
       for (int i = 0; i < 4; ++i) {
