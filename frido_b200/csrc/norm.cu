@@ -71,6 +71,41 @@ __global__ void __launch_bounds__(GN_THREADS) gn_stats_kernel(const FridoGnStats
   }
 }
 
+
+// Per-channel statistics of one NHWC tensor: sums[b][c] = (sum, sum of squares) over the pixels, fp64 - the same format the
+// tcgen05 conv epilogues accumulate (FridoConvParams.chan_sums), for tensors produced by the SIMT engine (the UNet's
+// pre_input conv): computed ONCE, every GroupNorm that reads the tensor - alone or as half of a skip concat - then takes the
+// producer-statistics path of norm_act instead of re-reducing the (concatenated) tensor.  groups = 0 selects this mode.
+__global__ void __launch_bounds__(256) chan_stats_kernel(const FridoGnStatsParams p, int pix_per_cta, int Qe, int PL, int nj) {
+  extern __shared__ float cst_sm[];  // [C][2] partial sums of this CTA
+  const int C = p.c0, Q = C >> 2;
+  const int b = blockIdx.y, tid = threadIdx.x;
+  for (int i = tid; i < 2 * C; i += blockDim.x) cst_sm[i] = 0.f;
+  __syncthreads();
+  if (tid < Qe * PL) {
+    const int pl = tid / Qe, ql = tid - pl * Qe;
+    const int pix0 = blockIdx.x * pix_per_cta, pix1 = min(pix0 + pix_per_cta, p.HW);
+    const float* a0 = p.a0 + (int64_t)b * p.HW * C;
+    for (int j = 0; j < nj; ++j) {
+      const int quad = ql + j * Qe;
+      if (quad >= Q) break;
+      float s[4] = {0.f, 0.f, 0.f, 0.f}, ss[4] = {0.f, 0.f, 0.f, 0.f};
+      for (int pix = pix0 + pl; pix < pix1; pix += PL) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(a0 + (int64_t)pix * C) + quad);
+        s[0] += v.x; ss[0] += v.x * v.x; s[1] += v.y; ss[1] += v.y * v.y;
+        s[2] += v.z; ss[2] += v.z * v.z; s[3] += v.w; ss[3] += v.w * v.w;
+      }
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        atomicAdd(&cst_sm[2 * (4 * quad + e)], s[e]);
+        atomicAdd(&cst_sm[2 * (4 * quad + e) + 1], ss[e]);
+      }
+    }
+  }
+  __syncthreads();
+  for (int i = tid; i < 2 * C; i += blockDim.x) atomicAdd(p.sums + (int64_t)b * 2 * C + i, (double)cst_sm[i]);
+}
+
 static int gn_chunk(int B, int HW) {
   // aim for >= ~4 CTAs per SM overall, at least 16 pixels per CTA
   int target = (148 * 4 + B - 1) / B;
@@ -442,6 +477,17 @@ extern "C" int frido_upsample2x(const FridoUpsampleParams* p, void* stream) {
 
 extern "C" int frido_gn_stats(const FridoGnStatsParams* p, void* stream) {
   if (!p || !p->a0 || !p->sums) return set_error(FRIDO_E_ARG, "gn_stats: null pointer");
+  if (p->groups == 0) {  // per-channel mode
+    if (p->a1 || p->c1 || (p->c0 & 3) || p->c0 <= 0 || p->c0 > 4096) return set_error(FRIDO_E_ARG, "gn_stats: per-channel mode takes one source, C % 4 == 0");
+    int ppc = gn_chunk(p->B, p->HW);
+    if (ppc < 64) ppc = 64;  // fewer, fatter CTAs: each one ends with 2C global fp64 atomics
+    const int Q = p->c0 >> 2, nj = (Q + 255) / 256, Qe = (Q + nj - 1) / nj;
+    int PL = 256 / Qe;
+    if (PL < 1) PL = 1;
+    dim3 grid((p->HW + ppc - 1) / ppc, p->B);
+    chan_stats_kernel<<<grid, 256, (size_t)2 * p->c0 * sizeof(float), (cudaStream_t)stream>>>(*p, ppc, Qe, PL, nj);
+    return check_launch("chan_stats");
+  }
   const int C = p->c0 + p->c1;
   if (p->groups <= 0 || p->groups > 64 || C % p->groups || (C & 3) || (p->c0 & 3) || C > GN_THREADS * 4 * GN_MAXQPT)
     return set_error(FRIDO_E_ARG, "gn_stats: unsupported channel count");

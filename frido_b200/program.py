@@ -311,6 +311,11 @@ class Program:
         self.hold(t)
         self._add(L.OP_ZERO, p, tag)
 
+    def chan_stats(self, a0, c0, csum, *, B, HW, tag="chan_stats"):
+        """Per-channel (sum, sum of squares) of an NHWC tensor into csum [B,c0,2] fp64 (zero on entry): the statistics a
+        tcgen05 conv epilogue would have produced, for tensors that come from the SIMT engine."""
+        self.gn_stats(a0, c0, csum, B=B, HW=HW, groups=0, tag=tag)
+
     def gn_stats(self, a0, c0, sums, *, B, HW, a1=None, c1=0, groups=32, tag="gn_stats"):
         p = L.GnStatsParams()
         p.a0, p.a1, p.c0, p.c1, p.B, p.HW, p.groups, p.sums = _ptr(a0), _ptr(a1), c0, c1, B, HW, groups, sums.data_ptr()

@@ -647,6 +647,12 @@ class UNetPlan:
         h = S.buf(B, H * W, mc)
         S.conv(Src.nchw(self.x_in, H, W, c_lo, self.c_end), self._conv_w(pi), h, B=B, Hin=H, Win=W, Hout=H, Wout=W,
                Cout=mc, ksize=3, pad=1, bias=self._vec(pi.bias), tag="pre_input")
+        # pre_input runs on the SIMT engine (3 input channels): one per-channel statistics pass over its output, so that
+        # both GroupNorms that read it (first ResBlock; last skip concat) take the producer-statistics path
+        cs_h = self._csum_new(mc)
+        if cs_h is not None and mc % 4 == 0:
+            S.chan_stats(h, mc, cs_h, B=B, HW=H * W, tag="pre_input.stats")
+            self._csum[id(h)] = cs_h
         hs = [(h, mc, H, W)]
         c, hh, ww = mc, H, W
         for blk in net.input_blocks:

@@ -98,7 +98,9 @@ int frido_conv2d(const FridoConvParams* p, void* stream);
 /* GroupNorm statistics over an NHWC tensor that may be the concat of two
  * sources: per (image, group) sum and sum of squares in fp64.
  * Replaces the reduction half of nn.GroupNorm(32) (util.py:214; attention.py:76;
- * taming model.py:34).  `sums` [B][groups][2] must be zero on entry. */
+ * taming model.py:34).  `sums` [B][groups][2] must be zero on entry.
+ * groups = 0: per-CHANNEL sums of a single source instead, `sums` [B][c0][2] - the format FridoConvParams.chan_sums
+ * produces and FridoNormActParams.csum0/csum1 consume (for tensors whose producer ran on the SIMT engine). */
 typedef struct FridoGnStatsParams {
   const float* a0; const float* a1; int32_t c0, c1;
   int32_t B, HW, groups;

@@ -187,6 +187,27 @@ def test_groupnorm_spade_silu(dev, C0, C1, HW, spade, silu):
     assert (out.cpu() - ref).abs().max() < 2e-5
 
 
+@pytest.mark.parametrize("B,HW,C", [(2, 4096, 192), (3, 77, 32), (1, 256, 1920)])
+def test_chan_stats_feeds_norm_act(dev, B, HW, C):
+    """gn_stats in per-channel mode produces what a conv epilogue's chan_sums would: norm_act on top of it == GroupNorm."""
+    g = torch.Generator().manual_seed(B + HW + C)
+    x = torch.randn(B, HW, C, generator=g) * 1.7 + 0.4
+    gamma, beta = torch.randn(C, generator=g), torch.randn(C, generator=g)
+    ref = F.group_norm(x.permute(0, 2, 1).reshape(B, C, HW, 1), 32, gamma, beta, 1e-5).reshape(B, C, HW).permute(0, 2, 1)
+    P = _prog(dev)
+    cs = torch.zeros(B, C, 2, dtype=torch.float64, device=dev)
+    out = torch.zeros(B, HW, C, device=dev)
+    xd = x.to(dev)
+    P.zero(cs)
+    P.chan_stats(xd, C, cs, B=B, HW=HW)
+    P.norm_act(xd, C, None, gamma.to(dev), beta.to(dev), out, B=B, HW=HW, eps=1e-5, silu=0, csum0=cs)
+    P.run()
+    P.run()
+    xx = x.double()
+    assert (cs.cpu()[..., 0] - xx.sum(1)).abs().max() < 1e-3 and (cs.cpu()[..., 1] - (xx * xx).sum(1)).abs().max() < 1e-2
+    assert (out.cpu() - ref).abs().max() < 2e-5
+
+
 @pytest.mark.parametrize("C", [32, 384, 576, 960])
 def test_layernorm(dev, C):
     g = torch.Generator().manual_seed(C)
