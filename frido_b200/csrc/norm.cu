@@ -77,11 +77,9 @@ __global__ void __launch_bounds__(GN_THREADS) gn_stats_kernel(const FridoGnStats
 // pre_input conv): computed ONCE, every GroupNorm that reads the tensor - alone or as half of a skip concat - then takes the
 // producer-statistics path of norm_act instead of re-reducing the (concatenated) tensor.  groups = 0 selects this mode.
 __global__ void __launch_bounds__(256) chan_stats_kernel(const FridoGnStatsParams p, int pix_per_cta, int Qe, int PL, int nj) {
-  extern __shared__ float cst_sm[];  // [C][2] partial sums of this CTA
+  extern __shared__ float cst_sm[];  // [PL][C][2] per-thread partial sums, combined in a fixed order (replays stay bit-identical)
   const int C = p.c0, Q = C >> 2;
   const int b = blockIdx.y, tid = threadIdx.x;
-  for (int i = tid; i < 2 * C; i += blockDim.x) cst_sm[i] = 0.f;
-  __syncthreads();
   if (tid < Qe * PL) {
     const int pl = tid / Qe, ql = tid - pl * Qe;
     const int pix0 = blockIdx.x * pix_per_cta, pix1 = min(pix0 + pix_per_cta, p.HW);
@@ -97,13 +95,17 @@ __global__ void __launch_bounds__(256) chan_stats_kernel(const FridoGnStatsParam
       }
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
-        atomicAdd(&cst_sm[2 * (4 * quad + e)], s[e]);
-        atomicAdd(&cst_sm[2 * (4 * quad + e) + 1], ss[e]);
+        cst_sm[2 * (pl * C + 4 * quad + e)] = s[e];
+        cst_sm[2 * (pl * C + 4 * quad + e) + 1] = ss[e];
       }
     }
   }
   __syncthreads();
-  for (int i = tid; i < 2 * C; i += blockDim.x) atomicAdd(p.sums + (int64_t)b * 2 * C + i, (double)cst_sm[i]);
+  for (int i = tid; i < 2 * C; i += blockDim.x) {
+    float t = 0.f;
+    for (int pl = 0; pl < PL; ++pl) t += cst_sm[2 * pl * C + i];
+    atomicAdd(p.sums + (int64_t)b * 2 * C + i, (double)t);
+  }
 }
 
 static int gn_chunk(int B, int HW) {
@@ -485,7 +487,9 @@ extern "C" int frido_gn_stats(const FridoGnStatsParams* p, void* stream) {
     int PL = 256 / Qe;
     if (PL < 1) PL = 1;
     dim3 grid((p->HW + ppc - 1) / ppc, p->B);
-    chan_stats_kernel<<<grid, 256, (size_t)2 * p->c0 * sizeof(float), (cudaStream_t)stream>>>(*p, ppc, Qe, PL, nj);
+    const size_t smem = (size_t)PL * 2 * p->c0 * sizeof(float);
+    if (smem > 48 * 1024) return set_error(FRIDO_E_ARG, "gn_stats: per-channel mode: too many channels");
+    chan_stats_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(*p, ppc, Qe, PL, nj);
     return check_launch("chan_stats");
   }
   const int C = p->c0 + p->c1;
