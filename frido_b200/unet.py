@@ -164,6 +164,23 @@ class PyUNetModel(nn.Module):
         return plan.eps.clone()
 
 
+def fold_self_attention(ca):
+    """Weight products of a self-attention CrossAttention module (attention.py:172-191, re-associated; x = LN(h)):
+         sim   = (x Wq^T)(x Wk^T)^T       = (x A^T) x^T        with A   = Wk^T Wq   (keys are x itself)
+         to_out(P (x Wv^T)) - b_o         = P (x Wv'^T)        with Wv' = Wo Wv     (values carry to_out)
+    Products are taken in fp64 and rounded once; returns (A, Wv') as [C,C] fp32 linear weights ([out,in])."""
+    wq, wk = ca.to_q.weight.detach().double(), ca.to_k.weight.detach().double()
+    wv, wo = ca.to_v.weight.detach().double(), ca.to_out[0].weight.detach().double()
+    return (wk.t() @ wq).float().contiguous(), (wo @ wv).float().contiguous()
+
+
+def fold_cross_attention_weights(ca):
+    """Linear weights that turn K = ctx Wk^T and V = ctx Wv^T into the operands of the fused cross-attention kernel:
+         K' = K Wq   (sim = (x Wq^T) K^T = x K'^T)        -> weight Wq^T   ([out,in] = [C,C])
+         V' = V Wo^T (to_out(P V) - b_o = P V')           -> weight Wo"""
+    return ca.to_q.weight.detach().t().contiguous(), ca.to_out[0].weight.detach()
+
+
 def _pack_conv(w):
     """OIHW -> [O][kh*kw][I] (K-major rows for the implicit GEMM)."""
     return w.detach().permute(0, 2, 3, 1).contiguous().view(w.shape[0], -1)
@@ -413,11 +430,11 @@ class UNetPlan:
         S, B = self.step, self.B
         ca = blk.attn1
         scale = float(C) ** -0.5
-        def fold_a():  # [C,C] weight of x -> x (Wk^T Wq)^T, product taken in fp64
-            return (ca.to_k.weight.detach().double().t() @ ca.to_q.weight.detach().double()).float().contiguous()
+        def fold_a():  # [C,C] weight of x -> x (Wk^T Wq)^T
+            return fold_self_attention(ca)[0]
 
         def fold_v():  # [C,C] weight of x -> x (Wo Wv)^T
-            return (ca.to_out[0].weight.detach().double() @ ca.to_v.weight.detach().double()).float().contiguous()
+            return fold_self_attention(ca)[1]
 
         b_o = self._vec(ca.to_out[0].bias)
         ln = S.buf(B, N, C)
@@ -471,9 +488,9 @@ class UNetPlan:
         vf = torch.empty(B, Lc, C, dtype=torch.float32, device=self.dev)
         kc = P.buf(B, Lc, C)
         P.linear(self.ctx, self._vec(ca.to_k.weight), kc, M=B * Lc, K=D, N=C, tag="ctx.k")
-        P.linear(kc, self._packed(lambda: ca.to_q.weight.detach().t().contiguous()), kf, M=B * Lc, K=C, N=C, tag="ctx.k.Wq")
+        P.linear(kc, self._packed(lambda: fold_cross_attention_weights(ca)[0]), kf, M=B * Lc, K=C, N=C, tag="ctx.k.Wq")
         P.linear(self.ctx, self._vec(ca.to_v.weight), kc, M=B * Lc, K=D, N=C, tag="ctx.v")
-        P.linear(kc, self._vec(ca.to_out[0].weight), vf, M=B * Lc, K=C, N=C, tag="ctx.v.Wo")
+        P.linear(kc, self._packed(lambda: fold_cross_attention_weights(ca)[1].clone()), vf, M=B * Lc, K=C, N=C, tag="ctx.v.Wo")
         P.release(kc)
         return kf, vf
 

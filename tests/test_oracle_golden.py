@@ -127,3 +127,40 @@ def test_encode_first_stage_vs_reference(golden_dir, tag):
     assert (h - g["h"]).abs().max() < TOL
     z = O.first_stage_encoding(h, list(ed), sf)
     assert (z - g["z"]).abs().max() < TOL
+
+
+def test_attention_weight_folds_match_the_oracle():
+    """The UNet plan re-associates the attention matmuls (frido_b200/unet.py: fold_self_attention,
+    fold_cross_attention_weights) so that the key projection and to_out leave the per-step work.  Exact algebra: the
+    folded form must reproduce the oracle's CrossAttention (attention.py:170-193) to fp32 rounding, for the
+    self-attention and for the cross-attention against a short condition."""
+    import torch.nn.functional as F
+    from frido_b200 import modules as M
+    from frido_b200.unet import fold_self_attention, fold_cross_attention_weights
+    from oracle import torch_oracle as O
+    torch.manual_seed(0)
+    C, D, N, L, B = 96, 40, 50, 7, 2
+    blk = M.BasicTransformerBlock(C, D)
+    for prm in blk.parameters():
+        prm.data.normal_(0, 0.2)
+    sd = {"b." + k: v.detach() for k, v in blk.state_dict().items()}
+    x = torch.randn(B, N, C)
+    ctx = torch.randn(B, L, D)
+    scale = C ** -0.5
+    # self-attention sub-block: h1 = x + to_out(attn1(LN(x)))
+    ln = F.layer_norm(x, (C,), sd["b.norm1.weight"], sd["b.norm1.bias"], 1e-5)
+    ref1 = O.cross_attention(ln, None, sd, "b.attn1") + x
+    w_a, w_v = fold_self_attention(blk.attn1)
+    t = F.linear(ln, w_a)                                    # x (Wk^T Wq)^T
+    p = (torch.einsum("bid,bjd->bij", t, ln) * scale).softmax(-1)   # keys are the LayerNorm output itself
+    got1 = torch.einsum("bij,bjd->bid", p, F.linear(ln, w_v)) + sd["b.attn1.to_out.0.bias"] + x
+    assert (got1 - ref1).abs().max() < 2e-5
+    # cross-attention sub-block: h2 = h1 + to_out(attn2(LN(h1), ctx))
+    ln2 = F.layer_norm(ref1, (C,), sd["b.norm2.weight"], sd["b.norm2.bias"], 1e-5)
+    ref2 = O.cross_attention(ln2, ctx, sd, "b.attn2") + ref1
+    wq_t, wo = fold_cross_attention_weights(blk.attn2)
+    kf = F.linear(F.linear(ctx, sd["b.attn2.to_k.weight"]), wq_t)   # K' = (ctx Wk^T) Wq
+    vf = F.linear(F.linear(ctx, sd["b.attn2.to_v.weight"]), wo)     # V' = (ctx Wv^T) Wo^T
+    p2 = (torch.einsum("bid,bjd->bij", ln2, kf) * scale).softmax(-1)
+    got2 = torch.einsum("bij,bjd->bid", p2, vf) + sd["b.attn2.to_out.0.bias"] + ref1
+    assert (got2 - ref2).abs().max() < 2e-5
