@@ -17,7 +17,7 @@ c_p = C.c_void_p
 
 ACT_NONE, ACT_RELU, ACT_SILU, ACT_GEGLU, ACT_GEGLU_FAST, ACT_GELU = 0, 1, 2, 3, 4, 5
 (OP_CONV, OP_GN_STATS, OP_NORM_ACT, OP_LAYERNORM, OP_SOFTMAX, OP_TIME_EMBED, OP_STEP_BEGIN, OP_UPDATE, OP_SNAP, OP_VQ,
- OP_ZERO, OP_UPSAMPLE, OP_EMBED, OP_MHA, OP_CONVT, OP_ASSEMBLE, OP_ATTN) = range(1, 18)
+ OP_ZERO, OP_UPSAMPLE, OP_EMBED, OP_MHA, OP_CONVT, OP_ASSEMBLE, OP_ATTN, OP_BLEND) = range(1, 19)
 
 
 class ConvParams(C.Structure):
@@ -121,12 +121,18 @@ class ToU8Params(C.Structure):
     _fields_ = [("x", c_p), ("B", c_i), ("C", c_i), ("HW", c_i), ("mode", c_i), ("out", c_p)]
 
 
+class BlendParams(C.Structure):
+    _fields_ = [("x", c_p), ("x_dup", c_p), ("x0", c_p), ("mask", c_p), ("noise", c_p), ("sqrt_acp", c_p), ("sqrt_1m_acp", c_p),
+                ("step", c_p), ("t_table", c_p), ("T", c_i), ("B", c_i), ("C", c_i), ("HW", c_i), ("seed", C.c_uint64),
+                ("seed_dev", c_p)]
+
+
 class _OpU(C.Union):
     _fields_ = [("conv", ConvParams), ("gn_stats", GnStatsParams), ("norm_act", NormActParams),
                 ("layernorm", LayerNormParams), ("softmax", SoftmaxParams), ("time_embed", TimeEmbedParams),
                 ("step_begin", StepBeginParams), ("update", UpdateParams), ("snap", SnapParams), ("vq", VqParams),
                 ("zero", ZeroParams), ("upsample", UpsampleParams), ("embed", EmbedParams), ("mha", MhaParams), ("convt", ConvT2dParams),
-                ("assemble", AssembleParams), ("attn", AttnParams)]
+                ("assemble", AssembleParams), ("attn", AttnParams), ("blend", BlendParams)]
 
 
 class Op(C.Structure):
@@ -135,17 +141,18 @@ class Op(C.Structure):
 
 _KIND_FIELD = {OP_CONV: "conv", OP_GN_STATS: "gn_stats", OP_NORM_ACT: "norm_act", OP_LAYERNORM: "layernorm",
                OP_SOFTMAX: "softmax", OP_TIME_EMBED: "time_embed", OP_STEP_BEGIN: "step_begin", OP_UPDATE: "update",
-               OP_SNAP: "snap", OP_VQ: "vq", OP_ZERO: "zero", OP_UPSAMPLE: "upsample", OP_EMBED: "embed", OP_MHA: "mha", OP_CONVT: "convt", OP_ASSEMBLE: "assemble", OP_ATTN: "attn"}
+               OP_SNAP: "snap", OP_VQ: "vq", OP_ZERO: "zero", OP_UPSAMPLE: "upsample", OP_EMBED: "embed", OP_MHA: "mha", OP_CONVT: "convt", OP_ASSEMBLE: "assemble", OP_ATTN: "attn",
+               OP_BLEND: "blend"}
 
 EXPORTS = [
     "frido_conv2d", "frido_gn_stats", "frido_norm_act", "frido_layernorm", "frido_softmax", "frido_time_embed",
     "frido_step_begin", "frido_sampler_update", "frido_stage_snap", "frido_vq_lookup", "frido_zero",
-    "frido_round_tf32", "frido_split_bf16", "frido_upsample2x", "frido_to_uint8", "frido_embed_tokens", "frido_mha_small", "frido_attn_small", "frido_conv_transpose2d", "frido_assemble_latent", "frido_run_program", "frido_abi_version", "frido_sizeof_op", "frido_last_error",
+    "frido_round_tf32", "frido_split_bf16", "frido_upsample2x", "frido_to_uint8", "frido_embed_tokens", "frido_mha_small", "frido_attn_small", "frido_conv_transpose2d", "frido_assemble_latent", "frido_mask_blend", "frido_run_program", "frido_abi_version", "frido_sizeof_op", "frido_last_error",
     "frido_launch_count", "frido_check_device",
 ]
 
 SK_WS_BYTES = 40 << 20
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 _lib = None
 
@@ -177,7 +184,7 @@ def lib():
     for name in ("frido_conv2d", "frido_gn_stats", "frido_norm_act", "frido_layernorm", "frido_softmax",
                  "frido_time_embed", "frido_step_begin", "frido_sampler_update", "frido_stage_snap", "frido_vq_lookup",
                  "frido_upsample2x", "frido_to_uint8", "frido_embed_tokens", "frido_mha_small", "frido_attn_small",
-                 "frido_conv_transpose2d", "frido_assemble_latent"):
+                 "frido_conv_transpose2d", "frido_assemble_latent", "frido_mask_blend"):
         getattr(L, name).argtypes = [c_p, c_p]
     if L.frido_abi_version() != ABI_VERSION:
         raise FridoError(f"ABI mismatch: library version {L.frido_abi_version()}, binding {ABI_VERSION} (rebuild: make -C frido_b200/csrc)")

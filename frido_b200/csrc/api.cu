@@ -47,6 +47,7 @@ extern "C" int frido_run_program(const FridoOp* ops, int32_t n, void* stream) {
       case FRIDO_OP_CONVT: rc = frido_conv_transpose2d(&op.u.convt, stream); break;
       case FRIDO_OP_ASSEMBLE: rc = frido_assemble_latent(&op.u.assemble, stream); break;
       case FRIDO_OP_UPSAMPLE: rc = frido_upsample2x(&op.u.upsample, stream); break;
+      case FRIDO_OP_BLEND: rc = frido_mask_blend(&op.u.blend, stream); break;
       case FRIDO_OP_ZERO: rc = frido_zero(op.u.zero.ptr, op.u.zero.nbytes, stream); break;
       default: rc = set_error(FRIDO_E_ARG, "run_program: unknown op kind");
     }

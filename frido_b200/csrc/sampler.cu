@@ -104,6 +104,24 @@ __global__ void __launch_bounds__(256) update_kernel(const FridoUpdateParams p) 
   }
 }
 
+// mask / x0 blend in front of a step (ddim.py:158-161): q_sample of the clean latent at this step's t, mixed in under the mask
+__global__ void __launch_bounds__(256) blend_kernel(const FridoBlendParams p) {
+  int i = *p.step;
+  if (i > p.T - 1) i = p.T - 1;
+  const int64_t t = p.t_table[i];
+  const float a = p.sqrt_acp[t], b = p.sqrt_1m_acp[t];  // extract_into_tensor(...) (frido.py:306-307)
+  const int64_t total = (int64_t)p.B * p.C * p.HW;
+  const uint64_t seed = p.seed ^ (p.seed_dev ? *p.seed_dev : 0ull);
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const float nz = p.noise ? p.noise[e] : philox_normal(seed, (1ull << 40) | (uint64_t)i, (uint64_t)e);
+    const float orig = __fadd_rn(__fmul_rn(a, p.x0[e]), __fmul_rn(b, nz));
+    const float m = p.mask[e];
+    const float v = __fadd_rn(__fmul_rn(orig, m), __fmul_rn(__fsub_rn(1.0f, m), p.x[e]));
+    p.x[e] = v;
+    if (p.x_dup) p.x_dup[e] = v;
+  }
+}
+
 __global__ void step_advance_kernel(int32_t* step) { *step += 1; }
 
 // avg_pool2d(2) n times == mean over 2^n x 2^n blocks only up to rounding; the
@@ -322,6 +340,17 @@ extern "C" int frido_sampler_update(const FridoUpdateParams* p, void* stream) {
     rc = check_launch("step_advance");
   }
   return rc;
+}
+
+extern "C" int frido_mask_blend(const FridoBlendParams* p, void* stream) {
+  if (!p || !p->x || !p->x0 || !p->mask || !p->sqrt_acp || !p->sqrt_1m_acp || !p->step || !p->t_table)
+    return set_error(FRIDO_E_ARG, "mask_blend: null pointer");
+  if (p->B <= 0 || p->C <= 0 || p->HW <= 0 || p->T <= 0) return set_error(FRIDO_E_ARG, "mask_blend: bad shape");
+  const int64_t total = (int64_t)p->B * p->C * p->HW;
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  blend_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(*p);
+  return check_launch("mask_blend");
 }
 
 extern "C" int frido_stage_snap(const FridoSnapParams* p, void* stream) {

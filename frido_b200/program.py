@@ -379,6 +379,15 @@ class Program:
         self.hold(x, eps, eps_uncond, coef, step, hist, eps_save, noise, seed_dev, x_prev, x_dup, pred_x0)
         self._add(L.OP_UPDATE, p, tag)
 
+    def blend(self, x, x0, mask, sqrt_acp, sqrt_1m_acp, step, t_table, *, B, Cdim, HW, T, noise=None, x_dup=None, seed=0,
+              seed_dev=None, tag="mask_blend"):
+        p = L.BlendParams()
+        p.x, p.x_dup, p.x0, p.mask, p.noise = x.data_ptr(), _ptr(x_dup), x0.data_ptr(), mask.data_ptr(), _ptr(noise)
+        p.sqrt_acp, p.sqrt_1m_acp, p.step, p.t_table, p.T = sqrt_acp.data_ptr(), sqrt_1m_acp.data_ptr(), step.data_ptr(), t_table.data_ptr(), T
+        p.B, p.C, p.HW, p.seed, p.seed_dev = B, Cdim, HW, seed, _ptr(seed_dev)
+        self.hold(x, x_dup, x0, mask, noise, sqrt_acp, sqrt_1m_acp, step, t_table, seed_dev)
+        self._add(L.OP_BLEND, p, tag)
+
     def snap(self, x, *, B, Ctot, H, W, c_start, c_end, n, tag="stage_snap"):
         p = L.SnapParams()
         p.x, p.B, p.C, p.H, p.W, p.c_start, p.c_end, p.n = x.data_ptr(), B, Ctot, H, W, c_start, c_end, n

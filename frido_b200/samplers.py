@@ -90,21 +90,23 @@ class _SamplerBase(object):
                img_callback=None, quantize_x0=False, eta=0.0, mask=None, x0=None, temperature=1.0, noise_dropout=0.0,
                score_corrector=None, corrector_kwargs=None, verbose=True, x_T=None, log_every_t=100,
                unconditional_guidance_scale=1.0, unconditional_conditioning=None, init_noise=None, noise_sequence=None,
-               seed=None, **kwargs):
+               seed=None, mask_noise_sequence=None, **kwargs):
         if conditioning is not None:
             cbs = (conditioning[list(conditioning.keys())[0]] if isinstance(conditioning, dict) else conditioning).shape[0]
             if cbs != batch_size:
                 print(f"Warning: Got {cbs} conditionings but batch-size is {batch_size}")
-        if mask is not None or quantize_x0 or score_corrector is not None or noise_dropout > 0.0:
-            raise NotImplementedError("mask/x0 inpainting, quantize_x0, score_corrector and noise_dropout are outside "
-                                      "the B200 sampling hot path (SURVEY.md §2)")
+        if quantize_x0 or score_corrector is not None or noise_dropout > 0.0:
+            raise NotImplementedError("quantize_x0, score_corrector and noise_dropout are outside the B200 sampling hot "
+                                      "path (SURVEY.md §2)")
+        if mask is not None:
+            assert x0 is not None  # ddim.py:159
         self.make_schedule(ddim_num_steps=S, ddim_eta=eta, verbose=verbose)
         C, H, W = shape
         if verbose:
             print(f"Data shape for {self.KIND.upper()} sampling is {(batch_size, C, H, W)}, eta {eta}")
         return self._sampling(conditioning, (batch_size, C, H, W), num_stage, x_T, log_every_t, temperature,
                               unconditional_guidance_scale, unconditional_conditioning, init_noise, noise_sequence, seed,
-                              callback, img_callback)
+                              callback, img_callback, mask, x0, mask_noise_sequence)
 
     def _cond_tensor(self, cond):
         if isinstance(cond, dict):
@@ -115,7 +117,7 @@ class _SamplerBase(object):
         return cond
 
     def _sampling(self, cond, shape, num_stage, x_T, log_every_t, temperature, cfg_scale, uc, init_noise, noise_sequence,
-                  seed, callback, img_callback):
+                  seed, callback, img_callback, mask=None, x0=None, mask_noise_sequence=None):
         model = self.model
         dev = model.betas.device
         if dev.type != "cuda":
@@ -138,20 +140,32 @@ class _SamplerBase(object):
             assert uc is not None
             uc = self._cond_tensor(uc).to(dev, torch.float32)
         T = self._T
-        intermediates = {"x_inter": [img], "pred_x0": [img]}
+        start = img.clone()  # entry 0 stays x_T like the reference's (it rebinds img every step; we update in place)
+        intermediates = {"x_inter": [start], "pred_x0": [start]}
         self.num_stage = num_stage
-        seed = int(torch.randint(0, 2**62, (1,)).item()) if seed is None else int(seed)
-        nk = 0
+        # host-side draw from torch's CPU generator (no device sync): the Philox seed of this call
+        seed = int(torch.randint(0, 2**62, (1,), device="cpu").item()) if seed is None else int(seed)
+        nk = mk = 0
         self.launches = 0
         for s in range(num_stage):
             c_start, c_end = sum(split[:s]), sum(split[: s + 1])
             if x_T is not None and s == 0:
                 print("Find x_T is not None. Auto adopt x_T into stage 0.")  # ddim.py:150-152
                 continue
-            st = self._stage(unet, s, B, H, W, cond.shape[1], use_cfg, cfg_scale, c_start, c_end, temperature)
+            masked = mask is not None
+            if masked:
+                # ddim.py:160-161: `img_orig * mask + (1. - mask) * img` with img = the channels of this stage; the reference
+                # leaves shape errors to broadcasting (with split heads only the stage that carries all of x0's channels works)
+                if tuple(torch.broadcast_shapes(tuple(x0.shape), tuple(mask.shape), (B, c_end, H, W))) != (B, c_end, H, W):
+                    raise RuntimeError(f"The size of tensor a ({x0.shape[1]}) must match the size of tensor b ({c_end}) at "
+                                       f"non-singleton dimension 1 (mask/x0 blend at stage {s}, ddim.py:161)")
+            st = self._stage(unet, s, B, H, W, cond.shape[1], use_cfg, cfg_scale, c_start, c_end, temperature, masked)
             plan = st["plan"]
             plan.repack_if_stale()
             x = plan.x_in
+            if masked:
+                st["x0"].copy_(x0.to(dev, torch.float32).expand(B, c_end, H, W))
+                st["mask"].copy_(mask.to(dev, torch.float32).expand(B, c_end, H, W))
             x[:B].copy_(img[:, :c_end])
             plan.ctx[:B].copy_(cond)
             if use_cfg:
@@ -170,13 +184,27 @@ class _SamplerBase(object):
                     nk += 1
                 if inj is not None:
                     st["noise"].copy_(inj[:, :c_end])
+                minj = None
+                if masked and mask_noise_sequence is not None:
+                    minj = mask_noise_sequence[mk]
+                    mk += 1
+                    st["mnoise"].copy_(minj[:, :c_end])
+                    if inj is None and self.ddim_eta != 0:
+                        st["noise"].normal_()  # the injected-blend program reads the step noise from this buffer too
                 if self.KIND == "plms" and i == 0:
+                    if masked:  # the blend (and the per-step SPADE maps it invalidates) precede both half steps (plms.py:162-165)
+                        pre = st["blend_inj"] if minj is not None else st["blend"]
+                        pre.run()
+                        self.launches += len(pre)
                     st["x_orig"].copy_(x[:B])
                     st["first_a"].run()
                     st["first_b"].run()
                     self.launches += len(st["first_a"]) + len(st["first_b"])
                 else:
-                    prog = st["inj"] if inj is not None else st["main"]
+                    if masked:
+                        prog = st["mask_inj"] if (inj is not None or minj is not None) else st["mask_main"]
+                    else:
+                        prog = st["inj"] if inj is not None else st["main"]
                     prog.replay()
                     self.launches += len(prog)
                 if callback:
@@ -195,11 +223,14 @@ class _SamplerBase(object):
                     snap.run()
                     self.launches += 1
         out = img if num_stage == len(split) else img[:, : sum(split[:num_stage])]
+        # the reference self-synchronises three times a step (ddim.py:237-240), so callers time sample() with the host clock
+        # (sample_diffusion.py:188-205): hand the result back only when the device has produced it
+        torch.cuda.current_stream(dev).synchronize()
         return out, intermediates
 
-    def _stage(self, unet, s, B, H, W, Lc, use_cfg, cfg_scale, c_start, c_end, temperature):
+    def _stage(self, unet, s, B, H, W, Lc, use_cfg, cfg_scale, c_start, c_end, temperature, masked=False):
         """Build (once) the per-stage programs and device state."""
-        key = (s, B, H, W, Lc, use_cfg, float(cfg_scale), self._T, float(temperature), self.KIND)
+        key = (s, B, H, W, Lc, use_cfg, float(cfg_scale), self._T, float(temperature), self.KIND, masked)
         st = self._stage_cache.get(key)
         if st is not None:
             st["coef"].copy_(self._coef)
@@ -227,17 +258,33 @@ class _SamplerBase(object):
                       temperature=float(temperature), x_dup=x_dup, pred_x0=st["pred_x0"],
                       hist=st.get("hist"), eps_save=st.get("eps_save"))
 
-        def full(name, use_next, upd_kwargs):
+        def full(name, use_next, upd_kwargs, front=None):
             pre = Program(dev, name)
             pre.step_begin(st["step"], st["t_table"], plan.ts, B=Bn, T=self._T, use_next=use_next)
             post = Program(dev, name)
             post.update(eps=eps_c, coef=st["coef"], step=st["step"], **upd_kwargs, **common)
             prog = Program(dev, name)
-            prog.ops = pre.ops + plan.step.ops + post.ops
-            prog.tags = pre.tags + plan.step.tags + post.tags
-            prog.keep = [pre, post, plan]
-            prog.flops = plan.step.flops
+            f_ops, f_tags = (front.ops, front.tags) if front is not None else ([], [])
+            prog.ops = f_ops + pre.ops + plan.step.ops + post.ops
+            prog.tags = f_tags + pre.tags + plan.step.tags + post.tags
+            prog.keep = [pre, post, plan, front]
+            prog.flops = plan.step.flops + (front.flops if front is not None else 0)
             return prog
+
+        def blend_front(name, noise):
+            """mask / x0 mode: the blend rewrites ALL channels before every step (ddim.py:158-161), so the coarse groups are no
+            longer frozen and the step-invariant hoist of the SPADE maps does not hold: the plan's prologue (h_cond, the
+            gamma|beta maps of every norm site) re-runs in front of each step."""
+            fr = Program(dev, name)
+            fr.blend(x[:B], st["x0"], st["mask"], self.model.sqrt_alphas_cumprod, self.model.sqrt_one_minus_alphas_cumprod,
+                     st["step"], st["t_table"], B=B, Cdim=c_end, HW=HW, T=self._T, noise=noise, x_dup=x_dup, seed=0xB1E4D + s,
+                     seed_dev=st["seed_dev"])
+            if plan.c_cond:
+                fr.ops = fr.ops + plan.prologue.ops
+                fr.tags = fr.tags + plan.prologue.tags
+                fr.flops += plan.prologue.flops
+                fr.keep.append(plan.prologue)
+            return fr
 
         order = 4 if plms else 0
         st["main"] = full(f"{self.KIND}.s{s}", 0, dict(x=x[:B], x_prev=x[:B], plms_order=order, plms_mode=0, advance=1,
@@ -247,6 +294,18 @@ class _SamplerBase(object):
         if plms:
             st["first_a"] = full("plms.first_a", 0, dict(x=st["x_orig"], x_prev=x[:B], plms_order=4, plms_mode=1, advance=0))
             st["first_b"] = full("plms.first_b", 1, dict(x=st["x_orig"], x_prev=x[:B], plms_order=4, plms_mode=2, advance=1))
+        if masked:
+            st["x0"] = torch.zeros(B, c_end, H, W, **f32)
+            st["mask"] = torch.zeros(B, c_end, H, W, **f32)
+            st["mnoise"] = torch.zeros(B, c_end, H, W, **f32)
+            st["blend"] = blend_front(f"{self.KIND}.s{s}.blend", None)
+            st["blend_inj"] = blend_front(f"{self.KIND}.s{s}.blend.inj", st["mnoise"])
+            st["mask_main"] = full(f"{self.KIND}.s{s}.mask", 0, dict(x=x[:B], x_prev=x[:B], plms_order=order, plms_mode=0, advance=1,
+                                                                      noise=None, seed=0x5EED + s, seed_dev=st["seed_dev"]),
+                                   front=st["blend"])
+            st["mask_inj"] = full(f"{self.KIND}.s{s}.mask.inj", 0, dict(x=x[:B], x_prev=x[:B], plms_order=order, plms_mode=0,
+                                                                         advance=1, noise=st["noise"]), front=st["blend_inj"])
+            st["mask_main"].capture()
         st["main"].capture()
         self._stage_cache[key] = st
         return st

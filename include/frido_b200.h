@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define FRIDO_ABI_VERSION 3
+#define FRIDO_ABI_VERSION 4
 #define FRIDO_SK_WS_BYTES (40ll << 20)
 
 #define FRIDO_OK 0
@@ -188,6 +188,25 @@ typedef struct FridoUpdateParams {
 } FridoUpdateParams;
 int frido_sampler_update(const FridoUpdateParams* p, void* stream);
 
+/* Inpainting / img2img blend in front of a sampler step (ddim.py:158-161; plms.py:162-165):
+ *   t = t_table[*step];  img_orig = sqrt_acp[t]*x0 + sqrt_1m_acp[t]*noise   (q_sample, frido.py:302-307)
+ *   x = img_orig*mask + (1 - mask)*x          -- same fp32 operation order as the reference, no FMA contraction.
+ * NCHW fp32; `mask` is already expanded to x's shape.  noise == NULL draws N(0,1) from Philox (the reference's
+ * torch.randn_like cannot be matched bit for bit; parity runs inject the noise on both sides). */
+typedef struct FridoBlendParams {
+  float* x;                  /* [B, C, H, W], blended in place */
+  float* x_dup;              /* optional second copy of the result (CFG 2B batch) or NULL */
+  const float* x0;           /* [B, C, H, W] clean latent */
+  const float* mask;         /* [B, C, H, W], 1 = keep x0 */
+  const float* noise;        /* injected N(0,1) [B, C, H, W] or NULL */
+  const float* sqrt_acp;     /* [num_timesteps] sqrt_alphas_cumprod (frido.py:150) */
+  const float* sqrt_1m_acp;  /* [num_timesteps] sqrt_one_minus_alphas_cumprod (frido.py:151) */
+  const int32_t* step; const int64_t* t_table; int32_t T;
+  int32_t B, C, HW;
+  uint64_t seed; const uint64_t* seed_dev;
+} FridoBlendParams;
+int frido_mask_blend(const FridoBlendParams* p, void* stream);
+
 /* Inter-stage snap (ddim.py:177-185): avg_pool2d(2) n times then nearest x2 n times
  * on channels [c_start,c_end) of an NCHW tensor, in place. */
 typedef struct FridoSnapParams {
@@ -294,7 +313,8 @@ enum FridoOpKind {
   FRIDO_OP_CONV = 1, FRIDO_OP_GN_STATS = 2, FRIDO_OP_NORM_ACT = 3, FRIDO_OP_LAYERNORM = 4,
   FRIDO_OP_SOFTMAX = 5, FRIDO_OP_TIME_EMBED = 6, FRIDO_OP_STEP_BEGIN = 7, FRIDO_OP_UPDATE = 8,
   FRIDO_OP_SNAP = 9, FRIDO_OP_VQ = 10, FRIDO_OP_ZERO = 11, FRIDO_OP_UPSAMPLE = 12,
-  FRIDO_OP_EMBED = 13, FRIDO_OP_MHA = 14, FRIDO_OP_CONVT = 15, FRIDO_OP_ASSEMBLE = 16, FRIDO_OP_ATTN = 17
+  FRIDO_OP_EMBED = 13, FRIDO_OP_MHA = 14, FRIDO_OP_CONVT = 15, FRIDO_OP_ASSEMBLE = 16, FRIDO_OP_ATTN = 17,
+  FRIDO_OP_BLEND = 18
 };
 typedef struct FridoZeroParams { void* ptr; int64_t nbytes; } FridoZeroParams;
 typedef struct FridoOp {
@@ -305,7 +325,7 @@ typedef struct FridoOp {
     FridoLayerNormParams layernorm; FridoSoftmaxParams softmax; FridoTimeEmbedParams time_embed;
     FridoStepBeginParams step_begin; FridoUpdateParams update; FridoSnapParams snap; FridoVqParams vq;
     FridoZeroParams zero; FridoUpsampleParams upsample; FridoEmbedParams embed; FridoMhaParams mha;
-    FridoConvT2dParams convt; FridoAssembleParams assemble; FridoAttnParams attn;
+    FridoConvT2dParams convt; FridoAssembleParams assemble; FridoAttnParams attn; FridoBlendParams blend;
   } u;
 } FridoOp;
 /* Launches ops[0..n) in order on `stream`; returns 0 or (-(1000+i)) if op i failed. */

@@ -256,10 +256,45 @@ def case_bert(base):
     print("bert done", {k: tuple(v["z"].shape) for k, v in g.items()})
 
 
+def case_mask(base):
+    """8f.3: the samplers' mask / x0 branch (ddim.py:158-161, plms.py:162-165) on the tiny 2-scale model of tiny2.pt
+    (same config, seed and weights).  With split heads the blend only type-checks when `img` carries all channels, i.e.
+    with `x_T` given (stage 0 is then skipped, ddim.py:150-152) - that is the case minted here.  q_sample's
+    torch.randn_like draws are replaced by a pre-drawn sequence (injected on the checker side as well)."""
+    cfg = tiny_cfg(base, 2)
+    model = ref_loader.build_model(cfg)
+    prep(model, seed=3)
+    model.scale_factor.copy_(torch.tensor([0.8, 1.3]))
+    DDIM, PLMS = ref_loader.activate()
+    B, C = 2, 6
+    ctx = synth.synth_input("ctx", (B, 5, 24), 1)
+    uc = synth.synth_input("uc", (B, 5, 24), 2)
+    x_T = synth.synth_input("mask_xT", (B, C, 8, 8), 21)
+    x0 = synth.synth_input("mask_x0", (B, C, 8, 8), 22)
+    mask = (synth.synth_input("mask_m", (B, 1, 8, 8), 23) > 0).float()
+    g = dict(x_T=x_T, x0=x0, mask=mask)
+    for tag, cls, S, kw in (("ddim4", DDIM, 4, {}), ("plms4", PLMS, 4, {}),
+                            ("ddimcfg2", DDIM, 2, dict(unconditional_guidance_scale=1.5, unconditional_conditioning=uc))):
+        nzs = [synth.synth_input(f"mask_nz_{tag}{k}", (B, C, 8, 8), 24) for k in range(S)]
+        it = iter(nzs)
+        orig = torch.randn_like
+        torch.randn_like = lambda t, *a, **k: next(it).clone()
+        try:
+            out, inter = cls(model).sample(S, B, (C, 8, 8), conditioning=ctx, num_stage=2, eta=0.0, verbose=False, log_every_t=1,
+                                           x_T=x_T, mask=mask, x0=x0, **kw)
+        finally:
+            torch.randn_like = orig
+        g[tag + "_out"] = out.clone()
+        g[tag + "_noises"] = nzs
+        g[tag + "_xinter1"] = inter["x_inter"][1].clone()
+    torch.save(g, os.path.join(OUT, "mask.pt"))
+    print("mask done", {k: tuple(v.shape) for k, v in g.items() if torch.is_tensor(v)})
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     base = ref_loader.load_config("configs/frido/layout2i/frido_f8f4_coco_seg.yaml")
-    which = sys.argv[1:] or ["sched", "tiny2", "tiny3", "l2i32", "bert", "enc"]
+    which = sys.argv[1:] or ["sched", "tiny2", "tiny3", "l2i32", "bert", "enc", "mask"]
     if "sched" in which:
         case_sched(base)
     if "tiny2" in which:
@@ -272,6 +307,8 @@ def main():
         case_bert(base)
     if "enc" in which:
         case_encode(base)
+    if "mask" in which:
+        case_mask(base)
 
 
 if __name__ == "__main__":

@@ -22,7 +22,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(L, name), name
     assert set(_lib.EXPORTS) == declared
-    assert L.frido_abi_version() == 3
+    assert L.frido_abi_version() == _lib.ABI_VERSION
     assert L.frido_sizeof_op() == __import__("ctypes").sizeof(_lib.Op)
 
 

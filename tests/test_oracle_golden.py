@@ -75,6 +75,25 @@ def test_tiny_model_vs_reference(golden_dir, tag):
         assert (img - g[ik]).abs().max() < 1e-4
 
 
+def test_mask_x0_branch_vs_reference(golden_dir):
+    """8f.3: inpainting blend (ddim.py:158-161, plms.py:162-165) with x_T given (stage 0 skipped), injected q_sample noise."""
+    g = _load(golden_dir, "mask.pt")
+    t2 = _load(golden_dir, "tiny2.pt")
+    sd = synth.synth_state_dict(t2["manifest"], t2["seed"])
+    B = 2
+    ctx = synth.synth_input("ctx", (B, 5, 24), 1)
+    uc = synth.synth_input("uc", (B, 5, 24), 2)
+    for tag, S, kw in (("ddim4", 4, {}), ("plms4", 4, dict(sampler="plms")), ("ddimcfg2", 2, dict(uc=uc, cfg_scale=1.5))):
+        tr = []
+        out = O.sample(sd, [3, 3], ctx, g["x_T"], S, mask=g["mask"], x0=g["x0"], mask_noises=g[tag + "_noises"], x_T_skip=True,
+                       trace=tr, **kw)
+        assert (out - g[tag + "_out"]).abs().max() < 1e-4, tag
+        assert (tr[0][2] - g[tag + "_xinter1"]).abs().max() < 1e-4, tag
+    # the blend really acts: without it the result differs
+    plain = O.sample(sd, [3, 3], ctx, g["x_T"], 4, x_T_skip=True)
+    assert (plain - g["ddim4_out"]).abs().max() > 1e-2
+
+
 @pytest.mark.slow
 def test_full_size_l2i_unet_step_and_decoder(golden_dir):
     """BASELINE config 1: single DDIM step on the full-size 511 M-parameter
