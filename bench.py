@@ -81,33 +81,135 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------------------------
-def cpu_port_sample(model, cfg, B_gpu, unet_batch=2):
-    """Times the oracle port on the host cores: one UNet eval per stage at batch `unet_batch` and one decode of
-    one image; extrapolates to the config's step count.  This is the checker used as a baseline, never shipped."""
+def _host_cores():
+    """Threads the CPU arms use: every core this process may run on (torchrun exports OMP_NUM_THREADS=1, which would
+    silently turn the baseline into a single-core run)."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except Exception:
+        n = os.cpu_count() or 1
+    torch.set_num_threads(n)
+    return torch.get_num_threads()
+
+
+def _reference_model(model, cfg, device):
+    """The reference's OWN FridoDiffusion (unmodified modules from /root/reference or the archive packed by
+    oracle/vendor_ref.py) carrying the same synthetic weights as `model`; None if the reference is not available."""
+    try:
+        from oracle import ref_loader
+        if not ref_loader.available():
+            return None
+        ref_loader.activate(cpu=(torch.device(device).type == "cpu"))
+        ref = ref_loader.build_model(cfg["model"])
+        sd = {k: v.detach().float().cpu() for k, v in model.state_dict().items()}
+        missing, unexpected = ref.load_state_dict(sd, strict=False)
+        bad = [k for k in missing if ".loss." not in k and "model_ema" not in k]
+        if bad:
+            raise RuntimeError(f"reference model misses {len(bad)} keys, e.g. {bad[:3]}")
+        return ref.to(device).eval()
+    except Exception as e:  # the baseline failing must not hide the GPU number
+        print(f"[bench] reference modules unavailable: {e!r}", file=sys.stderr)
+        return None
+
+
+def cpu_sample(model, cfg, batch, evals=3, ref=None, budget_s=40.0):
+    """Bounded sample of the workload on the host cores: after one warm-up evaluation, `evals` UNet
+    evaluations per stage at batch `batch` and one decode of `batch` images, extrapolated linearly to the config's
+    step count (every step has the same shapes).  `ref` = the reference's own model on CPU (kind "reference"), else
+    the oracle port (kind "port": oracle/torch_oracle.py, pinned against the reference's outputs in tests/)."""
     from oracle import torch_oracle as O
 
-    sd = {k: v.detach().float().cpu() for k, v in model.state_dict().items()}
+    cores = _host_cores()
     split = list(model.split_embed_dim_list)
     C, H, W = cfg["latent"]
     Lc, D = cfg["ctx"]
     g = torch.Generator().manual_seed(5)
-    ctx = torch.randn(unet_batch, Lc, D, generator=g)
-    ts = torch.full((unet_batch,), 501, dtype=torch.long)
-    t_stage = []
+    ctx = torch.randn(batch, Lc, D, generator=g)
+    ts = torch.full((batch,), 501, dtype=torch.long)
+    sf = [float(v) for v in model.scale_factor.cpu().tolist()]
+    if ref is None:
+        sd = {k: v.detach().float().cpu() for k, v in model.state_dict().items()}
+        unet = lambda x, s: O.unet_forward(sd, x, ts[: x.shape[0]], ctx[: x.shape[0]], s, split)
+        dec = lambda z: O.decode_first_stage(sd, z, split, sf)
+    else:
+        unet = lambda x, s: ref.apply_model(x, ts[: x.shape[0]], ctx[: x.shape[0]], stage=s)
+        dec = lambda z: ref.decode_first_stage(z)
+    t_stage, n_done = [], []
+    t_begin = time.perf_counter()
     for s in range(len(split)):
-        x = torch.randn(unet_batch, sum(split[: s + 1]), H, W, generator=g)
-        t0 = time.perf_counter()
-        O.unet_forward(sd, x, ts, ctx, s, split)
-        t_stage.append((time.perf_counter() - t0) / unet_batch)
-    z = torch.randn(1, C, H, W, generator=g)
+        x = torch.randn(batch, sum(split[: s + 1]), H, W, generator=g)
+        if s == 0:
+            unet(x[:1], s)  # warm-up (allocator, oneDNN primitives, page-in of the weights)
+            t_begin = time.perf_counter()
+        ts_ = []
+        for _ in range(evals):
+            t0 = time.perf_counter()
+            unet(x, s)
+            ts_.append(time.perf_counter() - t0)
+            if time.perf_counter() - t_begin > budget_s * (s + 1) / (len(split) + 1) and len(ts_) >= 1:
+                break
+        t_stage.append(statistics.median(ts_) / batch)
+        n_done.append(len(ts_))
+    z = torch.randn(batch, C, H, W, generator=g)
     t0 = time.perf_counter()
-    O.decode_first_stage(sd, z, split, [float(v) for v in model.scale_factor.cpu().tolist()])
+    dec(z)
+    t_dec = (time.perf_counter() - t0) / batch
+    n_evals = cfg["steps"] + (1 if cfg["sampler"] == "plms" else 0)
+    sec_per_img = n_evals * sum(t_stage) + t_dec
+    return dict(value=1.0 / sec_per_img, unit="images/sec", cores=cores, kind="reference" if ref is not None else "port",
+                sample=f"{'/'.join(str(n) for n in n_done)} UNet evals per stage at batch {batch} (median "
+                       f"{'/'.join(f'{t:.3f}' for t in t_stage)} s per image) + 1 decode of {batch} images ({t_dec:.3f} s per image), "
+                       f"extrapolated to {n_evals} evals per stage; torch {torch.__version__} CPU fp32, {cores} threads; "
+                       + ("the reference's own modules (oracle/_ref)" if ref is not None else "oracle port"))
+
+
+def gpu_eager_reference(model, cfg, dev, steps_small=4):
+    """Secondary software baseline: the reference's own modules in eager PyTorch on this
+    B200 through ITS public API (DDIMSampler.sample + decode_first_stage), same weights and shapes; `steps_small`
+    sampler steps per stage timed after a warm-up and extrapolated linearly to the config's step count."""
+    ref = _reference_model(model, cfg, dev)
+    if ref is None:
+        return None
+    from oracle import ref_loader
+    DDIM, PLMS = ref_loader.activate(cpu=False)
+    B = cfg["batch"]
+    C, H, W = cfg["latent"]
+    Lc, D = cfg["ctx"]
+    g = torch.Generator().manual_seed(1)
+    ctx = torch.randn(B, Lc, D, generator=g).to(dev)
+    smp = (DDIM if cfg["sampler"] == "ddim" else PLMS)(ref)
+    ns = len(model.split_embed_dim_list)
+    S = 1000 // (1000 // steps_small)  # the reference's schedule needs 1000 // S to tile [0, 1000)
+    import contextlib
+    import io
+
+    def run():
+        with contextlib.redirect_stdout(io.StringIO()), contextlib.redirect_stderr(io.StringIO()):
+            z, _ = smp.sample(S, B, (C, H, W), conditioning=ctx, num_stage=ns, eta=0.0, verbose=False)
+        return z
+
+    z = run()  # warm-up: cuDNN autotune, allocator
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    z = run()
+    torch.cuda.synchronize()
+    t_step = (time.perf_counter() - t0) / S  # both stages, one sampler step each
+    ref.decode_first_stage(z)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    ref.decode_first_stage(z)
+    torch.cuda.synchronize()
     t_dec = time.perf_counter() - t0
-    evals = cfg["steps"] + (1 if cfg["sampler"] == "plms" else 0)
-    sec_per_img = evals * sum(t_stage) + t_dec
-    return dict(value=1.0 / sec_per_img, unit="images/sec", cores=torch.get_num_threads(), kind="port",
-                sample=f"1 UNet eval per stage at batch {unet_batch} ({'/'.join(f'{t:.2f}' for t in t_stage)} s per image) + 1 decode "
-                       f"of 1 image ({t_dec:.2f} s), extrapolated to {evals} evals per stage; torch {torch.__version__} CPU fp32")
+    n_steps = cfg["steps"] + (1 if cfg["sampler"] == "plms" else 0)
+    sec = n_steps * t_step + t_dec
+    out = dict(value=round(B / sec, 4), unit="images/sec", kind="reference modules, eager PyTorch on this GPU",
+               ms_per_sampler_step_both_stages=round(1e3 * t_step, 2), ms_decode=round(1e3 * t_dec, 2),
+               tf32=dict(matmul=torch.backends.cuda.matmul.allow_tf32, cudnn=torch.backends.cudnn.allow_tf32),
+               sample=f"{S} {cfg['sampler'].upper()} steps x {ns} stages at batch {B} through the reference's sampler + 1 decode, "
+                      f"extrapolated to {n_steps} steps; torch {torch.__version__} defaults")
+    del ref, smp
+    torch.cuda.empty_cache()
+    return out
 
 
 def time_tc_launches(plan_step, reps=2):
@@ -156,6 +258,16 @@ def _traffic():
         return None
 
 
+def _parity():
+    """Free-running drift of the full sampler against the CPU oracle, measured by tools/prof/drift.py on the GPU box and
+    committed under profiles/ (bench.py itself does not spend a minute of host time on the oracle)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "drift.json")) as f:
+            return json.load(f)
+    except Exception:
+        return None
+
+
 def run_ours(args):
     import frido_b200 as fb
     from frido_b200 import configs
@@ -188,16 +300,19 @@ def run_ours(args):
     x0_h = torch.randn(B * world, C, H, W, generator=g)[rank * B:(rank + 1) * B].contiguous().pin_memory()
     ctx_d, x0_d = ctx_h.to(dev), x0_h.to(dev)
     gathered = None
+    fdec = 2 ** (model.first_stage_model.decoder.num_resolutions - 1)
 
     def one_batch(ctx, x0):
+        """sample -> decode with the script's output formatting fused into the decoder head (uint8 NHWC, what
+        custom_to_np produces, sample_diffusion.py:115-121) -> one all-gather of the uint8 images."""
         z, _ = sampler.sample(S, B, (C, H, W), conditioning=ctx, num_stage=ns, eta=0.0, verbose=False, log_every_t=10**9,
                               init_noise=x0)
-        img = model.decode_first_stage(z)
+        img = model.decode_first_stage_uint8(z, mode="np")
         if world > 1:  # the path's only collective: one all-gather of the finished images over NVLink
             nonlocal gathered
             if gathered is None:
                 gathered = torch.empty((world,) + tuple(img.shape), dtype=img.dtype, device=dev)
-            dist.all_gather_into_tensor(gathered, img.contiguous())
+            dist.all_gather_into_tensor(gathered, img)
         return img
 
     def sync():
@@ -208,7 +323,7 @@ def run_ours(args):
     launches_per_step = None
     for _ in range(args.warmup):
         img = one_batch(ctx_d, x0_d)
-        launches_per_step = sampler.launches + len(model.first_stage_model._plans[next(iter(model.first_stage_model._plans))].prog)
+        launches_per_step = sampler.launches + len(next(iter(model.first_stage_model._plans.values())).prog)
     sync()
     clocks = ClockSampler(local)
     clocks.start()
@@ -224,10 +339,12 @@ def run_ours(args):
     sync()
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     f0.record()
+    out_h = torch.empty(B, H * fdec, W * fdec, 3, dtype=torch.uint8).pin_memory()
     for _ in range(args.steps):
         c = ctx_h.to(dev, non_blocking=True)
         x = x0_h.to(dev, non_blocking=True)
-        out_h = one_batch(c, x).to("cpu", non_blocking=False)
+        out_h.copy_(one_batch(c, x), non_blocking=True)  # result read: this rank's finished images, uint8, into pinned memory
+        torch.cuda.current_stream().synchronize()
     f1.record()
     sync()
     ms_e2e = f0.elapsed_time(f1)
@@ -252,8 +369,7 @@ def run_ours(args):
         dec_plan = next(iter(model.first_stage_model._plans.values()))
         flops_per_img += dec_plan.prog.flops / B
         line = {
-            "metric": "images/sec DDIM-200 256x256 layout-to-image (sampling + decode)" if args.config == "l2i_coco"
-            else f"images/sec {cfg['sampler'].upper()}-{S} ({args.config}, sampling + decode)",
+            "metric": _metric_name(args.config, cfg),
             "value": round(value, 4), "unit": "images/sec", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": round(ms / args.steps, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": {"bf16x3": "bf16x3 (error-compensated: bf16 hi/lo operand split, 3 MMAs per product, fp32 accumulate, for every "
@@ -262,14 +378,13 @@ def run_ours(args):
                       "tc3": "tf32x3 (error-compensated 3xTF32 operands, fp32 accumulate: fp32-faithful)",
                       "tc": "tf32 (fp32 accumulate)", "simt": "f32"}[eng],
             "data": "synthetic (random-init weights with zero_module tensors re-drawn, N(0,1) context and start noise, eta=0)",
-            "config": {"workload": f"{args.config}: latent {C}x{H}x{W}, context {Lc}x{D}, {cfg['sampler'].upper()}-{S} x {ns} stages "
-                                   f"+ MS-VQGAN decode, batch {B} per GPU (BASELINE configs[1])" if args.config == "l2i_coco"
-                       else f"{args.config}: latent {C}x{H}x{W}, context {Lc}x{D}, batch {B} per GPU",
+            "config": {"workload": _workload_name(args.config, cfg, ns),
                        "batch_per_gpu": B, "sampler_steps": S, "stages": ns, "engine": eng,
                        "l2": "working set of one step (weights 2 GB + activations) >> 126 MB L2; no explicit flush",
-                       "parallelism": f"batch-sharded x{world}, one all-gather of images" if world > 1 else "single GPU"},
+                       "parallelism": f"batch-sharded x{world}, one all-gather of the uint8 images" if world > 1 else "single GPU"},
             "e2e": {"value": round(e2e_val, 4), "unit": "images/sec",
-                    "h2d_bytes_per_step": int(ctx_h.numel() * 4 + x0_h.numel() * 4), "d2h_bytes_per_step": int(out_h.numel() * 4)},
+                    "h2d_bytes_per_step": int(ctx_h.numel() * 4 + x0_h.numel() * 4), "d2h_bytes_per_step": int(out_h.numel()),
+                    "result": "uint8 NHWC images (custom_to_np format) of this rank's batch"},
             "gpu_launches": int(launches_per_step * args.steps),
             "clocks": clk,
             "roofline": {"bound": "tensor", "achieved": round(achieved, 2), "peak": peaks["bf16"], "unit": "TFLOP/s",
@@ -284,49 +399,71 @@ def run_ours(args):
             "tflop_per_image": round(flops_per_img / 1e12, 3),
             "achieved_tflops_whole_job": round(flops_per_img * value / 1e12 / world, 2),
         }
+        line["parity"] = _parity()
         if world == 1:
             try:
-                line["cpu_baseline"] = cpu_port_sample(model, cfg, B)
+                line["cpu_baseline"] = cpu_sample(model, cfg, min(B, 4), evals=2, ref=_reference_model(model, cfg, "cpu"), budget_s=30.0)
             except Exception as e:  # the checker failing must not hide the GPU number
                 line["cpu_baseline"] = {"error": repr(e)}
+            if os.environ.get("FRIDO_BENCH_GPU_EAGER", "1") == "1":
+                try:
+                    line["gpu_eager_reference"] = gpu_eager_reference(model, cfg, dev)
+                    if line["gpu_eager_reference"]:
+                        line["gpu_eager_reference"]["speedup_e2e"] = round(e2e_val / line["gpu_eager_reference"]["value"], 2)
+                except Exception as e:
+                    line["gpu_eager_reference"] = {"error": repr(e)}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
 
 def run_reference(args):
-    """Reference arm: the reference's own algorithm on the host CPU cores (the reference is pure PyTorch; its modules
-    cannot travel to the GPU box, so the pinned oracle port — validated against the real reference in
-    tests/test_oracle_golden.py — is what runs).  Rank 0 only."""
+    """Reference arm: the reference's own CPU implementation of the path on the box's host cores, all of them
+    (`oracle/_ref` = the reference's unmodified modules when the archive is present, else the pinned oracle port).
+    Each step = a bounded sample of the workload at the config's batch: 3 UNet evaluations per stage + 1 decode,
+    extrapolated linearly to the config's step count.  Rank 0 only."""
     if int(os.environ.get("RANK", "0")) != 0:
         return
     from frido_b200 import configs
 
+    cores = _host_cores()
     model, cfg = configs.build(args.config, "cpu")
     B = cfg["batch"]
+    ref = _reference_model(model, cfg, "cpu")
     vals = []
     t_all0 = time.perf_counter()
-    for i in range(args.warmup + args.steps):
+    for i in range(max(1, args.steps)):
         if i >= 1 and time.perf_counter() - t_all0 > 150:  # keep the whole run within a few minutes
             break
-        r = cpu_port_sample(model, cfg, B, unet_batch=1)
-        if i >= min(args.warmup, 1):
-            vals.append(r)
-    if not vals:
-        vals = [r]
+        vals.append(cpu_sample(model, cfg, B, evals=3, ref=ref, budget_s=100.0))
     v = statistics.median([x["value"] for x in vals])
     C, H, W = cfg["latent"]
-    line = {"impl": "reference", "metric": "images/sec DDIM-200 256x256 layout-to-image (sampling + decode)", "value": v,
-            "unit": "images/sec", "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": len(vals), "warmup": min(args.warmup, 1),
+    ns = len(model.split_embed_dim_list)
+    line = {"impl": "reference", "metric": _metric_name(args.config, cfg), "value": v,
+            "unit": "images/sec", "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": len(vals), "warmup": 1,
             "ms_per_step": round(1e3 * B / v, 1), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic (same weights / shapes as the GPU arm)",
-            "config": {"workload": f"{args.config}: latent {C}x{H}x{W}, context {cfg['ctx'][0]}x{cfg['ctx'][1]}, {cfg['sampler'].upper()}-{cfg['steps']} x "
-                                   f"{len(model.split_embed_dim_list)} stages + MS-VQGAN decode, batch {B} per GPU (BASELINE configs[1])",
-                       "batch_per_gpu": B, "sampler_steps": cfg["steps"], "engine": "reference algorithm on host CPU (oracle port)",
-                       "sample": "each step = 1 UNet eval per stage + 1 decode, extrapolated linearly to the full step count"},
+            "config": {"workload": _workload_name(args.config, cfg, ns), "batch_per_gpu": B, "sampler_steps": cfg["steps"], "stages": ns,
+                       "engine": "the reference's own modules on the host CPU" if ref is not None else "reference algorithm on host CPU (oracle port)",
+                       "sample": "each step = 3 UNet evals per stage + 1 decode at the config's batch, extrapolated linearly to the full step count",
+                       "cores": cores},
             "cpu_baseline": dict(vals[-1], value=v),
             "e2e": {"value": v, "unit": "images/sec", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     print(json.dumps(line), flush=True)
+
+
+def _metric_name(name, cfg):
+    if name == "l2i_coco":
+        return "images/sec DDIM-200 256x256 layout-to-image (sampling + decode)"
+    return f"images/sec {cfg['sampler'].upper()}-{cfg['steps']} ({name}, sampling + decode)"
+
+
+def _workload_name(name, cfg, ns):
+    C, H, W = cfg["latent"]
+    which = {"l2i_coco": "BASELINE configs[1]", "t2i_clip": "BASELINE configs[2]", "sg2i_vg": "BASELINE configs[3]",
+             "l2i_512": "BASELINE configs[4]"}.get(name, "")
+    return (f"{name}: latent {C}x{H}x{W}, context {cfg['ctx'][0]}x{cfg['ctx'][1]}, {cfg['sampler'].upper()}-{cfg['steps']} x {ns} stages "
+            f"+ MS-VQGAN decode, batch {cfg['batch']} per GPU ({which})")
 
 
 def main():

@@ -10,11 +10,12 @@ from ._lib import FridoError, lib  # noqa: F401
 from .cond import BERTEmbedder  # noqa: F401
 from .diffusion import DiffusionWrapper, FridoDiffusion, LitEma, instantiate_from_config  # noqa: F401
 from .first_stage import VQModelInterface, images_to_uint8  # noqa: F401
+from .output import SampleWriter  # noqa: F401
 from .samplers import DDIMSampler, PLMSSampler  # noqa: F401
 from .unet import PyUNetModel  # noqa: F401
 
 __all__ = ["FridoDiffusion", "DiffusionWrapper", "LitEma", "PyUNetModel", "VQModelInterface", "DDIMSampler",
-           "PLMSSampler", "FridoError", "instantiate_from_config", "lib"]
+           "PLMSSampler", "FridoError", "instantiate_from_config", "lib", "SampleWriter", "images_to_uint8"]
 
 
 def install_aliases():

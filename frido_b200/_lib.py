@@ -33,7 +33,7 @@ class ConvParams(C.Structure):
         ("o_sb", c_l), ("o_sp", c_l), ("o_sn", c_l), ("round_tf32", c_i), ("out_hi", c_p), ("out_lo", c_p), ("chan_sums", c_p),
         ("x0", c_p), ("x1", c_p), ("cx0", c_i), ("cx1", c_i), ("x0_sb", c_l), ("x0_sy", c_l), ("x0_sx", c_l),
         ("x1_sb", c_l), ("x1_sy", c_l), ("x1_sx", c_l),
-        ("sk_ws", c_p), ("sk_ws_bytes", c_l), ("engine", c_i),
+        ("out_u8", c_p), ("u8_mode", c_i), ("sk_ws", c_p), ("sk_ws_bytes", c_l), ("engine", c_i),
     ]
 
 

@@ -96,6 +96,21 @@ __device__ __forceinline__ float gelu_erf_fast(float v) {
   return 0.5f * v * (1.0f + copysignf(e, v));
 }
 
+// Output formatting of the sampling script, same fp32 operation order as the reference so the bytes are identical:
+//   mode 0 = custom_to_np  (scripts/sample_diffusion.py:115-121): ((x + 1) * 127.5).clamp(0, 255) -> uint8 (truncate)
+//   mode 1 = custom_to_pil (scripts/sample_diffusion.py:103-108): 255 * ((clamp(x,-1,1) + 1) / 2)  -> uint8 (truncate)
+__device__ __forceinline__ uint8_t format_u8(float x, int mode) {
+  float t;
+  if (mode == 0) {
+    t = __fmul_rn(__fadd_rn(x, 1.0f), 127.5f);
+    t = fminf(fmaxf(t, 0.f), 255.f);
+  } else {
+    const float cl = fminf(fmaxf(x, -1.f), 1.f);
+    t = __fmul_rn(255.0f, __fdiv_rn(__fadd_rn(cl, 1.0f), 2.0f));
+  }
+  return (uint8_t)(int)t;  // truncation, as torch .to(uint8) / numpy astype(uint8) on non-negative values
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -259,8 +259,10 @@ __global__ void __launch_bounds__(128) conv_smallcout_kernel(const FridoConvPara
       if (res) t += res[(int64_t)n * p.o_sn];
       if (p.act == FRIDO_ACT_RELU) t = fmaxf(t, 0.f);
       else if (p.act == FRIDO_ACT_SILU) t = silu_f(t);
-          else if (p.act == FRIDO_ACT_GELU) t = gelu_erf(t);
-      out[(int64_t)n * p.o_sn] = p.round_tf32 ? round_tf32(t) : t;
+      else if (p.act == FRIDO_ACT_GELU) t = gelu_erf(t);
+      t = p.round_tf32 ? round_tf32(t) : t;
+      out[(int64_t)n * p.o_sn] = t;
+      if (p.out_u8) p.out_u8[((int64_t)b * HWout + pix) * p.Cout + n] = format_u8(t, p.u8_mode);
     }
 }
 
@@ -339,7 +341,10 @@ __global__ void __launch_bounds__(SCT_TH * SCT_TW * SCT_PARTS) conv_smallcout_ti
       if (p.act == FRIDO_ACT_RELU) t = fmaxf(t, 0.f);
       else if (p.act == FRIDO_ACT_SILU) t = silu_f(t);
       else if (p.act == FRIDO_ACT_GELU) t = gelu_erf(t);
-      out[(int64_t)n * p.o_sn] = p.round_tf32 ? round_tf32(t) : t;
+      t = p.round_tf32 ? round_tf32(t) : t;
+      out[(int64_t)n * p.o_sn] = t;
+      // output formatting fused into the head (sample_diffusion.py:115-121): the byte comes from the very fp32 value stored
+      if (p.out_u8) p.out_u8[((int64_t)b * p.Hout * p.Wout + pix) * p.Cout + n] = format_u8(t, p.u8_mode);
     }
 }
 
@@ -401,6 +406,7 @@ int conv2d_simt(const FridoConvParams* p, cudaStream_t s) {
   if (p->ups != 1 && p->ups != 2) return set_error(FRIDO_E_ARG, "conv2d: ups must be 1 or 2");
   if (p->ksize != 1 && p->ksize != 3) return set_error(FRIDO_E_ARG, "conv2d: ksize must be 1 or 3");
   if (p->act == FRIDO_ACT_GEGLU && (p->Cout & 1)) return set_error(FRIDO_E_ARG, "conv2d: GEGLU needs even Cout");
+  if (p->out_u8 && (p->u8_mode != 0 && p->u8_mode != 1)) return set_error(FRIDO_E_ARG, "conv2d: u8_mode must be 0 or 1");
   const int Cin = p->c0 + p->c1;
   const int64_t Ktot = (int64_t)p->ksize * p->ksize * Cin;
   bool vecA = (Cin % 4 == 0) && (p->c0 % 4 == 0) && p->a0_sc == 1 && aligned16(p->a0) && p->a0_sb % 4 == 0 &&
@@ -412,7 +418,7 @@ int conv2d_simt(const FridoConvParams* p, cudaStream_t s) {
     return set_error(FRIDO_E_ARG, "conv2d: out_hi/out_lo must come together and not with GEGLU");
   if (vecA && vecW && !p->out_hi && !p->a1 && p->ksize == 1 && p->stride == 1 && p->ups == 1 && p->B == 1 && p->Hout == 1 && p->Hin == 1 &&
       p->Wout == p->Win && p->Wout <= SM_MAXROWS && p->o_sn == 1 && p->w_sb == 0 && p->act != FRIDO_ACT_GEGLU && p->act != FRIDO_ACT_GEGLU_FAST &&
-      p->Cout >= 64 && (size_t)p->Wout * Cin * 4 <= 96 * 1024) {
+      p->Cout >= 64 && (size_t)p->Wout * Cin * 4 <= 96 * 1024 && !p->out_u8) {
     static bool attr_l = false;
     if (!attr_l) {
       cudaFuncSetAttribute(linear_smallm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
@@ -441,6 +447,7 @@ int conv2d_simt(const FridoConvParams* p, cudaStream_t s) {
     conv_smallcout_kernel<<<g, 128, smem, s>>>(*p);
     return check_launch("conv2d_smallcout");
   }
+  if (p->out_u8) return set_error(FRIDO_E_ARG, "conv2d: out_u8 needs Cout <= 4 and a 16-byte aligned dense NHWC source (the small-Cout head kernels)");
   dim3 grid((p->Hout * p->Wout + BM - 1) / BM, (p->Cout + BN - 1) / BN, p->B);
   if (grid.y > 65535 || grid.z > 65535) return set_error(FRIDO_E_ARG, "conv2d: grid too large");
   if (vecA && vecW) conv_simt_kernel<true, true><<<grid, NT, 0, s>>>(*p);

@@ -818,6 +818,7 @@ static bool a16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) ==
 int conv2d_tc(const FridoConvParams* p, cudaStream_t s) {
   if (!p->a0 || !p->w || (!p->out && !(p->out_hi && p->o_sn != 1))) return set_error(FRIDO_E_ARG, "conv2d_tc: null pointer");
   if (p->ups != 1) return set_error(FRIDO_E_ARG, "conv2d_tc: ups must be 1 (materialise the upsample first)");
+  if (p->out_u8) return set_error(FRIDO_E_ARG, "conv2d_tc: out_u8 is a feature of the small-Cout head kernels (engine 0)");
   if (p->stride != 1 && !(p->stride == 2 && p->ksize == 3)) return set_error(FRIDO_E_ARG, "conv2d_tc: stride must be 1, or 2 for 3x3");
   if (p->ksize != 1 && p->ksize != 3) return set_error(FRIDO_E_ARG, "conv2d_tc: ksize must be 1 or 3");
   // pad = ksize/2, or 0 for the encoder's asymmetric stride-2 conv (taming model.py:68-72: pad right/bottom by 1 = TMA zero fill)

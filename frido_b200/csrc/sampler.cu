@@ -268,15 +268,7 @@ __global__ void to_uint8_kernel(const FridoToU8Params p) {
     const int hw = (int)(r % p.HW);
     const int b = (int)(r / p.HW);
     const float x = p.x[((int64_t)b * p.C + c) * p.HW + hw];
-    float t;
-    if (p.mode == 0) {
-      t = __fmul_rn(__fadd_rn(x, 1.0f), 127.5f);
-      t = fminf(fmaxf(t, 0.f), 255.f);
-    } else {
-      const float cl = fminf(fmaxf(x, -1.f), 1.f);
-      t = __fmul_rn(255.0f, __fdiv_rn(__fadd_rn(cl, 1.0f), 2.0f));
-    }
-    p.out[e] = (uint8_t)(int)t;  // truncation, as torch .to(uint8) / numpy astype(uint8) on non-negative values
+    p.out[e] = format_u8(x, p.mode);
   }
 }
 

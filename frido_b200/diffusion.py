@@ -291,6 +291,12 @@ class FridoDiffusion(nn.Module):
             raise NotImplementedError("predict_cids is not used by any shipped config")
         return self.first_stage_model.decode(z_in, return_code=return_code, scale_factor=self._scale_factors())
 
+    @torch.no_grad()
+    def decode_first_stage_uint8(self, z_in, mode="np", out=None):
+        """decode_first_stage + custom_to_np / custom_to_pil (scripts/sample_diffusion.py:103-121) as one device program:
+        returns uint8 NHWC [B,H,W,3]."""
+        return self.first_stage_model.decode_uint8(z_in, scale_factor=self._scale_factors(), mode=mode, out=out)
+
     def _scale_factors(self):
         n = len(self.first_stage_model.embed_dim)
         if not self.adopted_scale_factor:

@@ -125,22 +125,42 @@ class VQModelInterface(nn.Module):
             return z, [idx.view(B, -1).clone() for idx in plan.indices]
         return z
 
-    @torch.no_grad()
-    def decode(self, h_in, force_not_quantize=False, return_code=False, scale_factor=None):
-        """msvqgan.py:376-399.  `scale_factor` (list, one per scale) folds
-        decode_first_stage's per-group 1/scale (frido.py:832-838) into the VQ kernel."""
+    def _decode_plan(self, h_in, scale_factor, u8_mode=0):
         if not h_in.is_cuda:
             raise L.FridoError("VQModelInterface.decode runs on a CUDA device only (no CPU path)")
         B, C, H, W = h_in.shape
         sf = tuple(float(s) for s in (scale_factor if scale_factor is not None else [1.0] * len(self.embed_dim)))
-        key = (B, H, W, sf)
+        key = (B, H, W, sf, u8_mode)
         plan = self._plans.get(key)
         if plan is None:
-            plan = DecodePlan(self, B, H, W, sf)
+            plan = DecodePlan(self, B, H, W, sf, u8_mode)
             self._plans[key] = plan
         plan.repack_if_stale()
         plan.z.copy_(h_in)
         plan.prog.run()
+        return plan
+
+    @torch.no_grad()
+    def decode_uint8(self, h_in, scale_factor=None, mode="np", out=None):
+        """decode + the script's output formatting in one program: uint8 NHWC [B,H,W,3], byte-identical to
+        `custom_to_np(decode(h))` (mode "np", sample_diffusion.py:115-121: what goes into the .npz) or to
+        `custom_to_pil` (mode "pil", :103-108: what goes into the PNGs).  The bytes are written by conv_out's epilogue
+        from the fp32 value it stores; no fp32 image leaves the device.  `out`: optional destination (e.g. a slot of the
+        all-gather buffer)."""
+        plan = self._decode_plan(h_in, scale_factor, {"np": 0, "pil": 1}[mode])
+        if plan.image_u8 is None:
+            raise L.FridoError("decode_uint8: the decoder head has more than 4 output channels")
+        if out is not None:
+            out.copy_(plan.image_u8)
+            return out
+        return plan.image_u8.clone()
+
+    @torch.no_grad()
+    def decode(self, h_in, force_not_quantize=False, return_code=False, scale_factor=None):
+        """msvqgan.py:376-399.  `scale_factor` (list, one per scale) folds
+        decode_first_stage's per-group 1/scale (frido.py:832-838) into the VQ kernel."""
+        plan = self._decode_plan(h_in, scale_factor)
+        B = h_in.shape[0]
         dec = plan.image.clone()
         if return_code:
             code = [idx.view(B, -1).tolist() for idx in plan.indices]  # msvqgan.py:390
@@ -171,7 +191,7 @@ class _VQPlan:
                 round_tf32_(dst)
         P.prepare_weights()
 
-    def _decoder_body(self, dec, zin, H, W, out, nchw_out, tag):
+    def _decoder_body(self, dec, zin, H, W, out, nchw_out, tag, out_u8=None, u8_mode=0):
         """taming Decoder.forward (model.py:618-649) from its z input (NHWC [B,HW,zc]) to conv_out, written into `out`
         as NCHW (the image) or NHWC (the shared decoders of the encode side)."""
         P, B = self.prog, self.B
@@ -210,7 +230,7 @@ class _VQPlan:
         oc = dec.conv_out.weight.shape[0]
         kw = dict(o_sb=oc * hh * ww, o_sp=1, o_sn=hh * ww) if nchw_out else {}
         P.conv(Src.nhwc(t, hh, ww), self._conv_w(dec.conv_out), out, B=B, Hin=hh, Win=ww, Hout=hh, Wout=ww, Cout=oc,
-               ksize=3, pad=1, bias=self._vec(dec.conv_out.bias), tag=tag + ".conv_out", **kw)
+               ksize=3, pad=1, bias=self._vec(dec.conv_out.bias), out_u8=out_u8, u8_mode=u8_mode, tag=tag + ".conv_out", **kw)
         P.release(t)
         return hh, ww
 
@@ -305,7 +325,7 @@ class _VQPlan:
 
 
 class DecodePlan(_VQPlan):
-    def __init__(self, fs: VQModelInterface, B, H, W, sf):
+    def __init__(self, fs: VQModelInterface, B, H, W, sf, u8_mode=0):
         self.H, self.W = H, W
         dec = fs.decoder
         self._init_plan(fs, B, "decode", sum(1 for m in dec.modules() if isinstance(m, nn.GroupNorm)))
@@ -328,7 +348,9 @@ class DecodePlan(_VQPlan):
         f = 2 ** (dec.num_resolutions - 1)
         oc = dec.conv_out.weight.shape[0]
         self.image = torch.zeros(B, oc, H * f, W * f, dtype=torch.float32, device=dev)
-        self._decoder_body(dec, pq, H, W, self.image, True, "dec")
+        # the sampling script's output formatting (sample_diffusion.py:103-121) rides conv_out's epilogue: uint8 NHWC
+        self.image_u8 = torch.zeros(B, H * f, W * f, oc, dtype=torch.uint8, device=dev) if oc <= 4 else None
+        self._decoder_body(dec, pq, H, W, self.image, True, "dec", out_u8=self.image_u8, u8_mode=u8_mode)
         self._finish_plan()
 
 

@@ -131,7 +131,7 @@ class Program:
     def conv(self, a0, w, out, *, B, Hin, Win, Hout, Wout, Cout, ksize=1, stride=1, pad=0, ups=1, a1=None,
              bias=None, rowvec=None, rowvec_sb=0, res=None, alpha=1.0, act=L.ACT_NONE, o_sb=None, o_sp=None, o_sn=1,
              w_sb=0, w_ld=0, w_off=0, out_off=0, round_tf32=0, engine=None, csum=None, out_pair=None, w_pair=None,
-             alg_flops=None, side=None, tag="conv"):
+             alg_flops=None, side=None, out_u8=None, u8_mode=0, tag="conv"):
         """Returns True when `csum` (per-channel GroupNorm sums of the output, [B,Cout,2] fp64) was attached to the op:
         only the tcgen05 engines accumulate it, for dense NHWC outputs with >= 32 pixels per image."""
         if engine is None:
@@ -191,6 +191,11 @@ class Program:
         if out_pair is not None:
             p.out_hi, p.out_lo = out_pair[0].data_ptr() + 2 * out_off, out_pair[1].data_ptr() + 2 * out_off
             self.hold(out_pair[0], out_pair[1])
+        if out_u8 is not None:  # uint8 NHWC copy of the outputs (decoder head: sample_diffusion.py:103-121 fused into conv_out)
+            if engine != 0:
+                raise L.FridoError("conv: out_u8 is a feature of the small-Cout head kernels (SIMT engine)")
+            p.out_u8, p.u8_mode = out_u8.data_ptr(), u8_mode
+            self.hold(out_u8)
         tw = min(128, 1 << max(Wout - 1, 0).bit_length())
         th = min(128 // tw, 1 << max(Hout - 1, 0).bit_length())
         csum_ok = csum is not None and engine in (1, 2, 3) and o_sn == 1 and act not in (L.ACT_GEGLU, L.ACT_GEGLU_FAST) and tw * th >= 32

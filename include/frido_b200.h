@@ -84,6 +84,9 @@ typedef struct FridoConvParams {
   int32_t cx0, cx1;         /*   concatenated, sampled at the output pixel (stride 1 only); the weight rows carry the extra */
   int64_t x0_sb, x0_sy, x0_sx; /* cx0+cx1 columns after the taps.  Element strides: image, row, col (channel stride 1). */
   int64_t x1_sb, x1_sy, x1_sx;
+  uint8_t* out_u8;          /* optional (SIMT engine, Cout <= 4: the decoder's conv_out head): also store the outputs as uint8 NHWC */
+  int32_t u8_mode;          /*   [B,Hout,Wout,Cout], formatted like frido_to_uint8 (mode 0 = custom_to_np, 1 = custom_to_pil,
+                               scripts/sample_diffusion.py:103-121) from the same fp32 value that goes to `out` */
   void* sk_ws;              /* optional (tcgen05 engines only) stream-K workspace: launches with too few output tiles for
                                the 148 SMs split their K loops across CTAs and combine the partial sums here (in a fixed
                                order: results stay deterministic).  Zero it once; launches on one stream may share it. */

@@ -13,8 +13,13 @@ import sys
 import torch
 import yaml
 
-REF = os.environ.get("FRIDO_REFERENCE", "/root/reference")
 _HERE = os.path.dirname(os.path.abspath(__file__))
+REF = os.environ.get("FRIDO_REFERENCE", "/root/reference")
+if not os.path.isdir(os.path.join(REF, "frido")):
+    # GPU box: the archive packed by oracle/vendor_ref.py (git-ignored build artefact, travels with the snapshot)
+    sys.path.insert(0, os.path.dirname(_HERE))
+    from oracle import vendor_ref as _vr
+    REF = _vr.unpack() or REF
 
 _TARGET_REWRITE = {
     "ldm.models.diffusion.msldm.MSLatentDiffusion": "frido.models.diffusion.frido.FridoDiffusion",

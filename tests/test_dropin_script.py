@@ -82,3 +82,64 @@ print('ok')
 """
     out = _run(code, [COMPAT, ROOT, SHIMS, REF])
     assert out.strip().endswith("ok")
+
+
+@pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "scripts")), reason="reference checkout not present")
+def test_sample_writer_matches_the_scripts_on_wire_outputs(tmp_path):
+    """8f.4: SampleWriter's .npz / PNG files against the unmodified script's own `custom_to_np` + `np.savez` naming
+    (sample_diffusion.py:293-301) and `save_logs` (:306-334) on the same fp32 images."""
+    import numpy as np
+    import torch
+    from PIL import Image
+
+    import frido_b200 as fb
+
+    g = torch.Generator().manual_seed(4)
+    batches = [torch.randn(3, 3, 16, 16, generator=g) * 0.8 for _ in range(3)]
+    names = [[f"img_{b}_{i}.jpg" for i in range(3)] for b in range(3)]
+    torch.save(dict(batches=batches, names=names), tmp_path / "in.pt")
+    ref_dir = tmp_path / "ref"
+    code = f"""
+import importlib.util, sys, types, os
+import numpy as np, torch
+six = types.ModuleType('torch._six'); six.string_classes = (str, bytes); sys.modules['torch._six'] = six
+spec = importlib.util.spec_from_file_location('ref_sample_diffusion', {os.path.join(REF, 'scripts', 'sample_diffusion.py')!r})
+m = importlib.util.module_from_spec(spec); spec.loader.exec_module(m)
+d = torch.load({str(tmp_path / 'in.pt')!r})
+os.makedirs({str(ref_dir / 'numpy')!r}, exist_ok=True)
+all_images, n_saved = [], 0
+for x, fn in zip(d['batches'], d['names']):
+    logs = dict(sample=x, file_name=fn)
+    n_saved = m.save_logs(logs, {str(ref_dir / 'img')!r}, n_saved=n_saved, keys=['sample'])
+    all_images.extend([m.custom_to_np(x)])
+all_img = np.concatenate(all_images, axis=0)[:8]
+np.savez(os.path.join({str(ref_dir / 'numpy')!r}, 'x'.join(str(v) for v in all_img.shape) + '-samples.npz'), all_img)
+n2 = m.save_logs(dict(sample=d['batches'][0]), {str(ref_dir / 'img2')!r}, n_saved=5, keys=['sample'])
+assert n2 == 8
+"""
+    _run(code, [COMPAT, ROOT, SHIMS, REF])
+
+    def u8(x, mode):  # host restatement of frido_to_uint8 (the device kernel is pinned to it in tests/test_gpu_kernels.py)
+        if mode == "np":
+            return ((x + 1) * 127.5).clamp(0, 255).to(torch.uint8).permute(0, 2, 3, 1).contiguous()
+        return torch.from_numpy((255 * ((torch.clamp(x, -1.0, 1.0) + 1.0) / 2.0).permute(0, 2, 3, 1).numpy()).astype(np.uint8))
+
+    w = fb.SampleWriter(logdir=str(tmp_path / "ours" / "img"), nplog=str(tmp_path / "ours" / "numpy"), n_samples=8)
+    for x, fn in zip(batches, names):
+        w.add_batch(u8(x, "np"), u8(x, "pil"), file_names=fn)
+    path = w.finish()
+    ref_npz = sorted(os.listdir(ref_dir / "numpy"))
+    assert [os.path.basename(path)] == ref_npz == ["8x16x16x3-samples.npz"]
+    assert np.array_equal(np.load(path)["arr_0"], np.load(ref_dir / "numpy" / ref_npz[0])["arr_0"])
+    ours = sorted(os.listdir(tmp_path / "ours" / "img" / "sample"))
+    assert ours == sorted(os.listdir(ref_dir / "img" / "sample")) and len(ours) == 9
+    for f in ours:
+        a = np.asarray(Image.open(tmp_path / "ours" / "img" / "sample" / f))
+        b = np.asarray(Image.open(ref_dir / "img" / "sample" / f))
+        assert np.array_equal(a, b), f
+    # un-named samples are numbered from the running count (sample_diffusion.py:322-323)
+    w2 = fb.SampleWriter(logdir=str(tmp_path / "ours" / "img2"))
+    w2.n_saved = 5
+    w2.add_batch(u8(batches[0], "np"), u8(batches[0], "pil"))
+    w2.finish()
+    assert sorted(os.listdir(tmp_path / "ours" / "img2" / "sample")) == sorted(os.listdir(ref_dir / "img2" / "sample"))
