@@ -17,7 +17,7 @@ c_p = C.c_void_p
 
 ACT_NONE, ACT_RELU, ACT_SILU, ACT_GEGLU, ACT_GEGLU_FAST, ACT_GELU = 0, 1, 2, 3, 4, 5
 (OP_CONV, OP_GN_STATS, OP_NORM_ACT, OP_LAYERNORM, OP_SOFTMAX, OP_TIME_EMBED, OP_STEP_BEGIN, OP_UPDATE, OP_SNAP, OP_VQ,
- OP_ZERO, OP_UPSAMPLE, OP_EMBED, OP_MHA, OP_CONVT, OP_ASSEMBLE, OP_ATTN, OP_BLEND) = range(1, 19)
+ OP_ZERO, OP_UPSAMPLE, OP_EMBED, OP_MHA, OP_CONVT, OP_ASSEMBLE, OP_ATTN, OP_BLEND, OP_GN_FINALIZE) = range(1, 20)
 
 
 class ConvParams(C.Structure):
@@ -33,7 +33,7 @@ class ConvParams(C.Structure):
         ("o_sb", c_l), ("o_sp", c_l), ("o_sn", c_l), ("round_tf32", c_i), ("out_hi", c_p), ("out_lo", c_p), ("chan_sums", c_p),
         ("x0", c_p), ("x1", c_p), ("cx0", c_i), ("cx1", c_i), ("x0_sb", c_l), ("x0_sy", c_l), ("x0_sx", c_l),
         ("x1_sb", c_l), ("x1_sy", c_l), ("x1_sx", c_l),
-        ("out_u8", c_p), ("u8_mode", c_i), ("sk_ws", c_p), ("sk_ws_bytes", c_l), ("engine", c_i),
+        ("nrm_ab", c_p), ("nrm_gb", c_p), ("nrm_silu", c_i), ("out_u8", c_p), ("u8_mode", c_i), ("sk_ws", c_p), ("sk_ws_bytes", c_l), ("engine", c_i),
     ]
 
 
@@ -127,12 +127,17 @@ class BlendParams(C.Structure):
                 ("seed_dev", c_p)]
 
 
+class GnFinalizeParams(C.Structure):
+    _fields_ = [("c0", c_i), ("c1", c_i), ("B", c_i), ("HW", c_i), ("groups", c_i), ("eps", c_f), ("sums", c_p), ("csum0", c_p),
+                ("csum1", c_p), ("gamma", c_p), ("beta", c_p), ("ab", c_p)]
+
+
 class _OpU(C.Union):
     _fields_ = [("conv", ConvParams), ("gn_stats", GnStatsParams), ("norm_act", NormActParams),
                 ("layernorm", LayerNormParams), ("softmax", SoftmaxParams), ("time_embed", TimeEmbedParams),
                 ("step_begin", StepBeginParams), ("update", UpdateParams), ("snap", SnapParams), ("vq", VqParams),
                 ("zero", ZeroParams), ("upsample", UpsampleParams), ("embed", EmbedParams), ("mha", MhaParams), ("convt", ConvT2dParams),
-                ("assemble", AssembleParams), ("attn", AttnParams), ("blend", BlendParams)]
+                ("assemble", AssembleParams), ("attn", AttnParams), ("blend", BlendParams), ("gn_finalize", GnFinalizeParams)]
 
 
 class Op(C.Structure):
@@ -142,17 +147,17 @@ class Op(C.Structure):
 _KIND_FIELD = {OP_CONV: "conv", OP_GN_STATS: "gn_stats", OP_NORM_ACT: "norm_act", OP_LAYERNORM: "layernorm",
                OP_SOFTMAX: "softmax", OP_TIME_EMBED: "time_embed", OP_STEP_BEGIN: "step_begin", OP_UPDATE: "update",
                OP_SNAP: "snap", OP_VQ: "vq", OP_ZERO: "zero", OP_UPSAMPLE: "upsample", OP_EMBED: "embed", OP_MHA: "mha", OP_CONVT: "convt", OP_ASSEMBLE: "assemble", OP_ATTN: "attn",
-               OP_BLEND: "blend"}
+               OP_BLEND: "blend", OP_GN_FINALIZE: "gn_finalize"}
 
 EXPORTS = [
     "frido_conv2d", "frido_gn_stats", "frido_norm_act", "frido_layernorm", "frido_softmax", "frido_time_embed",
     "frido_step_begin", "frido_sampler_update", "frido_stage_snap", "frido_vq_lookup", "frido_zero",
-    "frido_round_tf32", "frido_split_bf16", "frido_upsample2x", "frido_to_uint8", "frido_embed_tokens", "frido_mha_small", "frido_attn_small", "frido_conv_transpose2d", "frido_assemble_latent", "frido_mask_blend", "frido_run_program", "frido_abi_version", "frido_sizeof_op", "frido_last_error",
+    "frido_round_tf32", "frido_split_bf16", "frido_upsample2x", "frido_to_uint8", "frido_embed_tokens", "frido_mha_small", "frido_attn_small", "frido_conv_transpose2d", "frido_assemble_latent", "frido_mask_blend", "frido_gn_finalize", "frido_run_program", "frido_abi_version", "frido_sizeof_op", "frido_last_error",
     "frido_launch_count", "frido_check_device",
 ]
 
 SK_WS_BYTES = 40 << 20
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 _lib = None
 
@@ -184,7 +189,7 @@ def lib():
     for name in ("frido_conv2d", "frido_gn_stats", "frido_norm_act", "frido_layernorm", "frido_softmax",
                  "frido_time_embed", "frido_step_begin", "frido_sampler_update", "frido_stage_snap", "frido_vq_lookup",
                  "frido_upsample2x", "frido_to_uint8", "frido_embed_tokens", "frido_mha_small", "frido_attn_small",
-                 "frido_conv_transpose2d", "frido_assemble_latent", "frido_mask_blend"):
+                 "frido_conv_transpose2d", "frido_assemble_latent", "frido_mask_blend", "frido_gn_finalize"):
         getattr(L, name).argtypes = [c_p, c_p]
     if L.frido_abi_version() != ABI_VERSION:
         raise FridoError(f"ABI mismatch: library version {L.frido_abi_version()}, binding {ABI_VERSION} (rebuild: make -C frido_b200/csrc)")

@@ -11,6 +11,7 @@ using namespace frido;
 
 extern "C" int frido_conv2d(const FridoConvParams* p, void* stream) {
   if (!p) return set_error(FRIDO_E_ARG, "conv2d: null params");
+  if (p->nrm_ab) return conv2d_nf(p, (cudaStream_t)stream);  // normalise-on-load (engine 3 only; conv_nf.cu)
   if (p->engine >= 1 && p->engine <= 3) return conv2d_tc(p, (cudaStream_t)stream);
   return conv2d_simt(p, (cudaStream_t)stream);
 }
@@ -47,6 +48,7 @@ extern "C" int frido_run_program(const FridoOp* ops, int32_t n, void* stream) {
       case FRIDO_OP_CONVT: rc = frido_conv_transpose2d(&op.u.convt, stream); break;
       case FRIDO_OP_ASSEMBLE: rc = frido_assemble_latent(&op.u.assemble, stream); break;
       case FRIDO_OP_UPSAMPLE: rc = frido_upsample2x(&op.u.upsample, stream); break;
+      case FRIDO_OP_GN_FINALIZE: rc = frido_gn_finalize(&op.u.gn_finalize, stream); break;
       case FRIDO_OP_BLEND: rc = frido_mask_blend(&op.u.blend, stream); break;
       case FRIDO_OP_ZERO: rc = frido_zero(op.u.zero.ptr, op.u.zero.nbytes, stream); break;
       default: rc = set_error(FRIDO_E_ARG, "run_program: unknown op kind");

@@ -124,5 +124,7 @@ __device__ __forceinline__ float warp_max(float v) {
 
 int conv2d_simt(const FridoConvParams* p, cudaStream_t s);
 int conv2d_tc(const FridoConvParams* p, cudaStream_t s);
+int conv2d_nf(const FridoConvParams* p, cudaStream_t s);
+bool conv2d_nf_eligible(const FridoConvParams* p);
 
 }  // namespace frido

@@ -216,6 +216,48 @@ __global__ void __launch_bounds__(NA_MAX_THREADS) norm_act_kernel(const FridoNor
 }
 
 // ----------------------------------------------------------------------------
+// GroupNorm statistics -> per-(image, channel) scale / shift for the convs that normalise on load (conv_nf.cu).  One CTA per
+// image; the group mean / rstd are formed exactly as in norm_act_kernel (fp64 sums, fp32 mean and rstd).
+// ----------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) gn_finalize_kernel(const FridoGnFinalizeParams p) {
+  __shared__ float s_mean[64], s_rstd[64];
+  pdl_trigger();
+  pdl_wait();
+  const int C = p.c0 + p.c1;
+  const int cg = C / p.groups;
+  const int b = blockIdx.x;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nw = blockDim.x >> 5;
+  for (int g = warp; g < p.groups; g += nw) {
+    double s0 = 0.0, s1 = 0.0;
+    if (p.csum0) {
+      for (int c = g * cg + lane; c < (g + 1) * cg; c += 32) {
+        const double* cs = (c < p.c0) ? p.csum0 + ((int64_t)b * p.c0 + c) * 2 : p.csum1 + ((int64_t)b * p.c1 + (c - p.c0)) * 2;
+        s0 += cs[0]; s1 += cs[1];
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) { s0 += __shfl_xor_sync(0xffffffffu, s0, o); s1 += __shfl_xor_sync(0xffffffffu, s1, o); }
+    } else {
+      const double* sm = p.sums + ((int64_t)b * p.groups + g) * 2;
+      s0 = sm[0]; s1 = sm[1];
+    }
+    if (lane == 0) {
+      const double cnt = (double)cg * (double)p.HW;
+      const double mean = s0 / cnt;
+      double var = s1 / cnt - mean * mean;
+      if (var < 0.0) var = 0.0;
+      s_mean[g] = (float)mean;
+      s_rstd[g] = (float)(1.0 / sqrt(var + (double)p.eps));
+    }
+  }
+  __syncthreads();
+  for (int c = tid; c < C; c += blockDim.x) {
+    const int g = c / cg;
+    const float a = s_rstd[g] * __ldg(p.gamma + c);
+    reinterpret_cast<float2*>(p.ab)[(int64_t)b * C + c] = make_float2(a, fmaf(-s_mean[g], a, __ldg(p.beta + c)));
+  }
+}
+
+// ----------------------------------------------------------------------------
 // LayerNorm: one warp per row, row cached in registers (C <= 1024), two-pass var
 // ----------------------------------------------------------------------------
 constexpr int LN_MAXQ = 8;
@@ -521,6 +563,16 @@ extern "C" int frido_norm_act(const FridoNormActParams* p, void* stream) {
   const int threads = (Qe * PL + 31) / 32 * 32;
   launch_pdl(norm_act_kernel, grid, dim3(threads), 0, (cudaStream_t)stream, *p, ppc, Qe, PL, nj);
   return check_launch("norm_act");
+}
+
+extern "C" int frido_gn_finalize(const FridoGnFinalizeParams* p, void* stream) {
+  if (!p || (!p->sums && !p->csum0) || !p->gamma || !p->beta || !p->ab) return set_error(FRIDO_E_ARG, "gn_finalize: null pointer");
+  if (p->csum0 && p->c1 > 0 && !p->csum1) return set_error(FRIDO_E_ARG, "gn_finalize: csum1 missing for the second source");
+  const int C = p->c0 + p->c1;
+  if (p->B <= 0 || p->HW <= 0 || p->groups <= 0 || p->groups > 64 || C <= 0 || C % p->groups || (reinterpret_cast<uintptr_t>(p->ab) & 7))
+    return set_error(FRIDO_E_ARG, "gn_finalize: unsupported shape");
+  launch_pdl(gn_finalize_kernel, dim3(p->B), dim3(256), 0, (cudaStream_t)stream, *p);
+  return check_launch("gn_finalize");
 }
 
 extern "C" int frido_layernorm(const FridoLayerNormParams* p, void* stream) {

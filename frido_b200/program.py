@@ -131,7 +131,7 @@ class Program:
     def conv(self, a0, w, out, *, B, Hin, Win, Hout, Wout, Cout, ksize=1, stride=1, pad=0, ups=1, a1=None,
              bias=None, rowvec=None, rowvec_sb=0, res=None, alpha=1.0, act=L.ACT_NONE, o_sb=None, o_sp=None, o_sn=1,
              w_sb=0, w_ld=0, w_off=0, out_off=0, round_tf32=0, engine=None, csum=None, out_pair=None, w_pair=None,
-             alg_flops=None, side=None, out_u8=None, u8_mode=0, tag="conv"):
+             alg_flops=None, side=None, out_u8=None, u8_mode=0, nrm=None, tag="conv"):
         """Returns True when `csum` (per-channel GroupNorm sums of the output, [B,Cout,2] fp64) was attached to the op:
         only the tcgen05 engines accumulate it, for dense NHWC outputs with >= 32 pixels per image."""
         if engine is None:
@@ -191,6 +191,12 @@ class Program:
         if out_pair is not None:
             p.out_hi, p.out_lo = out_pair[0].data_ptr() + 2 * out_off, out_pair[1].data_ptr() + 2 * out_off
             self.hold(out_pair[0], out_pair[1])
+        if nrm is not None:  # normalise-on-load: (ab [B,C,2], gb [B,HW,2C] or None, silu) - see nf_eligible
+            if engine != 3:
+                raise L.FridoError("conv: normalise-on-load needs the BF16x3 tcgen05 engine (check Program.nf_eligible first)")
+            ab, gb, silu = nrm
+            p.nrm_ab, p.nrm_gb, p.nrm_silu = ab.data_ptr(), _ptr(gb), int(silu)
+            self.hold(ab, gb)
         if out_u8 is not None:  # uint8 NHWC copy of the outputs (decoder head: sample_diffusion.py:103-121 fused into conv_out)
             if engine != 0:
                 raise L.FridoError("conv: out_u8 is a feature of the small-Cout head kernels (SIMT engine)")
@@ -216,6 +222,26 @@ class Program:
         """Would conv() run this shape on the tcgen05 engine?  (weights assumed freshly allocated, i.e. aligned)"""
         return bool(self.tc_code) and self._tc_ok(a0, a1, B, Hin, Win, Hout, Wout, Cout, ksize, stride, pad, 1, out, 0, 0, 0,
                                                   L.ACT_NONE, None, None, 1, out, 0, res)
+
+    def nf_eligible(self, a0, a1, out, *, B, H, W, Cout, ksize):
+        """Can conv() apply the GroupNorm (+SPADE) (+SiLU) of its input on load (csrc/conv_nf.cu)?  BF16x3 engine, 3x3 / 1x1
+        stride-1 conv, and a 128-pixel tile (at most 16 wide) whose halo fits the shared-memory slot with <= 4 images."""
+        if self.tc_code != 3 or os.environ.get("FRIDO_FUSE_NORM", "1") != "1":
+            return False
+        if not self.tc_eligible(a0, a1, out, B=B, Hin=H, Win=W, Hout=H, Wout=W, Cout=Cout, ksize=ksize, pad=ksize // 2):
+            return False
+        tw = min(16, 1 << max(W - 1, 0).bit_length())
+        th = min(128 // tw, 1 << max(H - 1, 0).bit_length())
+        tb = 128 // (tw * th)
+        hp = ksize // 2
+        return tb <= 4 and (tw + 2 * hp) * (th + 2 * hp) * tb <= 208
+
+    def gn_finalize(self, ab, gamma, beta, *, B, HW, c0, c1=0, eps, sums=None, csum0=None, csum1=None, groups=32, tag="gn_finalize"):
+        p = L.GnFinalizeParams()
+        p.c0, p.c1, p.B, p.HW, p.groups, p.eps = c0, c1, B, HW, groups, eps
+        p.sums, p.csum0, p.csum1, p.gamma, p.beta, p.ab = _ptr(sums), _ptr(csum0), _ptr(csum1), gamma.data_ptr(), beta.data_ptr(), ab.data_ptr()
+        self.hold(sums, csum0, csum1, gamma, beta, ab)
+        self._add(L.OP_GN_FINALIZE, p, tag)
 
     @staticmethod
     def _tc_ok(a0, a1, B, Hin, Win, Hout, Wout, Cout, ksize, stride, pad, ups, w, w_sb, w_ld, w_off, act, o_sb, o_sp, o_sn,

@@ -291,6 +291,33 @@ class UNetPlan:
                       c1=c1, gb=gb, silu=silu, round_tf32=prog.R, csum0=cs0, csum1=cs1, tag=site)
         return out
 
+    def _norm_on_load(self, prog, xs, cs, h, w, norm, eps, silu, out, Cout, ksize):
+        """GroupNorm(+SPADE)(+SiLU) handed to the consuming conv instead of a norm_act pass (csrc/conv_nf.cu): emits the
+        tiny statistics -> (scale, shift) kernel and returns (`nrm` argument of Program.conv, buffer to release after the
+        conv), or None when the conv cannot normalise on load (then `_norm` materialises the tensor as before)."""
+        B = self.B
+        a1 = Src.nhwc(xs[1], h, w) if len(xs) > 1 else None
+        if not prog.nf_eligible(Src.nhwc(xs[0], h, w), a1, out, B=B, H=h, W=w, Cout=Cout, ksize=ksize) or any(c % 32 for c in cs):
+            return None
+        hw = h * w
+        C = sum(cs)
+        x1 = xs[1] if len(xs) > 1 else None
+        c1 = cs[1] if len(xs) > 1 else 0
+        cs0 = self._csum.get(id(xs[0]))
+        cs1 = self._csum.get(id(x1)) if x1 is not None else None
+        sums = None
+        if cs0 is None or (x1 is not None and cs1 is None):  # no producer statistics: separate reduction pass
+            cs0 = cs1 = None
+            sums = self._gn_slot(prog)
+            prog.gn_stats(xs[0], cs[0], sums, B=B, HW=hw, a1=x1, c1=c1)
+        is_spade = isinstance(norm, M.SPADE)
+        g = norm.param_free_norm if is_spade else norm
+        gb = self._spade_site(norm, C, h, w) if (is_spade and self.c_cond) else None
+        ab = prog.buf(B, C, 2)
+        prog.gn_finalize(ab, self._vec(g.weight), self._vec(g.bias), B=B, HW=hw, c0=cs[0], c1=c1, eps=eps, sums=sums, csum0=cs0,
+                         csum1=cs1, tag="gn_finalize")
+        return (ab, gb, silu), ab
+
     def _spade_site(self, sp, C, h, w):
         """Prologue: gamma|beta = conv3x3(ReLU(conv3x3(nearest_resize(h_cond)))) (spade_norm.py:52-55)."""
         P, B = self.prologue, self.B
@@ -315,29 +342,41 @@ class UNetPlan:
         S, B = self.step, self.B
         hw = h * w
         cout = rb.out_channels
-        t1 = self._norm(S, xs, cs, h, w, rb.in_layers[0], 1e-5, 1, "res.norm1")
         h1 = S.buf(B, hw, cout)
         off = self._emb_off[id(rb)]
-        self._conv_stats(S, Src.nhwc(t1, h, w), self._conv_w(rb.in_layers[2]), h1, cout, B=B, Hin=h, Win=w, Hout=h, Wout=w,
-                         ksize=3, pad=1, bias=self._vec(rb.in_layers[2].bias), rowvec=self.emb_all[:, off:],
-                         rowvec_sb=self.emb_total, tag="res.conv1")
-        S.release(t1)
-        t2 = self._norm(S, [h1], [cout], h, w, rb.out_layers[0], 1e-5, 1, "res.norm2")
-        S.release(h1)
+        kw1 = dict(B=B, Hin=h, Win=w, Hout=h, Wout=w, ksize=3, pad=1, bias=self._vec(rb.in_layers[2].bias),
+                   rowvec=self.emb_all[:, off:], rowvec_sb=self.emb_total, tag="res.conv1")
+        nf = self._norm_on_load(S, xs, cs, h, w, rb.in_layers[0], 1e-5, 1, h1, cout, 3)
+        if nf is not None:  # GroupNorm -> [SPADE] -> SiLU applied by conv1 on load (pyunet.py:209-212 as one launch)
+            self._conv_stats(S, Src.nhwc(xs[0], h, w), self._conv_w(rb.in_layers[2]), h1, cout,
+                             a1=Src.nhwc(xs[1], h, w) if len(xs) > 1 else None, nrm=nf[0], **kw1)
+            S.release(nf[1])
+        else:
+            t1 = self._norm(S, xs, cs, h, w, rb.in_layers[0], 1e-5, 1, "res.norm1")
+            self._conv_stats(S, Src.nhwc(t1, h, w), self._conv_w(rb.in_layers[2]), h1, cout, **kw1)
+            S.release(t1)
         a1 = Src.nhwc(xs[1], h, w) if len(xs) > 1 else None
         out = S.buf(B, hw, cout)
+        nf = self._norm_on_load(S, [h1], [cout], h, w, rb.out_layers[0], 1e-5, 1, out, cout, 3)
+        if nf is not None:
+            src2, t2 = Src.nhwc(h1, h, w), None
+        else:
+            t2 = self._norm(S, [h1], [cout], h, w, rb.out_layers[0], 1e-5, 1, "res.norm2")
+            S.release(h1)
+            src2 = Src.nhwc(t2, h, w)
+        nrm2 = nf[0] if nf is not None else None
         sk = None
         is_conv = isinstance(rb.skip_connection, nn.Conv2d)
         if (is_conv and os.environ.get("FRIDO_FUSE_SKIP", "1") == "1" and all(c % 32 == 0 for c in cs) and
-                S.tc_eligible(Src.nhwc(t2, h, w), None, out, B=B, Hin=h, Win=w, Hout=h, Wout=w, Cout=cout, ksize=3, pad=1)):
+                S.tc_eligible(src2, None, out, B=B, Hin=h, Win=w, Hout=h, Wout=w, Cout=cout, ksize=3, pad=1)):
             # the 1x1 skip_connection conv (pyunet.py:248,299) rides on conv2's K loop: its input channels are extra
             # K steps read at the output pixel, its weights extra columns, the biases add up - no separate launch, no
             # round trip of the skip tensor through HBM
             sc_, c2_ = rb.skip_connection, rb.out_layers[3]
             w_cat = self._packed(lambda: torch.cat([_pack_conv(c2_.weight), sc_.weight.detach().reshape(cout, -1)], 1).contiguous())
             b_cat = self._packed(lambda: (c2_.bias.detach() + sc_.bias.detach()))
-            self._conv_stats(S, Src.nhwc(t2, h, w), w_cat, out, cout, B=B, Hin=h, Win=w, Hout=h, Wout=w, ksize=3, pad=1,
-                             bias=b_cat, side=(Src.nhwc(xs[0], h, w), a1), tag="res.conv2+skip")
+            self._conv_stats(S, src2, w_cat, out, cout, B=B, Hin=h, Win=w, Hout=h, Wout=w, ksize=3, pad=1,
+                             bias=b_cat, side=(Src.nhwc(xs[0], h, w), a1), nrm=nrm2, tag="res.conv2+skip")
         else:
             if is_conv:
                 sk = S.buf(B, hw, cout)
@@ -347,9 +386,13 @@ class UNetPlan:
             else:
                 assert len(xs) == 1
                 res = xs[0]
-            self._conv_stats(S, Src.nhwc(t2, h, w), self._conv_w(rb.out_layers[3]), out, cout, B=B, Hin=h, Win=w, Hout=h, Wout=w,
-                             ksize=3, pad=1, bias=self._vec(rb.out_layers[3].bias), res=res, tag="res.conv2")
-        S.release(t2)
+            self._conv_stats(S, src2, self._conv_w(rb.out_layers[3]), out, cout, B=B, Hin=h, Win=w, Hout=h, Wout=w,
+                             ksize=3, pad=1, bias=self._vec(rb.out_layers[3].bias), res=res, nrm=nrm2, tag="res.conv2")
+        if nf is not None:
+            S.release(nf[1])
+            S.release(h1)
+        else:
+            S.release(t2)
         if sk is not None:
             S.release(sk)
         return out
@@ -513,11 +556,17 @@ class UNetPlan:
     def _transformer(self, st, x, C, h, w):
         S, B = self.step, self.B
         N = h * w
-        t = self._norm(S, [x], [C], h, w, st.norm, 1e-6, 0, "st.norm")
         hcur = S.buf(B, N, C)
-        S.linear(t, self._packed(lambda: st.proj_in.weight.detach().view(C, C).clone()), hcur, M=B * N, K=C, N=C,
-                 bias=self._vec(st.proj_in.bias), tag="st.proj_in")
-        S.release(t)
+        w_in = self._packed(lambda: st.proj_in.weight.detach().view(C, C).clone())
+        nf = self._norm_on_load(S, [x], [C], h, w, st.norm, 1e-6, 0, hcur, C, 1)
+        if nf is not None:  # GroupNorm [+SPADE] applied by proj_in on load (attention.py:296-298 as one launch)
+            S.conv(Src.nhwc(x, h, w), w_in, hcur, B=B, Hin=h, Win=w, Hout=h, Wout=w, Cout=C, bias=self._vec(st.proj_in.bias),
+                   nrm=nf[0], tag="st.proj_in")
+            S.release(nf[1])
+        else:
+            t = self._norm(S, [x], [C], h, w, st.norm, 1e-6, 0, "st.norm")
+            S.linear(t, w_in, hcur, M=B * N, K=C, N=C, bias=self._vec(st.proj_in.bias), tag="st.proj_in")
+            S.release(t)
         for blk in st.transformer_blocks:
             if self._fold_self_attn():
                 h1 = self._self_attention_folded(hcur, blk, C, N)

@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define FRIDO_ABI_VERSION 4
+#define FRIDO_ABI_VERSION 5
 #define FRIDO_SK_WS_BYTES (40ll << 20)
 
 #define FRIDO_OK 0
@@ -84,6 +84,13 @@ typedef struct FridoConvParams {
   int32_t cx0, cx1;         /*   concatenated, sampled at the output pixel (stride 1 only); the weight rows carry the extra */
   int64_t x0_sb, x0_sy, x0_sx; /* cx0+cx1 columns after the taps.  Element strides: image, row, col (channel stride 1). */
   int64_t x1_sb, x1_sy, x1_sx;
+  const float* nrm_ab;      /* optional (engine 3, 3x3 / 1x1 stride-1 convs with shared weights): NORMALISE-ON-LOAD.  The conv reads */
+  const float* nrm_gb;      /*   act(x * a[b,c] + b[b,c]) instead of x, where nrm_ab = [B][c0+c1][2] holds (a, b) = (rstd*gamma_c, */
+  int32_t nrm_silu;         /*   beta_c - mean*rstd*gamma_c) per image and input channel (frido_gn_finalize), nrm_gb = optional SPADE
+                               maps [B,Hin*Win,2(c0+c1)] (gamma | beta: y = y*(1+gamma)+beta, spade_norm.py:58) and nrm_silu
+                               selects SiLU: GroupNorm -> [SPADE] -> SiLU -> conv (pyunet.py:209-240) in one launch, the
+                               normalised tensor never written to memory.  Zero padding applies to the ACTIVATED tensor, as
+                               in the reference.  The fused side input x0 | x1 stays raw. */
   uint8_t* out_u8;          /* optional (SIMT engine, Cout <= 4: the decoder's conv_out head): also store the outputs as uint8 NHWC */
   int32_t u8_mode;          /*   [B,Hout,Wout,Cout], formatted like frido_to_uint8 (mode 0 = custom_to_np, 1 = custom_to_pil,
                                scripts/sample_diffusion.py:103-121) from the same fp32 value that goes to `out` */
@@ -129,6 +136,18 @@ typedef struct FridoNormActParams {
   float* out;                             /* [B,HW,C] */
 } FridoNormActParams;
 int frido_norm_act(const FridoNormActParams* p, void* stream);
+
+/* GroupNorm statistics -> per-(image, channel) scale and shift for normalise-on-load (FridoConvParams.nrm_ab):
+ *   mean_g, rstd_g from `sums` (per group, frido_gn_stats) or from the producers' per-channel sums csum0 | csum1
+ *   (FridoConvParams.chan_sums), in fp64 exactly as frido_norm_act does;  ab[b][c] = (rstd_g*gamma_c, beta_c - mean_g*rstd_g*gamma_c).
+ * Replaces the statistics half of nn.GroupNorm(32) (util.py:214) for convs that apply the normalisation themselves. */
+typedef struct FridoGnFinalizeParams {
+  int32_t c0, c1, B, HW, groups; float eps;
+  const double* sums; const double* csum0; const double* csum1;
+  const float* gamma; const float* beta;
+  float* ab;                /* [B][c0+c1][2] */
+} FridoGnFinalizeParams;
+int frido_gn_finalize(const FridoGnFinalizeParams* p, void* stream);
 
 /* nn.LayerNorm over the last dim (attention.py:203-205), eps 1e-5. */
 typedef struct FridoLayerNormParams {
@@ -317,7 +336,7 @@ enum FridoOpKind {
   FRIDO_OP_SOFTMAX = 5, FRIDO_OP_TIME_EMBED = 6, FRIDO_OP_STEP_BEGIN = 7, FRIDO_OP_UPDATE = 8,
   FRIDO_OP_SNAP = 9, FRIDO_OP_VQ = 10, FRIDO_OP_ZERO = 11, FRIDO_OP_UPSAMPLE = 12,
   FRIDO_OP_EMBED = 13, FRIDO_OP_MHA = 14, FRIDO_OP_CONVT = 15, FRIDO_OP_ASSEMBLE = 16, FRIDO_OP_ATTN = 17,
-  FRIDO_OP_BLEND = 18
+  FRIDO_OP_BLEND = 18, FRIDO_OP_GN_FINALIZE = 19
 };
 typedef struct FridoZeroParams { void* ptr; int64_t nbytes; } FridoZeroParams;
 typedef struct FridoOp {
@@ -328,7 +347,7 @@ typedef struct FridoOp {
     FridoLayerNormParams layernorm; FridoSoftmaxParams softmax; FridoTimeEmbedParams time_embed;
     FridoStepBeginParams step_begin; FridoUpdateParams update; FridoSnapParams snap; FridoVqParams vq;
     FridoZeroParams zero; FridoUpsampleParams upsample; FridoEmbedParams embed; FridoMhaParams mha;
-    FridoConvT2dParams convt; FridoAssembleParams assemble; FridoAttnParams attn; FridoBlendParams blend;
+    FridoConvT2dParams convt; FridoAssembleParams assemble; FridoAttnParams attn; FridoBlendParams blend; FridoGnFinalizeParams gn_finalize;
   } u;
 } FridoOp;
 /* Launches ops[0..n) in order on `stream`; returns 0 or (-(1000+i)) if op i failed. */

@@ -28,6 +28,9 @@ _TARGET_REWRITE = {
 }
 
 
+_ORIG_CUDA = (torch.Tensor.cuda, torch.nn.Module.cuda)
+
+
 def available() -> bool:
     return os.path.isdir(os.path.join(REF, "frido"))
 
@@ -49,15 +52,18 @@ def activate(cpu: bool = True):
     if cpu:
         torch.Tensor.cuda = lambda self, *a, **k: self
         torch.nn.Module.cuda = lambda self, *a, **k: self
+    else:  # a previous CPU activation in this process must not leak into a GPU run
+        torch.Tensor.cuda, torch.nn.Module.cuda = _ORIG_CUDA
     from frido.models.diffusion.ddim import DDIMSampler
     from frido.models.diffusion.plms import PLMSSampler
 
     def _reg(self, name, attr):
         setattr(self, name, attr)
 
-    if cpu:
-        DDIMSampler.register_buffer = _reg
-        PLMSSampler.register_buffer = _reg
+    for cls in (DDIMSampler, PLMSSampler):
+        if not hasattr(cls, "_frido_orig_register_buffer"):
+            cls._frido_orig_register_buffer = cls.register_buffer
+        cls.register_buffer = _reg if cpu else cls._frido_orig_register_buffer
     return DDIMSampler, PLMSSampler
 
 

@@ -243,7 +243,7 @@ def test_full_size_l2i_step_and_decoder(dev, golden_dir, engine):
                 assert (p0.cpu() - g[f"step_s{s}_predx0"]).abs().max() < 40 * EPS_TOL  # x0 = (x - s1m*eps)/sqrt(a_t), 1/sqrt(a_996) = 38
 
 
-SWITCHES = ["FRIDO_SK", "FRIDO_ATTN_SMALL", "FRIDO_ATTN_FOLD", "FRIDO_FUSE_SKIP", "FRIDO_EPI_SPEC"]
+SWITCHES = ["FRIDO_SK", "FRIDO_ATTN_SMALL", "FRIDO_ATTN_FOLD", "FRIDO_FUSE_SKIP", "FRIDO_EPI_SPEC", "FRIDO_FUSE_NORM"]
 
 
 @pytest.mark.parametrize("off", SWITCHES)
@@ -281,6 +281,9 @@ def test_fusion_switches_keep_the_result(dev, golden_dir, off, monkeypatch):
         assert "attn1.out" in tags_off and "attn1.out" not in tags_def
     if off == "FRIDO_ATTN_SMALL":
         assert "attn2.block" in tags_def and "attn2.block" not in tags_off
+    if off == "FRIDO_FUSE_NORM":  # normalise-on-load: the GroupNorm / SPADE / SiLU passes in front of the convs are gone
+        assert "gn_finalize" in tags_def and "res.norm1" not in tags_def and "res.norm2" not in tags_def and "st.norm" not in tags_def
+        assert "res.norm1" in tags_off and "st.norm" in tags_off and "gn_finalize" not in tags_off
 
 
 def test_silent_in_place_weight_change_is_noticed(dev, golden_dir):
