@@ -33,7 +33,7 @@ class ConvParams(C.Structure):
         ("o_sb", c_l), ("o_sp", c_l), ("o_sn", c_l), ("round_tf32", c_i), ("out_hi", c_p), ("out_lo", c_p), ("chan_sums", c_p),
         ("x0", c_p), ("x1", c_p), ("cx0", c_i), ("cx1", c_i), ("x0_sb", c_l), ("x0_sy", c_l), ("x0_sx", c_l),
         ("x1_sb", c_l), ("x1_sy", c_l), ("x1_sx", c_l),
-        ("nrm_ab", c_p), ("nrm_gb", c_p), ("nrm_silu", c_i), ("out_u8", c_p), ("u8_mode", c_i), ("sk_ws", c_p), ("sk_ws_bytes", c_l), ("engine", c_i),
+        ("nrm_ab", c_p), ("nrm_gb", c_p), ("nrm_silu", c_i), ("a_presplit", c_i), ("out_u8", c_p), ("u8_mode", c_i), ("sk_ws", c_p), ("sk_ws_bytes", c_l), ("engine", c_i),
     ]
 
 
@@ -45,7 +45,7 @@ class GnStatsParams(C.Structure):
 class NormActParams(C.Structure):
     _fields_ = [("a0", c_p), ("a1", c_p), ("c0", c_i), ("c1", c_i), ("B", c_i), ("HW", c_i), ("groups", c_i),
                 ("sums", c_p), ("eps", c_f), ("csum0", c_p), ("csum1", c_p), ("gamma", c_p), ("beta", c_p), ("gb", c_p), ("silu", c_i),
-                ("round_tf32", c_i), ("out", c_p)]
+                ("round_tf32", c_i), ("out", c_p), ("out_split", c_i)]
 
 
 class LayerNormParams(C.Structure):
@@ -90,7 +90,7 @@ class ZeroParams(C.Structure):
 
 
 class UpsampleParams(C.Structure):
-    _fields_ = [("x", c_p), ("B", c_i), ("H", c_i), ("W", c_i), ("C", c_i), ("round_tf32", c_i), ("out", c_p)]
+    _fields_ = [("x", c_p), ("B", c_i), ("H", c_i), ("W", c_i), ("C", c_i), ("round_tf32", c_i), ("out", c_p), ("out_split", c_i)]
 
 
 class EmbedParams(C.Structure):
@@ -157,7 +157,7 @@ EXPORTS = [
 ]
 
 SK_WS_BYTES = 40 << 20
-ABI_VERSION = 5
+ABI_VERSION = 6
 
 _lib = None
 

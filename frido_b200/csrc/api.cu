@@ -11,7 +11,7 @@ using namespace frido;
 
 extern "C" int frido_conv2d(const FridoConvParams* p, void* stream) {
   if (!p) return set_error(FRIDO_E_ARG, "conv2d: null params");
-  if (p->nrm_ab) return conv2d_nf(p, (cudaStream_t)stream);  // normalise-on-load (engine 3 only; conv_nf.cu)
+  if (p->nrm_ab || p->a_presplit) return conv2d_nf(p, (cudaStream_t)stream);  // halo-resident operand path (engine 3; conv_nf.cu)
   if (p->engine >= 1 && p->engine <= 3) return conv2d_tc(p, (cudaStream_t)stream);
   return conv2d_simt(p, (cudaStream_t)stream);
 }

@@ -7,29 +7,38 @@
 // normalised activation never exists in HBM (the separate norm_act pass was 14 % of a UNet step and ~4.8 GB of HBM traffic).
 //
 // Operand path (differs from conv_tc.cu, whose A tile is re-fetched per filter tap):
-//   * the A operand of an output tile (TW x TH x TB = 128 pixels) is HALO-RESIDENT: per 32-channel chunk ONE TMA box
-//     {32 ch, TW+2, TH+2, TB} lands in shared memory (TMA zero-fills outside the image), [for SPADE two more boxes with the
-//     gamma / beta maps of the same pixels], and the four operand warps
-//       pass 1: apply y = x*a[b,c] + b[b,c]  (a = rstd*gamma_c, b = beta_c - mean*rstd*gamma_c from the producer's channel
-//               sums, frido_gn_finalize), the SPADE modulation and SiLU, force the halo outside the image back to exactly 0
-//               (conv padding pads the ACTIVATED tensor), split into bf16 hi / lo and write the pair back in place;
-//       pass 2: for each of the 9 taps copy the shifted 128 rows (thread = output pixel) into a tensor-memory slot
-//               (tcgen05.st) from where the TS-form MMAs take them.
-//     The normalisation, the activation and the operand split run ONCE per element instead of once per tap, and the
-//     L2 -> shared-memory traffic of the A operand drops ~6x.
-//   * weights: as conv_tc.cu (pre-split bf16 hi / lo, TMA, SWIZZLE_64B), K order = chunk-major: column (tap*C + chunk*32).
+//   * the A operand of an output tile (TW x TH x TB = 128 pixels, TW <= 16) is HALO-RESIDENT: per 32-channel chunk ONE TMA
+//     box {32 ch, TW+2, TH+2, TB} lands in a ring of shared-memory slots (TMA zero-fills outside the image), together with
+//     the chunk's (a, b) table, and the four operand warps
+//       PREP: apply y = x*a[b,c] + b[b,c]  (a = rstd*gamma_c, b = beta_c - mean*rstd*gamma_c from the producer's channel
+//             sums, frido_gn_finalize), the SPADE modulation y*(1+gamma)+beta (gamma / beta fetched with cp.async two steps
+//             ahead by the thread that uses them), SiLU, force the halo outside the image back to exactly 0 (conv padding
+//             pads the ACTIVATED tensor), split into bf16 hi / lo and write the pair back in place;
+//       FEED: for each of the 9 taps copy the shifted 128 rows (thread = output pixel) into a tensor-memory slot
+//             (tcgen05.st) from where the TS-form MMAs take them.
+//     PREP of chunk k+1 is software-pipelined into the FEED of chunk k (one 256-item step between consecutive taps), i.e.
+//     it runs in the time the feed would wait for the tensor core anyway.  The normalisation, the activation and the
+//     operand split run ONCE per element instead of once per tap, and the L2 -> shared-memory traffic of the A operand
+//     drops ~6x.
+//   * weights: as conv_tc.cu (pre-split bf16 hi / lo, TMA, SWIZZLE_64B); K order = chunk-major: column (tap*C + chunk*32).
 //   * extra K units after the chunks: the fused 1x1 side input (ResBlock skip_connection) reads RAW activations at the
 //     output pixel, exactly as in conv_tc.cu.
-// Warp roles (480 threads): 0 = weight TMA producer, 1 = TMEM allocator + MMA issuer, 2-9 = epilogue (shared with
-// conv_tc.cu), 10-13 = operand warps, 14 = halo TMA producer.
+// Warp roles (640 threads = 5 warpgroups, registers rebalanced with setmaxnreg): 0 = weight TMA producer, 1 = TMEM allocator +
+// MMA issuer, 2 = halo TMA producer, 4-11 = epilogue (shared with conv_tc.cu), 12-15 = feed (shared memory -> tensor memory,
+// nothing else), 16-19 = prep (normalise / activate / split in place, running ahead of the feed through the slot ring).
 #include "tc_common.cuh"
 
 namespace frido {
 
-constexpr int NF_THREADS = TC_THREADS_X3 + 32;
+constexpr int NF_THREADS = 640;                 // 5 warpgroups: control | epilogue x2 | feed | prep
 constexpr int NF_TSLOTS = TC_BF_MAX_STAGES;     // tensor-memory operand slots (32 columns each)
-constexpr int NF_AB_BYTES = 2048;               // [2][TB <= 4][32][2] fp32 scale/shift table of the current chunk
+constexpr int NF_MAX_ASLOTS = 6;
 constexpr int NF_MAX_HALO_ROWS = 208;
+constexpr int NF_BAR_EXTRA = 256;               // barrier area grows to 512 B (40 slots used)
+constexpr int NF_SMEM_BYTES = TC_SMEM_BYTES + NF_BAR_EXTRA;
+constexpr int NF_GB_DEPTH = 4;                  // cp.async ring of SPADE gamma / beta: three steps (36 KB per SM) in flight ahead of
+                                                // the step in use - the maps stream from HBM and the latency needs the bytes
+
 
 struct NfParams {
   int n_chunks;     // 32-channel chunks of the normalised input
@@ -37,46 +46,158 @@ struct NfParams {
   int hpad;         // 1 or 0
   int HW2, HH2;     // halo box: TW + 2*hpad, TH + 2*hpad
   int rows_h;       // HW2 * HH2 * TB
+  int m_plane, m_hw2;  // 16-bit reciprocal multipliers: r / (HW2*HH2) = (r * m_plane) >> 16, r / HW2 = (r * m_hw2) >> 16 (r < 4096)
   int side_units;   // (cx0 + cx1) / 32
-  int slot_bytes;   // one halo tile in shared memory (1 KB multiple)
+  int slot_bytes;   // one halo tile + the (a, b) table of its channels in shared memory (1 KB multiple)
+  int ab_off;       // byte offset of the table [TB][32][2] fp32 inside a slot (= rows_h * 128)
+  int a_slots;      // depth of the halo ring
   int w_stages;     // depth of the weight ring
   int has_gb;       // SPADE maps present
+  int has_norm;     // 0: plain conv through the halo-resident operand path (no normalisation)
+  int presplit;     // the chunks arrive as finished operand rows (FridoConvParams.a_presplit): nothing to prepare
   int Cn;           // c0 + c1
   int silu;
   int Hin, Win;
   const float* ab;  // [B][Cn][2]
+  const float* gb;  // [B][Hin*Win][2*Cn] or NULL
+  int dbg;          // profiling aid (FRIDO_NF_DBG bit mask; results are WRONG with any bit set): 1 = prep does no arithmetic,
+                    // 2 = no prep at all, 4 = no SiLU
 };
 
-__device__ __forceinline__ float silu_fast(float v) { return __fdividef(v, 1.0f + __expf(-v)); }
+// 1D bulk copy global -> shared, completion on an mbarrier (size and both addresses multiples of 16 bytes)
+__device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+               "r"(bytes), "r"(bar)
+               : "memory");
+}
+
+// SiLU on the two approximate MUFU ops (1-2 ulp each): 5 instructions per element
+__device__ __forceinline__ float silu_fast(float v) {
+  float e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(v * -1.4426950408889634f));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
+  return v * r;
+}
+
+constexpr int NF_IPT = 3;                       // prep items per thread per step: 12 independent element chains in flight
+constexpr int NF_STEP_ITEMS = NF_IPT * 128;
+constexpr int NF_MAX_STEPS = 5;                 // ceil(208 rows * 8 / 384)
+constexpr int NF_DESC_BYTES = 8192;             // >= NF_MAX_STEPS * NF_STEP_ITEMS * 4
+constexpr int NF_GB_STEP_BYTES = NF_STEP_ITEMS * 32;
+
+// One prep step of one thread: NF_IPT items, straight-line (a missing item computes on a valid dummy address and only its
+// store is predicated).  Item descriptor: [0,11) 16-byte index inside the slot (swizzled), [11,16) halo x, [16,21) halo y,
+// [21,23) image, bit 31 = the item exists in the halo tile.  NRM / GB / SILU are compile-time so the hot variants carry no
+// selects: the role is bound by instruction issue (one warp per scheduler), every removed instruction counts.
+template <bool NRM, bool GB, bool SILU>
+__device__ __forceinline__ void nf_prep_items(uint8_t* xs, const uint32_t* dsc, int first_row, int row_limit, bool halo, int ab_off,
+                                              int cq, const uint8_t* gbs, int ox, int oy, int b0, int Win, int Hin, int B, int TB) {
+  uint32_t d[NF_IPT];
+  float4 v[NF_IPT];
+#pragma unroll
+  for (int j = 0; j < NF_IPT; ++j) {
+    d[j] = dsc[j * 128];
+    if (first_row + 16 * j >= row_limit) d[j] &= 0x7FFFFFFFu;   // side tiles have 128 rows
+    v[j] = *reinterpret_cast<const float4*>(xs + ((d[j] >> 31) ? (d[j] & 0x7FFu) << 4 : 0u));
+  }
+#pragma unroll
+  for (int j = 0; j < NF_IPT; ++j) {
+    const int hx = (d[j] >> 11) & 31, hy = (d[j] >> 16) & 31, hb = (d[j] >> 21) & 3;
+    float4 w = v[j];
+    if (NRM) {
+      const float4* abp = reinterpret_cast<const float4*>(xs + ab_off + min(hb, TB - 1) * 256 + cq * 32);
+      const float4 s0 = abp[0], s1 = abp[1];  // (a, b) of channels 4cq, 4cq+1 | 4cq+2, 4cq+3 of the item's image
+      w.x = fmaf(w.x, s0.x, s0.y); w.y = fmaf(w.y, s0.z, s0.w); w.z = fmaf(w.z, s1.x, s1.y); w.w = fmaf(w.w, s1.z, s1.w);
+      if (GB) {
+        const float4* gp = reinterpret_cast<const float4*>(gbs + j * (128 * 32));
+        const float4 g = gp[0], e = gp[1];
+        w.x = fmaf(w.x, 1.0f + g.x, e.x); w.y = fmaf(w.y, 1.0f + g.y, e.y); w.z = fmaf(w.z, 1.0f + g.z, e.z); w.w = fmaf(w.w, 1.0f + g.w, e.w);
+      }
+      if (SILU) { w.x = silu_fast(w.x); w.y = silu_fast(w.y); w.z = silu_fast(w.z); w.w = silu_fast(w.w); }
+    }
+    // conv padding pads the ACTIVATED tensor with zeros: halo pixels outside the image (TMA filled them with 0 BEFORE the
+    // normalisation) go back to exactly 0
+    const bool ok = !halo || ((unsigned)(ox + hx) < (unsigned)Win && (unsigned)(oy + hy) < (unsigned)Hin && b0 + hb < B);
+    if (!ok) w = make_float4(0.f, 0.f, 0.f, 0.f);
+    const uint32_t h0 = pack_bf16x2(w.x, w.y), h1 = pack_bf16x2(w.z, w.w);
+    const uint32_t l0 = pack_bf16x2(w.x - bf16_lo_to_f32(h0), w.y - bf16_hi_to_f32(h0));
+    const uint32_t l1 = pack_bf16x2(w.z - bf16_lo_to_f32(h1), w.w - bf16_hi_to_f32(h1));
+    // the item's 16 bytes now hold hi words 2c, 2c+1 | lo words 2c, 2c+1 of its row
+    if (d[j] >> 31) *reinterpret_cast<uint4*>(xs + ((d[j] & 0x7FFu) << 4)) = make_uint4(h0, h1, l0, l1);
+  }
+}
+
+// K units of a tile, in the order every warp role walks them: the 32-channel chunks of the normalised input (9 k-steps
+// each for a 3x3 conv) spread evenly among the 32-channel units of the raw side input (1 k-step each): chunk i sits at
+// position floor(i * (nc + ns) / nc), e.g. c s c s ... for nc = ns and c s s s c s s s ... for ns = 3 nc.  A run of short
+// units is then never longer than the slot ring can prefetch behind the long unit in front of it; a dozen short units in
+// a row would expose the TMA + prep latency of each.
+__device__ __forceinline__ void nf_decode(const NfParams& q, int u, bool& chunk, int& idx) {
+  const int nc = q.n_chunks, total = q.n_chunks + q.side_units;
+  const int i = (u * nc + total - 1) / total;  // number of chunks placed before position u (or at it)
+  chunk = i < nc && (i * total) / nc == u;
+  idx = chunk ? i : u - min(i, nc);
+}
+
+// Position in the stream of (tile, unit) pairs a CTA processes.
+struct NfCursor {
+  SegIter it;
+  int tile, u0, u1, u, seq, idx, ox0, oy0, b0, slot;
+  uint32_t phase;  // halo-ring slot of this unit and the parity of its `full` barrier
+  bool valid, chunk;
+  __device__ __forceinline__ NfCursor(const TcParams& p, int n_units, int total_tiles)
+      : it(p, n_units, total_tiles), tile(0), u0(0), u1(0), u(-1), seq(-1), idx(0), ox0(0), oy0(0), b0(0), slot(-1), phase(0),
+        valid(true), chunk(false) {}
+  __device__ __forceinline__ void advance(const TcParams& p, const NfParams& q) {
+    ++seq; ++u;
+    if (++slot == q.a_slots) { slot = 0; phase ^= 1; }
+    if (u >= u1) {
+      if (!it.next(tile, u0, u1)) { valid = false; return; }
+      u = u0;
+      int mt = tile / p.tiles_n;
+      const int tx = mt % p.tiles_x; mt /= p.tiles_x;
+      const int ty = mt % p.tiles_y;
+      const int tb = mt / p.tiles_y;
+      ox0 = tx * p.TW; oy0 = ty * p.TH; b0 = tb * p.TB;
+    }
+    nf_decode(q, u, chunk, idx);
+  }
+};
+
+// register budgets per warpgroup (setmaxnreg).  The pool is what the CTA was launched with - 640 threads x 96 registers =
+// 61440 - not the SM's register file: 128 x 48 + 256 x 128 + 128 x 64 + 128 x 112 = 61440 (asking for more blocks forever).
+constexpr int NF_REGS_LAUNCH = 96, NF_REGS_CTRL = 48, NF_REGS_EPI = 128, NF_REGS_FEED = 64, NF_REGS_PREP = 112;
+static_assert(128 * NF_REGS_CTRL + 256 * NF_REGS_EPI + 128 * NF_REGS_FEED + 128 * NF_REGS_PREP <= NF_THREADS * NF_REGS_LAUNCH,
+              "setmaxnreg budgets exceed the CTA's register pool");
+template <int N> __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N> __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
 
 template <int EPI>
 __global__ void __launch_bounds__(NF_THREADS, 1)
 conv_nf_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
-               const __grid_constant__ CUtensorMap map_gb, const __grid_constant__ CUtensorMap map_w,
-               const __grid_constant__ CUtensorMap map_wlo, const __grid_constant__ CUtensorMap map_x0,
-               const __grid_constant__ CUtensorMap map_x1, const TcParams p, const NfParams q) {
+               const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_wlo,
+               const __grid_constant__ CUtensorMap map_x0, const __grid_constant__ CUtensorMap map_x1, const TcParams p,
+               const NfParams q) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
-  // operand region (TC_SMEM_BUDGET): x slot 0 | x slot 1 | [gamma | beta] | weight ring ... | ab table (last 2 KB)
-  const uint32_t xs_off = 0;
-  const uint32_t gb_off = 2u * q.slot_bytes;
-  const uint32_t w_off = gb_off + (q.has_gb ? 2u * q.slot_bytes : 0u);
+  // operand region (TC_SMEM_BUDGET): halo ring (a_slots x slot_bytes) | [SPADE gamma / beta ring] | weight ring
+  const uint32_t gb_ring = (uint32_t)q.a_slots * q.slot_bytes;
+  const uint32_t w_off = gb_ring + (q.has_gb ? (uint32_t)(NF_GB_DEPTH * NF_GB_STEP_BYTES) : 0u);
   const uint32_t b_bytes = (uint32_t)p.BN * TC_BK * 2;
   const uint32_t w_stage_bytes = 2u * b_bytes;
-  const uint32_t ab_off = TC_SMEM_BUDGET - NF_AB_BYTES;
   const uint32_t bar_base = smem_base + TC_SMEM_BUDGET + TC_STG_BYTES + TC_CSUM_BYTES;
-  // barrier slots: w_full[6] 0.. | w_empty[6] 6.. | t_full[4] 12.. | a_full[2] 16,17 | (18..23 shared with the epilogue role)
-  //                | t_empty[4] 24.. | a_empty[2] 28,29 | gb_full 30 | gb_empty 31
+  // barrier slots: w_full[6] 0.. | w_empty[6] 6.. | t_full[4] 12.. | (18..23 shared with the epilogue role) | t_empty[4] 24..
+  //                | a_full[6] 28.. | a_empty[6] 34.. | a_ready[6] 40..
   auto w_full = [&](int s) { return bar_base + 8u * s; };
   auto w_empty = [&](int s) { return bar_base + 8u * (TC_MAX_STAGES + s); };
   auto t_full = [&](int s) { return bar_base + 8u * (12 + s); };
-  auto a_full = [&](int s) { return bar_base + 8u * (16 + s); };
   auto tfull_bar = [&](int a) { return bar_base + 8u * (TC_BAR_TFULL + a); };
   auto tempty_bar = [&](int a) { return bar_base + 8u * (TC_BAR_TEMPTY + a); };
   auto t_empty = [&](int s) { return bar_base + 8u * (24 + s); };
-  auto a_empty = [&](int s) { return bar_base + 8u * (28 + s); };
-  const uint32_t gb_full = bar_base + 8u * 30, gb_empty = bar_base + 8u * 31;
+  auto a_full = [&](int s) { return bar_base + 8u * (28 + s); };    // TMA landed (halo tile + scale / shift table)
+  auto a_empty = [&](int s) { return bar_base + 8u * (34 + s); };   // the feed warps have read the slot for the last time
+  auto a_ready = [&](int s) { return bar_base + 8u * (40 + s); };   // the prep warps have turned the slot into bf16 hi | lo rows
   const uint32_t tmem_slot = bar_base + 8u * TC_BAR_TMEM_SLOT;
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
@@ -91,16 +212,15 @@ conv_nf_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&map_a0);
     if (p.c1) prefetch_tmap(&map_a1);
-    if (q.has_gb) prefetch_tmap(&map_gb);
     if (p.cx0) prefetch_tmap(&map_x0);
     if (p.cx1) prefetch_tmap(&map_x1);
     prefetch_tmap(&map_w);
     prefetch_tmap(&map_wlo);
     for (int s = 0; s < TC_MAX_STAGES; ++s) { mbar_init(w_full(s), 1); mbar_init(w_empty(s), 1); }
     for (int s = 0; s < NF_TSLOTS; ++s) { mbar_init(t_full(s), TC_SPLIT_WARPS); mbar_init(t_empty(s), 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(a_full(s), 1); mbar_init(a_empty(s), TC_SPLIT_WARPS); }
-    mbar_init(gb_full, 1);
-    mbar_init(gb_empty, TC_SPLIT_WARPS);
+    for (int s = 0; s < NF_MAX_ASLOTS; ++s) {
+      mbar_init(a_full(s), 1); mbar_init(a_empty(s), TC_SPLIT_WARPS); mbar_init(a_ready(s), TC_SPLIT_WARPS);
+    }
     for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), TC_EPI_WARPS); }
     fence_barrier_init();
   }
@@ -114,72 +234,48 @@ conv_nf_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
   const uint32_t tmem_base = *tmem_slot_ptr;
   pdl_wait();
 
-  if (warp == 0) {
-    // ===================== weight TMA producer =====================
-    if (lane == 0) {
+  if (warp < 4) {
+    // ===================== control warpgroup: 0 = weight TMA, 1 = MMA issuer, 2 = halo TMA, 3 = idle =====================
+    reg_dec<NF_REGS_CTRL>();
+    if (warp == 0 && lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      SegIter it(p, n_units, total_tiles);
-      int tile, u0, u1;
-      while (it.next(tile, u0, u1)) {
-        const int n0 = (tile % p.tiles_n) * p.BN;
-        for (int u = u0; u < u1; ++u) {
-          const bool nf = u < q.n_chunks;
-          const int nk = nf ? q.taps : 1;
-          for (int t = 0; t < nk; ++t) {
-            // weight columns run [tap][channel] then the side input's channels
-            const int col = nf ? t * q.Cn + u * TC_BK : q.taps * q.Cn + (u - q.n_chunks) * TC_BK;
-            mbar_wait(w_empty(stage), phase ^ 1);
-            const uint32_t sb = smem_base + w_off + stage * w_stage_bytes;
-            mbar_expect_tx(w_full(stage), w_stage_bytes);
-            tma_load_3d(sb, &map_w, w_full(stage), col, n0, 0);
-            tma_load_3d(sb + b_bytes, &map_wlo, w_full(stage), col, n0, 0);
-            if (++stage == q.w_stages) { stage = 0; phase ^= 1; }
-          }
+      NfCursor c(p, n_units, total_tiles);
+      for (c.advance(p, q); c.valid; c.advance(p, q)) {
+        const int n0 = (c.tile % p.tiles_n) * p.BN;
+        const int nk = c.chunk ? q.taps : 1;
+        for (int t = 0; t < nk; ++t) {
+          // weight columns run [tap][channel] then the side input's channels
+          const int col = c.chunk ? t * q.Cn + c.idx * TC_BK : q.taps * q.Cn + c.idx * TC_BK;
+          mbar_wait(w_empty(stage), phase ^ 1);
+          const uint32_t sb = smem_base + w_off + stage * w_stage_bytes;
+          mbar_expect_tx(w_full(stage), w_stage_bytes);
+          tma_load_3d(sb, &map_w, w_full(stage), col, n0, 0);
+          tma_load_3d(sb + b_bytes, &map_wlo, w_full(stage), col, n0, 0);
+          if (++stage == q.w_stages) { stage = 0; phase ^= 1; }
         }
       }
-    }
-  } else if (warp == 14) {
-    // ===================== halo TMA producer =====================
-    if (lane == 0) {
-      int aslot = 0;
-      uint32_t aphase = 0, gphase = 0;
-      SegIter it(p, n_units, total_tiles);
-      int tile, u0, u1;
-      while (it.next(tile, u0, u1)) {
-        int mt = tile / p.tiles_n;
-        const int tx = mt % p.tiles_x; mt /= p.tiles_x;
-        const int ty = mt % p.tiles_y;
-        const int tb = mt / p.tiles_y;
-        const int ox0 = tx * p.TW, oy0 = ty * p.TH, b0 = tb * p.TB;
-        for (int u = u0; u < u1; ++u) {
-          mbar_wait(a_empty(aslot), aphase ^ 1);
-          const uint32_t dst = smem_base + xs_off + aslot * q.slot_bytes;
-          if (u < q.n_chunks) {
-            const int ch = u * TC_BK;
-            if (q.has_gb) {
-              mbar_wait(gb_empty, gphase ^ 1);
-              gphase ^= 1;
-              mbar_expect_tx(gb_full, 2u * q.rows_h * 128u);
-              tma_load_4d(smem_base + gb_off, &map_gb, gb_full, ch, ox0 - q.hpad, oy0 - q.hpad, b0);
-              tma_load_4d(smem_base + gb_off + q.slot_bytes, &map_gb, gb_full, q.Cn + ch, ox0 - q.hpad, oy0 - q.hpad, b0);
-            }
-            mbar_expect_tx(a_full(aslot), (uint32_t)q.rows_h * 128u);
-            if (ch < p.c0) tma_load_4d(dst, &map_a0, a_full(aslot), ch, ox0 - q.hpad, oy0 - q.hpad, b0);
-            else           tma_load_4d(dst, &map_a1, a_full(aslot), ch - p.c0, ox0 - q.hpad, oy0 - q.hpad, b0);
-          } else {  // side input: the output pixel itself, raw
-            const int ch = (u - q.n_chunks) * TC_BK;
-            mbar_expect_tx(a_full(aslot), (uint32_t)TC_A_BYTES);
-            if (ch < p.cx0) tma_load_4d(dst, &map_x0, a_full(aslot), ch, ox0, oy0, b0);
-            else            tma_load_4d(dst, &map_x1, a_full(aslot), ch - p.cx0, ox0, oy0, b0);
-          }
-          if (++aslot == 2) { aslot = 0; aphase ^= 1; }
+    } else if (warp == 2 && lane == 0) {
+      NfCursor c(p, n_units, total_tiles);
+      for (c.advance(p, q); c.valid; c.advance(p, q)) {
+        mbar_wait(a_empty(c.slot), c.phase ^ 1);
+        const uint32_t dst = smem_base + c.slot * q.slot_bytes;
+        const int ch = c.idx * TC_BK;
+        if (c.chunk) {
+          // the (a, b) pairs of this chunk's 32 channels for the images of the tile ride on the same barrier
+          const int nimg = q.has_norm ? min(p.TB, p.B - c.b0) : 0;
+          mbar_expect_tx(a_full(c.slot), (uint32_t)q.rows_h * 128u + (uint32_t)nimg * 256u);
+          if (ch < p.c0) tma_load_4d(dst, &map_a0, a_full(c.slot), ch, c.ox0 - q.hpad, c.oy0 - q.hpad, c.b0);
+          else           tma_load_4d(dst, &map_a1, a_full(c.slot), ch - p.c0, c.ox0 - q.hpad, c.oy0 - q.hpad, c.b0);
+          for (int i = 0; i < nimg; ++i)
+            bulk_load(dst + q.ab_off + i * 256, q.ab + ((size_t)(c.b0 + i) * q.Cn + ch) * 2, 256u, a_full(c.slot));
+        } else {  // side input: the output pixel itself, raw
+          mbar_expect_tx(a_full(c.slot), (uint32_t)TC_A_BYTES);
+          if (ch < p.cx0) tma_load_4d(dst, &map_x0, a_full(c.slot), ch, c.ox0, c.oy0, c.b0);
+          else            tma_load_4d(dst, &map_x1, a_full(c.slot), ch - p.cx0, c.ox0, c.oy0, c.b0);
         }
       }
-    }
-  } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
+    } else if (warp == 1 && lane == 0) {
       const uint32_t idesc = umma_idesc_bf16(TC_BM, p.BN);
       int stage = 0, tslot = 0, acc = 0;
       uint32_t phase = 0, tphase = 0, acc_phase = 0;
@@ -191,7 +287,9 @@ conv_nf_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
         const uint32_t d_tmem = tmem_base + (uint32_t)acc * TC_BF_ACC_STRIDE;
         bool first = true;
         for (int u = u0; u < u1; ++u) {
-          const int nk = u < q.n_chunks ? q.taps : 1;
+          bool chunk; int idx;
+          nf_decode(q, u, chunk, idx);
+          const int nk = chunk ? q.taps : 1;
           for (int t = 0; t < nk; ++t) {
             mbar_wait(w_full(stage), phase);
             mbar_wait(t_full(tslot), tphase);
@@ -216,158 +314,151 @@ conv_nf_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
-  } else if (warp < 2 + TC_EPI_WARPS) {
-    tc_epilogue_role<EPI>(p, smem_raw, smem_base, bar_base, tmem_base, (uint32_t)TC_BF_ACC_STRIDE, n_units, total_tiles);
-  } else {
-    // ===================== operand warps (10..13): normalise-on-load, bf16 hi / lo split, tensor-memory feed =====================
-    const int m = (warp & 3) * 32 + lane;  // tile row = TMEM lane owned by this thread
-    const int t = threadIdx.x - TC_THREADS;  // 0..127
+  } else if (warp < 4 + TC_EPI_WARPS) {
+    reg_inc<NF_REGS_EPI>();
+    tc_epilogue_role<EPI, 4>(p, smem_raw, smem_base, bar_base, tmem_base, (uint32_t)TC_BF_ACC_STRIDE, n_units, total_tiles);
+  } else if (warp < 16) {
+    // ===================== feed warpgroup (12..15): shared memory -> tensor memory, nothing else =====================
+    // Every slot it sees already holds finished operand rows (128 B = per 16-byte chunk c: bf16x2 hi words 2c, 2c+1 | lo
+    // words 2c, 2c+1), written by the prep warpgroup.  Per k-step thread = output pixel reads its row - for a 3x3 chunk
+    // the row of tap (dy, dx) inside the halo tile - and stores it into a tensor-memory slot (tcgen05.st) for the TS-form
+    // MMAs.  The store of k-step k is only waited for at the start of k-step k+1 (after its shared-memory reads).
+    reg_dec<NF_REGS_FEED>();
+    const int m = (warp & 3) * 32 + lane;    // tile row = TMEM lane owned by this thread
     const uint32_t a_lane = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)TC_BF_A_COL;
-    float* abtab = reinterpret_cast<float*>(smem_gen + ab_off);  // [2][TB*32][2]
     const int px = m & (p.TW - 1), py = (m >> p.lTW) & (p.TH - 1), pb = m >> (p.lTW + p.lTH);
     const int r0 = (pb * q.HH2 + py) * q.HW2 + px;  // halo row of tap (0, 0) for this output pixel
-    const int hplane = q.HW2 * q.HH2;
-    int aslot = 0, tslot = 0, abuf = 0;
-    uint32_t aphase = 0, tphase = 0, gphase = 0;
-    SegIter it(p, n_units, total_tiles);
-    int tile, u0, u1;
-    while (it.next(tile, u0, u1)) {
-      int mt = tile / p.tiles_n;
-      const int tx = mt % p.tiles_x; mt /= p.tiles_x;
-      const int ty = mt % p.tiles_y;
-      const int tb = mt / p.tiles_y;
-      const int ox0 = tx * p.TW, oy0 = ty * p.TH, b0 = tb * p.TB;
-      for (int u = u0; u < u1; ++u) {
-        const bool nf = u < q.n_chunks;
-        float2 abv = make_float2(0.f, 0.f);
-        if (nf && t < p.TB * 32) {  // scale / shift of this chunk's channels for the images of the tile (global, L2-resident)
-          const int b = b0 + (t >> 5);
-          if (b < p.B) abv = __ldg(reinterpret_cast<const float2*>(q.ab) + (size_t)b * q.Cn + u * TC_BK + (t & 31));
+    int tseq = 0, pend = -1;
+    NfCursor F(p, n_units, total_tiles);
+    for (F.advance(p, q); F.valid; F.advance(p, q)) {
+      const uint8_t* xs = smem_gen + (size_t)F.slot * q.slot_bytes;
+      const bool halo = F.chunk && q.taps == 9;
+      const int nk = F.chunk ? q.taps : 1;
+      mbar_wait(a_ready(F.slot), F.phase);
+      for (int tap = 0; tap < nk; ++tap) {
+        int rr = m;
+        if (halo) { const int dy = tap / 3, dx = tap - 3 * dy; rr = r0 + dy * q.HW2 + dx; }
+        const uint8_t* row = xs + rr * 128;
+        const int sw = rr & 7;
+        uint32_t hi[16], lo[16];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const uint4 w = *reinterpret_cast<const uint4*>(row + ((c ^ sw) << 4));
+          hi[2 * c] = w.x; hi[2 * c + 1] = w.y; lo[2 * c] = w.z; lo[2 * c + 1] = w.w;
         }
-        mbar_wait(a_full(aslot), aphase);
-        const uint8_t* xs = smem_gen + xs_off + (size_t)aslot * q.slot_bytes;
-        float* ab = abtab + abuf * (NF_AB_BYTES / 8);
-        if (nf) {
-          if (t < p.TB * 32) reinterpret_cast<float2*>(ab)[t] = abv;
-          if (q.has_gb) mbar_wait(gb_full, gphase);
-          asm volatile("bar.sync 2, 128;" ::: "memory");
-        }
-        const uint8_t* gs = smem_gen + gb_off;
-        if (nf && q.taps == 9) {
-          // ---- pass 1: normalise (+SPADE) (+SiLU), zero the out-of-image halo, split, write the bf16 pair back in place ----
-          for (int r = t; r < q.rows_h; r += TC_SPLIT_THREADS) {
-            const int hb = r / hplane;
-            const int rem = r - hb * hplane;
-            const int hy = rem / q.HW2, hx = rem - hy * q.HW2;
-            const int ix = ox0 - q.hpad + hx, iy = oy0 - q.hpad + hy;
-            const bool valid = ix >= 0 && ix < q.Win && iy >= 0 && iy < q.Hin && (b0 + hb) < p.B;
-            uint8_t* row = const_cast<uint8_t*>(xs) + r * 128;
-            const float4* abr = reinterpret_cast<const float4*>(ab + hb * 64);
-            const int sw = r & 7;
-            uint32_t hi[16], lo[16];
-#pragma unroll
-            for (int c = 0; c < 8; ++c) {
-              float4 v = *reinterpret_cast<const float4*>(row + ((c ^ sw) << 4));
-              const float4 s0 = abr[2 * c], s1 = abr[2 * c + 1];  // (a, b) of channels 4c, 4c+1 | 4c+2, 4c+3
-              v.x = fmaf(v.x, s0.x, s0.y); v.y = fmaf(v.y, s0.z, s0.w); v.z = fmaf(v.z, s1.x, s1.y); v.w = fmaf(v.w, s1.z, s1.w);
-              if (q.has_gb) {
-                const float4 g = *reinterpret_cast<const float4*>(gs + r * 128 + ((c ^ sw) << 4));
-                const float4 e = *reinterpret_cast<const float4*>(gs + q.slot_bytes + r * 128 + ((c ^ sw) << 4));
-                v.x = fmaf(v.x, 1.0f + g.x, e.x); v.y = fmaf(v.y, 1.0f + g.y, e.y);
-                v.z = fmaf(v.z, 1.0f + g.z, e.z); v.w = fmaf(v.w, 1.0f + g.w, e.w);
-              }
-              if (q.silu) { v.x = silu_fast(v.x); v.y = silu_fast(v.y); v.z = silu_fast(v.z); v.w = silu_fast(v.w); }
-              if (!valid) v = make_float4(0.f, 0.f, 0.f, 0.f);
-              const uint32_t h0 = pack_bf16x2(v.x, v.y), h1 = pack_bf16x2(v.z, v.w);
-              hi[2 * c] = h0; hi[2 * c + 1] = h1;
-              lo[2 * c] = pack_bf16x2(v.x - bf16_lo_to_f32(h0), v.y - bf16_hi_to_f32(h0));
-              lo[2 * c + 1] = pack_bf16x2(v.z - bf16_lo_to_f32(h1), v.w - bf16_hi_to_f32(h1));
-            }
-            // row layout after the pass: 16-byte chunks 0..3 = hi words, 4..7 = lo words (same swizzle)
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              *reinterpret_cast<uint4*>(row + ((j ^ sw) << 4)) = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
-              *reinterpret_cast<uint4*>(row + (((j + 4) ^ sw) << 4)) = make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
-            }
-          }
-          asm volatile("bar.sync 2, 128;" ::: "memory");
-          if (q.has_gb) {  // the gamma / beta staging is free for the next chunk
-            gphase ^= 1;
-            if (lane == 0) mbar_arrive(gb_empty);
-          }
-          // ---- pass 2: one tensor-memory slot per tap, thread = output pixel, rows shifted inside the halo tile ----
-          for (int tap = 0; tap < 9; ++tap) {
-            const int dy = tap / 3, dx = tap - 3 * dy;
-            const int rr = r0 + dy * q.HW2 + dx;
-            const uint8_t* row = xs + rr * 128;
-            const int sw = rr & 7;
-            uint32_t hi[16], lo[16];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const uint4 a = *reinterpret_cast<const uint4*>(row + ((j ^ sw) << 4));
-              const uint4 b = *reinterpret_cast<const uint4*>(row + (((j + 4) ^ sw) << 4));
-              hi[4 * j] = a.x; hi[4 * j + 1] = a.y; hi[4 * j + 2] = a.z; hi[4 * j + 3] = a.w;
-              lo[4 * j] = b.x; lo[4 * j + 1] = b.y; lo[4 * j + 2] = b.z; lo[4 * j + 3] = b.w;
-            }
-            mbar_wait(t_empty(tslot), tphase ^ 1);  // the MMAs that last read this slot have retired
-            tc_fence_after();
-            tmem_st16(a_lane + (uint32_t)(tslot * 32), hi);
-            tmem_st16(a_lane + (uint32_t)(tslot * 32 + 16), lo);
-            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(t_full(tslot));
-            if (++tslot == NF_TSLOTS) { tslot = 0; tphase ^= 1; }
-          }
-        } else {
-          // ---- one k-step straight from the 128-row tile: the 1x1 normalised conv (proj_in) or the raw side input ----
-          const uint8_t* row = xs + m * 128;
-          const float4* abr = reinterpret_cast<const float4*>(ab + pb * 64);
-          const int sw = m & 7;
-          uint32_t hi[16], lo[16];
-#pragma unroll
-          for (int c = 0; c < 8; ++c) {
-            float4 v = *reinterpret_cast<const float4*>(row + ((c ^ sw) << 4));
-            if (nf) {
-              const float4 s0 = abr[2 * c], s1 = abr[2 * c + 1];
-              v.x = fmaf(v.x, s0.x, s0.y); v.y = fmaf(v.y, s0.z, s0.w); v.z = fmaf(v.z, s1.x, s1.y); v.w = fmaf(v.w, s1.z, s1.w);
-              if (q.has_gb) {
-                const float4 g = *reinterpret_cast<const float4*>(gs + m * 128 + ((c ^ sw) << 4));
-                const float4 e = *reinterpret_cast<const float4*>(gs + q.slot_bytes + m * 128 + ((c ^ sw) << 4));
-                v.x = fmaf(v.x, 1.0f + g.x, e.x); v.y = fmaf(v.y, 1.0f + g.y, e.y);
-                v.z = fmaf(v.z, 1.0f + g.z, e.z); v.w = fmaf(v.w, 1.0f + g.w, e.w);
-              }
-              if (q.silu) { v.x = silu_fast(v.x); v.y = silu_fast(v.y); v.z = silu_fast(v.z); v.w = silu_fast(v.w); }
-            }
-            const uint32_t h0 = pack_bf16x2(v.x, v.y), h1 = pack_bf16x2(v.z, v.w);
-            hi[2 * c] = h0; hi[2 * c + 1] = h1;
-            lo[2 * c] = pack_bf16x2(v.x - bf16_lo_to_f32(h0), v.y - bf16_hi_to_f32(h0));
-            lo[2 * c + 1] = pack_bf16x2(v.z - bf16_lo_to_f32(h1), v.w - bf16_hi_to_f32(h1));
-          }
-          if (nf && q.has_gb) {
-            gphase ^= 1;
-            __syncwarp();
-            if (lane == 0) mbar_arrive(gb_empty);
-          }
-          mbar_wait(t_empty(tslot), tphase ^ 1);
-          tc_fence_after();
-          tmem_st16(a_lane + (uint32_t)(tslot * 32), hi);
-          tmem_st16(a_lane + (uint32_t)(tslot * 32 + 16), lo);
+        if (pend >= 0) {  // complete the previous k-step: its tcgen05.st had this k-step's loads to land
           asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(t_full(tslot));
-          if (++tslot == NF_TSLOTS) { tslot = 0; tphase ^= 1; }
+          if (lane == 0) mbar_arrive(t_full(pend));
         }
-        // this warp is done with the halo slot: hand it back to the TMA producer (generic-proxy accesses ordered before the
-        // async-proxy refill)
-        fence_proxy_async();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(a_empty(aslot));
-        if (++aslot == 2) { aslot = 0; aphase ^= 1; }
-        if (nf) abuf ^= 1;
+        const int tslot = tseq & (NF_TSLOTS - 1);
+        mbar_wait(t_empty(tslot), (uint32_t)(((tseq >> 2) & 1) ^ 1));  // the MMAs that last read this slot have retired
+        tc_fence_after();
+        tmem_st16(a_lane + (uint32_t)(tslot * 32), hi);
+        tmem_st16(a_lane + (uint32_t)(tslot * 32 + 16), lo);
+        pend = tslot;
+        ++tseq;
       }
+      // done with the slot (its rows are in registers / tensor memory): hand it back to the TMA producer
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(a_empty(F.slot));
     }
+    if (pend >= 0) {
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(t_full(pend));
+    }
+    static_assert(NF_TSLOTS == 4, "the feed assumes four tensor-memory operand slots");
+  } else {
+    // ===================== prep warpgroup (16..19): turn a landed slot into operand rows, in place =====================
+    // For a chunk of the normalised input: y = x*a[b,c] + b[b,c], SPADE y*(1+gamma)+beta, SiLU, zero outside the image
+    // (conv padding pads the ACTIVATED tensor), bf16 hi / lo split.  For a raw side-input tile: the split only.
+    // Item = (row, 16-byte chunk = 4 channels); its hi / lo words go back into the 16 bytes it read, so items are
+    // independent.  Item k of thread t is (row t/8 + 16 k, chunk t%8): the thread's channels never change, 8 consecutive
+    // threads cover one 128-byte row (conflict-free), halo coordinates advance incrementally.  The warpgroup runs ahead of
+    // the feed through the slot ring (bounded by `a_full`), so its latency never sits on the tensor core's critical path.
+    reg_inc<NF_REGS_PREP>();
+    const int t = threadIdx.x - 512;  // 0..127
+    const int cq = t & 7, rq = t >> 3;
+    const int hplane = q.HW2 * q.HH2;
+    const int n_steps = (q.rows_h * 8 + NF_STEP_ITEMS - 1) / NF_STEP_ITEMS;  // per chunk (side tiles: 128 rows)
+    const int n_steps_side = (TC_BM * 8 + NF_STEP_ITEMS - 1) / NF_STEP_ITEMS;
+    // item descriptors, worked out once (they depend on neither the chunk nor the tile); each thread reads back only the
+    // entries it wrote
+    uint32_t* desc = reinterpret_cast<uint32_t*>(smem_gen + TC_SMEM_BUDGET - NF_DESC_BYTES);
+    for (int k = 0; k < n_steps * NF_IPT; ++k) {
+      const int r = rq + 16 * k;
+      uint32_t d = 0;
+      if (r < q.rows_h) {
+        const int hb = r / hplane, rem = r - hb * hplane, hy = rem / q.HW2, hx = rem - hy * q.HW2;
+        d = (uint32_t)(r * 8 + (cq ^ (r & 7))) | ((uint32_t)hx << 11) | ((uint32_t)hy << 16) | ((uint32_t)hb << 21) | 0x80000000u;
+      }
+      desc[k * 128 + t] = d;
+    }
+    const bool do_gb = q.has_gb != 0, do_silu = q.silu && !(q.dbg & 4);
+    NfCursor P(p, n_units, total_tiles), G(p, n_units, total_tiles);
+    auto next_chunk = [&](NfCursor& c) { do { c.advance(p, q); } while (c.valid && !c.chunk); };
+    int g_step = 0, g_ring = 0, p_ring = 0;
+    // cp.async group of one prep step: gamma | beta (16 B each) of this thread's items; always commits (possibly empty)
+    auto gb_issue = [&]() {
+      if (G.valid) {
+#pragma unroll
+        for (int j = 0; j < NF_IPT; ++j) {
+          const uint32_t d = desc[(g_step * NF_IPT + j) * 128 + t];
+          if (d >> 31) {
+            const int ix = G.ox0 - q.hpad + (int)((d >> 11) & 31), iy = G.oy0 - q.hpad + (int)((d >> 16) & 31), b = G.b0 + (int)((d >> 21) & 3);
+            const bool ok = (unsigned)ix < (unsigned)q.Win && (unsigned)iy < (unsigned)q.Hin && b < p.B;
+            const float* src = q.gb + (ok ? (((size_t)b * q.Hin + iy) * q.Win + ix) * (size_t)(2 * q.Cn) + G.idx * TC_BK + 4 * cq : 0);
+            const uint32_t dst = smem_base + gb_ring + g_ring * NF_GB_STEP_BYTES + (j * 128 + t) * 32;
+            const int nbytes = ok ? 16 : 0;  // src-size 0: zero fill, nothing is read
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(nbytes) : "memory");
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst + 16), "l"(src + (ok ? q.Cn : 0)), "r"(nbytes) : "memory");
+          }
+        }
+        if (++g_ring == NF_GB_DEPTH) g_ring = 0;
+        if (++g_step == n_steps) { g_step = 0; next_chunk(G); }
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    if (do_gb) {  // NF_GB_DEPTH - 1 steps of SPADE maps are always in flight ahead of the step being computed
+      next_chunk(G);
+      for (int i = 0; i < NF_GB_DEPTH - 1; ++i) gb_issue();
+    }
+    for (P.advance(p, q); P.valid; P.advance(p, q)) {
+      mbar_wait(a_full(P.slot), P.phase);
+      uint8_t* xs = smem_gen + (size_t)P.slot * q.slot_bytes;
+      const bool nrm = P.chunk && q.has_norm && !(q.dbg & 1);
+      const bool gbs = nrm && do_gb;
+      const int rows = P.chunk ? q.rows_h : TC_BM;
+      const int steps = ((q.dbg & 2) || (P.chunk && q.presplit)) ? 0 : (P.chunk ? n_steps : n_steps_side);
+      const int ox = P.ox0 - q.hpad, oy = P.oy0 - q.hpad;
+      for (int st = 0; st < steps; ++st) {
+        const uint32_t* dsc = desc + st * NF_STEP_ITEMS + t;
+        const uint8_t* gsm = smem_gen + gb_ring + p_ring * NF_GB_STEP_BYTES + t * 32;
+        const int first_row = rq + 16 * NF_IPT * st;
+        if (gbs) {
+          gb_issue();  // step n + DEPTH - 1 goes out; all but the newest DEPTH - 1 groups (i.e. step n) must have landed
+          asm volatile("cp.async.wait_group %0;" ::"n"(NF_GB_DEPTH - 1) : "memory");
+          if (do_silu) nf_prep_items<true, true, true>(xs, dsc, first_row, rows, true, q.ab_off, cq, gsm, ox, oy, P.b0, q.Win, q.Hin, p.B, p.TB);
+          else         nf_prep_items<true, true, false>(xs, dsc, first_row, rows, true, q.ab_off, cq, gsm, ox, oy, P.b0, q.Win, q.Hin, p.B, p.TB);
+          if (++p_ring == NF_GB_DEPTH) p_ring = 0;
+        } else if (nrm) {
+          if (do_silu) nf_prep_items<true, false, true>(xs, dsc, first_row, rows, true, q.ab_off, cq, gsm, ox, oy, P.b0, q.Win, q.Hin, p.B, p.TB);
+          else         nf_prep_items<true, false, false>(xs, dsc, first_row, rows, true, q.ab_off, cq, gsm, ox, oy, P.b0, q.Win, q.Hin, p.B, p.TB);
+        } else {  // raw tile (side input, or a plain conv through the halo path): mask + split only
+          nf_prep_items<false, false, false>(xs, dsc, first_row, rows, P.chunk, q.ab_off, cq, gsm, ox, oy, P.b0, q.Win, q.Hin, p.B, p.TB);
+        }
+      }
+      // rows are final: release them to the feed warps (and order these generic-proxy writes before the TMA refill that
+      // follows the feed's release of the slot)
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(a_ready(P.slot));
+    }
+    if (do_gb) asm volatile("cp.async.wait_group 0;" ::: "memory");
   }
 
   tc_fence_before();
@@ -385,7 +476,8 @@ static bool make_map4_box(CUtensorMap* m, const float* base, uint64_t C, uint64_
 }
 
 bool conv2d_nf_eligible(const FridoConvParams* p) {
-  if (p->engine != 3 || !p->nrm_ab || !p->w_lo) return false;
+  if (p->engine != 3 || (!p->nrm_ab && !p->a_presplit) || !p->w_lo) return false;
+  if (p->a_presplit && (p->nrm_ab || p->ksize != 3)) return false;
   if (p->ups != 1 || p->stride != 1 || (p->ksize != 1 && p->ksize != 3) || p->pad != p->ksize / 2) return false;
   if (p->w_sb || p->o_sn != 1 || !p->out) return false;
   if (p->Hout != p->Hin || p->Wout != p->Win) return false;
@@ -407,7 +499,7 @@ int conv2d_nf(const FridoConvParams* p, cudaStream_t s) {
   if (p->Cout % 64) return set_error(FRIDO_E_ARG, "conv2d_nf: Cout must be a multiple of 64");
   if (p->a0_sc != 1 || (p->a1 && p->a1_sc != 1)) return set_error(FRIDO_E_ARG, "conv2d_nf: channel stride must be 1");
   if (!a16(p->a0) || !a16(p->w) || !a16(p->w_lo) || (p->a1 && !a16(p->a1)) || !a16(p->out) || (p->res && !a16(p->res)) ||
-      (reinterpret_cast<uintptr_t>(p->nrm_ab) & 7) || (p->nrm_gb && !a16(p->nrm_gb)))
+      (p->nrm_ab && !a16(p->nrm_ab)) || (p->nrm_gb && !a16(p->nrm_gb)))
     return set_error(FRIDO_E_ARG, "conv2d_nf: pointers must be 16-byte aligned");
   if (p->a0_sx % 4 || p->a0_sy % 4 || p->a0_sb % 4 || (p->a1 && (p->a1_sx % 4 || p->a1_sy % 4 || p->a1_sb % 4)))
     return set_error(FRIDO_E_ARG, "conv2d_nf: strides must be multiples of 16 bytes");
@@ -444,14 +536,22 @@ int conv2d_nf(const FridoConvParams* p, cudaStream_t s) {
   q.n_chunks = Cn / TC_BK; q.taps = taps; q.hpad = p->ksize / 2;
   q.HW2 = t.TW + 2 * q.hpad; q.HH2 = t.TH + 2 * q.hpad; q.rows_h = q.HW2 * q.HH2 * t.TB;
   q.side_units = (p->cx0 + p->cx1) / TC_BK;
-  q.slot_bytes = (q.rows_h * 128 + 1023) / 1024 * 1024;
-  q.has_gb = p->nrm_gb != nullptr; q.Cn = Cn; q.silu = p->nrm_silu; q.Hin = p->Hin; q.Win = p->Win; q.ab = p->nrm_ab;
+  q.ab_off = q.rows_h * 128;
+  q.slot_bytes = (q.ab_off + t.TB * 256 + 1023) / 1024 * 1024;
+  q.m_plane = 65536 / (q.HW2 * q.HH2) + 1; q.m_hw2 = 65536 / q.HW2 + 1;  // exact for r < 4096 (r <= 207 here)
+  q.has_gb = p->nrm_gb != nullptr; q.has_norm = p->nrm_ab != nullptr; q.presplit = p->a_presplit != 0; q.Cn = Cn; q.silu = p->nrm_silu; q.Hin = p->Hin; q.Win = p->Win;
+  q.ab = p->nrm_ab; q.gb = p->nrm_gb;
+  q.dbg = 0;
+  if (const char* e = getenv("FRIDO_NF_DBG")) q.dbg = atoi(e);
+  // halo ring: about half of the operand budget (4 slots of a 3x3 halo tile, 6 of a 1x1 tile), the rest is the weight ring
+  q.a_slots = p->ksize == 3 ? (q.has_gb ? 3 : 4) : NF_MAX_ASLOTS;
   const int n_units = q.n_chunks + q.side_units;
   const int ksteps = q.n_chunks * taps + q.side_units;
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const int ring_budget = TC_SMEM_BUDGET - NF_AB_BYTES - (q.has_gb ? 4 : 2) * q.slot_bytes;
+  const int ring_budget = TC_SMEM_BUDGET - q.a_slots * q.slot_bytes - (q.has_gb ? NF_GB_DEPTH * NF_GB_STEP_BYTES : 0) -
+                          NF_DESC_BYTES;
   auto stage_clk = [&](int n) { return 256 + 5 * n / 2; };  // per k-step, as conv_tc.cu's BF16x3 model
   const int cands[3] = {192, 128, 64};
   int bn = 64;
@@ -518,16 +618,12 @@ int conv2d_nf(const FridoConvParams* p, cudaStream_t s) {
   q.w_stages = ring_budget / (bn * 128);
   if (q.w_stages > TC_MAX_STAGES) q.w_stages = TC_MAX_STAGES;
 
-  CUtensorMap ma0, ma1, mgb, mw, mwlo, mx0, mx1;
+  CUtensorMap ma0, ma1, mw, mwlo, mx0, mx1;
   if (!make_map4_box(&ma0, p->a0, p->c0, p->Win, p->Hin, p->B, p->a0_sx, p->a0_sy, p->a0_sb, q.HW2, q.HH2, t.TB))
     return set_error(FRIDO_E_ARG, "conv2d_nf: cuTensorMapEncodeTiled(a0) failed");
   ma1 = ma0;
   if (p->a1 && !make_map4_box(&ma1, p->a1, p->c1, p->Win, p->Hin, p->B, p->a1_sx, p->a1_sy, p->a1_sb, q.HW2, q.HH2, t.TB))
     return set_error(FRIDO_E_ARG, "conv2d_nf: cuTensorMapEncodeTiled(a1) failed");
-  mgb = ma0;
-  if (p->nrm_gb && !make_map4_box(&mgb, p->nrm_gb, 2 * Cn, p->Win, p->Hin, p->B, 2 * Cn, (int64_t)p->Win * 2 * Cn,
-                                  (int64_t)p->Hin * p->Win * 2 * Cn, q.HW2, q.HH2, t.TB))
-    return set_error(FRIDO_E_ARG, "conv2d_nf: cuTensorMapEncodeTiled(gb) failed");
   mx0 = ma0; mx1 = ma0;
   if (p->x0 && !make_map4_box(&mx0, p->x0, p->cx0, p->Wout, p->Hout, p->B, p->x0_sx, p->x0_sy, p->x0_sb, t.TW, t.TH, t.TB))
     return set_error(FRIDO_E_ARG, "conv2d_nf: cuTensorMapEncodeTiled(x0) failed");
@@ -536,14 +632,14 @@ int conv2d_nf(const FridoConvParams* p, cudaStream_t s) {
   if (!make_map3(&mw, p->w, Ktot, p->Cout, 1, w_ld, 0, bn, true) || !make_map3(&mwlo, p->w_lo, Ktot, p->Cout, 1, w_ld, 0, bn, true))
     return set_error(FRIDO_E_ARG, "conv2d_nf: cuTensorMapEncodeTiled(w) failed");
 
-  using KernelFn = void (*)(CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, TcParams, NfParams);
+  using KernelFn = void (*)(CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, TcParams, NfParams);
   static const KernelFn kernels[EPI_COUNT] = {conv_nf_kernel<EPI_GENERIC>, conv_nf_kernel<EPI_BIAS>, conv_nf_kernel<EPI_BIAS_RES>,
                                               conv_nf_kernel<EPI_BIAS_RV_CS>, conv_nf_kernel<EPI_BIAS_RES_CS>, conv_nf_kernel<EPI_GENERIC>,
                                               conv_nf_kernel<EPI_BIAS_CS>, conv_nf_kernel<EPI_BIAS_PAIR>};
   static bool attr[64] = {};
   if (dev >= 0 && dev < 64 && !attr[dev]) {  // the opt-in is per device
     for (int i = 0; i < EPI_COUNT; ++i)
-      if (cudaFuncSetAttribute(kernels[i], cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES) != cudaSuccess)
+      if (cudaFuncSetAttribute(kernels[i], cudaFuncAttributeMaxDynamicSharedMemorySize, NF_SMEM_BYTES) != cudaSuccess)
         return set_error(FRIDO_E_LAUNCH, "conv2d_nf: cannot opt in to dynamic shared memory");
     attr[dev] = true;
   }
@@ -564,7 +660,7 @@ int conv2d_nf(const FridoConvParams* p, cudaStream_t s) {
   }
   const int total = m_tiles * t.tiles_n;
   const int grid = t.sk ? sk_grid : (total < sms ? total : sms);
-  launch_pdl(kernels[epi], dim3(grid), dim3(NF_THREADS), TC_SMEM_BYTES, s, ma0, ma1, mgb, mw, mwlo, mx0, mx1, t, q);
+  launch_pdl(kernels[epi], dim3(grid), dim3(NF_THREADS), NF_SMEM_BYTES, s, ma0, ma1, mw, mwlo, mx0, mx1, t, q);
   return check_launch("conv2d_nf");
 }
 

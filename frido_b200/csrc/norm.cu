@@ -208,6 +208,14 @@ __global__ void __launch_bounds__(NA_MAX_THREADS) norm_act_kernel(const FridoNor
             if (silu) y = silu_f(y);
             x[e] = rnd ? round_tf32(y) : y;
           }
+          if (p.out_split) {  // the BF16x3 engine's operand form: bf16x2 hi(c0,c1), hi(c2,c3), lo(c0,c1), lo(c2,c3)
+            uint16_t h[4], l[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) split_bf16(x[e], h[e], l[e]);
+            *reinterpret_cast<uint4*>(out + (int64_t)px * C + c) =
+                make_uint4((uint32_t)h[0] | ((uint32_t)h[1] << 16), (uint32_t)h[2] | ((uint32_t)h[3] << 16),
+                           (uint32_t)l[0] | ((uint32_t)l[1] << 16), (uint32_t)l[2] | ((uint32_t)l[3] << 16));
+          } else
           *reinterpret_cast<float4*>(out + (int64_t)px * C + c) = make_float4(x[0], x[1], x[2], x[3]);
         }
       }
@@ -417,6 +425,13 @@ __global__ void __launch_bounds__(256) upsample2x_kernel(const FridoUpsamplePara
     const int b = (int)(r / (2 * p.H));
     float4 v = __ldg(reinterpret_cast<const float4*>(p.x + (((int64_t)b * p.H + (oy >> 1)) * p.W + (ox >> 1)) * p.C) + q);
     if (p.round_tf32) { v.x = round_tf32(v.x); v.y = round_tf32(v.y); v.z = round_tf32(v.z); v.w = round_tf32(v.w); }
+    if (p.out_split) {
+      uint16_t h0, h1, h2, h3, l0, l1, l2, l3;
+      split_bf16(v.x, h0, l0); split_bf16(v.y, h1, l1); split_bf16(v.z, h2, l2); split_bf16(v.w, h3, l3);
+      reinterpret_cast<uint4*>(p.out + (((int64_t)b * 2 * p.H + oy) * 2 * p.W + ox) * p.C)[q] =
+          make_uint4((uint32_t)h0 | ((uint32_t)h1 << 16), (uint32_t)h2 | ((uint32_t)h3 << 16),
+                     (uint32_t)l0 | ((uint32_t)l1 << 16), (uint32_t)l2 | ((uint32_t)l3 << 16));
+    } else
     reinterpret_cast<float4*>(p.out + (((int64_t)b * 2 * p.H + oy) * 2 * p.W + ox) * p.C)[q] = v;
   }
 }

@@ -237,10 +237,11 @@ enum { EPI_GENERIC = 0, EPI_BIAS = 1, EPI_BIAS_RES = 2, EPI_BIAS_RV_CS = 3, EPI_
 constexpr int TC_BAR_TFULL = 3 * TC_MAX_STAGES, TC_BAR_TEMPTY = 3 * TC_MAX_STAGES + 2, TC_BAR_TMEM_SLOT = 3 * TC_MAX_STAGES + 4,
               TC_BAR_SK_FLAG = 3 * TC_MAX_STAGES + 5;
 
-// ===================== epilogue role (8 warps; threadIdx.x in [64, 320)) =====================
+// ===================== epilogue role (8 warps starting at warp EW0) =====================
 // `ksteps` is the length of a tile's K loop in the units the work iterator counts (k-steps in conv_tc.cu, operand units in
 // conv_nf.cu); the stream-K bookkeeping only needs it to be the same everywhere.
-template <int EPI>
+// EW0 = index of the first of the eight epilogue warps (a multiple of 2 so that warp & 3 walks the TMEM lane quarters).
+template <int EPI, int EW0 = 2>
 __device__ __forceinline__ void tc_epilogue_role(const TcParams& p, uint8_t* smem_raw, uint32_t smem_base, uint32_t bar_base,
                                                  uint32_t tmem_base, uint32_t acc_stride, int ksteps, int total_tiles) {
   const int warp = threadIdx.x >> 5;
@@ -252,13 +253,13 @@ __device__ __forceinline__ void tc_epilogue_role(const TcParams& p, uint8_t* sme
   // is transposed through a 2 KB per-warp swizzled staging tile so that every global instruction covers 8 rows x
   // 64 contiguous bytes, and bias / timestep row / residual / activation are applied in that arrangement.
   // Transposed outputs (V^T: o_sp == 1) are already coalesced across lanes and go out directly.
-  const int ew = warp - 2;
+  const int ew = warp - EW0;
   const int q = warp & 3;            // TMEM lane quarter this warp may access
   const int half = ew >> 2;
   const int row = q * 32 + lane;     // tile row owned by this thread (direct path)
   float4* stg = reinterpret_cast<float4*>(smem_raw + (smem_base - smem_u32(smem_raw)) + TC_SMEM_BUDGET) + ew * 128;
   float* cacc = reinterpret_cast<float*>(smem_raw + (smem_base - smem_u32(smem_raw)) + TC_SMEM_BUDGET + TC_STG_BYTES);
-  const int et = threadIdx.x - 64;   // 0..255 among the epilogue warps
+  const int et = threadIdx.x - 32 * EW0;   // 0..255 among the epilogue warps
   const int img_q = (q * 32) >> (p.lTW + p.lTH);  // image slot of this warp's rows inside the tile (all 32 rows share it)
   const int sub = lane >> 2, c4 = lane & 3;
   const int hcols = p.BN >> 1;

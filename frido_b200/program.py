@@ -131,7 +131,7 @@ class Program:
     def conv(self, a0, w, out, *, B, Hin, Win, Hout, Wout, Cout, ksize=1, stride=1, pad=0, ups=1, a1=None,
              bias=None, rowvec=None, rowvec_sb=0, res=None, alpha=1.0, act=L.ACT_NONE, o_sb=None, o_sp=None, o_sn=1,
              w_sb=0, w_ld=0, w_off=0, out_off=0, round_tf32=0, engine=None, csum=None, out_pair=None, w_pair=None,
-             alg_flops=None, side=None, out_u8=None, u8_mode=0, nrm=None, tag="conv"):
+             alg_flops=None, side=None, out_u8=None, u8_mode=0, nrm=None, presplit=False, tag="conv"):
         """Returns True when `csum` (per-channel GroupNorm sums of the output, [B,Cout,2] fp64) was attached to the op:
         only the tcgen05 engines accumulate it, for dense NHWC outputs with >= 32 pixels per image."""
         if engine is None:
@@ -197,6 +197,10 @@ class Program:
             ab, gb, silu = nrm
             p.nrm_ab, p.nrm_gb, p.nrm_silu = ab.data_ptr(), _ptr(gb), int(silu)
             self.hold(ab, gb)
+        if presplit:  # a0 | a1 were written in the engine's operand form (norm_act / upsample2x with out_split)
+            if engine != 3 or nrm is not None:
+                raise L.FridoError("conv: a pre-split operand needs the BF16x3 tcgen05 engine (check Program.nf_eligible first)")
+            p.a_presplit = 1
         if out_u8 is not None:  # uint8 NHWC copy of the outputs (decoder head: sample_diffusion.py:103-121 fused into conv_out)
             if engine != 0:
                 raise L.FridoError("conv: out_u8 is a feature of the small-Cout head kernels (SIMT engine)")
@@ -226,7 +230,7 @@ class Program:
     def nf_eligible(self, a0, a1, out, *, B, H, W, Cout, ksize):
         """Can conv() apply the GroupNorm (+SPADE) (+SiLU) of its input on load (csrc/conv_nf.cu)?  BF16x3 engine, 3x3 / 1x1
         stride-1 conv, and a 128-pixel tile (at most 16 wide) whose halo fits the shared-memory slot with <= 4 images."""
-        if self.tc_code != 3 or os.environ.get("FRIDO_FUSE_NORM", "1") != "1":
+        if self.tc_code != 3:
             return False
         if not self.tc_eligible(a0, a1, out, B=B, Hin=H, Win=W, Hout=H, Wout=W, Cout=Cout, ksize=ksize, pad=ksize // 2):
             return False
@@ -322,9 +326,9 @@ class Program:
         self.flops += 4 * B * N * Nk * Cdim
         self._add(L.OP_ATTN, p, tag)
 
-    def upsample2x(self, x, out, *, B, H, W, Cdim, round_tf32=0, tag="upsample2x"):
+    def upsample2x(self, x, out, *, B, H, W, Cdim, round_tf32=0, out_split=0, tag="upsample2x"):
         p = L.UpsampleParams()
-        p.x, p.B, p.H, p.W, p.C, p.round_tf32, p.out = x.data_ptr(), B, H, W, Cdim, round_tf32, out.data_ptr()
+        p.x, p.B, p.H, p.W, p.C, p.round_tf32, p.out, p.out_split = x.data_ptr(), B, H, W, Cdim, round_tf32, out.data_ptr(), int(out_split)
         self.hold(x, out)
         self._add(L.OP_UPSAMPLE, p, tag)
 
@@ -354,13 +358,13 @@ class Program:
         self._add(L.OP_GN_STATS, p, tag)
 
     def norm_act(self, a0, c0, sums, gamma, beta, out, *, B, HW, eps, a1=None, c1=0, gb=None, silu=1, groups=32,
-                 round_tf32=0, csum0=None, csum1=None, tag="norm_act"):
+                 round_tf32=0, csum0=None, csum1=None, out_split=0, tag="norm_act"):
         p = L.NormActParams()
         p.a0, p.a1, p.c0, p.c1, p.B, p.HW, p.groups = _ptr(a0), _ptr(a1), c0, c1, B, HW, groups
         p.sums, p.eps, p.gamma, p.beta, p.gb = _ptr(sums), eps, gamma.data_ptr(), beta.data_ptr(), _ptr(gb)
         p.csum0, p.csum1 = _ptr(csum0), _ptr(csum1)
         self.hold(csum0, csum1)
-        p.silu, p.round_tf32, p.out = silu, round_tf32, out.data_ptr()
+        p.silu, p.round_tf32, p.out, p.out_split = silu, round_tf32, out.data_ptr(), int(out_split)
         self.hold(a0, a1, sums, gamma, beta, gb, out)
         self._add(L.OP_NORM_ACT, p, tag)
 

@@ -268,8 +268,9 @@ class UNetPlan:
         self._gn_slots.append(t)
         return t
 
-    def _norm(self, prog, xs, cs, h, w, norm, eps, silu, site):
-        """GroupNorm(+SPADE)(+SiLU) over the (possibly concatenated) NHWC sources xs -> new buffer."""
+    def _norm(self, prog, xs, cs, h, w, norm, eps, silu, site, out_split=0):
+        """GroupNorm(+SPADE)(+SiLU) over the (possibly concatenated) NHWC sources xs -> new buffer (out_split: written in the
+        BF16x3 engine's operand form for a conv that takes `presplit=True`)."""
         B = self.B
         hw = h * w
         C = sum(cs)
@@ -288,16 +289,35 @@ class UNetPlan:
         gb = self._spade_site(norm, C, h, w) if (is_spade and self.c_cond) else None
         out = prog.buf(B, hw, C)
         prog.norm_act(xs[0], cs[0], sums, self._vec(g.weight), self._vec(g.bias), out, B=B, HW=hw, eps=eps, a1=a1,
-                      c1=c1, gb=gb, silu=silu, round_tf32=prog.R, csum0=cs0, csum1=cs1, tag=site)
+                      c1=c1, gb=gb, silu=silu, round_tf32=prog.R, csum0=cs0, csum1=cs1, out_split=out_split, tag=site)
         return out
+
+    def _norm_mode(self, prog, xs, cs, h, w, norm, out, Cout, ksize):
+        """How the GroupNorm (+SPADE) (+SiLU) in front of a conv reaches the tensor core (FRIDO_FUSE_NORM):
+          'fused' (1)  the conv normalises on load (csrc/conv_nf.cu): no norm_act pass, no normalised tensor in memory;
+          'split' (2)  norm_act writes the engine's bf16 hi | lo operand form and the conv's halo-resident path just feeds it;
+          'plain' (0)  norm_act writes fp32, the conv re-fetches and splits the tile per filter tap (csrc/conv_tc.cu).
+        Default 'auto': fused where the conv has a single N tile and no SPADE maps to stream (the prep work of a fused conv
+        is repeated per N tile, and the maps are re-read per N tile and per halo), split elsewhere."""
+        mode = os.environ.get("FRIDO_FUSE_NORM", "auto")
+        a1 = Src.nhwc(xs[1], h, w) if len(xs) > 1 else None
+        if mode == "0" or any(c % 32 for c in cs) or not prog.nf_eligible(Src.nhwc(xs[0], h, w), a1, out, B=self.B, H=h, W=w, Cout=Cout, ksize=ksize):
+            return "plain"
+        if ksize == 1:
+            return "fused" if os.environ.get("FRIDO_FUSE_NORM_1X1", "0") == "1" else "plain"
+        if mode == "1":
+            return "fused"
+        if mode == "2":
+            return "split"
+        spade = isinstance(norm, M.SPADE) and bool(self.c_cond)
+        return "fused" if (not spade and Cout <= 192) else "split"
 
     def _norm_on_load(self, prog, xs, cs, h, w, norm, eps, silu, out, Cout, ksize):
         """GroupNorm(+SPADE)(+SiLU) handed to the consuming conv instead of a norm_act pass (csrc/conv_nf.cu): emits the
         tiny statistics -> (scale, shift) kernel and returns (`nrm` argument of Program.conv, buffer to release after the
         conv), or None when the conv cannot normalise on load (then `_norm` materialises the tensor as before)."""
         B = self.B
-        a1 = Src.nhwc(xs[1], h, w) if len(xs) > 1 else None
-        if not prog.nf_eligible(Src.nhwc(xs[0], h, w), a1, out, B=B, H=h, W=w, Cout=Cout, ksize=ksize) or any(c % 32 for c in cs):
+        if self._norm_mode(prog, xs, cs, h, w, norm, out, Cout, ksize) != "fused":
             return None
         hw = h * w
         C = sum(cs)
@@ -352,8 +372,9 @@ class UNetPlan:
                              a1=Src.nhwc(xs[1], h, w) if len(xs) > 1 else None, nrm=nf[0], **kw1)
             S.release(nf[1])
         else:
-            t1 = self._norm(S, xs, cs, h, w, rb.in_layers[0], 1e-5, 1, "res.norm1")
-            self._conv_stats(S, Src.nhwc(t1, h, w), self._conv_w(rb.in_layers[2]), h1, cout, **kw1)
+            sp = self._norm_mode(S, xs, cs, h, w, rb.in_layers[0], h1, cout, 3) == "split"
+            t1 = self._norm(S, xs, cs, h, w, rb.in_layers[0], 1e-5, 1, "res.norm1", out_split=int(sp))
+            self._conv_stats(S, Src.nhwc(t1, h, w), self._conv_w(rb.in_layers[2]), h1, cout, presplit=sp, **kw1)
             S.release(t1)
         a1 = Src.nhwc(xs[1], h, w) if len(xs) > 1 else None
         out = S.buf(B, hw, cout)
@@ -361,10 +382,12 @@ class UNetPlan:
         if nf is not None:
             src2, t2 = Src.nhwc(h1, h, w), None
         else:
-            t2 = self._norm(S, [h1], [cout], h, w, rb.out_layers[0], 1e-5, 1, "res.norm2")
+            sp2 = self._norm_mode(S, [h1], [cout], h, w, rb.out_layers[0], out, cout, 3) == "split"
+            t2 = self._norm(S, [h1], [cout], h, w, rb.out_layers[0], 1e-5, 1, "res.norm2", out_split=int(sp2))
             S.release(h1)
             src2 = Src.nhwc(t2, h, w)
         nrm2 = nf[0] if nf is not None else None
+        sp2 = nf is None and sp2
         sk = None
         is_conv = isinstance(rb.skip_connection, nn.Conv2d)
         if (is_conv and os.environ.get("FRIDO_FUSE_SKIP", "1") == "1" and all(c % 32 == 0 for c in cs) and
@@ -376,7 +399,7 @@ class UNetPlan:
             w_cat = self._packed(lambda: torch.cat([_pack_conv(c2_.weight), sc_.weight.detach().reshape(cout, -1)], 1).contiguous())
             b_cat = self._packed(lambda: (c2_.bias.detach() + sc_.bias.detach()))
             self._conv_stats(S, src2, w_cat, out, cout, B=B, Hin=h, Win=w, Hout=h, Wout=w, ksize=3, pad=1,
-                             bias=b_cat, side=(Src.nhwc(xs[0], h, w), a1), nrm=nrm2, tag="res.conv2+skip")
+                             bias=b_cat, side=(Src.nhwc(xs[0], h, w), a1), nrm=nrm2, presplit=sp2, tag="res.conv2+skip")
         else:
             if is_conv:
                 sk = S.buf(B, hw, cout)
@@ -387,7 +410,7 @@ class UNetPlan:
                 assert len(xs) == 1
                 res = xs[0]
             self._conv_stats(S, src2, self._conv_w(rb.out_layers[3]), out, cout, B=B, Hin=h, Win=w, Hout=h, Wout=w,
-                             ksize=3, pad=1, bias=self._vec(rb.out_layers[3].bias), res=res, nrm=nrm2, tag="res.conv2")
+                             ksize=3, pad=1, bias=self._vec(rb.out_layers[3].bias), res=res, nrm=nrm2, presplit=sp2, tag="res.conv2")
         if nf is not None:
             S.release(nf[1])
             S.release(h1)
@@ -654,9 +677,13 @@ class UNetPlan:
                 if S.tc_code and cs[0] % 64 == 0:
                     # tensor-core path: materialise the nearest x2 copy (TF32-rounded), then a plain 3x3 conv
                     up = S.buf(B, 4 * h * w, cs[0])
-                    S.upsample2x(xs[0], up, B=B, H=h, W=w, Cdim=cs[0], round_tf32=S.R)
+                    # the x2 copy is written in the engine's operand form when the conv can take its halo-resident path
+                    sp = (os.environ.get("FRIDO_FUSE_NORM", "auto") != "0" and cs[0] % 32 == 0 and
+                          S.nf_eligible(Src.nhwc(up, 2 * h, 2 * w), None, x, B=B, H=2 * h, W=2 * w, Cout=cs[0], ksize=3))
+                    S.upsample2x(xs[0], up, B=B, H=h, W=w, Cdim=cs[0], round_tf32=S.R, out_split=int(sp))
                     self._conv_stats(S, Src.nhwc(up, 2 * h, 2 * w), self._conv_w(layer.conv), x, cs[0], B=B, Hin=2 * h,
-                                     Win=2 * w, Hout=2 * h, Wout=2 * w, ksize=3, pad=1, bias=self._vec(layer.conv.bias), tag="up")
+                                     Win=2 * w, Hout=2 * h, Wout=2 * w, ksize=3, pad=1, bias=self._vec(layer.conv.bias),
+                                     presplit=sp, tag="up")
                     S.release(up)
                 else:
                     S.conv(Src.nhwc(xs[0], h, w), self._conv_w(layer.conv), x, B=B, Hin=h, Win=w, Hout=2 * h, Wout=2 * w,

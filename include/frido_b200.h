@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define FRIDO_ABI_VERSION 5
+#define FRIDO_ABI_VERSION 6
 #define FRIDO_SK_WS_BYTES (40ll << 20)
 
 #define FRIDO_OK 0
@@ -91,6 +91,10 @@ typedef struct FridoConvParams {
                                selects SiLU: GroupNorm -> [SPADE] -> SiLU -> conv (pyunet.py:209-240) in one launch, the
                                normalised tensor never written to memory.  Zero padding applies to the ACTIVATED tensor, as
                                in the reference.  The fused side input x0 | x1 stays raw. */
+  int32_t a_presplit;       /* engine 3, 3x3 stride-1 convs: a0 | a1 already hold the operand in the engine's split form (per 16 bytes =
+                               4 channels: bf16x2 hi(c0,c1), hi(c2,c3), lo(c0,c1), lo(c2,c3), what frido_norm_act /
+                               frido_upsample2x write with out_split = 1; same size as the fp32 tensor).  The conv then runs
+                               the halo-resident operand path of csrc/conv_nf.cu with no per-element work at all. */
   uint8_t* out_u8;          /* optional (SIMT engine, Cout <= 4: the decoder's conv_out head): also store the outputs as uint8 NHWC */
   int32_t u8_mode;          /*   [B,Hout,Wout,Cout], formatted like frido_to_uint8 (mode 0 = custom_to_np, 1 = custom_to_pil,
                                scripts/sample_diffusion.py:103-121) from the same fp32 value that goes to `out` */
@@ -134,6 +138,9 @@ typedef struct FridoNormActParams {
   int32_t silu;
   int32_t round_tf32;
   float* out;                             /* [B,HW,C] */
+  int32_t out_split;                      /* 1: write each group of 4 channels as the BF16x3 engine's operand (bf16x2 hi, hi, lo,
+                                             lo; see FridoConvParams.a_presplit) instead of 4 floats: the consuming conv then
+                                             needs no operand split */
 } FridoNormActParams;
 int frido_norm_act(const FridoNormActParams* p, void* stream);
 
@@ -254,7 +261,7 @@ int frido_vq_lookup(const FridoVqParams* p, void* stream);
 
 /* F.interpolate(scale_factor=2, mode="nearest") on an NHWC tensor (pyunet.py:119; taming
  * model.py:50) — used in front of the tcgen05 engine (the SIMT engine folds it into addressing). */
-typedef struct FridoUpsampleParams { const float* x; int32_t B, H, W, C; int32_t round_tf32; float* out; } FridoUpsampleParams;
+typedef struct FridoUpsampleParams { const float* x; int32_t B, H, W, C; int32_t round_tf32; float* out; int32_t out_split; } FridoUpsampleParams;
 int frido_upsample2x(const FridoUpsampleParams* p, void* stream);
 
 /* Condition encoder (BERTEmbedder = x-transformer encoder, frido/modules/x_transformer.py).

@@ -264,7 +264,7 @@ def test_fusion_switches_keep_the_result(dev, golden_dir, off, monkeypatch):
         ctx = synth.synth_input("ctx", (1, 26, 640), 1).to(dev).expand(B, -1, -1).contiguous()
         x = synth.synth_input("x1", (1, 6, 32, 32), 2).to(dev).expand(B, -1, -1, -1).contiguous()
         e = unet(x, torch.full((B,), 996, dtype=torch.long, device=dev), context=ctx, stage=1)
-        tags = set(unet.plan(1, B, 32, 32, 26).step.tags)
+        tags = list(unet.plan(1, B, 32, 32, 26).step.tags)
         return e.cpu(), tags
 
     e_def, tags_def = run()
@@ -281,9 +281,35 @@ def test_fusion_switches_keep_the_result(dev, golden_dir, off, monkeypatch):
         assert "attn1.out" in tags_off and "attn1.out" not in tags_def
     if off == "FRIDO_ATTN_SMALL":
         assert "attn2.block" in tags_def and "attn2.block" not in tags_off
-    if off == "FRIDO_FUSE_NORM":  # normalise-on-load: the GroupNorm / SPADE / SiLU passes in front of the convs are gone
-        assert "gn_finalize" in tags_def and "res.norm1" not in tags_def and "res.norm2" not in tags_def and "st.norm" not in tags_def
-        assert "res.norm1" in tags_off and "st.norm" in tags_off and "gn_finalize" not in tags_off
+    if off == "FRIDO_FUSE_NORM":  # stage 1 of this model has SPADE maps at every site: default = split operands, no fused norms
+        assert "gn_finalize" not in tags_off and sum(t in ("res.norm1", "res.norm2") for t in tags_off) == 44
+
+
+@pytest.mark.parametrize("mode", ["0", "1", "2", "auto"])
+def test_norm_modes_keep_the_result(dev, golden_dir, mode, monkeypatch):
+    """FRIDO_FUSE_NORM: GroupNorm (+SPADE) + SiLU in front of the ResBlock convs as a separate fp32 pass (0), applied by the
+    conv on load (1), or written by norm_act in the engine's split operand form (2); 'auto' picks per site.  Full-size UNet,
+    both stages (stage 1 = SPADE maps at every site), against the reference's golden eps."""
+    import frido_b200 as fb
+    from oracle import synth
+    monkeypatch.setenv("FRIDO_FUSE_NORM", mode)
+    g = _load(golden_dir, "l2i32.pt")
+    unet = fb.PyUNetModel(**g["unet_cfg"])
+    synth.fill_module_(unet, g["seed"], "model.diffusion_model.")
+    unet = unet.to(dev)
+    B = 4
+    ctx = synth.synth_input("ctx", (1, 26, 640), 1).to(dev).expand(B, -1, -1).contiguous()
+    for s in (0, 1):
+        x = synth.synth_input(f"x{s}", (1, 3 * (s + 1), 32, 32), 2).to(dev).expand(B, -1, -1, -1).contiguous()
+        e = unet(x, torch.full((B,), 996, dtype=torch.long, device=dev), context=ctx, stage=s).cpu()
+        tags = list(unet.plan(s, B, 32, 32, 26).step.tags)
+        err = (e[0] - g[f"eps_s{s}_t996"][0]).abs().max().item()
+        assert err < 1e-3, (mode, s, err)
+        n_norm = sum(t in ("res.norm1", "res.norm2") for t in tags)
+        if mode == "1":
+            assert "gn_finalize" in tags and n_norm <= 16, (s, n_norm)  # only the 4x4 level (8 images per tile) keeps its passes
+        if mode in ("0", "2"):
+            assert "gn_finalize" not in tags and n_norm == 44
 
 
 def test_silent_in_place_weight_change_is_noticed(dev, golden_dir):

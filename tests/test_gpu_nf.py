@@ -48,7 +48,7 @@ CASES = [
     (4, 64, 32, 128, 8, 8, 3, True, True, 96),      # skip concat (two sources), 2 images per tile, side input over both sources
     (2, 192, 0, 192, 32, 32, 3, False, True, 0),    # 8 tiles per image: interior tiles whose halo is real neighbour data
     (2, 192, 0, 192, 32, 32, 3, True, True, 64),    # the 64^2-level ResBlock conv2 + skip shape, scaled down
-    (1, 960, 960, 960, 8, 8, 3, True, True, 0),     # long K loop (60 chunks x 9 taps), half-empty tile (TB=2, B=1)
+    (3, 960, 960, 960, 8, 8, 3, True, True, 0),     # long K loop (60 chunks x 9 taps), half-empty second tile (TB=2, B=3)
     (3, 96, 0, 256, 9, 7, 3, True, True, 0),        # ragged spatial size: partial tiles, masked rows
     (2, 384, 0, 384, 32, 32, 1, True, False, 0),    # SpatialTransformer norm -> proj_in (1x1, no SiLU)
     (16, 576, 0, 576, 16, 16, 1, False, False, 0),
@@ -114,10 +114,12 @@ def test_conv_nf_matches_fp64_and_the_unfused_path(dev, case, sk_mode):
     gbd = _nhwc(gb).to(dev).view(B, H * W, 2 * Cin) if spade else None
     # statistics: per-channel sums, the format conv epilogues produce (chan_sums)
     cs0 = torch.zeros(B, C0, 2, dtype=torch.float64, device=dev)
+    P.zero(cs0)  # the program is replayed below: every accumulator is cleared by the program itself
     P.chan_stats(d0, C0, cs0, B=B, HW=H * W)
     cs1 = None
     if C1:
         cs1 = torch.zeros(B, C1, 2, dtype=torch.float64, device=dev)
+        P.zero(cs1)
         P.chan_stats(d1, C1, cs1, B=B, HW=H * W)
     ab = torch.zeros(B, Cin, 2, device=dev)
     P.gn_finalize(ab, gw, gbias, B=B, HW=H * W, c0=C0, c1=C1, eps=eps, csum0=cs0, csum1=cs1)
@@ -133,6 +135,7 @@ def test_conv_nf_matches_fp64_and_the_unfused_path(dev, case, sk_mode):
     out1 = torch.zeros(B, H * W, Cout, device=dev)
     out2 = torch.zeros(B, H * W, Cout, device=dev)
     csum = torch.zeros(B, Cout, 2, dtype=torch.float64, device=dev)
+    P.zero(csum)
     kw = dict(B=B, Hin=H, Win=W, Hout=H, Wout=W, Cout=Cout, ksize=k, pad=k // 2, a1=a1, bias=bias.to(dev), engine=3,
               nrm=(ab, gbd, int(silu)))
     if not side:
@@ -145,6 +148,16 @@ def test_conv_nf_matches_fp64_and_the_unfused_path(dev, case, sk_mode):
     out3 = torch.zeros(B, H * W, Cout, device=dev)
     wd3 = _pack(w).to(dev)
     P.conv(Src.nhwc(t, H, W), wd3, out3, B=B, Hin=H, Win=W, Hout=H, Wout=W, Cout=Cout, ksize=k, pad=k // 2, bias=bias.to(dev), engine=3)
+    # the split path: norm_act writes the engine's operand form, the conv's halo-resident path feeds it as is
+    out4 = None
+    if k == 3:
+        t4 = torch.zeros(B, H * W, Cin, device=dev)
+        P.norm_act(d0, C0, None, gw, gbias, t4, B=B, HW=H * W, eps=eps, a1=d1, c1=C1, gb=gbd, silu=int(silu), csum0=cs0, csum1=cs1,
+                   out_split=1)
+        out4 = torch.zeros(B, H * W, Cout, device=dev)
+        P.conv(Src.nhwc(t4, H, W), wd, out4, B=B, Hin=H, Win=W, Hout=H, Wout=W, Cout=Cout, ksize=k, pad=k // 2, bias=bias.to(dev),
+               engine=3, presplit=True, side=side_arg, rowvec=rowvec.to(dev), rowvec_sb=Cout,
+               res=None if side else _nhwc(res).to(dev).view(B, H * W, Cout))
     P.prepare_weights()
     P.run()
     torch.cuda.synchronize(dev)
@@ -160,8 +173,9 @@ def test_conv_nf_matches_fp64_and_the_unfused_path(dev, case, sk_mode):
         d13 = (nchw(out1) - nchw(out3)).abs().max().item()
         assert e1 < tol and d13 < tol, (case, e1, e3, d13, tol)
     e2 = (nchw(out2) - ref_full).abs().max().item()
-    print(f"case {case}: fused err {e2:.3e}, two-launch err {e3:.3e}, tol {tol:.3e}, |ref| {ref_full.abs().max():.2f}")
-    assert e2 < tol and e3 < tol, (case, e2, e3, tol)
+    e4 = (nchw(out4) - ref_full).abs().max().item() if out4 is not None else 0.0
+    print(f"case {case}: fused err {e2:.3e}, split err {e4:.3e}, two-launch err {e3:.3e}, tol {tol:.3e}, |ref| {ref_full.abs().max():.2f}")
+    assert e2 < tol and e3 < tol and e4 < tol, (case, e2, e3, e4, tol)
     if ok:  # channel sums of the stored outputs (what the NEXT GroupNorm consumes)
         o = nchw(out2)
         want = torch.stack([o.sum((2, 3)), (o * o).sum((2, 3))], -1)
@@ -169,7 +183,6 @@ def test_conv_nf_matches_fp64_and_the_unfused_path(dev, case, sk_mode):
         assert torch.allclose(got, want, rtol=1e-5, atol=1e-3), (case, (got - want).abs().max())
     if sk_mode != "off":  # replay: stream-K arrival counters back at zero, fixed summation order -> bit-identical
         first = out2.clone()
-        csum.zero_()
         P.run()
         torch.cuda.synchronize(dev)
         assert torch.equal(out2, first)

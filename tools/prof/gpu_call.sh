@@ -1,9 +1,12 @@
 mkdir -p gpurun_out
-nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.limit --format=csv > gpurun_out/r02a_smi.txt 2>&1
-timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/r02a_pytest.log 2>&1; echo "pytest rc=$?" >> gpurun_out/r02a_pytest.log
-timeout 420 python tools/prof/drift.py --steps 200 --out gpurun_out/r02a_drift.json > gpurun_out/r02a_drift.log 2>&1
-timeout 700 python bench.py --steps 3 --warmup 3 > gpurun_out/r02a_bench.json 2> gpurun_out/r02a_bench.err
-timeout 300 ncu --set full --clock-control none --import-source on -k regex:conv_tc -s 4 -c 2 -o gpurun_out/r02a_conv_long python tools/prof/conv_bench.py 9 7 > gpurun_out/r02a_ncu_long.log 2>&1
-timeout 400 ncu --profile-from-start off --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none --csv --log-file gpurun_out/r02a_step.csv python tools/prof/ncu_step.py > gpurun_out/r02a_ncu_step.log 2>&1
-cp gpurun_out/step_ops.json gpurun_out/r02a_step_ops.json
-tail -3 gpurun_out/r02a_pytest.log; cat gpurun_out/r02a_drift.json; cat gpurun_out/r02a_bench.json | head -c 3000
+T=r02i
+timeout -k 5 150 python -m pytest tests/test_gpu_nf.py -x -q --timeout=60 -p no:cacheprovider > gpurun_out/${T}_nf.log 2>&1; echo "rc=$?" >> gpurun_out/${T}_nf.log
+tail -3 gpurun_out/${T}_nf.log
+if grep -q "rc=0" gpurun_out/${T}_nf.log; then
+  timeout -k 5 300 python -m pytest tests/test_gpu_model.py -x -q --timeout=150 -k "norm_modes or fusion_switches" > gpurun_out/${T}_model.log 2>&1; echo "rc=$?" >> gpurun_out/${T}_model.log
+  tail -4 gpurun_out/${T}_model.log
+  for st in 0 1; do for m in 0 1 2 auto; do
+    FRIDO_FUSE_NORM=$m PSTAGE=$st timeout 200 python tools/prof/perop.py > gpurun_out/${T}_perop_s${st}_m${m}.log 2>&1
+    echo "stage $st mode $m: $(grep GRAPH gpurun_out/${T}_perop_s${st}_m${m}.log | cut -c1-60)"
+  done; done
+fi
