@@ -99,8 +99,9 @@ def _reference_model(model, cfg, device):
         from oracle import ref_loader
         if not ref_loader.available():
             return None
-        ref_loader.activate(cpu=(torch.device(device).type == "cpu"))
-        ref = ref_loader.build_model(cfg["model"])
+        on_cpu = torch.device(device).type == "cpu"
+        ref_loader.activate(cpu=on_cpu)
+        ref = ref_loader.build_model(cfg["model"], cpu=on_cpu)
         sd = {k: v.detach().float().cpu() for k, v in model.state_dict().items()}
         missing, unexpected = ref.load_state_dict(sd, strict=False)
         bad = [k for k in missing if ".loss." not in k and "model_ema" not in k]
@@ -401,17 +402,19 @@ def run_ours(args):
         }
         line["parity"] = _parity()
         if world == 1:
-            try:
-                line["cpu_baseline"] = cpu_sample(model, cfg, min(B, 4), evals=2, ref=_reference_model(model, cfg, "cpu"), budget_s=30.0)
-            except Exception as e:  # the checker failing must not hide the GPU number
-                line["cpu_baseline"] = {"error": repr(e)}
+            # the GPU-eager run of the reference's modules goes first: the CPU arm below patches .cuda() to a no-op
             if os.environ.get("FRIDO_BENCH_GPU_EAGER", "1") == "1":
                 try:
                     line["gpu_eager_reference"] = gpu_eager_reference(model, cfg, dev)
                     if line["gpu_eager_reference"]:
                         line["gpu_eager_reference"]["speedup_e2e"] = round(e2e_val / line["gpu_eager_reference"]["value"], 2)
                 except Exception as e:
-                    line["gpu_eager_reference"] = {"error": repr(e)}
+                    import traceback
+                    line["gpu_eager_reference"] = {"error": repr(e), "where": traceback.format_exc().strip().splitlines()[-7:]}
+            try:
+                line["cpu_baseline"] = cpu_sample(model, cfg, min(B, 4), evals=2, ref=_reference_model(model, cfg, "cpu"), budget_s=30.0)
+            except Exception as e:  # the checker failing must not hide the GPU number
+                line["cpu_baseline"] = {"error": repr(e)}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -17,7 +17,7 @@ c_p = C.c_void_p
 
 ACT_NONE, ACT_RELU, ACT_SILU, ACT_GEGLU, ACT_GEGLU_FAST, ACT_GELU = 0, 1, 2, 3, 4, 5
 (OP_CONV, OP_GN_STATS, OP_NORM_ACT, OP_LAYERNORM, OP_SOFTMAX, OP_TIME_EMBED, OP_STEP_BEGIN, OP_UPDATE, OP_SNAP, OP_VQ,
- OP_ZERO, OP_UPSAMPLE, OP_EMBED, OP_MHA, OP_CONVT, OP_ASSEMBLE, OP_ATTN, OP_BLEND, OP_GN_FINALIZE) = range(1, 20)
+ OP_ZERO, OP_UPSAMPLE, OP_EMBED, OP_MHA, OP_CONVT, OP_ASSEMBLE, OP_ATTN, OP_BLEND, OP_GN_FINALIZE, OP_FLASH) = range(1, 21)
 
 
 class ConvParams(C.Structure):
@@ -132,12 +132,18 @@ class GnFinalizeParams(C.Structure):
                 ("csum1", c_p), ("gamma", c_p), ("beta", c_p), ("ab", c_p)]
 
 
+class FlashParams(C.Structure):
+    _fields_ = [("q_hi", c_p), ("q_lo", c_p), ("q_sb", c_l), ("q_ld", c_l), ("k_hi", c_p), ("k_lo", c_p), ("k_sb", c_l), ("k_ld", c_l),
+                ("vt_hi", c_p), ("vt_lo", c_p), ("vt_sb", c_l), ("vt_ld", c_l), ("B", c_i), ("N", c_i), ("C", c_i), ("scale", c_f),
+                ("bias", c_p), ("res", c_p), ("r_sb", c_l), ("r_ld", c_l), ("out", c_p), ("o_sb", c_l), ("o_ld", c_l)]
+
+
 class _OpU(C.Union):
     _fields_ = [("conv", ConvParams), ("gn_stats", GnStatsParams), ("norm_act", NormActParams),
                 ("layernorm", LayerNormParams), ("softmax", SoftmaxParams), ("time_embed", TimeEmbedParams),
                 ("step_begin", StepBeginParams), ("update", UpdateParams), ("snap", SnapParams), ("vq", VqParams),
                 ("zero", ZeroParams), ("upsample", UpsampleParams), ("embed", EmbedParams), ("mha", MhaParams), ("convt", ConvT2dParams),
-                ("assemble", AssembleParams), ("attn", AttnParams), ("blend", BlendParams), ("gn_finalize", GnFinalizeParams)]
+                ("assemble", AssembleParams), ("attn", AttnParams), ("blend", BlendParams), ("gn_finalize", GnFinalizeParams), ("flash", FlashParams)]
 
 
 class Op(C.Structure):
@@ -147,17 +153,18 @@ class Op(C.Structure):
 _KIND_FIELD = {OP_CONV: "conv", OP_GN_STATS: "gn_stats", OP_NORM_ACT: "norm_act", OP_LAYERNORM: "layernorm",
                OP_SOFTMAX: "softmax", OP_TIME_EMBED: "time_embed", OP_STEP_BEGIN: "step_begin", OP_UPDATE: "update",
                OP_SNAP: "snap", OP_VQ: "vq", OP_ZERO: "zero", OP_UPSAMPLE: "upsample", OP_EMBED: "embed", OP_MHA: "mha", OP_CONVT: "convt", OP_ASSEMBLE: "assemble", OP_ATTN: "attn",
-               OP_BLEND: "blend", OP_GN_FINALIZE: "gn_finalize"}
+               OP_BLEND: "blend", OP_GN_FINALIZE: "gn_finalize", OP_FLASH: "flash"}
 
 EXPORTS = [
     "frido_conv2d", "frido_gn_stats", "frido_norm_act", "frido_layernorm", "frido_softmax", "frido_time_embed",
     "frido_step_begin", "frido_sampler_update", "frido_stage_snap", "frido_vq_lookup", "frido_zero",
-    "frido_round_tf32", "frido_split_bf16", "frido_upsample2x", "frido_to_uint8", "frido_embed_tokens", "frido_mha_small", "frido_attn_small", "frido_conv_transpose2d", "frido_assemble_latent", "frido_mask_blend", "frido_gn_finalize", "frido_run_program", "frido_abi_version", "frido_sizeof_op", "frido_last_error",
+    "frido_round_tf32", "frido_split_bf16", "frido_upsample2x", "frido_to_uint8", "frido_embed_tokens", "frido_mha_small", "frido_attn_small", "frido_conv_transpose2d", "frido_assemble_latent", "frido_mask_blend", "frido_gn_finalize", "frido_attn_flash", "frido_attn_flash_eligible", "frido_pack_permute3", "frido_pack_conv_weight", "frido_matmul_f64acc",
+    "frido_fold_self_attention", "frido_vec_add", "frido_workspace_bytes", "frido_run_program", "frido_abi_version", "frido_sizeof_op", "frido_last_error",
     "frido_launch_count", "frido_check_device",
 ]
 
 SK_WS_BYTES = 40 << 20
-ABI_VERSION = 6
+ABI_VERSION = 7
 
 _lib = None
 
@@ -186,10 +193,18 @@ def lib():
     L.frido_zero.argtypes = [c_p, c_l, c_p]
     L.frido_round_tf32.argtypes = [c_p, c_p, c_l, c_p]
     L.frido_split_bf16.argtypes = [c_p, c_p, c_p, c_l, c_p]
+    L.frido_attn_flash_eligible.argtypes = [c_i, c_i, c_i]
+    L.frido_pack_permute3.argtypes = [c_p, c_l, c_l, c_l, c_p, c_l, c_l, c_l, c_i, c_i, c_i, c_p]
+    L.frido_pack_conv_weight.argtypes = [c_p, c_i, c_i, c_i, c_i, c_p, c_l, c_p]
+    L.frido_matmul_f64acc.argtypes = [c_p, c_l, c_l, c_p, c_l, c_l, c_i, c_i, c_i, c_p, c_l, c_p]
+    L.frido_fold_self_attention.argtypes = [c_p, c_p, c_p, c_p, c_i, c_p, c_p, c_p]
+    L.frido_vec_add.argtypes = [c_p, c_p, c_p, c_l, c_p]
+    L.frido_workspace_bytes.argtypes = [c_p, c_i]
+    L.frido_workspace_bytes.restype = C.c_int64
     for name in ("frido_conv2d", "frido_gn_stats", "frido_norm_act", "frido_layernorm", "frido_softmax",
                  "frido_time_embed", "frido_step_begin", "frido_sampler_update", "frido_stage_snap", "frido_vq_lookup",
                  "frido_upsample2x", "frido_to_uint8", "frido_embed_tokens", "frido_mha_small", "frido_attn_small",
-                 "frido_conv_transpose2d", "frido_assemble_latent", "frido_mask_blend", "frido_gn_finalize"):
+                 "frido_conv_transpose2d", "frido_assemble_latent", "frido_mask_blend", "frido_gn_finalize", "frido_attn_flash"):
         getattr(L, name).argtypes = [c_p, c_p]
     if L.frido_abi_version() != ABI_VERSION:
         raise FridoError(f"ABI mismatch: library version {L.frido_abi_version()}, binding {ABI_VERSION} (rebuild: make -C frido_b200/csrc)")

@@ -49,6 +49,7 @@ extern "C" int frido_run_program(const FridoOp* ops, int32_t n, void* stream) {
       case FRIDO_OP_ASSEMBLE: rc = frido_assemble_latent(&op.u.assemble, stream); break;
       case FRIDO_OP_UPSAMPLE: rc = frido_upsample2x(&op.u.upsample, stream); break;
       case FRIDO_OP_GN_FINALIZE: rc = frido_gn_finalize(&op.u.gn_finalize, stream); break;
+      case FRIDO_OP_FLASH: rc = frido_attn_flash(&op.u.flash, stream); break;
       case FRIDO_OP_BLEND: rc = frido_mask_blend(&op.u.blend, stream); break;
       case FRIDO_OP_ZERO: rc = frido_zero(op.u.zero.ptr, op.u.zero.nbytes, stream); break;
       default: rc = set_error(FRIDO_E_ARG, "run_program: unknown op kind");

@@ -326,6 +326,28 @@ class Program:
         self.flops += 4 * B * N * Nk * Cdim
         self._add(L.OP_ATTN, p, tag)
 
+    @staticmethod
+    def flash_eligible(B, N, Cdim):
+        """Streaming-softmax tcgen05 attention (csrc/attn_flash.cu): whole 128-token tiles, channels in 32s; FRIDO_FLASH=0 keeps
+        the QK^T -> softmax -> PV launches."""
+        return os.environ.get("FRIDO_FLASH", "1") == "1" and bool(L.lib().frido_attn_flash_eligible(B, N, Cdim))
+
+    def flash(self, q_pair, k_pair, vt_pair, out, *, B, N, Cdim, scale, vt_sb, vt_ld, bias=None, res=None, tag="attn.flash"):
+        """out = res + bias + softmax(scale q k^T) v in one launch; q_pair / k_pair = (hi, lo) bf16 [B,N,C] tensors, vt_pair the
+        values channel-major: element (b, c, key) at b * vt_sb + c * vt_ld + key."""
+        p = L.FlashParams()
+        p.q_hi, p.q_lo, p.q_sb, p.q_ld = q_pair[0].data_ptr(), q_pair[1].data_ptr(), N * Cdim, Cdim
+        p.k_hi, p.k_lo, p.k_sb, p.k_ld = k_pair[0].data_ptr(), k_pair[1].data_ptr(), N * Cdim, Cdim
+        p.vt_hi, p.vt_lo, p.vt_sb, p.vt_ld = vt_pair[0].data_ptr(), vt_pair[1].data_ptr(), vt_sb, vt_ld
+        p.B, p.N, p.C, p.scale = B, N, Cdim, scale
+        p.bias = _ptr(bias)
+        if res is not None:
+            p.res, p.r_sb, p.r_ld = res.data_ptr(), N * Cdim, Cdim
+        p.out, p.o_sb, p.o_ld = out.data_ptr(), N * Cdim, Cdim
+        self.hold(*q_pair, *k_pair, *vt_pair, out, bias, res)
+        self.flops += 4 * B * N * N * Cdim
+        self._add(L.OP_FLASH, p, tag)
+
     def upsample2x(self, x, out, *, B, H, W, Cdim, round_tf32=0, out_split=0, tag="upsample2x"):
         p = L.UpsampleParams()
         p.x, p.B, p.H, p.W, p.C, p.round_tf32, p.out, p.out_split = x.data_ptr(), B, H, W, Cdim, round_tf32, out.data_ptr(), int(out_split)

@@ -519,8 +519,10 @@ class UNetPlan:
         ln_pair = (S.buf(B, N, C, **bf), S.buf(B, N, C, **bf)) if pair else None
         S.layernorm(hcur, self._vec(blk.norm1.weight), self._vec(blk.norm1.bias), ln, rows=B * N, Cdim=C, round_tf32=S.R,
                     out_pair=ln_pair)
+        flash = pair and S.flash_eligible(B, N, C)
         t = S.buf(B, N, C)
-        S.linear(ln, self._packed(fold_a), t, M=B * N, K=C, N=C, round_tf32=S.R, tag="attn1.q")
+        t_pair = (S.buf(B, N, C, **bf), S.buf(B, N, C, **bf)) if flash else None
+        S.linear(ln, self._packed(fold_a), t, M=B * N, K=C, N=C, round_tf32=S.R, out_pair=t_pair, tag="attn1.q")
         # V'^T for all images at once, [C, B*N]: the folded value weights (Wo Wv) are the A operand (C rows) and the
         # tokens x play the weight matrix ([B*N rows][K=C], bf16 pair from the LayerNorm) - a dense row-major store
         # instead of a transposing epilogue.  Image b's V'^T is the column block [b*N, (b+1)*N).
@@ -528,6 +530,12 @@ class UNetPlan:
         vT_pair = (S.buf(C, B * N, **bf), S.buf(C, B * N, **bf)) if pair else None
         S.conv(Src(self._packed(fold_v), C, 0, 0, C, 1), ln, vT, B=1, Hin=1, Win=C, Hout=1, Wout=C, Cout=B * N, w_ld=C,
                round_tf32=S.R, out_pair=vT_pair, w_pair=ln_pair, tag="attn1.vT")
+        if flash:  # scores, softmax and PV in one launch (csrc/attn_flash.cu): no [B,N,N] tensor
+            S.flash(t_pair, ln_pair, vT_pair, h1, B=B, N=N, Cdim=C, scale=scale, vt_sb=N, vt_ld=B * N, bias=b_o, res=hcur,
+                    tag="attn1.flash")
+            for t_ in (t, vT, ln) + ln_pair + vT_pair + t_pair:
+                S.release(t_)
+            return h1
         sc = S.buf(B, N, N)
         S.conv(Src(t, C, N * C, 0, C, 1), ln, sc, B=B, Hin=1, Win=N, Hout=1, Wout=N, Cout=N, w_sb=N * C, w_ld=C,
                o_sb=N * N, o_sp=N, w_pair=ln_pair, tag="attn1.qk^T")

@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define FRIDO_ABI_VERSION 6
+#define FRIDO_ABI_VERSION 7
 #define FRIDO_SK_WS_BYTES (40ll << 20)
 
 #define FRIDO_OK 0
@@ -301,6 +301,26 @@ typedef struct FridoAttnParams {
 } FridoAttnParams;
 int frido_attn_small(const FridoAttnParams* p, void* stream);
 
+/* Streaming-softmax attention on the tcgen05 tensor cores (csrc/attn_flash.cu), one head of C channels:
+ *   out = res + bias + softmax(scale * Q K^T) V        (attention.py:170-193; taming model.py:166-192)
+ * in ONE launch - scores in tensor memory, running row maximum / sum in registers, P handed back to the tensor core
+ * through shared memory; the [B,N,N] score tensor never exists.  All three matmul operands arrive in the BF16x3 engine's
+ * pre-split form (bf16 hi / lo pairs, what frido_conv2d's out_hi / out_lo and frido_layernorm's out_hi / out_lo write):
+ *   q, k  : [B][N][C]   rows of C bf16, row stride q_ld / k_ld, image stride q_sb / k_sb (elements)
+ *   vt    : V transposed, channel-major: element (b, c, key) at  b * vt_sb + c * vt_ld + key
+ * N % 128 == 0, C % 32 == 0.  out / res: fp32 [B][N][C] with row stride o_ld / r_ld. */
+typedef struct FridoFlashParams {
+  const void* q_hi; const void* q_lo; int64_t q_sb, q_ld;
+  const void* k_hi; const void* k_lo; int64_t k_sb, k_ld;
+  const void* vt_hi; const void* vt_lo; int64_t vt_sb, vt_ld;
+  int32_t B, N, C; float scale;
+  const float* bias;                                          /* optional [C] */
+  const float* res; int64_t r_sb, r_ld;                       /* optional residual */
+  float* out; int64_t o_sb, o_ld;
+} FridoFlashParams;
+int frido_attn_flash(const FridoFlashParams* p, void* stream);
+int frido_attn_flash_eligible(int32_t B, int32_t N, int32_t C);
+
 /* MS-VQGAN encode side.
  * nn.ConvTranspose2d(Cin, Cout, 4, stride=2, padding=1) on NHWC (msvqgan.py:82-84): out [B,2H,2W,Cout] dense;
  * w is the PyTorch layout [Cin][Cout][4][4]. */
@@ -335,6 +355,27 @@ int frido_split_bf16(const float* src, void* hi, void* lo, int64_t n, void* stre
 int frido_round_tf32(const float* src, float* dst, int64_t n, void* stream);
 
 /* ---------------------------------------------------------------------------
+ * Weight packing (pack_weights / workspace_bytes).  Checkpoint tensors keep the reference's layouts
+ * (Conv2d OIHW, Linear [out,in]); the engines read K-major rows [C_out][tap][C_in] with fused operands concatenated.
+ * Every transformation the host runtime applies is one of these launches (csrc/pack.cu), all on device pointers.
+ * ------------------------------------------------------------------------- */
+/* dst[a*d0 + b*d1 + c*d2] = src[a*s0 + b*s1 + c*s2] for a < n0, b < n1, c < n2 (strides in floats): permutes,
+ * concatenation along rows / columns (offset dst), transposes, GEGLU (value_j, gate_j) row interleave. */
+int frido_pack_permute3(const float* src, int64_t s0, int64_t s1, int64_t s2, float* dst, int64_t d0, int64_t d1, int64_t d2,
+                        int32_t n0, int32_t n1, int32_t n2, void* stream);
+/* Conv2d weight OIHW -> [O][KH*KW][I] rows of length dst_ld >= KH*KW*I (pyunet.py / taming model.py convs). */
+int frido_pack_conv_weight(const float* w, int32_t O, int32_t I, int32_t KH, int32_t KW, float* dst, int64_t dst_ld, void* stream);
+/* out[m][n] = sum_k a[m*a_rs + k*a_cs] * b[k*b_rs + n*b_cs], fp64 products and sums in k order, rounded to fp32 once. */
+int frido_matmul_f64acc(const float* a, int64_t a_rs, int64_t a_cs, const float* b, int64_t b_rs, int64_t b_cs, int32_t M, int32_t N,
+                        int32_t K, float* out, int64_t o_ld, void* stream);
+/* Self-attention weight folds of one CrossAttention module (attention.py:172-191 re-associated; all [C][C] row-major):
+ *   a_out = Wk^T Wq   (sim = (x a_out^T) x^T: the keys are the tokens themselves)
+ *   wv_out = Wo Wv    (the values carry to_out) */
+int frido_fold_self_attention(const float* wq, const float* wk, const float* wv, const float* wo, int32_t C, float* a_out,
+                              float* wv_out, void* stream);
+int frido_vec_add(const float* a, const float* b, float* out, int64_t n, void* stream);
+
+/* ---------------------------------------------------------------------------
  * Native op-program executor: the host runtime builds a flat array of ops once
  * per (stage, batch) and replays it (inside a CUDA graph) every step.
  * ------------------------------------------------------------------------- */
@@ -343,7 +384,7 @@ enum FridoOpKind {
   FRIDO_OP_SOFTMAX = 5, FRIDO_OP_TIME_EMBED = 6, FRIDO_OP_STEP_BEGIN = 7, FRIDO_OP_UPDATE = 8,
   FRIDO_OP_SNAP = 9, FRIDO_OP_VQ = 10, FRIDO_OP_ZERO = 11, FRIDO_OP_UPSAMPLE = 12,
   FRIDO_OP_EMBED = 13, FRIDO_OP_MHA = 14, FRIDO_OP_CONVT = 15, FRIDO_OP_ASSEMBLE = 16, FRIDO_OP_ATTN = 17,
-  FRIDO_OP_BLEND = 18, FRIDO_OP_GN_FINALIZE = 19
+  FRIDO_OP_BLEND = 18, FRIDO_OP_GN_FINALIZE = 19, FRIDO_OP_FLASH = 20
 };
 typedef struct FridoZeroParams { void* ptr; int64_t nbytes; } FridoZeroParams;
 typedef struct FridoOp {
@@ -354,11 +395,15 @@ typedef struct FridoOp {
     FridoLayerNormParams layernorm; FridoSoftmaxParams softmax; FridoTimeEmbedParams time_embed;
     FridoStepBeginParams step_begin; FridoUpdateParams update; FridoSnapParams snap; FridoVqParams vq;
     FridoZeroParams zero; FridoUpsampleParams upsample; FridoEmbedParams embed; FridoMhaParams mha;
-    FridoConvT2dParams convt; FridoAssembleParams assemble; FridoAttnParams attn; FridoBlendParams blend; FridoGnFinalizeParams gn_finalize;
+    FridoConvT2dParams convt; FridoAssembleParams assemble; FridoAttnParams attn; FridoBlendParams blend; FridoGnFinalizeParams gn_finalize; FridoFlashParams flash;
   } u;
 } FridoOp;
 /* Launches ops[0..n) in order on `stream`; returns 0 or (-(1000+i)) if op i failed. */
 int frido_run_program(const FridoOp* ops, int32_t n, void* stream);
+
+/* Bytes of scratch (FridoConvParams.sk_ws) the ops of a program need; the caller allocates it (a torch tensor in the
+ * Python host) and passes it in every tcgen05 conv.  ops == NULL: the upper bound for any program. */
+int64_t frido_workspace_bytes(const FridoOp* ops, int32_t n);
 
 int frido_abi_version(void);
 int frido_sizeof_op(void);

@@ -98,12 +98,12 @@ class AttrDict(dict):
         return AttrDict(v) if isinstance(v, dict) and not isinstance(v, AttrDict) else v
 
 
-def build_model(cfg_model: dict, cond_stage: bool = False):
+def build_model(cfg_model: dict, cond_stage: bool = False, cpu: bool = True):
     """instantiate_from_config(cfg['model']) on CPU with ckpt_path=None and no EMA.
     cond_stage=False replaces the (out-of-scope, 32-layer) condition encoder
     with '__is_unconditional__' *after* fixing conditioning_key, so the UNet
     still takes crossattn context."""
-    activate()
+    activate(cpu=cpu)
     from frido.util import instantiate_from_config
 
     cfg = copy.deepcopy(cfg_model)

@@ -38,6 +38,10 @@ for i, op in enumerate(ops):
         a = op.u.attn
         fl = 4 * a.B * a.N * a.Nk * a.C; key = tags[i]
         rows.append((t, f"{tags[i]:16s} attn B{a.B} N{a.N} Nk{a.Nk} C{a.C} ln{int(bool(a.ln_gamma))}  {t*1e3:8.1f} us  {fl/t/1e9:8.1f} TF/s"))
+    elif op.kind == L.OP_FLASH:
+        a = op.u.flash
+        fl = 4 * a.B * a.N * a.N * a.C; key = tags[i]
+        rows.append((t, f"{tags[i]:16s} flash B{a.B} N{a.N} C{a.C}  {t*1e3:8.1f} us  {fl/t/1e9:8.1f} TF/s"))
     elif op.kind == L.OP_NORM_ACT:
         a = op.u.norm_act
         by = 4 * a.B * a.HW * (a.c0 + a.c1) * (4 if a.gb else 2)
