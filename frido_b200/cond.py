@@ -13,6 +13,7 @@ import torch
 from torch import nn
 
 from . import _lib as L
+from . import packing as PK
 from . import modules as M
 from .program import Program
 
@@ -126,15 +127,15 @@ class _EmbedPlan:
         self.tokens = torch.zeros(B, Lseq, dtype=torch.int64, device=dev)
         M_ = B * Lseq
         x = P.buf(B, Lseq, D)
-        P.embed_tokens(self.tokens, self._p(lambda: tw.token_emb.weight.detach().clone()),
-                       self._p(lambda: tw.pos_emb.emb.weight.detach().clone()), x, B=B, Lseq=Lseq, D=D)
+        P.embed_tokens(self.tokens, self._p(lambda: PK.copy(tw.token_emb.weight)),
+                       self._p(lambda: PK.copy(tw.pos_emb.emb.weight)), x, B=B, Lseq=Lseq, D=D)
         for norm, blk, _ in tw.attn_layers.layers:
             ln = P.buf(M_, D)
             P.layernorm(x, self._v(norm.weight), self._v(norm.bias), ln, rows=M_, Cdim=D, round_tf32=P.R)
             if isinstance(blk, _Attention):
                 H, Dh = blk.heads, blk.dim_head
                 inner = H * Dh
-                wqkv = self._p(lambda b=blk: torch.cat([b.to_q.weight.detach(), b.to_k.weight.detach(), b.to_v.weight.detach()], 0))
+                wqkv = self._p(lambda b=blk: PK.cat_rows([b.to_q.weight, b.to_k.weight, b.to_v.weight]))
                 qkv = P.buf(M_, 3 * inner)
                 P.linear(ln, wqkv, qkv, M=M_, K=D, N=3 * inner, tag="enc.qkv")
                 att = P.buf(M_, inner)
@@ -164,10 +165,10 @@ class _EmbedPlan:
         return dst
 
     def _v(self, prm):
-        return self._p(lambda: prm.detach().clone())
+        return self._p(lambda: PK.copy(prm))
 
     def repack(self):
         """Weights are re-read on every call (the encoder may be trainable / EMA-swapped)."""
         for dst, fn in self.packers:
-            dst.copy_(fn())
+            PK.place(fn().view(1, -1), dst.view(1, -1))
         self.prog.prepare_weights()

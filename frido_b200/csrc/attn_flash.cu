@@ -23,11 +23,9 @@
 namespace frido {
 
 constexpr int FA_SLOT = 32768;
-constexpr int FA_SLOTS = 4;
-constexpr int FA_P_OFF = FA_SLOTS * FA_SLOT;         // P_hi (2 K-atoms x 16 KB) | P_lo
-constexpr int FA_XCH_OFF = FA_P_OFF + 65536;         // float[2][2][128] block-maximum exchange between the two column halves
-constexpr int FA_BAR_OFF = FA_XCH_OFF + 2048;
-constexpr int FA_SMEM_BYTES = FA_BAR_OFF + 256 + 1024 /*align slack*/;
+constexpr int FA_SLOTS = 5;                          // ring depth when the 1024-B alignment pad leaves room, else one less
+constexpr int FA_P_OFF = 65536 + 2048 + 128;         // P_hi (2 K-atoms x 16 KB) | P_lo, counted back from the END of the window
+constexpr int FA_SMEM_BYTES = 232448;                // everything an SM has (227 KB)
 constexpr int FA_S_COL = 384;
 constexpr int FA_SM_WARPS = 8;
 constexpr int FA_THREADS = 64 + 32 * FA_SM_WARPS;
@@ -48,12 +46,17 @@ attn_flash_kernel(const __grid_constant__ CUtensorMap map_qh, const __grid_const
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (smem_base - smem_u32(smem_raw));
-  const uint32_t bar_base = smem_base + FA_BAR_OFF;
+  // layout: ring (NS x 32 KB) | P_hi | P_lo | max exchange (2 KB) | barriers (128 B).  Five slots fit when the 1024-B
+  // alignment pad of the window is <= 896 B; a worse-aligned window gets four.
+  const int NS = (int)(smem_base - smem_u32(smem_raw)) + FA_SLOTS * FA_SLOT + FA_P_OFF <= FA_SMEM_BYTES ? FA_SLOTS : FA_SLOTS - 1;
+  const uint32_t ring = smem_base;
+  const int p_off = NS * FA_SLOT, xch_off = p_off + 65536, bar_off = xch_off + 2048;
+  const uint32_t bar_base = smem_base + bar_off;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (FA_SLOTS + s); };
   const uint32_t s_full = bar_base + 8u * (2 * FA_SLOTS), s_empty = s_full + 8, p_full = s_full + 16, p_empty = s_full + 24,
                  o_full = s_full + 32, tmem_slot = s_full + 40;
-  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem + FA_BAR_OFF + 8 * (2 * FA_SLOTS) + 40);
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem + bar_off + 8 * (2 * FA_SLOTS) + 40);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -96,24 +99,24 @@ attn_flash_kernel(const __grid_constant__ CUtensorMap map_qh, const __grid_const
       auto load_s = [&](int j) {
         for (int c = 0; c < kchunks; ++c) {
           mbar_wait(empty_bar(stage), phase ^ 1);
-          const uint32_t sl = smem_base + stage * FA_SLOT;
+          const uint32_t sl = ring + stage * FA_SLOT;
           mbar_expect_tx(full_bar(stage), 4u * 8192u);
           tma_load_3d(sl, &map_qh, full_bar(stage), c * 32, m0, b);
           tma_load_3d(sl + 8192, &map_ql, full_bar(stage), c * 32, m0, b);
           tma_load_3d(sl + 16384, &map_kh, full_bar(stage), c * 32, j * 128, b);
           tma_load_3d(sl + 24576, &map_kl, full_bar(stage), c * 32, j * 128, b);
-          if (++stage == FA_SLOTS) { stage = 0; phase ^= 1; }
+          if (++stage == NS) { stage = 0; phase ^= 1; }
         }
       };
       auto load_v = [&](int j) {
         for (int ks = 0; ks < 4; ++ks)
           for (int h = 0; h < p.ND; ++h) {
             mbar_wait(empty_bar(stage), phase ^ 1);
-            const uint32_t sl = smem_base + stage * FA_SLOT;
+            const uint32_t sl = ring + stage * FA_SLOT;
             mbar_expect_tx(full_bar(stage), 2u * (uint32_t)p.DN * 64u);
             tma_load_3d(sl, &map_vh, full_bar(stage), j * 128 + ks * 32, dv0 + h * p.DN, b);
             tma_load_3d(sl + 16384, &map_vl, full_bar(stage), j * 128 + ks * 32, dv0 + h * p.DN, b);
-            if (++stage == FA_SLOTS) { stage = 0; phase ^= 1; }
+            if (++stage == NS) { stage = 0; phase ^= 1; }
           }
       };
       load_s(0);
@@ -125,7 +128,7 @@ attn_flash_kernel(const __grid_constant__ CUtensorMap map_qh, const __grid_const
     if (lane == 0) {
       const uint32_t idesc_s = umma_idesc_bf16(128, 128), idesc_o = umma_idesc_bf16(128, p.DN);
       const uint32_t s_tmem = tmem_base + FA_S_COL;
-      const uint32_t p_hi = smem_base + FA_P_OFF, p_lo = p_hi + 32768;
+      const uint32_t p_hi = smem_base + p_off, p_lo = p_hi + 32768;
       int stage = 0;
       uint32_t phase = 0;
       auto issue_s = [&](int j) {
@@ -133,7 +136,7 @@ attn_flash_kernel(const __grid_constant__ CUtensorMap map_qh, const __grid_const
         for (int c = 0; c < kchunks; ++c) {
           mbar_wait(full_bar(stage), phase);
           tc_fence_after();
-          const uint32_t sl = smem_base + stage * FA_SLOT;
+          const uint32_t sl = ring + stage * FA_SLOT;
 #pragma unroll
           for (int k = 0; k < 2; ++k) {
             const uint64_t ah = umma_desc_sw64(sl + k * 32), al = umma_desc_sw64(sl + 8192 + k * 32);
@@ -143,7 +146,7 @@ attn_flash_kernel(const __grid_constant__ CUtensorMap map_qh, const __grid_const
             umma_bf16(s_tmem, ah, bl, idesc_s, 1u);
           }
           umma_commit(empty_bar(stage));
-          if (++stage == FA_SLOTS) { stage = 0; phase ^= 1; }
+          if (++stage == NS) { stage = 0; phase ^= 1; }
         }
         umma_commit(s_full);
       };
@@ -154,7 +157,7 @@ attn_flash_kernel(const __grid_constant__ CUtensorMap map_qh, const __grid_const
           for (int h = 0; h < p.ND; ++h) {
             mbar_wait(full_bar(stage), phase);
             tc_fence_after();
-            const uint32_t sl = smem_base + stage * FA_SLOT;
+            const uint32_t sl = ring + stage * FA_SLOT;
             const uint32_t d = tmem_base + (uint32_t)(h * p.DN);
 #pragma unroll
             for (int k = 0; k < 2; ++k) {
@@ -167,7 +170,7 @@ attn_flash_kernel(const __grid_constant__ CUtensorMap map_qh, const __grid_const
               umma_bf16(d, ph, vl, idesc_o, 1u);
             }
             umma_commit(empty_bar(stage));
-            if (++stage == FA_SLOTS) { stage = 0; phase ^= 1; }
+            if (++stage == NS) { stage = 0; phase ^= 1; }
           }
         umma_commit(p_empty);  // P(j) consumed, O holds blocks 0..j
       };
@@ -182,8 +185,8 @@ attn_flash_kernel(const __grid_constant__ CUtensorMap map_qh, const __grid_const
     const int half = (warp - 2) >> 2;     // which 64 keys of the block / which half of the output columns
     const int row = q * 32 + lane;
     const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
-    float* xch = reinterpret_cast<float*>(smem + FA_XCH_OFF);
-    uint8_t* prow_hi = smem + FA_P_OFF + half * 16384 + row * 128;
+    float* xch = reinterpret_cast<float*>(smem + xch_off);
+    uint8_t* prow_hi = smem + p_off + half * 16384 + row * 128;
     uint8_t* prow_lo = prow_hi + 32768;
     const int ocols = p.DV >> 1;          // output columns per thread
     const int oc0 = half * ocols;
@@ -217,6 +220,15 @@ attn_flash_kernel(const __grid_constant__ CUtensorMap map_qh, const __grid_const
         m_ref = mb;
       }
       const bool any = __any_sync(0xffffffffu, need);
+      // p = exp2((s - m_ref) * scale * log2 e), in place, while PV(j-1) is still running
+      const float mneg = -m_ref * p.sl2;
+      float lsum = 0.f;
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        const float e0 = exp2f(fmaf(__uint_as_float(s0[i]), p.sl2, mneg)), e1 = exp2f(fmaf(__uint_as_float(s1[i]), p.sl2, mneg));
+        lsum += e0 + e1;
+        s0[i] = __float_as_uint(e0); s1[i] = __float_as_uint(e1);
+      }
       if (j > 0) { mbar_wait(p_empty, (uint32_t)((j - 1) & 1)); tc_fence_after(); }  // PV(j-1) retired: P is free, O is stable
       if (any) {
         for (int c = 0; c < ocols; c += 16) {
@@ -228,22 +240,15 @@ attn_flash_kernel(const __grid_constant__ CUtensorMap map_qh, const __grid_const
         }
         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
       }
-      const float mneg = -m_ref * p.sl2;
-      float lsum = 0.f;
 #pragma unroll
       for (int c = 0; c < 8; ++c) {
-        float pv[8];
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          const uint32_t raw = (c < 4) ? s0[c * 8 + e] : s1[(c - 4) * 8 + e];
-          pv[e] = exp2f(fmaf(__uint_as_float(raw), p.sl2, mneg));
-          lsum += pv[e];
-        }
         uint32_t h[4], lo[4];
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          h[e] = pack_bf16x2(pv[2 * e], pv[2 * e + 1]);
-          lo[e] = pack_bf16x2(pv[2 * e] - bf16_lo_to_f32(h[e]), pv[2 * e + 1] - bf16_hi_to_f32(h[e]));
+          const float a = __uint_as_float((c < 4) ? s0[c * 8 + 2 * e] : s1[(c - 4) * 8 + 2 * e]);
+          const float b2 = __uint_as_float((c < 4) ? s0[c * 8 + 2 * e + 1] : s1[(c - 4) * 8 + 2 * e + 1]);
+          h[e] = pack_bf16x2(a, b2);
+          lo[e] = pack_bf16x2(a - bf16_lo_to_f32(h[e]), b2 - bf16_hi_to_f32(h[e]));
         }
         const int off = (c ^ (row & 7)) << 4;
         *reinterpret_cast<uint4*>(prow_hi + off) = make_uint4(h[0], h[1], h[2], h[3]);

@@ -382,19 +382,29 @@ __device__ __forceinline__ void tc_epilogue_role(const TcParams& p, uint8_t* sme
       // use of the bias was the epilogue's top stall)
       float4 bias_nx = make_float4(0.f, 0.f, 0.f, 0.f);
       if (has_bias) bias_nx = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + 4 * c4));
+      // the residual tile of a chunk is fetched ONE CHUNK AHEAD (like the bias): a DRAM / L2 round trip is longer than a whole
+      // chunk of epilogue work, and with the loads issued at the top of their own chunk every chunk of a short-K GEMM's
+      // epilogue stalled for a full memory latency
+      float4 rres_nx[4];
+      auto load_res = [&](int cc, float4 (&dst)[4]) {
+        const int nn = n0 + cc + 4 * c4;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          dst[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (obase[j] >= 0) {
+            if (geglu) { const float2 t2 = *reinterpret_cast<const float2*>(p.res + obase[j] + (nn >> 1)); dst[j].x = t2.x; dst[j].y = t2.y; }
+            else dst[j] = *reinterpret_cast<const float4*>(p.res + obase[j] + nn);
+          }
+        }
+      };
+      if (has_res) load_res(0, rres_nx);
       for (int c = 0; c < hcols; c += 16) {
         const int n = n0 + c + 4 * c4;
-        // residual loads of this chunk go out first: their latency overlaps the TMEM load + transpose
         float4 rres[4];
         if (has_res) {
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            rres[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (obase[j] >= 0) {
-              if (geglu) { const float2 t2 = *reinterpret_cast<const float2*>(p.res + obase[j] + (n >> 1)); rres[j].x = t2.x; rres[j].y = t2.y; }
-              else rres[j] = *reinterpret_cast<const float4*>(p.res + obase[j] + n);
-            }
-          }
+          for (int j = 0; j < 4; ++j) rres[j] = rres_nx[j];
+          if (c + 16 < hcols) load_res(c + 16, rres_nx);
         }
         const float4 bias4 = bias_nx;
         if (has_bias && c + 16 < hcols) bias_nx = __ldg(reinterpret_cast<const float4*>(p.bias + n + 16));

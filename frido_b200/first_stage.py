@@ -24,6 +24,7 @@ from . import modules as M
 from .program import Program, Src
 from .program import round_tf32_
 from .unet import _pack_conv
+from . import packing as PK
 
 
 @torch.no_grad()
@@ -241,14 +242,14 @@ class _VQPlan:
         return dst
 
     def _vec(self, p):
-        return self._packed(lambda: p.detach().clone())
+        return self._packed(lambda: PK.copy(p))
 
     def _conv_w(self, conv):
         return self._packed(lambda: _pack_conv(conv.weight))
 
     def repack(self):
         for dst, fn in self.packers:
-            dst.copy_(fn())
+            PK.place(fn().view(1, -1), dst.view(1, -1))
             if id(dst) in self._mma_ids:
                 round_tf32_(dst)
         self.prog.prepare_weights()
@@ -283,7 +284,7 @@ class _VQPlan:
         res, sk = x, None
         if cin != cout:
             sk = P.buf(B, h * w, cout)
-            P.conv(Src.nhwc(x, h, w), self._packed(lambda: rb.nin_shortcut.weight.detach().view(cout, cin).clone()), sk, B=B,
+            P.conv(Src.nhwc(x, h, w), self._packed(lambda: PK.copy(rb.nin_shortcut.weight.detach().view(cout, cin))), sk, B=B,
                    Hin=h, Win=w, Hout=h, Wout=w, Cout=cout, bias=self._vec(rb.nin_shortcut.bias), tag=tag + ".nin")
             res = sk
         out = P.buf(B, h * w, cout)
@@ -301,24 +302,36 @@ class _VQPlan:
         C = ab.q.weight.shape[0]
         N = h * w
         t = self._gn(x, C, h, w, ab.norm, 0)
-        wqk = self._packed(lambda: torch.cat([ab.q.weight.detach().view(C, C), ab.k.weight.detach().view(C, C)], 0))
-        bqk = self._packed(lambda: torch.cat([ab.q.bias.detach(), ab.k.bias.detach()], 0))
+        wqk = self._packed(lambda: PK.cat_rows([ab.q.weight.detach().view(C, C), ab.k.weight.detach().view(C, C)]))
+        bqk = self._packed(lambda: PK.cat_rows([ab.q.bias, ab.k.bias]))
+        flash = P.tc_code == 3 and P.flash_eligible(B, N, C)
+        bf = dict(dtype=torch.bfloat16)
         qk = P.buf(B, N, 2 * C)
-        P.linear(t, wqk, qk, M=B * N, K=C, N=2 * C, bias=bqk, round_tf32=P.R, tag=tag + ".qk")
+        qk_pair = (P.buf(B, N, 2 * C, **bf), P.buf(B, N, 2 * C, **bf)) if flash else None
+        P.linear(t, wqk, qk, M=B * N, K=C, N=2 * C, bias=bqk, round_tf32=P.R, out_pair=qk_pair, tag=tag + ".qk")
         vT = P.buf(B, C, N)
-        P.conv(Src(t, C, N * C, 0, C, 1), self._packed(lambda: ab.v.weight.detach().view(C, C).clone()), vT, B=B, Hin=1, Win=N,
-               Hout=1, Wout=N, Cout=C, bias=self._vec(ab.v.bias), o_sb=C * N, o_sp=1, o_sn=N, round_tf32=P.R, tag=tag + ".vT")
+        vT_pair = (P.buf(B, C, N, **bf), P.buf(B, C, N, **bf)) if flash else None
+        P.conv(Src(t, C, N * C, 0, C, 1), self._packed(lambda: PK.copy(ab.v.weight.detach().view(C, C))), vT, B=B, Hin=1, Win=N,
+               Hout=1, Wout=N, Cout=C, bias=self._vec(ab.v.bias), o_sb=C * N, o_sp=1, o_sn=N, round_tf32=P.R, out_pair=vT_pair,
+               tag=tag + ".vT")
         P.release(t)
-        sc = P.buf(B, N, N)
-        P.conv(Src(qk, C, N * 2 * C, 0, 2 * C, 1), qk, sc, B=B, Hin=1, Win=N, Hout=1, Wout=N, Cout=N, w_sb=N * 2 * C,
-               w_ld=2 * C, w_off=C, tag=tag + ".qk^T")
-        P.softmax(sc, rows=B * N, n=N, ld=N, scale=float(int(C) ** (-0.5)), round_tf32=P.R, tag=tag + ".softmax")
         o = P.buf(B, N, C)
-        P.conv(Src(sc, N, N * N, 0, N, 1), vT, o, B=B, Hin=1, Win=N, Hout=1, Wout=N, Cout=C, w_sb=C * N, w_ld=N,
-               round_tf32=P.R, tag=tag + ".pv")
-        P.release(qk); P.release(vT); P.release(sc)
+        if flash:
+            # scores, softmax and PV in one launch (csrc/attn_flash.cu): the [B,N,N] tensor (1 GB at 64x64, B=16) never exists
+            P.flash(qk_pair, qk_pair, vT_pair, o, B=B, N=N, Cdim=C, scale=float(int(C) ** (-0.5)), vt_sb=C * N, vt_ld=N,
+                    q_ld=2 * C, k_off=C, k_ld=2 * C, tag=tag + ".flash")
+            for t_ in (qk, vT) + qk_pair + vT_pair:
+                P.release(t_)
+        else:
+            sc = P.buf(B, N, N)
+            P.conv(Src(qk, C, N * 2 * C, 0, 2 * C, 1), qk, sc, B=B, Hin=1, Win=N, Hout=1, Wout=N, Cout=N, w_sb=N * 2 * C,
+                   w_ld=2 * C, w_off=C, tag=tag + ".qk^T")
+            P.softmax(sc, rows=B * N, n=N, ld=N, scale=float(int(C) ** (-0.5)), round_tf32=P.R, tag=tag + ".softmax")
+            P.conv(Src(sc, N, N * N, 0, N, 1), vT, o, B=B, Hin=1, Win=N, Hout=1, Wout=N, Cout=C, w_sb=C * N, w_ld=N,
+                   round_tf32=P.R, tag=tag + ".pv")
+            P.release(qk); P.release(vT); P.release(sc)
         out = P.buf(B, N, C)
-        P.linear(o, self._packed(lambda: ab.proj_out.weight.detach().view(C, C).clone()), out, M=B * N, K=C, N=C,
+        P.linear(o, self._packed(lambda: PK.copy(ab.proj_out.weight.detach().view(C, C))), out, M=B * N, K=C, N=C,
                  bias=self._vec(ab.proj_out.bias), res=x, tag=tag + ".proj_out")
         P.release(o); P.release(x)
         return out
@@ -343,7 +356,7 @@ class DecodePlan(_VQPlan):
             start += e
         zc = fs.post_quant_conv.weight.shape[0]
         pq = P.buf(B, H * W, zc)
-        P.conv(Src.nhwc(quant, H, W), self._packed(lambda: fs.post_quant_conv.weight.detach().view(zc, Ct).clone()), pq, B=B,
+        P.conv(Src.nhwc(quant, H, W), self._packed(lambda: PK.copy(fs.post_quant_conv.weight.detach().view(zc, Ct))), pq, B=B,
                Hin=H, Win=W, Hout=H, Wout=W, Cout=zc, bias=self._vec(fs.post_quant_conv.bias), tag="post_quant_conv")
         f = 2 ** (dec.num_resolutions - 1)
         oc = dec.conv_out.weight.shape[0]
@@ -429,7 +442,7 @@ class EncodePlan(_VQPlan):
             if ii > 0:
                 ct, pq = fs.upsample[ii - 1], fs.shared_post_quant_conv[ii - 1]
                 wt, bt = self._vec(ct.weight), self._vec(ct.bias)
-                wp, bp = self._packed(lambda pq=pq: pq.weight.detach().view(zc0, e0).clone()), self._vec(pq.bias)
+                wp, bp = self._packed(lambda pq=pq: PK.copy(pq.weight.detach().view(zc0, e0))), self._vec(pq.bias)
                 for j in range(ii):
                     u = P.buf(B, th * tw, e0)
                     src, ld, off = prev[j]
@@ -447,7 +460,7 @@ class EncodePlan(_VQPlan):
                 q_in, src_c = cat, ctot
             hq = P.buf(B, th * tw, e)
             mq = fs.ms_quant_conv[ii]
-            P.conv(Src.nhwc(q_in, th, tw, c_total=src_c), self._packed(lambda mq=mq, e=e, k=src_c: mq.weight.detach().view(e, k).clone()),
+            P.conv(Src.nhwc(q_in, th, tw, c_total=src_c), self._packed(lambda mq=mq, e=e, k=src_c: PK.copy(mq.weight.detach().view(e, k))),
                    hq, B=B, Hin=th, Win=tw, Hout=th, Wout=tw, Cout=e, bias=self._vec(mq.bias), tag="enc.ms_quant_conv")
             sh = (fh // th).bit_length() - 1
             P.assemble_latent(hq, self.latent, B=B, H=fh, W=fw, e=e, sh=sh, scale=sf[ii], C_total=Ct, c_off=coff, tag="enc.assemble")

@@ -332,12 +332,17 @@ class Program:
         the QK^T -> softmax -> PV launches."""
         return os.environ.get("FRIDO_FLASH", "1") == "1" and bool(L.lib().frido_attn_flash_eligible(B, N, Cdim))
 
-    def flash(self, q_pair, k_pair, vt_pair, out, *, B, N, Cdim, scale, vt_sb, vt_ld, bias=None, res=None, tag="attn.flash"):
-        """out = res + bias + softmax(scale q k^T) v in one launch; q_pair / k_pair = (hi, lo) bf16 [B,N,C] tensors, vt_pair the
-        values channel-major: element (b, c, key) at b * vt_sb + c * vt_ld + key."""
+    def flash(self, q_pair, k_pair, vt_pair, out, *, B, N, Cdim, scale, vt_sb, vt_ld, bias=None, res=None, q_off=0, q_ld=None,
+              q_sb=None, k_off=0, k_ld=None, k_sb=None, tag="attn.flash"):
+        """out = res + bias + softmax(scale q k^T) v in one launch; q_pair / k_pair = (hi, lo) bf16 tensors holding the rows
+        [B,N,C] at element offset q_off / k_off with row stride q_ld / k_ld (default: dense), vt_pair the values
+        channel-major: element (b, c, key) at b * vt_sb + c * vt_ld + key."""
         p = L.FlashParams()
-        p.q_hi, p.q_lo, p.q_sb, p.q_ld = q_pair[0].data_ptr(), q_pair[1].data_ptr(), N * Cdim, Cdim
-        p.k_hi, p.k_lo, p.k_sb, p.k_ld = k_pair[0].data_ptr(), k_pair[1].data_ptr(), N * Cdim, Cdim
+        q_ld, k_ld = q_ld or Cdim, k_ld or Cdim
+        p.q_hi, p.q_lo = q_pair[0].data_ptr() + 2 * q_off, q_pair[1].data_ptr() + 2 * q_off
+        p.q_sb, p.q_ld = q_sb or N * q_ld, q_ld
+        p.k_hi, p.k_lo = k_pair[0].data_ptr() + 2 * k_off, k_pair[1].data_ptr() + 2 * k_off
+        p.k_sb, p.k_ld = k_sb or N * k_ld, k_ld
         p.vt_hi, p.vt_lo, p.vt_sb, p.vt_ld = vt_pair[0].data_ptr(), vt_pair[1].data_ptr(), vt_sb, vt_ld
         p.B, p.N, p.C, p.scale = B, N, Cdim, scale
         p.bias = _ptr(bias)
@@ -346,6 +351,7 @@ class Program:
         p.out, p.o_sb, p.o_ld = out.data_ptr(), N * Cdim, Cdim
         self.hold(*q_pair, *k_pair, *vt_pair, out, bias, res)
         self.flops += 4 * B * N * N * Cdim
+        self.tc_flops += 4 * B * N * N * Cdim
         self._add(L.OP_FLASH, p, tag)
 
     def upsample2x(self, x, out, *, B, H, W, Cdim, round_tf32=0, out_split=0, tag="upsample2x"):

@@ -21,6 +21,7 @@ from torch import nn
 
 from . import _lib as L
 from . import modules as M
+from . import packing as PK
 from .program import Program, Src, round_tf32_
 
 
@@ -169,21 +170,19 @@ def fold_self_attention(ca):
          sim   = (x Wq^T)(x Wk^T)^T       = (x A^T) x^T        with A   = Wk^T Wq   (keys are x itself)
          to_out(P (x Wv^T)) - b_o         = P (x Wv'^T)        with Wv' = Wo Wv     (values carry to_out)
     Products are taken in fp64 and rounded once; returns (A, Wv') as [C,C] fp32 linear weights ([out,in])."""
-    wq, wk = ca.to_q.weight.detach().double(), ca.to_k.weight.detach().double()
-    wv, wo = ca.to_v.weight.detach().double(), ca.to_out[0].weight.detach().double()
-    return (wk.t() @ wq).float().contiguous(), (wo @ wv).float().contiguous()
+    return PK.fold_self_attention(ca.to_q.weight, ca.to_k.weight, ca.to_v.weight, ca.to_out[0].weight)
 
 
 def fold_cross_attention_weights(ca):
     """Linear weights that turn K = ctx Wk^T and V = ctx Wv^T into the operands of the fused cross-attention kernel:
          K' = K Wq   (sim = (x Wq^T) K^T = x K'^T)        -> weight Wq^T   ([out,in] = [C,C])
          V' = V Wo^T (to_out(P V) - b_o = P V')           -> weight Wo"""
-    return ca.to_q.weight.detach().t().contiguous(), ca.to_out[0].weight.detach()
+    return PK.transpose(ca.to_q.weight), PK.copy(ca.to_out[0].weight)
 
 
 def _pack_conv(w):
-    """OIHW -> [O][kh*kw][I] (K-major rows for the implicit GEMM)."""
-    return w.detach().permute(0, 2, 3, 1).contiguous().view(w.shape[0], -1)
+    """OIHW -> [O][kh*kw][I] (K-major rows for the implicit GEMM); a native launch (csrc/pack.cu)."""
+    return PK.conv_weight(w)
 
 
 class UNetPlan:
@@ -221,7 +220,7 @@ class UNetPlan:
 
     def repack(self):
         for dst, fn in self.packers:
-            dst.copy_(fn())
+            PK.place(fn().view(1, -1), dst.view(1, -1))
             if id(dst) in self._mma_ids:
                 round_tf32_(dst)
         self.prologue.prepare_weights()
@@ -245,7 +244,7 @@ class UNetPlan:
         return self._packed(lambda: _pack_conv(conv.weight))
 
     def _vec(self, p):
-        return self._packed(lambda: p.detach().clone())
+        return self._packed(lambda: PK.copy(p))
 
     # ---- helpers ---------------------------------------------------------
     def _csum_new(self, C):
@@ -350,8 +349,8 @@ class UNetPlan:
         P.conv(Src.nhwc(self.h_cond, self.H, self.W, mc, sub=sub), self._conv_w(sp.mlp_shared[0]), actv, B=B, Hin=h,
                Win=w, Hout=h, Wout=w, Cout=nh, ksize=3, pad=1, bias=self._vec(sp.mlp_shared[0].bias), act=L.ACT_RELU,
                round_tf32=P.R, tag="spade.shared")
-        wgb = self._packed(lambda: torch.cat([_pack_conv(sp.mlp_gamma.weight), _pack_conv(sp.mlp_beta.weight)], 0))
-        bgb = self._packed(lambda: torch.cat([sp.mlp_gamma.bias.detach(), sp.mlp_beta.bias.detach()], 0))
+        wgb = self._packed(lambda: PK.conv_rows([sp.mlp_gamma.weight, sp.mlp_beta.weight]))
+        bgb = self._packed(lambda: PK.cat_rows([sp.mlp_gamma.bias, sp.mlp_beta.bias]))
         gb = torch.empty(B, hw, 2 * C, dtype=torch.float32, device=self.dev)  # lives across steps: not pooled
         P.conv(Src.nhwc(actv, h, w), wgb, gb, B=B, Hin=h, Win=w, Hout=h, Wout=w, Cout=2 * C, ksize=3, pad=1, bias=bgb,
                tag="spade.gamma_beta")
@@ -396,8 +395,8 @@ class UNetPlan:
             # K steps read at the output pixel, its weights extra columns, the biases add up - no separate launch, no
             # round trip of the skip tensor through HBM
             sc_, c2_ = rb.skip_connection, rb.out_layers[3]
-            w_cat = self._packed(lambda: torch.cat([_pack_conv(c2_.weight), sc_.weight.detach().reshape(cout, -1)], 1).contiguous())
-            b_cat = self._packed(lambda: (c2_.bias.detach() + sc_.bias.detach()))
+            w_cat = self._packed(lambda: PK.conv_plus_side(c2_.weight, sc_.weight))
+            b_cat = self._packed(lambda: PK.vec_add(c2_.bias, sc_.bias))
             self._conv_stats(S, src2, w_cat, out, cout, B=B, Hin=h, Win=w, Hout=h, Wout=w, ksize=3, pad=1,
                              bias=b_cat, side=(Src.nhwc(xs[0], h, w), a1), nrm=nrm2, presplit=sp2, tag="res.conv2+skip")
         else:
@@ -426,7 +425,7 @@ class UNetPlan:
         scale = float(C) ** -0.5
         if ctx_kv is None and self._small_attn(N, C):
             # fewer than 128 tokens per image (8x8 level): one q|k|v GEMM + the fused short-sequence attention kernel
-            wqkv = self._packed(lambda: torch.cat([ca.to_q.weight.detach(), ca.to_k.weight.detach(), ca.to_v.weight.detach()], 0))
+            wqkv = self._packed(lambda: PK.cat_rows([ca.to_q.weight, ca.to_k.weight, ca.to_v.weight]))
             qkv = S.buf(B, N, 3 * C)
             S.linear(x, wqkv, qkv, M=B * N, K=C, N=3 * C, tag=tag + ".qkv")
             o = S.buf(B, N, C)
@@ -435,7 +434,7 @@ class UNetPlan:
             S.release(qkv)
             return o
         if ctx_kv is None:  # self-attention: fused q|k projection, V written transposed
-            wqk = self._packed(lambda: torch.cat([ca.to_q.weight.detach(), ca.to_k.weight.detach()], 0))
+            wqk = self._packed(lambda: PK.cat_rows([ca.to_q.weight, ca.to_k.weight]))
             qk = S.buf(B, N, 2 * C)
             # BF16x3: K and V^T later act as the W operand of QK^T / PV, so their producers also emit the bf16 hi/lo pair
             pair = S.tc_code == 3 and N >= 128
@@ -507,7 +506,7 @@ class UNetPlan:
         h1 = S.buf(B, N, C)
         if self._small_attn(N, C):  # fewer than 128 tokens per image (8x8 level): fused SIMT attention kernel
             S.layernorm(hcur, self._vec(blk.norm1.weight), self._vec(blk.norm1.bias), ln, rows=B * N, Cdim=C)
-            w_av = self._packed(lambda: torch.cat([fold_a(), fold_v()], 0).contiguous())
+            w_av = self._packed(lambda: PK.cat_rows(list(fold_self_attention(ca))))
             qv = S.buf(B, N, 2 * C)
             S.linear(ln, w_av, qv, M=B * N, K=C, N=2 * C, tag="attn1.qv")
             S.attn_small(qv, ln, qv, h1, B=B, N=N, Nk=N, Cdim=C, scale=scale, q_sb=N * 2 * C, q_ld=2 * C, k_sb=N * C, k_ld=C,
@@ -564,7 +563,7 @@ class UNetPlan:
         P.linear(self.ctx, self._vec(ca.to_k.weight), kc, M=B * Lc, K=D, N=C, tag="ctx.k")
         P.linear(kc, self._packed(lambda: fold_cross_attention_weights(ca)[0]), kf, M=B * Lc, K=C, N=C, tag="ctx.k.Wq")
         P.linear(self.ctx, self._vec(ca.to_v.weight), kc, M=B * Lc, K=D, N=C, tag="ctx.v")
-        P.linear(kc, self._packed(lambda: fold_cross_attention_weights(ca)[1].clone()), vf, M=B * Lc, K=C, N=C, tag="ctx.v.Wo")
+        P.linear(kc, self._packed(lambda: fold_cross_attention_weights(ca)[1]), vf, M=B * Lc, K=C, N=C, tag="ctx.v.Wo")
         P.release(kc)
         return kf, vf
 
@@ -588,7 +587,7 @@ class UNetPlan:
         S, B = self.step, self.B
         N = h * w
         hcur = S.buf(B, N, C)
-        w_in = self._packed(lambda: st.proj_in.weight.detach().view(C, C).clone())
+        w_in = self._packed(lambda: PK.copy(st.proj_in.weight.detach().view(C, C)))
         nf = self._norm_on_load(S, [x], [C], h, w, st.norm, 1e-6, 0, hcur, C, 1)
         if nf is not None:  # GroupNorm [+SPADE] applied by proj_in on load (attention.py:296-298 as one launch)
             S.conv(Src.nhwc(x, h, w), w_in, hcur, B=B, Hin=h, Win=w, Hout=h, Wout=w, Cout=C, bias=self._vec(st.proj_in.bias),
@@ -642,11 +641,10 @@ class UNetPlan:
             inner = proj.weight.shape[0] // 2
 
             def _inter(p=proj, inner=inner):  # GEGLU (attention.py:42-44): rows (value_j, gate_j) interleaved
-                wv, wg = p.weight.detach()[:inner], p.weight.detach()[inner:]
-                return torch.stack([wv, wg], 1).reshape(2 * inner, -1).contiguous()
+                return PK.interleave_rows(p.weight.detach()[:inner], p.weight.detach()[inner:])
 
             def _inter_b(p=proj, inner=inner):
-                return torch.stack([p.bias.detach()[:inner], p.bias.detach()[inner:]], 1).reshape(-1).contiguous()
+                return PK.interleave_rows(p.bias.detach()[:inner], p.bias.detach()[inner:])
 
             ff = S.buf(B, N, inner)
             S.linear(ln, self._packed(_inter), ff, M=B * N, K=C, N=2 * inner, bias=self._packed(_inter_b), act=L.ACT_GEGLU,
@@ -659,7 +657,7 @@ class UNetPlan:
             hcur = h3
         out = S.buf(B, N, C)
         # same GEMM as a 1x1 conv over [B,h,w,C] (so the epilogue can attribute rows to images for the GroupNorm sums)
-        self._conv_stats(S, Src.nhwc(hcur, h, w), self._packed(lambda: st.proj_out.weight.detach().view(C, C).clone()), out, C,
+        self._conv_stats(S, Src.nhwc(hcur, h, w), self._packed(lambda: PK.copy(st.proj_out.weight.detach().view(C, C))), out, C,
                          B=B, Hin=h, Win=w, Hout=h, Wout=w, bias=self._vec(st.proj_out.bias), res=x, tag="st.proj_out")
         S.release(hcur)
         return out
@@ -724,7 +722,7 @@ class UNetPlan:
         S.linear(te, self._vec(net.time_embed[0].weight), e1, M=B, K=mc, N=ted, bias=self._vec(net.time_embed[0].bias),
                  act=L.ACT_SILU, tag="time_embed.0")
         semb = S.buf(B, ted)  # SiLU(emb): every consumer applies SiLU first (pyunet.py:226)
-        stage_row = self._packed(lambda: net.stage_emb.weight.detach()[s].clone()) if net.num_stage > 1 else None
+        stage_row = self._packed(lambda: PK.copy(net.stage_emb.weight.detach()[s])) if net.num_stage > 1 else None
         S.linear(e1, self._vec(net.time_embed[2].weight), semb, M=B, K=ted, N=ted, bias=self._vec(net.time_embed[2].bias),
                  rowvec=stage_row, act=L.ACT_SILU, tag="time_embed.2")
         rbs = [m for m in net.modules() if isinstance(m, M.ResBlock)]
@@ -734,8 +732,8 @@ class UNetPlan:
             off += rb.out_channels
         self.emb_total = off
         self.emb_all = S.buf(B, off)
-        S.linear(semb, self._packed(lambda: torch.cat([rb.emb_layers[1].weight.detach() for rb in rbs], 0)), self.emb_all,
-                 M=B, K=ted, N=off, bias=self._packed(lambda: torch.cat([rb.emb_layers[1].bias.detach() for rb in rbs], 0)),
+        S.linear(semb, self._packed(lambda: PK.cat_rows([rb.emb_layers[1].weight for rb in rbs])), self.emb_all,
+                 M=B, K=ted, N=off, bias=self._packed(lambda: PK.cat_rows([rb.emb_layers[1].bias for rb in rbs])),
                  tag="emb_layers(all)")
         # --- split head (pyunet.py:899-914) ---
         if self.c_cond:

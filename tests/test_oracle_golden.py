@@ -152,11 +152,19 @@ def test_attention_weight_folds_match_the_oracle():
     """The UNet plan re-associates the attention matmuls (frido_b200/unet.py: fold_self_attention,
     fold_cross_attention_weights) so that the key projection and to_out leave the per-step work.  Exact algebra: the
     folded form must reproduce the oracle's CrossAttention (attention.py:170-193) to fp32 rounding, for the
-    self-attention and for the cross-attention against a short condition."""
+    self-attention and for the cross-attention against a short condition.  The folds themselves are native launches
+    (csrc/pack.cu) and are compared with these same expressions on the GPU (tests/test_gpu_pack.py)."""
     import torch.nn.functional as F
     from frido_b200 import modules as M
-    from frido_b200.unet import fold_self_attention, fold_cross_attention_weights
     from oracle import torch_oracle as O
+
+    def fold_self_attention(ca):   # (Wk^T Wq, Wo Wv), fp64 products rounded once
+        wq, wk, wv, wo = (m.weight.detach().double() for m in (ca.to_q, ca.to_k, ca.to_v, ca.to_out[0]))
+        return (wk.t() @ wq).float(), (wo @ wv).float()
+
+    def fold_cross_attention_weights(ca):   # (Wq^T, Wo)
+        return ca.to_q.weight.detach().t().contiguous(), ca.to_out[0].weight.detach()
+
     torch.manual_seed(0)
     C, D, N, L, B = 96, 40, 50, 7, 2
     blk = M.BasicTransformerBlock(C, D)

@@ -49,13 +49,14 @@ for i, op in enumerate(ops):
         rows.append((t, f"{tags[i]:16s} norm B{a.B} HW{a.HW} C{a.c0}+{a.c1} spade{int(bool(a.gb))}  {t*1e3:8.1f} us  {by/t/1e6:8.1f} GB/s"))
     else:
         fl = 0; key = tags[i] if op.kind != L.OP_GN_STATS else 'gn_stats'
+        rows.append((t, f"{key:16s} kind{op.kind}  {t*1e3:8.1f} us"))
     agg[key][0] += t; agg[key][1] += fl; agg[key][2] += 1
 tot = sum(best.values())
 print(f"stage {stage} B {B}: total eager per-op sum {tot:.2f} ms over {len(ops)} ops")
 for k, (t, fl, n) in sorted(agg.items(), key=lambda kv: -kv[1][0]):
     print(f"{k:24s} n={n:3d} {t:8.3f} ms {100*t/tot:5.1f}%  {fl/t/1e9 if t else 0:8.1f} TF/s")
-print('--- slowest convs')
-for t, r in sorted(rows, reverse=True)[:60]:
+print('--- slowest ops')
+for t, r in sorted(rows, reverse=True)[:(10**6 if os.environ.get('PALL') else 60)]:
     print(r)
 print('--- least efficient big convs')
 rows_eff = [(fl_t, r) for fl_t, r in ((float(r.split()[-2]), r) for _, r in rows) if True]
