@@ -280,11 +280,10 @@ __global__ void __launch_bounds__(ATTN_WARPS * 32, SINGLE ? 2 : 1) attn_small_ke
 
 template <int NJ, int R, bool SINGLE>
 static int launch_attn2(const FridoAttnParams* p, int KC, cudaStream_t s) {
-  static bool attr = false;
-  if (!attr) {
+  static DevOnce attr;
+  if (attr.need()) {
     if (cudaFuncSetAttribute(attn_small_kernel<NJ, R, SINGLE>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATTN_SMEM_MAX) != cudaSuccess)
       return set_error(FRIDO_E_LAUNCH, "attn_small: cannot opt in to dynamic shared memory");
-    attr = true;
   }
   const size_t smem = (size_t)2 * KC * p->C * sizeof(float);
   dim3 grid((p->N + ATTN_WARPS * R - 1) / (ATTN_WARPS * R), p->B);

@@ -55,6 +55,19 @@ inline void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t s
   cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);  // errors surface in check_launch
 }
 
+// cudaFuncSetAttribute (the > 48 KB dynamic shared memory opt-in) is PER DEVICE: one flag per (call site, device), so a
+// process that drives several GPUs opts in on each of them.
+struct DevOnce {
+  bool done[64] = {};
+  bool need() {
+    int d = 0;
+    if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= 64) return true;
+    if (done[d]) return false;
+    done[d] = true;
+    return true;
+  }
+};
+
 inline int check_launch(const char* what) {
   ++g_launch_count;
   g_prev_kernel = true;

@@ -419,22 +419,18 @@ int conv2d_simt(const FridoConvParams* p, cudaStream_t s) {
   if (vecA && vecW && !p->out_hi && !p->a1 && p->ksize == 1 && p->stride == 1 && p->ups == 1 && p->B == 1 && p->Hout == 1 && p->Hin == 1 &&
       p->Wout == p->Win && p->Wout <= SM_MAXROWS && p->o_sn == 1 && p->w_sb == 0 && p->act != FRIDO_ACT_GEGLU && p->act != FRIDO_ACT_GEGLU_FAST &&
       p->Cout >= 64 && (size_t)p->Wout * Cin * 4 <= 96 * 1024 && !p->out_u8) {
-    static bool attr_l = false;
-    if (!attr_l) {
-      cudaFuncSetAttribute(linear_smallm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
-      attr_l = true;
-    }
+    static DevOnce attr_l;
+    if (attr_l.need()) cudaFuncSetAttribute(linear_smallm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
     const int cols_per_cta = 8 * SM_COLS_PER_WARP;
     linear_smallm_kernel<<<(p->Cout + cols_per_cta - 1) / cols_per_cta, 256, (size_t)p->Wout * Cin * 4, s>>>(*p);
     return check_launch("linear_smallm");
   }
   if (vecA && !p->out_hi && p->Cout <= SC_MAXCOUT && p->act != FRIDO_ACT_GEGLU && (size_t)p->Cout * Ktot * 4 <= 96 * 1024 && Ktot % 4 == 0) {
     const size_t smem = (size_t)p->Cout * Ktot * 4;
-    static bool attr = false;
-    if (!attr) {
+    static DevOnce attr;
+    if (attr.need()) {
       cudaFuncSetAttribute(conv_smallcout_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
       cudaFuncSetAttribute(conv_smallcout_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-      attr = true;
     }
     const size_t smem_t = (size_t)(SCT_TH + 2) * (SCT_TW + 2) * (Cin / 4 + 1) * 16 + smem;
     if (p->ksize == 3 && p->stride == 1 && p->pad == 1 && p->ups == 1 && !p->a1 && p->Hout == p->Hin && p->Wout == p->Win &&

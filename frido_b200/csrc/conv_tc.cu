@@ -443,14 +443,13 @@ int conv2d_tc(const FridoConvParams* p, cudaStream_t s) {
                                                 conv_tc_kernel<2, EPI_BIAS_RV_CS>, conv_tc_kernel<2, EPI_BIAS_RES_CS>,
                                                 conv_tc_kernel<2, EPI_BIAS_GEGLU>, conv_tc_kernel<2, EPI_BIAS_CS>,
                                                 conv_tc_kernel<2, EPI_BIAS_PAIR>};
-  static bool attr = false;
-  if (!attr) {
+  static DevOnce attr;
+  if (attr.need()) {
     bool ok = cudaFuncSetAttribute(conv_tc_kernel<0, EPI_GENERIC>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES) == cudaSuccess &&
               cudaFuncSetAttribute(conv_tc_kernel<1, EPI_GENERIC>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES) == cudaSuccess;
     for (int i = 0; i < EPI_COUNT && ok; ++i)
       ok = cudaFuncSetAttribute(bf_kernels[i], cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES) == cudaSuccess;
     if (!ok) return set_error(FRIDO_E_LAUNCH, "conv2d_tc: cannot opt in to dynamic shared memory");
-    attr = true;
   }
   // epilogue variant (BF16x3 only): the feature set of this launch, if one of the specialised kernels covers it
   int epi = EPI_GENERIC;

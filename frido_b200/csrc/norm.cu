@@ -516,11 +516,8 @@ extern "C" int frido_mha_small(const FridoMhaParams* p, void* stream) {
   if (!p || !p->qkv || !p->out || p->B <= 0 || p->L <= 0 || p->H <= 0 || p->Dh <= 0) return set_error(FRIDO_E_ARG, "mha_small: bad argument");
   const size_t smem = ((size_t)p->L * (p->Dh + 1) + (size_t)p->L * p->Dh + 8 * (size_t)p->L) * sizeof(float);
   if (smem > 200 * 1024) return set_error(FRIDO_E_ARG, "mha_small: sequence too long for shared memory");
-  static bool attr = false;
-  if (!attr) {
-    cudaFuncSetAttribute(mha_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    attr = true;
-  }
+  static DevOnce attr;
+  if (attr.need()) cudaFuncSetAttribute(mha_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   mha_small_kernel<<<p->B * p->H, 256, smem, (cudaStream_t)stream>>>(*p);
   return check_launch("mha_small");
 }

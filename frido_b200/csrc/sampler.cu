@@ -360,11 +360,8 @@ extern "C" int frido_vq_lookup(const FridoVqParams* p, void* stream) {
   if (p->e_dim <= 0 || p->e_dim > 8 || p->n_e <= 0) return set_error(FRIDO_E_ARG, "vq: e_dim must be 1..8");
   const size_t smem = ((size_t)p->n_e * p->e_dim + p->n_e) * sizeof(float);
   if (smem > 200 * 1024) return set_error(FRIDO_E_ARG, "vq: codebook exceeds shared memory");
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaFuncSetAttribute(vq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    attr_set = true;
-  }
+  static DevOnce attr_set;
+  if (attr_set.need()) cudaFuncSetAttribute(vq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   const int64_t n = (int64_t)p->B * p->HW;
   vq_kernel<<<(unsigned)((n + 255) / 256), 256, smem, (cudaStream_t)stream>>>(*p);
   return check_launch("vq_lookup");

@@ -1,12 +1,9 @@
 mkdir -p gpurun_out
-T=r02l
-timeout -k 5 240 python -m pytest tests/test_gpu_flash.py tests/test_gpu_pack.py -x -q --timeout=60 -p no:cacheprovider > gpurun_out/${T}_flash.log 2>&1; echo "rc=$?" >> gpurun_out/${T}_flash.log
-tail -8 gpurun_out/${T}_flash.log
-if grep -q "rc=0" gpurun_out/${T}_flash.log; then
-  timeout 120 python tools/prof/flash_bench.py > gpurun_out/${T}_flashbench.log 2>&1; cat gpurun_out/${T}_flashbench.log
-  PSTAGE=0 timeout 200 python tools/prof/perop.py > gpurun_out/${T}_perop_s0.log 2>&1
-  echo "$(grep GRAPH gpurun_out/${T}_perop_s0.log | cut -c1-60)"; grep "attn1" gpurun_out/${T}_perop_s0.log | head -6
-  timeout 200 ncu --set full --clock-control none --import-source on -k regex:attn_flash -s 3 -c 1 -o gpurun_out/${T}_flash python tools/prof/flash_bench.py 16x1024x384 > gpurun_out/${T}_ncu.log 2>&1; tail -2 gpurun_out/${T}_ncu.log
-  timeout -k 5 900 python -m pytest tests -m gpu -x -q --timeout=300 > gpurun_out/${T}_pytest.log 2>&1; echo "rc=$?" >> gpurun_out/${T}_pytest.log
-  tail -4 gpurun_out/${T}_pytest.log
-fi
+T=r02n
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.limit --format=csv > gpurun_out/${T}_smi.txt 2>&1
+timeout 700 python bench.py --steps 3 --warmup 3 > gpurun_out/${T}_bench.json 2> gpurun_out/${T}_bench.err; echo "bench rc=$?"
+tail -c 2500 gpurun_out/${T}_bench.json
+timeout 420 python tools/prof/drift.py --steps 200 --out gpurun_out/${T}_drift.json > gpurun_out/${T}_drift.log 2>&1; cat gpurun_out/${T}_drift.json | head -30
+timeout 400 ncu --profile-from-start off --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none --csv --log-file gpurun_out/${T}_step.csv python tools/prof/ncu_step.py > gpurun_out/${T}_ncu_step.log 2>&1
+cp gpurun_out/step_ops.json gpurun_out/${T}_step_ops.json
+timeout 500 python bench.py --impl reference --steps 1 --warmup 0 > gpurun_out/${T}_ref.json 2> gpurun_out/${T}_ref.err; echo "ref rc=$?"; tail -c 800 gpurun_out/${T}_ref.json

@@ -19,6 +19,9 @@ for op, tag in zip(plan.step.ops, plan.step.tags):
         c = op.u.conv
         d.update(engine=c.engine, flops=2 * c.B * c.Hout * c.Wout * c.Cout * (c.ksize * c.ksize * (c.c0 + c.c1) + c.cx0 + c.cx1),
                  shape=f"B{c.B} {c.Hout}x{c.Wout} cin{c.c0}+{c.c1} cout{c.Cout} k{c.ksize} s{c.stride}")
+    elif op.kind == L.OP_FLASH:
+        a = op.u.flash
+        d.update(engine=3, flops=4 * a.B * a.N * a.N * a.C, shape=f"B{a.B} N{a.N} C{a.C}")
     ops.append(d)
 json.dump(ops, open('/root/repo/gpurun_out/step_ops.json', 'w'))
 torch.cuda.profiler.start()
