@@ -243,13 +243,13 @@ def test_full_size_l2i_step_and_decoder(dev, golden_dir, engine):
                 assert (p0.cpu() - g[f"step_s{s}_predx0"]).abs().max() < 40 * EPS_TOL  # x0 = (x - s1m*eps)/sqrt(a_t), 1/sqrt(a_996) = 38
 
 
-SWITCHES = ["FRIDO_SK", "FRIDO_ATTN_SMALL", "FRIDO_ATTN_FOLD", "FRIDO_FUSE_SKIP", "FRIDO_EPI_SPEC", "FRIDO_FUSE_NORM"]
+SWITCHES = ["FRIDO_SK", "FRIDO_ATTN_SMALL", "FRIDO_ATTN_FOLD", "FRIDO_FUSE_SKIP", "FRIDO_EPI_SPEC", "FRIDO_FUSE_NORM", "FRIDO_FLASH"]
 
 
 @pytest.mark.parametrize("off", SWITCHES)
 def test_fusion_switches_keep_the_result(dev, golden_dir, off, monkeypatch):
     """Every scheduling / fusion step of the UNet plan (stream-K, fused short-sequence attention, folded attention weight
-    products, skip_connection fused into conv2, specialised epilogues) can be switched off; the full-size UNet's eps with a
+    products, skip_connection fused into conv2, specialised epilogues, norm modes, streaming-softmax attention) can be switched off; the full-size UNet's eps with a
     switch off must still match the golden vectors of the unmodified reference, and agree with the default plan to fp32
     re-association level."""
     import frido_b200 as fb
@@ -281,6 +281,9 @@ def test_fusion_switches_keep_the_result(dev, golden_dir, off, monkeypatch):
         assert "attn1.out" in tags_off and "attn1.out" not in tags_def
     if off == "FRIDO_ATTN_SMALL":
         assert "attn2.block" in tags_def and "attn2.block" not in tags_off
+    if off == "FRIDO_FLASH":  # streaming-softmax kernel vs QK^T -> softmax -> PV with the scores in HBM
+        assert "attn1.flash" in tags_def and "attn1.softmax" not in tags_def
+        assert "attn1.flash" not in tags_off and "attn1.softmax" in tags_off
     if off == "FRIDO_FUSE_NORM":  # stage 1 of this model has SPADE maps at every site: default = split operands, no fused norms
         assert "gn_finalize" not in tags_off and sum(t in ("res.norm1", "res.norm2") for t in tags_off) == 44
 

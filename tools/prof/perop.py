@@ -5,11 +5,11 @@ torch.set_grad_enabled(False)
 import frido_b200 as fb
 from frido_b200 import configs, _lib as L
 dev = torch.device('cuda:0')
-model, cfg = configs.build('l2i_coco', dev)
-B = int(os.environ.get('PB', '16'))
+model, cfg = configs.build(os.environ.get('PCONFIG', 'l2i_coco'), dev)
+B = int(os.environ.get('PB', str(cfg['batch'])))
 unet = model.model.diffusion_model
 stage = int(os.environ.get('PSTAGE', '1'))
-plan = unet.plan(stage, B, 64, 64, 26)
+plan = unet.plan(stage, B, cfg['latent'][1], cfg['latent'][2], cfg['ctx'][0])
 plan.prologue.run(); plan.step.run(); torch.cuda.synchronize()
 lib = L.lib()
 ops, tags = plan.step.ops, plan.step.tags
