@@ -2,7 +2,7 @@
 reference's checkpoints (`state_dict` keys and tensor layouts) load unchanged
 (SURVEY.md §8b).  These modules hold weights only: none of them has a torch
 forward — the arithmetic lives in the CUDA library and is scheduled by
-unet_engine.py / decoder_engine.py.
+unet.py (UNetPlan) / first_stage.py (DecodePlan, EncodePlan) / cond.py.
 
 Key layout follows frido/modules/diffusionmodules/pyunet.py:477-835,
 frido/modules/attention.py:152-287, frido/modules/diffusionmodules/spade_norm.py:26-42

@@ -35,7 +35,11 @@ _SK_WS = {}
 
 def sk_workspace(device):
     """One zero-initialised stream-K workspace per device (FridoConvParams.sk_ws): launches on a stream execute in order and
-    every launch leaves its arrival counters at zero, so all programs of a device share it."""
+    every launch leaves its arrival counters at zero, so all programs of a device share it.
+    CONTRACT (single stream per device): programs of one device must not run CONCURRENTLY on different streams - the arrival
+    counters and partial-accumulator slots are shared, and the library's launch-chaining flag is per process.  The host
+    runtime only ever enqueues on torch's current stream (and the graphs captured from it); a host that wants two concurrent
+    streams on one device passes each its own `sk_ws` (frido_workspace_bytes) in FridoConvParams."""
     device = torch.device(device)
     key = (device.type, device.index if device.index is not None else torch.cuda.current_device())
     ws = _SK_WS.get(key)
