@@ -58,7 +58,7 @@ __device__ __forceinline__ float row_sum(float v) {
 
 // SINGLE: all keys fit one chunk (Nk <= KC): straight-line code, q is dead before the accumulator comes alive.
 template <int NJ, int R, bool SINGLE>
-__global__ void __launch_bounds__(ATTN_WARPS * 32, SINGLE ? 2 : 1) attn_small_kernel(const FridoAttnParams p, int KC) {
+__global__ void __launch_bounds__(ATTN_WARPS * 32, SINGLE ? 2 : 1) attn_small_kernel(const FridoAttnParams p, int KC, int iters) {
   constexpr int KB = 32 / R;  // keys per reduction block (32 (key,row) pairs)
   constexpr int NB = R;       // blocks per chunk (KC <= 32)
   extern __shared__ float4 attn_sm[];
@@ -67,7 +67,6 @@ __global__ void __launch_bounds__(ATTN_WARPS * 32, SINGLE ? 2 : 1) attn_small_ke
   float4* Vs = attn_sm + (size_t)KC * Q;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.y;
-  const int row0 = (blockIdx.x * ATTN_WARPS + warp) * R;
   pdl_trigger();
   pdl_wait();
 
@@ -87,6 +86,10 @@ __global__ void __launch_bounds__(ATTN_WARPS * 32, SINGLE ? 2 : 1) attn_small_ke
   };
   stage(0, min(KC, p.Nk));
 
+  // `iters` row groups per CTA (SINGLE only): the staged K / V chunk is reused, so launches whose CTAs would come in more
+  // than one wave pay the staging once per CTA instead of once per 8*R rows
+  for (int it = 0; it < iters; ++it) {
+  const int row0 = ((blockIdx.x * iters + it) * ATTN_WARPS + warp) * R;
   float4 q[R][NJ], o[R][NJ];
 #pragma unroll
   for (int r = 0; r < R; ++r) {
@@ -276,6 +279,7 @@ __global__ void __launch_bounds__(ATTN_WARPS * 32, SINGLE ? 2 : 1) attn_small_ke
       }
     }
   }
+  }  // row groups
 }
 
 template <int NJ, int R, bool SINGLE>
@@ -286,8 +290,15 @@ static int launch_attn2(const FridoAttnParams* p, int KC, cudaStream_t s) {
       return set_error(FRIDO_E_LAUNCH, "attn_small: cannot opt in to dynamic shared memory");
   }
   const size_t smem = (size_t)2 * KC * p->C * sizeof(float);
-  dim3 grid((p->N + ATTN_WARPS * R - 1) / (ATTN_WARPS * R), p->B);
-  launch_pdl(attn_small_kernel<NJ, R, SINGLE>, grid, dim3(ATTN_WARPS * 32), smem, s, *p, KC);
+  const int groups = (p->N + ATTN_WARPS * R - 1) / (ATTN_WARPS * R);
+  // row groups per CTA: grow until the launch fits one wave of resident CTAs (at most 4)
+  int iters = 1;
+  if (SINGLE) {
+    const int per_sm = smem > 110 * 1024 ? 1 : 2;
+    while (iters < 4 && (long long)((groups + iters - 1) / iters) * p->B > 148LL * per_sm) ++iters;
+  }
+  dim3 grid((groups + iters - 1) / iters, p->B);
+  launch_pdl(attn_small_kernel<NJ, R, SINGLE>, grid, dim3(ATTN_WARPS * 32), smem, s, *p, KC, iters);
   return check_launch("attn_small");
 }
 

@@ -296,8 +296,9 @@ class UNetPlan:
           'fused' (1)  the conv normalises on load (csrc/conv_nf.cu): no norm_act pass, no normalised tensor in memory;
           'split' (2)  norm_act writes the engine's bf16 hi | lo operand form and the conv's halo-resident path just feeds it;
           'plain' (0)  norm_act writes fp32, the conv re-fetches and splits the tile per filter tap (csrc/conv_tc.cu).
-        Default 'auto': fused where the conv has a single N tile and no SPADE maps to stream (the prep work of a fused conv
-        is repeated per N tile, and the maps are re-read per N tile and per halo), split elsewhere."""
+        Default 'auto': fused where there are no SPADE maps to stream (stage 0, and models without SPADE: measured 12.56 ms
+        per step against 12.74 with only the single-N-tile sites fused and 12.85 plain), split where there are (a fused conv
+        re-reads the maps per N tile and per halo: 14.4 against 13.1 ms)."""
         mode = os.environ.get("FRIDO_FUSE_NORM", "auto")
         a1 = Src.nhwc(xs[1], h, w) if len(xs) > 1 else None
         if mode == "0" or any(c % 32 for c in cs) or not prog.nf_eligible(Src.nhwc(xs[0], h, w), a1, out, B=self.B, H=h, W=w, Cout=Cout, ksize=ksize):
@@ -309,7 +310,8 @@ class UNetPlan:
         if mode == "2":
             return "split"
         spade = isinstance(norm, M.SPADE) and bool(self.c_cond)
-        return "fused" if (not spade and Cout <= 192) else "split"
+        wide = os.environ.get("FRIDO_FUSE_NORM_WIDE", "1") == "1"   # A/B aid: 0 = fuse only single-N-tile convs (C_out <= 192)
+        return "fused" if (not spade and (wide or Cout <= 192)) else "split"
 
     def _norm_on_load(self, prog, xs, cs, h, w, norm, eps, silu, out, Cout, ksize):
         """GroupNorm(+SPADE)(+SiLU) handed to the consuming conv instead of a norm_act pass (csrc/conv_nf.cu): emits the
