@@ -291,7 +291,7 @@ class UNetPlan:
                       c1=c1, gb=gb, silu=silu, round_tf32=prog.R, csum0=cs0, csum1=cs1, out_split=out_split, tag=site)
         return out
 
-    def _norm_mode(self, prog, xs, cs, h, w, norm, out, Cout, ksize):
+    def _norm_mode(self, prog, xs, cs, h, w, norm, out, Cout, ksize, side=False):
         """How the GroupNorm (+SPADE) (+SiLU) in front of a conv reaches the tensor core (FRIDO_FUSE_NORM):
           'fused' (1)  the conv normalises on load (csrc/conv_nf.cu): no norm_act pass, no normalised tensor in memory;
           'split' (2)  norm_act writes the engine's bf16 hi | lo operand form and the conv's halo-resident path just feeds it;
@@ -305,6 +305,8 @@ class UNetPlan:
             return "plain"
         if ksize == 1:
             return "fused" if os.environ.get("FRIDO_FUSE_NORM_1X1", "0") == "1" else "plain"
+        if side and mode == "auto" and os.environ.get("FRIDO_FUSE_NORM_SIDE", "1") == "0":
+            return "plain"   # A/B aid: convs that carry the fused 1x1 skip input stay on conv_tc.cu
         if mode == "1":
             return "fused"
         if mode == "2":
@@ -313,12 +315,12 @@ class UNetPlan:
         wide = os.environ.get("FRIDO_FUSE_NORM_WIDE", "1") == "1"   # A/B aid: 0 = fuse only single-N-tile convs (C_out <= 192)
         return "fused" if (not spade and (wide or Cout <= 192)) else "split"
 
-    def _norm_on_load(self, prog, xs, cs, h, w, norm, eps, silu, out, Cout, ksize):
+    def _norm_on_load(self, prog, xs, cs, h, w, norm, eps, silu, out, Cout, ksize, side=False):
         """GroupNorm(+SPADE)(+SiLU) handed to the consuming conv instead of a norm_act pass (csrc/conv_nf.cu): emits the
         tiny statistics -> (scale, shift) kernel and returns (`nrm` argument of Program.conv, buffer to release after the
         conv), or None when the conv cannot normalise on load (then `_norm` materialises the tensor as before)."""
         B = self.B
-        if self._norm_mode(prog, xs, cs, h, w, norm, out, Cout, ksize) != "fused":
+        if self._norm_mode(prog, xs, cs, h, w, norm, out, Cout, ksize, side) != "fused":
             return None
         hw = h * w
         C = sum(cs)
@@ -379,11 +381,12 @@ class UNetPlan:
             S.release(t1)
         a1 = Src.nhwc(xs[1], h, w) if len(xs) > 1 else None
         out = S.buf(B, hw, cout)
-        nf = self._norm_on_load(S, [h1], [cout], h, w, rb.out_layers[0], 1e-5, 1, out, cout, 3)
+        side2 = isinstance(rb.skip_connection, nn.Conv2d) and os.environ.get("FRIDO_FUSE_SKIP", "1") == "1"
+        nf = self._norm_on_load(S, [h1], [cout], h, w, rb.out_layers[0], 1e-5, 1, out, cout, 3, side=side2)
         if nf is not None:
             src2, t2 = Src.nhwc(h1, h, w), None
         else:
-            sp2 = self._norm_mode(S, [h1], [cout], h, w, rb.out_layers[0], out, cout, 3) == "split"
+            sp2 = self._norm_mode(S, [h1], [cout], h, w, rb.out_layers[0], out, cout, 3, side=side2) == "split"
             t2 = self._norm(S, [h1], [cout], h, w, rb.out_layers[0], 1e-5, 1, "res.norm2", out_split=int(sp2))
             S.release(h1)
             src2 = Src.nhwc(t2, h, w)

@@ -1,13 +1,9 @@
 mkdir -p gpurun_out
-T=r02p
-run() { # name, env...
-  name=$1; shift
-  env "$@" PSTAGE=0 timeout 200 python tools/prof/perop.py > gpurun_out/${T}_perop_s0_$name.log 2>&1
-  echo "$name: $(grep GRAPH gpurun_out/${T}_perop_s0_$name.log | cut -c1-60)"
-}
-run narrow FRIDO_FUSE_NORM_WIDE=0
-run wide FRIDO_FUSE_NORM_WIDE=1
-run wide1x1 FRIDO_FUSE_NORM_WIDE=1 FRIDO_FUSE_NORM_1X1=1
-run plain FRIDO_FUSE_NORM=0
-timeout -k 5 500 python -m pytest tests/test_gpu_model.py -x -q --timeout=300 -k "norm_modes or fusion_switches" > gpurun_out/${T}_model.log 2>&1; echo "rc=$?" >> gpurun_out/${T}_model.log
-tail -3 gpurun_out/${T}_model.log
+T=r02q
+timeout -k 5 400 python -m pytest tests/test_gpu_kernels.py -x -q --timeout=120 -k "attn" > gpurun_out/${T}_attn.log 2>&1; echo "rc=$?" >> gpurun_out/${T}_attn.log
+tail -3 gpurun_out/${T}_attn.log
+for st in 0 1; do
+PALL=1 PSTAGE=$st timeout 200 python tools/prof/perop.py > gpurun_out/${T}_perop_s$st.log 2>&1
+echo "$(grep GRAPH gpurun_out/${T}_perop_s$st.log | cut -c1-60)"; grep "^attn2.block\|^attn1.fused" gpurun_out/${T}_perop_s$st.log
+done
+grep "attn2.block  \|attn1.fused  " gpurun_out/${T}_perop_s0.log | sort | uniq -c | sort -rn | head -12
