@@ -20,6 +20,10 @@
 //   tile i overlaps the main loop of tile i+1.
 #include "tc_common.cuh"
 
+#ifndef FRIDO_TC_PAIR_DEFAULT
+#define FRIDO_TC_PAIR_DEFAULT 0
+#endif
+
 namespace frido {
 
 // ----------------------------------------------------------------------------
@@ -276,6 +280,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
   }
 }
 
+int conv2d_tc_pair_launch(const TcParams& t, int epi, int clusters, const CUtensorMap& ma0, const CUtensorMap& ma1,
+                          const CUtensorMap& mw, const CUtensorMap& mwlo, const CUtensorMap& mx0, const CUtensorMap& mx1,
+                          cudaStream_t s);
+
 int conv2d_tc(const FridoConvParams* p, cudaStream_t s) {
   if (!p->a0 || !p->w || (!p->out && !(p->out_hi && p->o_sn != 1))) return set_error(FRIDO_E_ARG, "conv2d_tc: null pointer");
   if (p->ups != 1) return set_error(FRIDO_E_ARG, "conv2d_tc: ups must be 1 (materialise the upsample first)");
@@ -358,7 +366,7 @@ int conv2d_tc(const FridoConvParams* p, cudaStream_t s) {
   }
   // Stream-K for launches that cannot fill the machine with whole tiles (8x8 / 16x16 levels, long K): compare the
   // data-parallel schedule chosen above with an even split of all (tile, k-step) iterations over the SMs, in clocks.
-  t.sk = 0; t.sk_per = 0; t.sk_ws = nullptr; t.sk_cnt = nullptr;
+  t.sk = 0; t.sk_per = 0; t.sk_ws = nullptr; t.sk_cnt = nullptr; t.pair = 0;
   int sk_grid = 0;
   {
     const int ksteps = p->ksize * p->ksize * (Cin / TC_BK) + (p->cx0 + p->cx1) / TC_BK;
@@ -469,6 +477,24 @@ int conv2d_tc(const FridoConvParams* p, cudaStream_t s) {
       } else if (p->act == FRIDO_ACT_GEGLU_FAST && !res && !rv && !cs) {
         epi = EPI_BIAS_GEGLU;
       }
+    }
+  }
+  // CTA-pair schedule (conv_tc2.cu, cta_group::2): two M tiles of one N tile per cluster, each CTA holds half of the W tile.
+  // FRIDO_TC_PAIR: 0 = never, 1 = launches with at least one full wave of pairs (default), 2 = whenever legal (tests)
+  {
+    const char* e = getenv("FRIDO_TC_PAIR");
+    const int pair_env = e ? atoi(e) : FRIDO_TC_PAIR_DEFAULT;
+    const long long items = (long long)(m_tiles / 2) * t.tiles_n;
+    if (bf && pair_env && !t.sk && !p->w_sb && m_tiles % 2 == 0 && bn % 32 == 0 && (pair_env == 2 || items >= sms / 2)) {
+      t.pair = 1;
+      CUtensorMap mwh, mwl;
+      if (!make_map3(&mwh, p->w, Ktot, p->Cout, 1, w_ld, 0, bn / 2, true) || !make_map3(&mwl, p->w_lo, Ktot, p->Cout, 1, w_ld, 0, bn / 2, true))
+        return set_error(FRIDO_E_ARG, "conv2d_tc: cuTensorMapEncodeTiled(w, pair) failed");
+      const int sb = TC_A_BYTES + 2 * (bn / 2) * TC_BK * 2;
+      t.stages = TC_SMEM_BUDGET / sb;   // shared-memory ring; the tensor-memory operand ring behind it has TC_BF_MAX_STAGES slots
+      if (t.stages > TC_MAX_STAGES) t.stages = TC_MAX_STAGES;
+      const int clusters = (int)(items < sms / 2 ? items : sms / 2);
+      return conv2d_tc_pair_launch(t, epi, clusters, ma0, ma1, mwh, mwl, mx0, mx1, s);
     }
   }
   const bool x3 = p->engine == 2;

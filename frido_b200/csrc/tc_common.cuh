@@ -54,14 +54,23 @@ struct TcParams {
   int sk_per;           // iterations (k-steps) per CTA
   float4* sk_ws;        // [2 * grid][BN/16][4][128] float4 partial-accumulator slots
   int* sk_cnt;          // [tiles] arrival counters, zero between launches
+  // CTA-pair schedule (conv_tc2.cu, cta_group::2): a cluster of two CTAs takes the M tiles (2q, 2q+1) of one N tile; work items
+  // are (q, n-tile) pairs, one per cluster at a time
+  int pair;             // 1 = CTA-pair kernel
 };
 
 // Work iterator shared by all warp roles: yields (tile, [k0, k1)) segments in the same order everywhere.
 struct SegIter {
-  int sk, ksteps, total_tiles, stride, cur, end;
+  int sk, ksteps, total_tiles, stride, cur, end, pair, rank, tiles_n;
   __device__ __forceinline__ SegIter(const TcParams& p, int ksteps_, int total_tiles_)
-      : sk(p.sk), ksteps(ksteps_), total_tiles(total_tiles_), stride((int)gridDim.x) {
-    if (sk) {
+      : sk(p.sk), ksteps(ksteps_), total_tiles(total_tiles_), stride((int)gridDim.x), pair(p.pair), rank(0), tiles_n(p.tiles_n) {
+    if (pair) {  // items = (M-tile pair, N tile); cluster c starts at item c and strides by the number of clusters
+      rank = (int)(blockIdx.x & 1);
+      cur = (int)(blockIdx.x >> 1);
+      stride = (int)(gridDim.x >> 1);
+      total_tiles = total_tiles_ >> 1;  // items
+      end = 0;
+    } else if (sk) {
       cur = (int)blockIdx.x * p.sk_per;
       end = min(cur + p.sk_per, total_tiles_ * ksteps_);
     } else {
@@ -70,6 +79,12 @@ struct SegIter {
     }
   }
   __device__ __forceinline__ bool next(int& tile, int& k0, int& k1) {
+    if (pair) {
+      if (cur >= total_tiles) return false;
+      const int q = cur / tiles_n, nt = cur - q * tiles_n;
+      tile = (2 * q + rank) * tiles_n + nt; k0 = 0; k1 = ksteps; cur += stride;
+      return true;
+    }
     if (!sk) {
       if (cur >= total_tiles) return false;
       tile = cur; k0 = 0; k1 = ksteps; cur += stride;
@@ -107,6 +122,22 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       "WAIT_DONE:\n"
       "}\n" ::"r"(bar), "r"(parity)
       : "memory");
+}
+// ---- thread-block cluster helpers (CTA-pair kernel)
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of `local_addr` (a shared::cta address) in the CTA of rank `rank`
+__device__ __forceinline__ uint32_t mapa_rank(uint32_t local_addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(rank));
+  return r;
+}
+// Remote arrive with the default (.release.cta) semantics, as CUTLASS's ClusterBarrier::arrive(cta_id): what the waiter consumes
+// was produced through tcgen05 / TMA and is ordered by the tcgen05 fences, not by this arrive.  (`.release.cluster` compiles
+// to MEMBAR.ALL.GPU + ERRBAR per arrive - measured: it alone held the pair kernel at 0.9 us per k-step.)
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -204,6 +235,24 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint6
       "}\n" ::"r"(tmem_d),
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
+}
+// cta_group::2: one instruction drives the tensor cores of both CTAs of the pair (M = 256: 128 rows per CTA, each CTA holds its
+// own A rows in tensor memory and HALF of the B tile's rows in shared memory at the same offset); issued by the leader CTA only
+__device__ __forceinline__ void umma_bf16_ts_2cta(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// completion of all prior MMAs of the pair -> one arrive on the barrier at this shared-memory offset in BOTH CTAs
+__device__ __forceinline__ void umma_commit_2cta(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+               "h"((uint16_t)3)
+               : "memory");
 }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
@@ -308,7 +357,7 @@ __device__ __forceinline__ void tc_epilogue_role(const TcParams& p, uint8_t* sme
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar(acc));  // the accumulator is free again
+      if (lane == 0) mbar_arrive(tempty_bar(acc));  // the accumulator is free again (stream-K is never a pair launch)
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       first_seg = false;
       c_first = (tile * ksteps) / p.sk_per;
@@ -516,7 +565,10 @@ __device__ __forceinline__ void tc_epilogue_role(const TcParams& p, uint8_t* sme
     if (!from_ws) {
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar(acc));
+      if (lane == 0) {
+        if (p.pair) mbar_arrive_cluster(mapa_rank(tempty_bar(acc), 0));  // the leader CTA's MMA thread waits for both epilogues
+        else mbar_arrive(tempty_bar(acc));
+      }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   }

@@ -45,4 +45,4 @@ for si in sel:
             ts.append(a.elapsed_time(b) * 1e3)
         ts.sort()
         t = ts[len(ts) // 2]
-        print(f"B{B} {H}x{W} cin{cin} cout{cout} k{k} BN={bn or 'auto':>4}  {t:8.1f} us  {fl / t / 1e6:7.1f} TF/s  (min {ts[0]:.1f})", flush=True)
+        print(f"pair={os.environ.get('FRIDO_TC_PAIR', '-')} B{B} {H}x{W} cin{cin} cout{cout} k{k} BN={bn or 'auto':>4}  {t:8.1f} us  {fl / t / 1e6:7.1f} TF/s  (min {ts[0]:.1f})", flush=True)

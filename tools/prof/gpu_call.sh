@@ -1,9 +1,8 @@
 mkdir -p gpurun_out
-T=r02q
-timeout -k 5 400 python -m pytest tests/test_gpu_kernels.py -x -q --timeout=120 -k "attn" > gpurun_out/${T}_attn.log 2>&1; echo "rc=$?" >> gpurun_out/${T}_attn.log
-tail -3 gpurun_out/${T}_attn.log
-for st in 0 1; do
-PALL=1 PSTAGE=$st timeout 200 python tools/prof/perop.py > gpurun_out/${T}_perop_s$st.log 2>&1
-echo "$(grep GRAPH gpurun_out/${T}_perop_s$st.log | cut -c1-60)"; grep "^attn2.block\|^attn1.fused" gpurun_out/${T}_perop_s$st.log
-done
-grep "attn2.block  \|attn1.fused  " gpurun_out/${T}_perop_s0.log | sort | uniq -c | sort -rn | head -12
+T=r02u
+timeout -k 5 120 python -m pytest tests/test_gpu_pair.py -x -q --timeout=40 -p no:cacheprovider > gpurun_out/${T}_pair.log 2>&1; echo "rc=$?" >> gpurun_out/${T}_pair.log
+tail -5 gpurun_out/${T}_pair.log
+if grep -q "rc=0" gpurun_out/${T}_pair.log; then
+  for pr in 0 2; do FRIDO_TC_PAIR=$pr FRIDO_SK=0 timeout 120 python tools/prof/conv_bench.py 7 8 9 4 5 >> gpurun_out/${T}_convbench.log 2>&1; done
+  cat gpurun_out/${T}_convbench.log
+fi
