@@ -28,6 +28,10 @@
 // nothing else), 16-19 = prep (normalise / activate / split in place, running ahead of the feed through the slot ring).
 #include "tc_common.cuh"
 
+#ifndef FRIDO_NF_PAIR_DEFAULT
+#define FRIDO_NF_PAIR_DEFAULT 0   // measured neutral on this engine (its feed / prep warps, not the W operand, set its pace)
+#endif
+
 namespace frido {
 
 constexpr int NF_THREADS = 640;                 // 5 warpgroups: control | epilogue x2 | feed | prep
@@ -172,7 +176,7 @@ static_assert(128 * NF_REGS_CTRL + 256 * NF_REGS_EPI + 128 * NF_REGS_FEED + 128 
 template <int N> __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
 template <int N> __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
 
-template <int EPI>
+template <int EPI, bool PAIR>
 __global__ void __launch_bounds__(NF_THREADS, 1)
 conv_nf_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
                const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_wlo,
@@ -184,7 +188,11 @@ conv_nf_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
   // operand region (TC_SMEM_BUDGET): halo ring (a_slots x slot_bytes) | [SPADE gamma / beta ring] | weight ring
   const uint32_t gb_ring = (uint32_t)q.a_slots * q.slot_bytes;
   const uint32_t w_off = gb_ring + (q.has_gb ? (uint32_t)(NF_GB_DEPTH * NF_GB_STEP_BYTES) : 0u);
-  const uint32_t b_bytes = (uint32_t)p.BN * TC_BK * 2;
+  // CTA-pair launches (PAIR, tcgen05.mma.cta_group::2 - see conv_tc2.cu): each CTA of the cluster owns one M tile (its own halo,
+  // prep and feed) and HALF of the W tile's rows; the leader CTA issues the MMAs for both
+  const uint32_t rank = PAIR ? (blockIdx.x & 1u) : 0u;
+  const int HBN = PAIR ? (p.BN >> 1) : p.BN;
+  const uint32_t b_bytes = (uint32_t)HBN * TC_BK * 2;
   const uint32_t w_stage_bytes = 2u * b_bytes;
   const uint32_t bar_base = smem_base + TC_SMEM_BUDGET + TC_STG_BYTES + TC_CSUM_BYTES;
   // barrier slots: w_full[6] 0.. | w_empty[6] 6.. | t_full[4] 12.. | (18..23 shared with the epilogue role) | t_empty[4] 24..
@@ -217,19 +225,26 @@ conv_nf_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
     prefetch_tmap(&map_w);
     prefetch_tmap(&map_wlo);
     for (int s = 0; s < TC_MAX_STAGES; ++s) { mbar_init(w_full(s), 1); mbar_init(w_empty(s), 1); }
-    for (int s = 0; s < NF_TSLOTS; ++s) { mbar_init(t_full(s), TC_SPLIT_WARPS); mbar_init(t_empty(s), 1); }
+    const uint32_t ncta = PAIR ? 2u : 1u;  // the leader's t_full / tempty barriers collect both CTAs of a pair
+    for (int s = 0; s < NF_TSLOTS; ++s) { mbar_init(t_full(s), ncta * TC_SPLIT_WARPS); mbar_init(t_empty(s), 1); }
     for (int s = 0; s < NF_MAX_ASLOTS; ++s) {
       mbar_init(a_full(s), 1); mbar_init(a_empty(s), TC_SPLIT_WARPS); mbar_init(a_ready(s), TC_SPLIT_WARPS);
     }
-    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), TC_EPI_WARPS); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), ncta * TC_EPI_WARPS); }
     fence_barrier_init();
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512u) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (PAIR) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512u) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512u) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   tc_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();  // the peer's barriers exist before anyone arrives on them remotely
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
   pdl_wait();
@@ -242,7 +257,7 @@ conv_nf_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
       uint32_t phase = 0;
       NfCursor c(p, n_units, total_tiles);
       for (c.advance(p, q); c.valid; c.advance(p, q)) {
-        const int n0 = (c.tile % p.tiles_n) * p.BN;
+        const int n0 = (c.tile % p.tiles_n) * p.BN + (int)rank * HBN;
         const int nk = c.chunk ? q.taps : 1;
         for (int t = 0; t < nk; ++t) {
           // weight columns run [tap][channel] then the side input's channels
@@ -275,8 +290,9 @@ conv_nf_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
           else            tma_load_4d(dst, &map_x1, a_full(c.slot), ch - p.cx0, c.ox0, c.oy0, c.b0);
         }
       }
-    } else if (warp == 1 && lane == 0) {
-      const uint32_t idesc = umma_idesc_bf16(TC_BM, p.BN);
+    } else if (warp == 1 && lane == 0 && rank == 0) {
+      const bool pr = PAIR;
+      const uint32_t idesc = umma_idesc_bf16(pr ? 2 * TC_BM : TC_BM, p.BN);
       int stage = 0, tslot = 0, acc = 0;
       uint32_t phase = 0, tphase = 0, acc_phase = 0;
       SegIter it(p, n_units, total_tiles);
@@ -299,18 +315,25 @@ conv_nf_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
             for (int k = 0; k < TC_BK / 16; ++k) {
               const uint32_t ah = tmem_base + (uint32_t)(TC_BF_A_COL + tslot * 32 + k * 8), al = ah + 16;
               const uint64_t bh = umma_desc_sw64(sb + k * 32), bl = umma_desc_sw64(sb + b_bytes + k * 32);
-              umma_bf16_ts(d_tmem, ah, bh, idesc, (first && k == 0) ? 0u : 1u);
-              umma_bf16_ts(d_tmem, al, bh, idesc, 1u);
-              umma_bf16_ts(d_tmem, ah, bl, idesc, 1u);
+              if (pr) {
+                umma_bf16_ts_2cta(d_tmem, ah, bh, idesc, (first && k == 0) ? 0u : 1u);
+                umma_bf16_ts_2cta(d_tmem, al, bh, idesc, 1u);
+                umma_bf16_ts_2cta(d_tmem, ah, bl, idesc, 1u);
+              } else {
+                umma_bf16_ts(d_tmem, ah, bh, idesc, (first && k == 0) ? 0u : 1u);
+                umma_bf16_ts(d_tmem, al, bh, idesc, 1u);
+                umma_bf16_ts(d_tmem, ah, bl, idesc, 1u);
+              }
             }
             first = false;
-            umma_commit(w_empty(stage));   // frees the weight stage ...
-            umma_commit(t_empty(tslot));   // ... and the tensor-memory operand slot when these MMAs retire
+            // frees the weight stage and the tensor-memory operand slot when these MMAs retire (in both CTAs of a pair)
+            if (pr) { umma_commit_2cta(w_empty(stage)); umma_commit_2cta(t_empty(tslot)); }
+            else    { umma_commit(w_empty(stage)); umma_commit(t_empty(tslot)); }
             if (++stage == q.w_stages) { stage = 0; phase ^= 1; }
             if (++tslot == NF_TSLOTS) { tslot = 0; tphase ^= 1; }
           }
         }
-        umma_commit(tfull_bar(acc));  // accumulator ready for the epilogue
+        if (pr) umma_commit_2cta(tfull_bar(acc)); else umma_commit(tfull_bar(acc));  // accumulator ready for the epilogue(s)
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
@@ -329,6 +352,19 @@ conv_nf_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
     const int px = m & (p.TW - 1), py = (m >> p.lTW) & (p.TH - 1), pb = m >> (p.lTW + p.lTH);
     const int r0 = (pb * q.HH2 + py) * q.HW2 + px;  // halo row of tap (0, 0) for this output pixel
     int tseq = 0, pend = -1;
+    // pair launches: a k-step is only announced (to the LEADER's t_full) once this CTA's half of the W tile has landed too -
+    // the weight ring advances in lockstep with the k-steps, so the feed can follow it
+    int wst = 0;
+    uint32_t wph = 0;
+    auto announce = [&](int slot_) {
+      if (PAIR) {
+        mbar_wait(w_full(wst), wph);
+        if (++wst == q.w_stages) { wst = 0; wph ^= 1; }
+        if (lane == 0) mbar_arrive_cluster(mapa_rank(t_full(slot_), 0));
+      } else if (lane == 0) {
+        mbar_arrive(t_full(slot_));
+      }
+    };
     NfCursor F(p, n_units, total_tiles);
     for (F.advance(p, q); F.valid; F.advance(p, q)) {
       const uint8_t* xs = smem_gen + (size_t)F.slot * q.slot_bytes;
@@ -350,7 +386,7 @@ conv_nf_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
           asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(t_full(pend));
+          announce(pend);
         }
         const int tslot = tseq & (NF_TSLOTS - 1);
         mbar_wait(t_empty(tslot), (uint32_t)(((tseq >> 2) & 1) ^ 1));  // the MMAs that last read this slot have retired
@@ -369,7 +405,7 @@ conv_nf_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
       asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(t_full(pend));
+      announce(pend);
     }
     static_assert(NF_TSLOTS == 4, "the feed assumes four tensor-memory operand slots");
   } else {
@@ -463,9 +499,11 @@ conv_nf_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
 
   tc_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();  // nobody frees tensor memory or exits while the pair's MMAs / remote arrives may still touch it
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    if (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    else        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
   }
 }
 
@@ -615,7 +653,15 @@ int conv2d_nf(const FridoConvParams* p, cudaStream_t s) {
   t.out_hi = (uint16_t*)p->out_hi; t.out_lo = (uint16_t*)p->out_lo;
   t.stages = 0;
   if (p->chan_sums && (t.TW * t.TH < 32 || t.TB > 4)) return set_error(FRIDO_E_ARG, "conv2d_nf: chan_sums needs >= 32 pixels per image");
-  q.w_stages = ring_budget / (bn * 128);
+  // CTA-pair schedule (cta_group::2): FRIDO_NF_PAIR = 0 never (default) | 1 launches with a full wave of pairs | 2 whenever legal
+  {
+    const char* e = getenv("FRIDO_NF_PAIR");
+    const int pair_env = e ? atoi(e) : FRIDO_NF_PAIR_DEFAULT;
+    const long long items = (long long)(m_tiles / 2) * t.tiles_n;
+    if (pair_env && !t.sk && m_tiles % 2 == 0 && (pair_env == 2 || items >= sms / 2)) t.pair = 1;
+  }
+  const int w_rows = t.pair ? bn / 2 : bn;   // W rows per CTA and stage
+  q.w_stages = ring_budget / (w_rows * 128);
   if (q.w_stages > TC_MAX_STAGES) q.w_stages = TC_MAX_STAGES;
 
   CUtensorMap ma0, ma1, mw, mwlo, mx0, mx1;
@@ -629,17 +675,24 @@ int conv2d_nf(const FridoConvParams* p, cudaStream_t s) {
     return set_error(FRIDO_E_ARG, "conv2d_nf: cuTensorMapEncodeTiled(x0) failed");
   if (p->x1 && !make_map4_box(&mx1, p->x1, p->cx1, p->Wout, p->Hout, p->B, p->x1_sx, p->x1_sy, p->x1_sb, t.TW, t.TH, t.TB))
     return set_error(FRIDO_E_ARG, "conv2d_nf: cuTensorMapEncodeTiled(x1) failed");
-  if (!make_map3(&mw, p->w, Ktot, p->Cout, 1, w_ld, 0, bn, true) || !make_map3(&mwlo, p->w_lo, Ktot, p->Cout, 1, w_ld, 0, bn, true))
+  if (!make_map3(&mw, p->w, Ktot, p->Cout, 1, w_ld, 0, w_rows, true) || !make_map3(&mwlo, p->w_lo, Ktot, p->Cout, 1, w_ld, 0, w_rows, true))
     return set_error(FRIDO_E_ARG, "conv2d_nf: cuTensorMapEncodeTiled(w) failed");
 
   using KernelFn = void (*)(CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, TcParams, NfParams);
-  static const KernelFn kernels[EPI_COUNT] = {conv_nf_kernel<EPI_GENERIC>, conv_nf_kernel<EPI_BIAS>, conv_nf_kernel<EPI_BIAS_RES>,
-                                              conv_nf_kernel<EPI_BIAS_RV_CS>, conv_nf_kernel<EPI_BIAS_RES_CS>, conv_nf_kernel<EPI_GENERIC>,
-                                              conv_nf_kernel<EPI_BIAS_CS>, conv_nf_kernel<EPI_BIAS_PAIR>};
+  // [0..7]: single-CTA kernels, [8..15]: CTA-pair kernels (a kernel that contains cta_group::2 / cluster-barrier instructions
+  // cannot be launched without a cluster: "cluster misconfiguration")
+  static const KernelFn kernels_all[2 * EPI_COUNT] = {
+      conv_nf_kernel<EPI_GENERIC, false>, conv_nf_kernel<EPI_BIAS, false>, conv_nf_kernel<EPI_BIAS_RES, false>,
+      conv_nf_kernel<EPI_BIAS_RV_CS, false>, conv_nf_kernel<EPI_BIAS_RES_CS, false>, conv_nf_kernel<EPI_GENERIC, false>,
+      conv_nf_kernel<EPI_BIAS_CS, false>, conv_nf_kernel<EPI_BIAS_PAIR, false>,
+      conv_nf_kernel<EPI_GENERIC, true>, conv_nf_kernel<EPI_BIAS, true>, conv_nf_kernel<EPI_BIAS_RES, true>,
+      conv_nf_kernel<EPI_BIAS_RV_CS, true>, conv_nf_kernel<EPI_BIAS_RES_CS, true>, conv_nf_kernel<EPI_GENERIC, true>,
+      conv_nf_kernel<EPI_BIAS_CS, true>, conv_nf_kernel<EPI_BIAS_PAIR, true>};
+  const KernelFn* kernels = kernels_all + (t.pair ? EPI_COUNT : 0);
   static bool attr[64] = {};
   if (dev >= 0 && dev < 64 && !attr[dev]) {  // the opt-in is per device
-    for (int i = 0; i < EPI_COUNT; ++i)
-      if (cudaFuncSetAttribute(kernels[i], cudaFuncAttributeMaxDynamicSharedMemorySize, NF_SMEM_BYTES) != cudaSuccess)
+    for (int i = 0; i < 2 * EPI_COUNT; ++i)
+      if (cudaFuncSetAttribute(kernels_all[i], cudaFuncAttributeMaxDynamicSharedMemorySize, NF_SMEM_BYTES) != cudaSuccess)
         return set_error(FRIDO_E_LAUNCH, "conv2d_nf: cannot opt in to dynamic shared memory");
     attr[dev] = true;
   }
@@ -659,6 +712,20 @@ int conv2d_nf(const FridoConvParams* p, cudaStream_t s) {
     }
   }
   const int total = m_tiles * t.tiles_n;
+  if (t.pair) {  // clusters of two CTAs, one (M-tile pair, N tile) item per cluster at a time
+    const int items = total / 2;
+    const int clusters = items < sms / 2 ? items : sms / 2;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * clusters); cfg.blockDim = dim3(NF_THREADS); cfg.dynamicSmemBytes = NF_SMEM_BYTES; cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    cudaLaunchKernelEx(&cfg, kernels[epi], ma0, ma1, mw, mwlo, mx0, mx1, t, q);
+    const int rc = check_launch("conv2d_nf(cta pair)");
+    g_prev_kernel = false;
+    return rc;
+  }
   const int grid = t.sk ? sk_grid : (total < sms ? total : sms);
   launch_pdl(kernels[epi], dim3(grid), dim3(NF_THREADS), NF_SMEM_BYTES, s, ma0, ma1, mw, mwlo, mx0, mx1, t, q);
   return check_launch("conv2d_nf");

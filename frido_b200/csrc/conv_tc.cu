@@ -21,7 +21,7 @@
 #include "tc_common.cuh"
 
 #ifndef FRIDO_TC_PAIR_DEFAULT
-#define FRIDO_TC_PAIR_DEFAULT 0
+#define FRIDO_TC_PAIR_DEFAULT 1
 #endif
 
 namespace frido {

@@ -297,7 +297,7 @@ class UNetPlan:
           'split' (2)  norm_act writes the engine's bf16 hi | lo operand form and the conv's halo-resident path just feeds it;
           'plain' (0)  norm_act writes fp32, the conv re-fetches and splits the tile per filter tap (csrc/conv_tc.cu).
         Default 'auto': fused where there are no SPADE maps to stream (stage 0, and models without SPADE: measured 12.56 ms
-        per step against 12.74 with only the single-N-tile sites fused and 12.85 plain), split where there are (a fused conv
+        per step against 12.74 with only the single-N-tile sites fused and 12.85 plain), plain where there are (a fused conv
         re-reads the maps per N tile and per halo: 14.4 against 13.1 ms)."""
         mode = os.environ.get("FRIDO_FUSE_NORM", "auto")
         a1 = Src.nhwc(xs[1], h, w) if len(xs) > 1 else None
@@ -313,7 +313,11 @@ class UNetPlan:
             return "split"
         spade = isinstance(norm, M.SPADE) and bool(self.c_cond)
         wide = os.environ.get("FRIDO_FUSE_NORM_WIDE", "1") == "1"   # A/B aid: 0 = fuse only single-N-tile convs (C_out <= 192)
-        return "fused" if (not spade and (wide or Cout <= 192)) else "split"
+        if not spade and (wide or Cout <= 192):
+            return "fused"
+        # SPADE sites: a separate norm_act pass streams the maps once; its conv then runs on the CTA-pair kernel of conv_tc.cu
+        # (measured 13.27 ms per stage-1 step) or, with FRIDO_SPADE_SPLIT=1, reads split operands through conv_nf.cu (13.43)
+        return "split" if os.environ.get("FRIDO_SPADE_SPLIT", "0") == "1" else "plain"
 
     def _norm_on_load(self, prog, xs, cs, h, w, norm, eps, silu, out, Cout, ksize, side=False):
         """GroupNorm(+SPADE)(+SiLU) handed to the consuming conv instead of a norm_act pass (csrc/conv_nf.cu): emits the

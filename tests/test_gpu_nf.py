@@ -29,16 +29,22 @@ def _pack(w):
     return w.permute(0, 2, 3, 1).contiguous().view(w.shape[0], -1)
 
 
-@pytest.fixture(params=["auto", "force", "off"])
+@pytest.fixture(params=["auto", "force", "off", "pair"])
 def sk_mode(request):
+    """Schedules of the engine: stream-K by cost model / whenever legal / never, and 'pair' = the CTA-pair (cta_group::2)
+    kernels whenever legal (FRIDO_NF_PAIR=2, FRIDO_TC_PAIR=2) with stream-K off."""
     import os
-    old = os.environ.get("FRIDO_SK")
-    os.environ["FRIDO_SK"] = {"auto": "1", "force": "2", "off": "0"}[request.param]
+    old = {k: os.environ.get(k) for k in ("FRIDO_SK", "FRIDO_NF_PAIR", "FRIDO_TC_PAIR")}
+    os.environ["FRIDO_SK"] = {"auto": "1", "force": "2", "off": "0", "pair": "0"}[request.param]
+    if request.param == "pair":
+        os.environ["FRIDO_NF_PAIR"] = "2"
+        os.environ["FRIDO_TC_PAIR"] = "2"
     yield request.param
-    if old is None:
-        os.environ.pop("FRIDO_SK", None)
-    else:
-        os.environ["FRIDO_SK"] = old
+    for k, v in old.items():
+        if v is None:
+            os.environ.pop(k, None)
+        else:
+            os.environ[k] = v
 
 
 CASES = [

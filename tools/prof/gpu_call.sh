@@ -1,8 +1,12 @@
 mkdir -p gpurun_out
-T=r02u
-timeout -k 5 120 python -m pytest tests/test_gpu_pair.py -x -q --timeout=40 -p no:cacheprovider > gpurun_out/${T}_pair.log 2>&1; echo "rc=$?" >> gpurun_out/${T}_pair.log
-tail -5 gpurun_out/${T}_pair.log
-if grep -q "rc=0" gpurun_out/${T}_pair.log; then
-  for pr in 0 2; do FRIDO_TC_PAIR=$pr FRIDO_SK=0 timeout 120 python tools/prof/conv_bench.py 7 8 9 4 5 >> gpurun_out/${T}_convbench.log 2>&1; done
-  cat gpurun_out/${T}_convbench.log
-fi
+T=r02z
+for st in 0 1; do
+PSTAGE=$st timeout 200 python tools/prof/perop.py > gpurun_out/${T}_perop_s$st.log 2>&1
+echo "s$st default: $(grep GRAPH gpurun_out/${T}_perop_s$st.log | cut -c1-60)"
+done
+FRIDO_SPADE_SPLIT=1 PSTAGE=1 timeout 200 python tools/prof/perop.py > gpurun_out/${T}_perop_s1_split.log 2>&1
+echo "s1 split: $(grep GRAPH gpurun_out/${T}_perop_s1_split.log | cut -c1-60)"
+FRIDO_TC_PAIR=0 PSTAGE=1 timeout 200 python tools/prof/perop.py > gpurun_out/${T}_perop_s1_nopair.log 2>&1
+echo "s1 plain nopair: $(grep GRAPH gpurun_out/${T}_perop_s1_nopair.log | cut -c1-60)"
+timeout -k 5 1200 python -m pytest tests -m gpu -x -q --timeout=300 > gpurun_out/${T}_pytest.log 2>&1; echo "rc=$?" >> gpurun_out/${T}_pytest.log
+tail -4 gpurun_out/${T}_pytest.log
