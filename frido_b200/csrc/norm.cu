@@ -134,21 +134,26 @@ __global__ void __launch_bounds__(NA_MAX_THREADS) norm_act_kernel(const FridoNor
   const int Q = C >> 2;
   const int cg = C / p.groups;
   const int b = blockIdx.y;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nw = blockDim.x >> 5;
-  for (int g = warp; g < p.groups; g += nw) {  // one warp per group: lanes stride over the group's channels
+  const int tid = threadIdx.x;
+  // group statistics: EIGHT lanes per group (all groups of the CTA in one or two rounds instead of one warp per group in
+  // sequence: the dependent load -> reduce -> sqrt chain of this prologue was ~5 us of every launch, fully exposed in the step)
+  for (int g0 = 0; g0 < p.groups; g0 += (int)(blockDim.x >> 3)) {
+    const int g = g0 + (tid >> 3), sub = tid & 7;
     double s0 = 0.0, s1 = 0.0;
-    if (p.csum0) {  // group sums from the producers' per-channel sums (the group may straddle the two sources)
-      for (int c = g * cg + lane; c < (g + 1) * cg; c += 32) {
-        const double* cs = (c < p.c0) ? p.csum0 + ((int64_t)b * p.c0 + c) * 2 : p.csum1 + ((int64_t)b * p.c1 + (c - p.c0)) * 2;
-        s0 += cs[0]; s1 += cs[1];
+    if (g < p.groups) {
+      if (p.csum0) {  // group sums from the producers' per-channel sums (the group may straddle the two sources)
+        for (int c = g * cg + sub; c < (g + 1) * cg; c += 8) {
+          const double* cs = (c < p.c0) ? p.csum0 + ((int64_t)b * p.c0 + c) * 2 : p.csum1 + ((int64_t)b * p.c1 + (c - p.c0)) * 2;
+          s0 += cs[0]; s1 += cs[1];
+        }
+      } else if (sub == 0) {
+        const double* sm = p.sums + ((int64_t)b * p.groups + g) * 2;
+        s0 = sm[0]; s1 = sm[1];
       }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) { s0 += __shfl_xor_sync(0xffffffffu, s0, o); s1 += __shfl_xor_sync(0xffffffffu, s1, o); }
-    } else {
-      const double* sm = p.sums + ((int64_t)b * p.groups + g) * 2;
-      s0 = sm[0]; s1 = sm[1];
     }
-    if (lane == 0) {
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) { s0 += __shfl_xor_sync(0xffffffffu, s0, o); s1 += __shfl_xor_sync(0xffffffffu, s1, o); }
+    if (g < p.groups && sub == 0) {
       const double cnt = (double)cg * (double)p.HW;
       const double mean = s0 / cnt;
       double var = s1 / cnt - mean * mean;
@@ -234,21 +239,25 @@ __global__ void __launch_bounds__(256) gn_finalize_kernel(const FridoGnFinalizeP
   const int C = p.c0 + p.c1;
   const int cg = C / p.groups;
   const int b = blockIdx.x;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nw = blockDim.x >> 5;
-  for (int g = warp; g < p.groups; g += nw) {
+  const int tid = threadIdx.x;
+  // eight lanes per group, all 32 groups in one round (same scheme and summation order as norm_act_kernel)
+  for (int g0 = 0; g0 < p.groups; g0 += (int)(blockDim.x >> 3)) {
+    const int g = g0 + (tid >> 3), sub = tid & 7;
     double s0 = 0.0, s1 = 0.0;
-    if (p.csum0) {
-      for (int c = g * cg + lane; c < (g + 1) * cg; c += 32) {
-        const double* cs = (c < p.c0) ? p.csum0 + ((int64_t)b * p.c0 + c) * 2 : p.csum1 + ((int64_t)b * p.c1 + (c - p.c0)) * 2;
-        s0 += cs[0]; s1 += cs[1];
+    if (g < p.groups) {
+      if (p.csum0) {
+        for (int c = g * cg + sub; c < (g + 1) * cg; c += 8) {
+          const double* cs = (c < p.c0) ? p.csum0 + ((int64_t)b * p.c0 + c) * 2 : p.csum1 + ((int64_t)b * p.c1 + (c - p.c0)) * 2;
+          s0 += cs[0]; s1 += cs[1];
+        }
+      } else if (sub == 0) {
+        const double* sm = p.sums + ((int64_t)b * p.groups + g) * 2;
+        s0 = sm[0]; s1 = sm[1];
       }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) { s0 += __shfl_xor_sync(0xffffffffu, s0, o); s1 += __shfl_xor_sync(0xffffffffu, s1, o); }
-    } else {
-      const double* sm = p.sums + ((int64_t)b * p.groups + g) * 2;
-      s0 = sm[0]; s1 = sm[1];
     }
-    if (lane == 0) {
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) { s0 += __shfl_xor_sync(0xffffffffu, s0, o); s1 += __shfl_xor_sync(0xffffffffu, s1, o); }
+    if (g < p.groups && sub == 0) {
       const double cnt = (double)cg * (double)p.HW;
       const double mean = s0 / cnt;
       double var = s1 / cnt - mean * mean;
@@ -563,7 +572,8 @@ extern "C" int frido_norm_act(const FridoNormActParams* p, void* stream) {
   if (p->groups <= 0 || p->groups > 64 || C % p->groups || (C & 3) || (p->c0 & 3))
     return set_error(FRIDO_E_ARG, "norm_act: unsupported channel count");
   if ((p->c1 > 0) != (p->a1 != nullptr)) return set_error(FRIDO_E_ARG, "norm_act: a1/c1 mismatch");
-  const int ppc = gn_chunk(p->B, p->HW);
+  int ppc = gn_chunk(p->B, p->HW);
+  if (ppc == 16 && (long long)p->B * ((p->HW + 15) / 16) < 148) ppc = 8;  // 8x8 / 4x4 levels: at least ~one CTA per SM
   dim3 grid((p->HW + ppc - 1) / ppc, p->B);
   const int Q = C >> 2;
   const int nj = (Q + 255) / 256;

@@ -1,8 +1,8 @@
 mkdir -p gpurun_out
-T=r02C
-for cfg in "1 0" "0 2" "1 1"; do set -- $cfg; echo "SK=$1 PAIR=$2" >> gpurun_out/${T}_convbench.log
-FRIDO_SK=$1 FRIDO_TC_PAIR=$2 timeout 150 python tools/prof/conv_bench.py 7 8 9 4 5 0 1 >> gpurun_out/${T}_convbench.log 2>&1; done
-cat gpurun_out/${T}_convbench.log
-for cfg in "1 0" "0 2" "1 1"; do set -- $cfg; echo "SK=$1 PAIR=$2" >> gpurun_out/${T}_linbench.log
-FRIDO_SK=$1 FRIDO_TC_PAIR=$2 LB_SEL=1,3,4,5,7,8,10 timeout 150 python tools/prof/lin_bench.py >> gpurun_out/${T}_linbench.log 2>&1; done
-cat gpurun_out/${T}_linbench.log
+T=r02E
+timeout -k 5 300 python -m pytest tests/test_gpu_kernels.py tests/test_gpu_nf.py -x -q --timeout=120 -k "norm or gn or nf or finalize" > gpurun_out/${T}_k.log 2>&1; echo "rc=$?" >> gpurun_out/${T}_k.log; tail -3 gpurun_out/${T}_k.log
+for st in 0 1; do
+PALL=1 PSTAGE=$st timeout 200 python tools/prof/perop.py > gpurun_out/${T}_perop_s$st.log 2>&1
+echo "s$st: $(grep GRAPH gpurun_out/${T}_perop_s$st.log | cut -c1-60)"; grep "^res.norm\|^st.norm\|^gn_finalize" gpurun_out/${T}_perop_s$st.log
+done
+timeout -k 5 600 python -m pytest tests/test_gpu_model.py tests/test_gpu_benched.py -x -q --timeout=300 > gpurun_out/${T}_model.log 2>&1; echo "rc=$?" >> gpurun_out/${T}_model.log; tail -3 gpurun_out/${T}_model.log
