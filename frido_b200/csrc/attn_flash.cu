@@ -20,11 +20,17 @@
 //   Output slices (DV < C) recompute S; the launcher picks the split that minimises waves x work.
 #include "tc_common.cuh"
 
+#ifndef FRIDO_FLASH_PAIR_DEFAULT
+#define FRIDO_FLASH_PAIR_DEFAULT 0
+#endif
+
 namespace frido {
 
 constexpr int FA_SLOT = 32768;
 constexpr int FA_SLOTS = 5;                          // ring depth when the 1024-B alignment pad leaves room, else one less
-constexpr int FA_P_OFF = 65536 + 2048 + 128;         // P_hi (2 K-atoms x 16 KB) | P_lo, counted back from the END of the window
+constexpr int FA_SLOT_PAIR = 24576;                  // CTA-pair kernel: a CTA holds only half of the K / V^T rows of a stage ...
+constexpr int FA_SLOTS_PAIR = 6;                     // ... so six slots fit (always: 144 KB + 66 KB)
+constexpr int FA_P_OFF = 65536 + 2048 + 256;         // P_hi (2 K-atoms x 16 KB) | P_lo, counted back from the END of the window
 constexpr int FA_SMEM_BYTES = 232448;                // everything an SM has (227 KB)
 constexpr int FA_S_COL = 384;
 constexpr int FA_SM_WARPS = 8;
@@ -39,6 +45,12 @@ struct FaParams {
   float* out; long long o_sb, o_ld;
 };
 
+// PAIR: a cluster of two CTAs (tcgen05.mma.cta_group::2) takes two adjacent query tiles of one image.  Both tiles need the
+// same K / V^T chunks, so each CTA loads HALF of a chunk's rows (64 of the 128 keys of an S stage, DN/2 of the DN channels of a
+// PV stage) and the pair instruction reads both halves: the B-operand share of the shared-memory traffic that bounds the
+// single-CTA kernel halves.  The leader CTA issues all MMAs; the peer's MMA warp only relays "my half has landed" to the leader,
+// the peer's softmax warps arrive on the leader's barriers, and the leader's commits are multicast to both CTAs.
+template <bool PAIR>
 __global__ void __launch_bounds__(FA_THREADS, 1)
 attn_flash_kernel(const __grid_constant__ CUtensorMap map_qh, const __grid_constant__ CUtensorMap map_ql,
                   const __grid_constant__ CUtensorMap map_kh, const __grid_constant__ CUtensorMap map_kl,
@@ -48,24 +60,36 @@ attn_flash_kernel(const __grid_constant__ CUtensorMap map_qh, const __grid_const
   uint8_t* smem = smem_raw + (smem_base - smem_u32(smem_raw));
   // layout: ring (NS x 32 KB) | P_hi | P_lo | max exchange (2 KB) | barriers (128 B).  Five slots fit when the 1024-B
   // alignment pad of the window is <= 896 B; a worse-aligned window gets four.
-  const int NS = (int)(smem_base - smem_u32(smem_raw)) + FA_SLOTS * FA_SLOT + FA_P_OFF <= FA_SMEM_BYTES ? FA_SLOTS : FA_SLOTS - 1;
+  constexpr int SLOT = PAIR ? FA_SLOT_PAIR : FA_SLOT;
+  constexpr int MAXS = PAIR ? FA_SLOTS_PAIR : FA_SLOTS;
+  const int NS = PAIR ? FA_SLOTS_PAIR
+                      : ((int)(smem_base - smem_u32(smem_raw)) + FA_SLOTS * FA_SLOT + FA_P_OFF <= FA_SMEM_BYTES ? FA_SLOTS : FA_SLOTS - 1);
   const uint32_t ring = smem_base;
-  const int p_off = NS * FA_SLOT, xch_off = p_off + 65536, bar_off = xch_off + 2048;
+  const int p_off = NS * SLOT, xch_off = p_off + 65536, bar_off = xch_off + 2048;
   const uint32_t bar_base = smem_base + bar_off;
+  // barriers: full[MAXS] | empty[MAXS] | peer_full[MAXS] (leader: the peer's half of the stage has landed) | s_full s_empty p_full
+  // p_empty o_full | tmem slot
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
-  auto empty_bar = [&](int s) { return bar_base + 8u * (FA_SLOTS + s); };
-  const uint32_t s_full = bar_base + 8u * (2 * FA_SLOTS), s_empty = s_full + 8, p_full = s_full + 16, p_empty = s_full + 24,
+  auto empty_bar = [&](int s) { return bar_base + 8u * (MAXS + s); };
+  auto peer_full = [&](int s) { return bar_base + 8u * (2 * MAXS + s); };
+  const uint32_t s_full = bar_base + 8u * (3 * MAXS), s_empty = s_full + 8, p_full = s_full + 16, p_empty = s_full + 24,
                  o_full = s_full + 32, tmem_slot = s_full + 40;
-  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem + bar_off + 8 * (2 * FA_SLOTS) + 40);
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem + bar_off + 8 * (3 * MAXS) + 40);
+  const uint32_t rank = PAIR ? (blockIdx.x & 1u) : 0u;
+  // remote (leader) copies of the barriers the softmax warps arrive on
+  auto arrive_on_leader = [&](uint32_t bar) {
+    if (PAIR) mbar_arrive_cluster(mapa_rank(bar, 0)); else mbar_arrive(bar);
+  };
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   pdl_trigger();
 
-  int x = (int)blockIdx.x;
+  int x = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
   const int ds = x % p.nsplit; x /= p.nsplit;
-  const int mt = x % p.m_tiles;
-  const int b = x / p.m_tiles;
+  const int mtn = PAIR ? (p.m_tiles >> 1) : p.m_tiles;
+  const int mt = PAIR ? 2 * (x % mtn) + (int)rank : x % mtn;
+  const int b = x / mtn;
   const int m0 = mt * 128;
   const int dv0 = ds * p.DV;
   const int kchunks = p.C / 32;
@@ -73,20 +97,26 @@ attn_flash_kernel(const __grid_constant__ CUtensorMap map_qh, const __grid_const
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&map_qh); prefetch_tmap(&map_ql); prefetch_tmap(&map_kh); prefetch_tmap(&map_kl);
     prefetch_tmap(&map_vh); prefetch_tmap(&map_vl);
-    for (int s = 0; s < FA_SLOTS; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int s = 0; s < MAXS; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); mbar_init(peer_full(s), 1); }
     mbar_init(s_full, 1);
-    mbar_init(s_empty, FA_SM_WARPS);
-    mbar_init(p_full, FA_SM_WARPS);
+    mbar_init(s_empty, (PAIR ? 2 : 1) * FA_SM_WARPS);   // leader's copy collects both CTAs' softmax warps
+    mbar_init(p_full, (PAIR ? 2 : 1) * FA_SM_WARPS);
     mbar_init(p_empty, 1);
     mbar_init(o_full, 1);
     fence_barrier_init();
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512u) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (PAIR) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512u) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512u) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   tc_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
   pdl_wait();
@@ -99,12 +129,20 @@ attn_flash_kernel(const __grid_constant__ CUtensorMap map_qh, const __grid_const
       auto load_s = [&](int j) {
         for (int c = 0; c < kchunks; ++c) {
           mbar_wait(empty_bar(stage), phase ^ 1);
-          const uint32_t sl = ring + stage * FA_SLOT;
-          mbar_expect_tx(full_bar(stage), 4u * 8192u);
-          tma_load_3d(sl, &map_qh, full_bar(stage), c * 32, m0, b);
-          tma_load_3d(sl + 8192, &map_ql, full_bar(stage), c * 32, m0, b);
-          tma_load_3d(sl + 16384, &map_kh, full_bar(stage), c * 32, j * 128, b);
-          tma_load_3d(sl + 24576, &map_kl, full_bar(stage), c * 32, j * 128, b);
+          const uint32_t sl = ring + stage * SLOT;
+          if (PAIR) {  // own Q rows, this CTA's 64 of the 128 keys
+            mbar_expect_tx(full_bar(stage), 2u * 8192u + 2u * 4096u);
+            tma_load_3d(sl, &map_qh, full_bar(stage), c * 32, m0, b);
+            tma_load_3d(sl + 8192, &map_ql, full_bar(stage), c * 32, m0, b);
+            tma_load_3d(sl + 16384, &map_kh, full_bar(stage), c * 32, j * 128 + (int)rank * 64, b);
+            tma_load_3d(sl + 20480, &map_kl, full_bar(stage), c * 32, j * 128 + (int)rank * 64, b);
+          } else {
+            mbar_expect_tx(full_bar(stage), 4u * 8192u);
+            tma_load_3d(sl, &map_qh, full_bar(stage), c * 32, m0, b);
+            tma_load_3d(sl + 8192, &map_ql, full_bar(stage), c * 32, m0, b);
+            tma_load_3d(sl + 16384, &map_kh, full_bar(stage), c * 32, j * 128, b);
+            tma_load_3d(sl + 24576, &map_kl, full_bar(stage), c * 32, j * 128, b);
+          }
           if (++stage == NS) { stage = 0; phase ^= 1; }
         }
       };
@@ -112,10 +150,17 @@ attn_flash_kernel(const __grid_constant__ CUtensorMap map_qh, const __grid_const
         for (int ks = 0; ks < 4; ++ks)
           for (int h = 0; h < p.ND; ++h) {
             mbar_wait(empty_bar(stage), phase ^ 1);
-            const uint32_t sl = ring + stage * FA_SLOT;
-            mbar_expect_tx(full_bar(stage), 2u * (uint32_t)p.DN * 64u);
-            tma_load_3d(sl, &map_vh, full_bar(stage), j * 128 + ks * 32, dv0 + h * p.DN, b);
-            tma_load_3d(sl + 16384, &map_vl, full_bar(stage), j * 128 + ks * 32, dv0 + h * p.DN, b);
+            const uint32_t sl = ring + stage * SLOT;
+            if (PAIR) {  // this CTA's DN/2 of the DN channels
+              const int hdn = p.DN >> 1;
+              mbar_expect_tx(full_bar(stage), 2u * (uint32_t)hdn * 64u);
+              tma_load_3d(sl, &map_vh, full_bar(stage), j * 128 + ks * 32, dv0 + h * p.DN + (int)rank * hdn, b);
+              tma_load_3d(sl + 8192, &map_vl, full_bar(stage), j * 128 + ks * 32, dv0 + h * p.DN + (int)rank * hdn, b);
+            } else {
+              mbar_expect_tx(full_bar(stage), 2u * (uint32_t)p.DN * 64u);
+              tma_load_3d(sl, &map_vh, full_bar(stage), j * 128 + ks * 32, dv0 + h * p.DN, b);
+              tma_load_3d(sl + 16384, &map_vl, full_bar(stage), j * 128 + ks * 32, dv0 + h * p.DN, b);
+            }
             if (++stage == NS) { stage = 0; phase ^= 1; }
           }
       };
@@ -124,60 +169,79 @@ attn_flash_kernel(const __grid_constant__ CUtensorMap map_qh, const __grid_const
       load_v(p.nkv - 1);
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
-      const uint32_t idesc_s = umma_idesc_bf16(128, 128), idesc_o = umma_idesc_bf16(128, p.DN);
+    // ===================== MMA issuer (PAIR: leader CTA only; the peer's warp relays its `full` barriers) =====================
+    if (lane == 0 && rank == 0) {
+      const uint32_t idesc_s = umma_idesc_bf16(PAIR ? 256 : 128, 128), idesc_o = umma_idesc_bf16(PAIR ? 256 : 128, p.DN);
       const uint32_t s_tmem = tmem_base + FA_S_COL;
       const uint32_t p_hi = smem_base + p_off, p_lo = p_hi + 32768;
+      constexpr uint32_t KLO = PAIR ? 20480u : 24576u;   // offset of the K_lo rows inside an S stage
+      constexpr uint32_t VLO = PAIR ? 8192u : 16384u;    // offset of the V_lo rows inside a PV stage
       int stage = 0;
       uint32_t phase = 0;
+      auto mma = [&](uint32_t d, uint64_t a, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+        if (PAIR) umma_bf16_2cta(d, a, bdesc, idesc, acc); else umma_bf16(d, a, bdesc, idesc, acc);
+      };
+      auto commit = [&](uint32_t bar) { if (PAIR) umma_commit_2cta(bar); else umma_commit(bar); };
+      auto wait_stage = [&]() {
+        mbar_wait(full_bar(stage), phase);
+        if (PAIR) mbar_wait(peer_full(stage), phase);
+        tc_fence_after();
+      };
       auto issue_s = [&](int j) {
         if (j > 0) { mbar_wait(s_empty, (uint32_t)((j - 1) & 1)); tc_fence_after(); }  // the softmax warps hold S(j-1) in registers
         for (int c = 0; c < kchunks; ++c) {
-          mbar_wait(full_bar(stage), phase);
-          tc_fence_after();
-          const uint32_t sl = ring + stage * FA_SLOT;
+          wait_stage();
+          const uint32_t sl = ring + stage * SLOT;
 #pragma unroll
           for (int k = 0; k < 2; ++k) {
             const uint64_t ah = umma_desc_sw64(sl + k * 32), al = umma_desc_sw64(sl + 8192 + k * 32);
-            const uint64_t bh = umma_desc_sw64(sl + 16384 + k * 32), bl = umma_desc_sw64(sl + 24576 + k * 32);
-            umma_bf16(s_tmem, ah, bh, idesc_s, (c | k) ? 1u : 0u);
-            umma_bf16(s_tmem, al, bh, idesc_s, 1u);
-            umma_bf16(s_tmem, ah, bl, idesc_s, 1u);
+            const uint64_t bh = umma_desc_sw64(sl + 16384 + k * 32), bl = umma_desc_sw64(sl + KLO + k * 32);
+            mma(s_tmem, ah, bh, idesc_s, (c | k) ? 1u : 0u);
+            mma(s_tmem, al, bh, idesc_s, 1u);
+            mma(s_tmem, ah, bl, idesc_s, 1u);
           }
-          umma_commit(empty_bar(stage));
+          commit(empty_bar(stage));
           if (++stage == NS) { stage = 0; phase ^= 1; }
         }
-        umma_commit(s_full);
+        commit(s_full);
       };
       auto issue_pv = [&](int j) {
         mbar_wait(p_full, (uint32_t)(j & 1));
         tc_fence_after();
         for (int ks = 0; ks < 4; ++ks)
           for (int h = 0; h < p.ND; ++h) {
-            mbar_wait(full_bar(stage), phase);
-            tc_fence_after();
-            const uint32_t sl = ring + stage * FA_SLOT;
+            wait_stage();
+            const uint32_t sl = ring + stage * SLOT;
             const uint32_t d = tmem_base + (uint32_t)(h * p.DN);
 #pragma unroll
             for (int k = 0; k < 2; ++k) {
               const int k16 = ks * 2 + k;
               const uint32_t poff = (uint32_t)((k16 >> 2) * 16384 + (k16 & 3) * 32);
               const uint64_t ph = umma_desc_sw128(p_hi + poff), pl = umma_desc_sw128(p_lo + poff);
-              const uint64_t vh = umma_desc_sw64(sl + k * 32), vl = umma_desc_sw64(sl + 16384 + k * 32);
-              umma_bf16(d, ph, vh, idesc_o, (j | k16) ? 1u : 0u);
-              umma_bf16(d, pl, vh, idesc_o, 1u);
-              umma_bf16(d, ph, vl, idesc_o, 1u);
+              const uint64_t vh = umma_desc_sw64(sl + k * 32), vl = umma_desc_sw64(sl + VLO + k * 32);
+              mma(d, ph, vh, idesc_o, (j | k16) ? 1u : 0u);
+              mma(d, pl, vh, idesc_o, 1u);
+              mma(d, ph, vl, idesc_o, 1u);
             }
-            umma_commit(empty_bar(stage));
+            commit(empty_bar(stage));
             if (++stage == NS) { stage = 0; phase ^= 1; }
           }
-        umma_commit(p_empty);  // P(j) consumed, O holds blocks 0..j
+        commit(p_empty);  // P(j) consumed, O holds blocks 0..j
       };
       issue_s(0);
       for (int j = 1; j < p.nkv; ++j) { issue_s(j); issue_pv(j - 1); }
       issue_pv(p.nkv - 1);
-      umma_commit(o_full);
+      commit(o_full);
+    } else if (PAIR && lane == 0) {
+      // peer CTA: tell the leader when this CTA's half of each stage has landed (same stage sequence as the MMA issuer)
+      int stage = 0;
+      uint32_t phase = 0;
+      const int total = p.nkv * (kchunks + 4 * p.ND);
+      for (int i = 0; i < total; ++i) {
+        mbar_wait(full_bar(stage), phase);
+        mbar_arrive_cluster(mapa_rank(peer_full(stage), 0));
+        if (++stage == NS) { stage = 0; phase ^= 1; }
+      }
     }
   } else {
     // ===================== softmax + epilogue (warps 2..9) =====================
@@ -199,7 +263,7 @@ attn_flash_kernel(const __grid_constant__ CUtensorMap map_qh, const __grid_const
       tmem_ld32(lane_base + FA_S_COL + half * 64 + 32, s1);
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(s_empty);
+      if (lane == 0) arrive_on_leader(s_empty);
       float mb = __uint_as_float(s0[0]);
 #pragma unroll
       for (int i = 1; i < 32; ++i) mb = fmaxf(mb, __uint_as_float(s0[i]));
@@ -258,7 +322,7 @@ attn_flash_kernel(const __grid_constant__ CUtensorMap map_qh, const __grid_const
       fence_proxy_async();  // generic-proxy writes of P -> visible to the tensor core
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(p_full);
+      if (lane == 0) arrive_on_leader(p_full);
     }
     // ---- epilogue: out = res + bias + O / l
     {
@@ -296,9 +360,11 @@ attn_flash_kernel(const __grid_constant__ CUtensorMap map_qh, const __grid_const
 
   tc_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    if (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    else      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
   }
 }
 
@@ -350,21 +416,38 @@ extern "C" int frido_attn_flash(const FridoFlashParams* p, void* stream) {
   t.sl2 = p->scale * 1.4426950408889634f;
   t.bias = p->bias; t.res = p->res; t.r_sb = p->r_sb; t.r_ld = p->r_ld;
   t.out = p->out; t.o_sb = p->o_sb; t.o_ld = p->o_ld;
+  // CTA-pair kernel (cta_group::2): two adjacent query tiles per cluster.  FRIDO_FLASH_PAIR = 1 (default) | 0
+  bool pair = t.m_tiles % 2 == 0 && t.DN % 16 == 0;
+  if (const char* e = getenv("FRIDO_FLASH_PAIR")) pair = pair && atoi(e) != 0;
+  else pair = pair && FRIDO_FLASH_PAIR_DEFAULT;
+  const uint32_t krows = pair ? 64u : 128u, vrows = pair ? (uint32_t)t.DN / 2 : (uint32_t)t.DN;
   CUtensorMap mqh, mql, mkh, mkl, mvh, mvl;
   if (!make_map3(&mqh, p->q_hi, p->C, p->N, p->B, p->q_ld, p->q_sb, 128, true) ||
       !make_map3(&mql, p->q_lo, p->C, p->N, p->B, p->q_ld, p->q_sb, 128, true) ||
-      !make_map3(&mkh, p->k_hi, p->C, p->N, p->B, p->k_ld, p->k_sb, 128, true) ||
-      !make_map3(&mkl, p->k_lo, p->C, p->N, p->B, p->k_ld, p->k_sb, 128, true) ||
-      !make_map3(&mvh, p->vt_hi, p->N, p->C, p->B, p->vt_ld, p->vt_sb, (uint32_t)t.DN, true) ||
-      !make_map3(&mvl, p->vt_lo, p->N, p->C, p->B, p->vt_ld, p->vt_sb, (uint32_t)t.DN, true))
+      !make_map3(&mkh, p->k_hi, p->C, p->N, p->B, p->k_ld, p->k_sb, krows, true) ||
+      !make_map3(&mkl, p->k_lo, p->C, p->N, p->B, p->k_ld, p->k_sb, krows, true) ||
+      !make_map3(&mvh, p->vt_hi, p->N, p->C, p->B, p->vt_ld, p->vt_sb, vrows, true) ||
+      !make_map3(&mvl, p->vt_lo, p->N, p->C, p->B, p->vt_ld, p->vt_sb, vrows, true))
     return set_error(FRIDO_E_ARG, "attn_flash: cuTensorMapEncodeTiled failed");
-  static bool attr[64] = {};
-  if (dev < 64 && !attr[dev]) {
-    if (cudaFuncSetAttribute(attn_flash_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM_BYTES) != cudaSuccess)
+  static DevOnce attr;
+  if (attr.need()) {
+    if (cudaFuncSetAttribute(attn_flash_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM_BYTES) != cudaSuccess ||
+        cudaFuncSetAttribute(attn_flash_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM_BYTES) != cudaSuccess)
       return set_error(FRIDO_E_LAUNCH, "attn_flash: cannot opt in to dynamic shared memory");
-    attr[dev] = true;
   }
   const int grid = p->B * t.m_tiles * t.nsplit;
-  launch_pdl(attn_flash_kernel, dim3(grid), dim3(FA_THREADS), FA_SMEM_BYTES, (cudaStream_t)stream, mqh, mql, mkh, mkl, mvh, mvl, t);
+  if (pair) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(FA_THREADS); cfg.dynamicSmemBytes = FA_SMEM_BYTES; cfg.stream = (cudaStream_t)stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    cudaLaunchKernelEx(&cfg, attn_flash_kernel<true>, mqh, mql, mkh, mkl, mvh, mvl, t);
+    const int rc = check_launch("attn_flash(cta pair)");
+    g_prev_kernel = false;
+    return rc;
+  }
+  launch_pdl(attn_flash_kernel<false>, dim3(grid), dim3(FA_THREADS), FA_SMEM_BYTES, (cudaStream_t)stream, mqh, mql, mkh, mkl, mvh, mvl, t);
   return check_launch("attn_flash");
 }

@@ -248,6 +248,17 @@ __device__ __forceinline__ void umma_bf16_ts_2cta(uint32_t tmem_d, uint32_t tmem
       "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// SS form of the pair instruction: each CTA's A rows and its half of the B rows come from its own shared memory (same offsets)
+__device__ __forceinline__ void umma_bf16_2cta(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 // completion of all prior MMAs of the pair -> one arrive on the barrier at this shared-memory offset in BOTH CTAs
 __device__ __forceinline__ void umma_commit_2cta(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),

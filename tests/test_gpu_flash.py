@@ -78,8 +78,20 @@ CASES = [
 ]
 
 
+@pytest.fixture(params=["single", "pair"])
+def pair_mode(request):
+    """single-CTA kernel / CTA-pair kernel (tcgen05.mma.cta_group::2; shapes with an odd number of query tiles fall back)."""
+    old = os.environ.get("FRIDO_FLASH_PAIR")
+    os.environ["FRIDO_FLASH_PAIR"] = "1" if request.param == "pair" else "0"
+    yield request.param
+    if old is None:
+        os.environ.pop("FRIDO_FLASH_PAIR", None)
+    else:
+        os.environ["FRIDO_FLASH_PAIR"] = old
+
+
 @pytest.mark.parametrize("case", CASES)
-def test_flash_matches_fp64(dev, case):
+def test_flash_matches_fp64(dev, case, pair_mode):
     B, N, Cd, split, layout = case
     g = torch.Generator().manual_seed(1000 + N + Cd)
     q = torch.randn(B, N, Cd, generator=g).to(dev)
@@ -103,7 +115,7 @@ def test_flash_matches_fp64(dev, case):
     assert err <= 2e-4 * ref.abs().max().item(), (case, err)
 
 
-def test_flash_rescale_path(dev):
+def test_flash_rescale_path(dev, pair_mode):
     """Scores that keep growing along the key axis: every key block raises the row maximum by far more than 2^8, so the
     accumulator rescale runs at every block; plus a no-bias / no-residual launch."""
     B, N, Cd = 1, 512, 64

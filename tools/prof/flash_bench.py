@@ -52,4 +52,4 @@ for B, N, Cd in shapes:
     b.record(stream)
     torch.cuda.synchronize()
     us = a.elapsed_time(b) / reps * 1e3
-    print(f"flash B{B} N{N} C{Cd}: {us:8.1f} us  {4 * B * N * N * Cd / us / 1e6:7.1f} TF/s algorithmic", flush=True)
+    print(f"pair={os.environ.get('FRIDO_FLASH_PAIR', '-')} flash B{B} N{N} C{Cd}: {us:8.1f} us  {4 * B * N * N * Cd / us / 1e6:7.1f} TF/s algorithmic", flush=True)
