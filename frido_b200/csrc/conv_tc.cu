@@ -366,7 +366,7 @@ int conv2d_tc(const FridoConvParams* p, cudaStream_t s) {
   }
   // Stream-K for launches that cannot fill the machine with whole tiles (8x8 / 16x16 levels, long K): compare the
   // data-parallel schedule chosen above with an even split of all (tile, k-step) iterations over the SMs, in clocks.
-  t.sk = 0; t.sk_per = 0; t.sk_ws = nullptr; t.sk_cnt = nullptr; t.pair = 0;
+  t.sk = 0; t.sk_per = 0; t.sk_ws = nullptr; t.sk_cnt = nullptr; t.pair = 0; t.dbg_w = nullptr;
   int sk_grid = 0;
   {
     const int ksteps = p->ksize * p->ksize * (Cin / TC_BK) + (p->cx0 + p->cx1) / TC_BK;
@@ -487,6 +487,7 @@ int conv2d_tc(const FridoConvParams* p, cudaStream_t s) {
     const long long items = (long long)(m_tiles / 2) * t.tiles_n;
     if (bf && pair_env && !t.sk && !p->w_sb && m_tiles % 2 == 0 && bn % 32 == 0 && (pair_env == 2 || items >= sms / 2)) {
       t.pair = 1;
+      if (getenv("FRIDO_TC_DBG_BULKW")) t.dbg_w = p->w;  // timing experiment (wrong results)
       CUtensorMap mwh, mwl;
       if (!make_map3(&mwh, p->w, Ktot, p->Cout, 1, w_ld, 0, bn / 2, true) || !make_map3(&mwl, p->w_lo, Ktot, p->Cout, 1, w_ld, 0, bn / 2, true))
         return set_error(FRIDO_E_ARG, "conv2d_tc: cuTensorMapEncodeTiled(w, pair) failed");

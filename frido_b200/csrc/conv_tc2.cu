@@ -114,8 +114,14 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_con
             if (ch < p.cx0) tma_load_4d(sa, &map_x0, full_bar(stage), ch, ox0 * p.stride, oy0 * p.stride, b0);
             else            tma_load_4d(sa, &map_x1, full_bar(stage), ch - p.cx0, ox0 * p.stride, oy0 * p.stride, b0);
           }
-          tma_load_3d(sa + off_w, &map_w, full_bar(stage), ks * TC_BK, n0, 0);
-          tma_load_3d(sa + off_wlo, &map_wlo, full_bar(stage), ks * TC_BK, n0, 0);
+          if (p.dbg_w) {  // timing experiment only: the same bytes as two contiguous bulk copies (one request each)
+            const char* src = reinterpret_cast<const char*>(p.dbg_w) + (size_t)((ks * 2 + (int)rank) & 63) * 2 * b_bytes;
+            bulk_load_1d(sa + off_w, src, b_bytes, full_bar(stage));
+            bulk_load_1d(sa + off_wlo, src + b_bytes, b_bytes, full_bar(stage));
+          } else {
+            tma_load_3d(sa + off_w, &map_w, full_bar(stage), ks * TC_BK, n0, 0);
+            tma_load_3d(sa + off_wlo, &map_wlo, full_bar(stage), ks * TC_BK, n0, 0);
+          }
           if (++stage == NS) { stage = 0; phase ^= 1; }
         }
       }

@@ -57,6 +57,7 @@ struct TcParams {
   // CTA-pair schedule (conv_tc2.cu, cta_group::2): a cluster of two CTAs takes the M tiles (2q, 2q+1) of one N tile; work items
   // are (q, n-tile) pairs, one per cluster at a time
   int pair;             // 1 = CTA-pair kernel
+  const void* dbg_w;    // profiling aid (FRIDO_TC_DBG_BULKW=1, results are WRONG): W stages come as contiguous bulk copies from here
 };
 
 // Work iterator shared by all warp roles: yields (tile, [k0, k1)) segments in the same order everywhere.
@@ -155,6 +156,12 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map
       "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst),
       "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
+}
+// 1D bulk copy global -> shared, completion on an mbarrier (size and both addresses multiples of 16 bytes)
+__device__ __forceinline__ void bulk_load_1d(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+               "r"(bytes), "r"(bar)
+               : "memory");
 }
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");

@@ -1,8 +1,8 @@
 mkdir -p gpurun_out
-T=r02F
-timeout -k 5 200 python -m pytest tests/test_gpu_flash.py -x -q --timeout=40 -p no:cacheprovider > gpurun_out/${T}_flash.log 2>&1; echo "rc=$?" >> gpurun_out/${T}_flash.log
-tail -12 gpurun_out/${T}_flash.log
-if grep -q "rc=0" gpurun_out/${T}_flash.log; then
-  for pr in 0 1; do FRIDO_FLASH_PAIR=$pr timeout 120 python tools/prof/flash_bench.py >> gpurun_out/${T}_flashbench.log 2>&1; done
-  cat gpurun_out/${T}_flashbench.log
-fi
+T=r02G
+for dbg in 0 1; do
+  if [ $dbg = 1 ]; then export FRIDO_TC_DBG_BULKW=1; fi
+  echo "bulkW=$dbg" >> gpurun_out/${T}_convbench.log
+  FRIDO_TC_PAIR=2 FRIDO_SK=0 timeout 120 python tools/prof/conv_bench.py 7 8 9 >> gpurun_out/${T}_convbench.log 2>&1
+done
+cat gpurun_out/${T}_convbench.log
