@@ -605,7 +605,7 @@ int conv2d_nf(const FridoConvParams* p, cudaStream_t s) {
     if (v >= 64 && v <= TC_BF_ACC_STRIDE && v % 64 == 0 && p->Cout % v == 0 && ring_budget / (v * 128) >= 2) bn = v;
   }
   // stream-K over operand UNITS (a chunk's 9 taps stay together: the halo tile is normalised once)
-  t.sk = 0; t.sk_per = 0; t.sk_ws = nullptr; t.sk_cnt = nullptr; t.pair = 0; t.dbg_w = nullptr;
+  t.sk = 0; t.sk_per = 0; t.sk_ws = nullptr; t.sk_cnt = nullptr; t.pair = 0; t.dbg_w = nullptr; t.dbg = 0;
   int sk_grid = 0;
   {
     const char* sk_e = getenv("FRIDO_SK");

@@ -129,8 +129,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
           mbar_wait(empty_bar(stage), phase ^ 1);
           const uint32_t sa = smem_base + stage * stage_bytes;
           const uint32_t sb = sa + off_w;
-          mbar_expect_tx(full_bar(stage), stage_tx);
-          if (ks < ksteps_main) {
+          mbar_expect_tx(full_bar(stage), (BF && (p.dbg & 1)) ? stage_tx - TC_A_BYTES : stage_tx);
+          if (BF && (p.dbg & 1)) {
+            // timing experiment: the A tile is not fetched at all
+          } else if (ks < ksteps_main) {
             const int tap = ks / kchunks;
             const int kc = ks - tap * kchunks;
             const int dy = tap / p.ksize, dx = tap - dy * p.ksize;
@@ -215,6 +217,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
         mbar_wait(full_bar(stage), phase);
         const uint8_t* srow = smem_raw + (smem_base - smem_u32(smem_raw)) + (size_t)stage * stage_bytes + r * 128;
         uint32_t hi[16], lo[16];
+        if (p.dbg & 4) {
+#pragma unroll
+          for (int c = 0; c < 16; ++c) { hi[c] = (uint32_t)(ks + c); lo[c] = (uint32_t)r; }
+        } else if (p.dbg & 2) {
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            const uint4 v = *reinterpret_cast<const uint4*>(srow + ((c ^ (r & 7)) << 4));
+            hi[2 * c] = v.x; hi[2 * c + 1] = v.y; lo[2 * c] = v.z; lo[2 * c + 1] = v.w;
+          }
+        } else
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
           const float4 v = *reinterpret_cast<const float4*>(srow + ((c ^ (r & 7)) << 4));
@@ -366,7 +378,8 @@ int conv2d_tc(const FridoConvParams* p, cudaStream_t s) {
   }
   // Stream-K for launches that cannot fill the machine with whole tiles (8x8 / 16x16 levels, long K): compare the
   // data-parallel schedule chosen above with an even split of all (tile, k-step) iterations over the SMs, in clocks.
-  t.sk = 0; t.sk_per = 0; t.sk_ws = nullptr; t.sk_cnt = nullptr; t.pair = 0; t.dbg_w = nullptr;
+  t.sk = 0; t.sk_per = 0; t.sk_ws = nullptr; t.sk_cnt = nullptr; t.pair = 0; t.dbg_w = nullptr; t.dbg = 0;
+  if (const char* e = getenv("FRIDO_TC_DBG")) t.dbg = atoi(e);
   int sk_grid = 0;
   {
     const int ksteps = p->ksize * p->ksize * (Cin / TC_BK) + (p->cx0 + p->cx1) / TC_BK;
@@ -503,6 +516,7 @@ int conv2d_tc(const FridoConvParams* p, cudaStream_t s) {
   t.stages = TC_SMEM_BUDGET / stage_bytes;
   if (t.stages > TC_MAX_STAGES) t.stages = TC_MAX_STAGES;
   if (bf && t.stages > TC_BF_MAX_STAGES) t.stages = TC_BF_MAX_STAGES;
+  if (const char* e = getenv("FRIDO_TC_STAGES")) { const int v = atoi(e); if (v >= 2 && v < t.stages) t.stages = v; }  // profiling aid
   const int total = m_tiles * t.tiles_n;
   const int grid = t.sk ? sk_grid : (total < sms ? total : sms);
   if (bf) launch_pdl(bf_kernels[epi], dim3(grid), dim3(TC_THREADS_X3), TC_SMEM_BYTES, s, ma0, ma1, mw, mwlo, mx0, mx1, t);

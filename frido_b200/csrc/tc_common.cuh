@@ -57,6 +57,8 @@ struct TcParams {
   // CTA-pair schedule (conv_tc2.cu, cta_group::2): a cluster of two CTAs takes the M tiles (2q, 2q+1) of one N tile; work items
   // are (q, n-tile) pairs, one per cluster at a time
   int pair;             // 1 = CTA-pair kernel
+  int dbg;              // profiling aid (FRIDO_TC_DBG bit mask, results are WRONG with any bit set): 1 = no A-tile TMA, 2 = splitter
+                        // does no arithmetic, 4 = splitter does not touch shared memory either
   const void* dbg_w;    // profiling aid (FRIDO_TC_DBG_BULKW=1, results are WRONG): W stages come as contiguous bulk copies from here
 };
 
