@@ -42,8 +42,14 @@ namespace frido {
 // executes ~300 instructions per 32x16 chunk at ~12 clocks each (instruction-cache misses and branch resolution on the
 // uniform feature tests) and, at 22 k clocks per tile, outlasts the 12 k-step main loop it is supposed to hide behind.
 
+// MODE 2 runs one more warp (warp 14): the W tiles get their own TMA issuer.  Measured (tools/prof/conv_bench.py, FRIDO_TC_DBG /
+// FRIDO_TC_STAGES): the k-step of this engine was 725 + 1.0 x BN clocks - a fixed cost that did not move with the MMA width, the W
+// bytes or the ring depth beyond 4, and dropped 23 % without the A-tile TMA: ONE thread issuing three TMA instructions (plus the
+// tap / channel coordinate arithmetic) per k-step set the pace of the whole pipeline.
+constexpr int TC_THREADS_BF = TC_THREADS_X3 + 32;
+
 template <int MODE, int EPI>
-__global__ void __launch_bounds__(MODE ? TC_THREADS_X3 : TC_THREADS, 1)
+__global__ void __launch_bounds__(MODE == 2 ? TC_THREADS_BF : (MODE ? TC_THREADS_X3 : TC_THREADS), 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
                const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_wlo,
                const __grid_constant__ CUtensorMap map_x0, const __grid_constant__ CUtensorMap map_x1, const TcParams p) {
@@ -90,7 +96,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
     prefetch_tmap(&map_w);
     if (BF) prefetch_tmap(&map_wlo);
     for (int s = 0; s < NS; ++s) {
-      mbar_init(full_bar(s), 1);
+      mbar_init(full_bar(s), BF ? 2 : 1);       // BF16x3: the A and the W issuer each arrive (with their byte counts)
       mbar_init(empty_bar(s), 1);
       mbar_init(split_bar(s), TC_SPLIT_WARPS);  // one arrive per splitter warp
     }
@@ -129,7 +135,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
           mbar_wait(empty_bar(stage), phase ^ 1);
           const uint32_t sa = smem_base + stage * stage_bytes;
           const uint32_t sb = sa + off_w;
-          mbar_expect_tx(full_bar(stage), (BF && (p.dbg & 1)) ? stage_tx - TC_A_BYTES : stage_tx);
+          mbar_expect_tx(full_bar(stage), BF ? ((p.dbg & 1) ? 0u : (uint32_t)TC_A_BYTES) : stage_tx);
           if (BF && (p.dbg & 1)) {
             // timing experiment: the A tile is not fetched at all
           } else if (ks < ksteps_main) {
@@ -146,8 +152,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
             else            tma_load_4d(sa, &map_x1, full_bar(stage), ch - p.cx0, ox0 * p.stride, oy0 * p.stride, b0);
           }
           // weight columns run [tap][channel] then the side input's channels: k-step ks starts at column 32 * ks
-          tma_load_3d(sb, &map_w, full_bar(stage), ks * TC_BK, n0, p.w_batched ? b0 : 0);
-          if (BF) tma_load_3d(sa + off_wlo, &map_wlo, full_bar(stage), ks * TC_BK, n0, p.w_batched ? b0 : 0);
+          if (!BF) tma_load_3d(sb, &map_w, full_bar(stage), ks * TC_BK, n0, p.w_batched ? b0 : 0);   // BF16x3: warp 14 issues W
           if (++stage == NS) { stage = 0; phase ^= 1; }
         }
       }
@@ -202,6 +207,26 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
     }
   } else if (warp < 2 + TC_EPI_WARPS) {
     tc_epilogue_role<EPI>(p, smem_raw, smem_base, bar_base, tmem_base, acc_stride, ksteps, total_tiles);
+  } else if (BF && warp == 14) {
+    // ===================== W-tile TMA issuer (BF16x3): hi and lo tiles of every k-step =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      SegIter it(p, ksteps, total_tiles);
+      int tile, k0, k1;
+      while (it.next(tile, k0, k1)) {
+        const int n0 = (tile % p.tiles_n) * p.BN;
+        const int wb = p.w_batched ? (tile / p.tiles_n / (p.tiles_x * p.tiles_y)) * p.TB : 0;
+        for (int ks = k0; ks < k1; ++ks) {
+          mbar_wait(empty_bar(stage), phase ^ 1);
+          const uint32_t sa = smem_base + stage * stage_bytes;
+          mbar_expect_tx(full_bar(stage), 2u * b_bytes);
+          tma_load_3d(sa + off_w, &map_w, full_bar(stage), ks * TC_BK, n0, wb);
+          tma_load_3d(sa + off_wlo, &map_wlo, full_bar(stage), ks * TC_BK, n0, wb);
+          if (++stage == NS) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
   } else if (BF) {
     // ===================== splitter (warps 10..13), BF16x3: fp32 A tile (smem) -> bf16 hi / lo halves in TMEM ==========
     // source: 128 rows x 128 B, SWIZZLE_128B (16-B chunk c of row r sits at chunk c ^ (r & 7)).  Thread = row (the warp
@@ -519,7 +544,7 @@ int conv2d_tc(const FridoConvParams* p, cudaStream_t s) {
   if (const char* e = getenv("FRIDO_TC_STAGES")) { const int v = atoi(e); if (v >= 2 && v < t.stages) t.stages = v; }  // profiling aid
   const int total = m_tiles * t.tiles_n;
   const int grid = t.sk ? sk_grid : (total < sms ? total : sms);
-  if (bf) launch_pdl(bf_kernels[epi], dim3(grid), dim3(TC_THREADS_X3), TC_SMEM_BYTES, s, ma0, ma1, mw, mwlo, mx0, mx1, t);
+  if (bf) launch_pdl(bf_kernels[epi], dim3(grid), dim3(TC_THREADS_BF), TC_SMEM_BYTES, s, ma0, ma1, mw, mwlo, mx0, mx1, t);
   else if (x3) launch_pdl(conv_tc_kernel<1, EPI_GENERIC>, dim3(grid), dim3(TC_THREADS_X3), TC_SMEM_BYTES, s, ma0, ma1, mw, mwlo, mx0, mx1, t);
   else launch_pdl(conv_tc_kernel<0, EPI_GENERIC>, dim3(grid), dim3(TC_THREADS), TC_SMEM_BYTES, s, ma0, ma1, mw, mwlo, mx0, mx1, t);
   return check_launch(bf ? "conv2d_tc(bf16x3)" : x3 ? "conv2d_tc(3xTF32)" : "conv2d_tc");

@@ -13,8 +13,10 @@
 
 namespace frido {
 
+constexpr int TC2_THREADS = TC_THREADS_X3 + 32;   // + warp 14: the W tiles' own TMA issuer (see conv_tc.cu)
+
 template <int EPI>
-__global__ void __launch_bounds__(TC_THREADS_X3, 1)
+__global__ void __launch_bounds__(TC2_THREADS, 1)
 conv_tc_pair_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
                     const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_wlo,
                     const __grid_constant__ CUtensorMap map_x0, const __grid_constant__ CUtensorMap map_x1, const TcParams p) {
@@ -48,7 +50,6 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_con
   const int ksteps = ksteps_main + (p.cx0 + p.cx1) / TC_BK;
   const int m_tiles = p.tiles_x * p.tiles_y * p.tiles_b;
   const int total_tiles = m_tiles * p.tiles_n;
-  const uint32_t stage_tx = TC_A_BYTES + 2u * b_bytes;
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&map_a0);
@@ -58,7 +59,7 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_con
     prefetch_tmap(&map_w);
     prefetch_tmap(&map_wlo);
     for (int s = 0; s < NS; ++s) {
-      mbar_init(full_bar(s), 1);
+      mbar_init(full_bar(s), 2);                       // the A issuer and the W issuer each arrive with their byte counts
       mbar_init(empty_bar(s), 1);                      // one multicast commit from the leader
     }
     for (int t = 0; t < TC_BF_MAX_STAGES; ++t) {
@@ -90,17 +91,15 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_con
       SegIter it(p, ksteps, total_tiles);
       int tile, k0, k1;
       while (it.next(tile, k0, k1)) {
-        const int nt = tile % p.tiles_n;
         int mt = tile / p.tiles_n;
         const int tx = mt % p.tiles_x; mt /= p.tiles_x;
         const int ty = mt % p.tiles_y;
         const int tb = mt / p.tiles_y;
         const int ox0 = tx * p.TW, oy0 = ty * p.TH, b0 = tb * p.TB;
-        const int n0 = nt * p.BN + (int)rank * HBN;
         for (int ks = k0; ks < k1; ++ks) {
           mbar_wait(empty_bar(stage), phase ^ 1);
           const uint32_t sa = smem_base + stage * stage_bytes;
-          mbar_expect_tx(full_bar(stage), stage_tx);
+          mbar_expect_tx(full_bar(stage), (uint32_t)TC_A_BYTES);
           if (ks < ksteps_main) {
             const int tap = ks / kchunks;
             const int kc = ks - tap * kchunks;
@@ -113,14 +112,6 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_con
             const int ch = (ks - ksteps_main) * TC_BK;
             if (ch < p.cx0) tma_load_4d(sa, &map_x0, full_bar(stage), ch, ox0 * p.stride, oy0 * p.stride, b0);
             else            tma_load_4d(sa, &map_x1, full_bar(stage), ch - p.cx0, ox0 * p.stride, oy0 * p.stride, b0);
-          }
-          if (p.dbg_w) {  // timing experiment only: the same bytes as two contiguous bulk copies (one request each)
-            const char* src = reinterpret_cast<const char*>(p.dbg_w) + (size_t)((ks * 2 + (int)rank) & 63) * 2 * b_bytes;
-            bulk_load_1d(sa + off_w, src, b_bytes, full_bar(stage));
-            bulk_load_1d(sa + off_wlo, src + b_bytes, b_bytes, full_bar(stage));
-          } else {
-            tma_load_3d(sa + off_w, &map_w, full_bar(stage), ks * TC_BK, n0, 0);
-            tma_load_3d(sa + off_wlo, &map_wlo, full_bar(stage), ks * TC_BK, n0, 0);
           }
           if (++stage == NS) { stage = 0; phase ^= 1; }
         }
@@ -163,6 +154,31 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_con
     }
   } else if (warp < 2 + TC_EPI_WARPS) {
     tc_epilogue_role<EPI>(p, smem_raw, smem_base, bar_base, tmem_base, acc_stride, ksteps, total_tiles);
+  } else if (warp == 14) {
+    // ===================== W-tile TMA issuer: this CTA's half of the hi and lo tiles of every k-step =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      SegIter it(p, ksteps, total_tiles);
+      int tile, k0, k1;
+      while (it.next(tile, k0, k1)) {
+        const int n0 = (tile % p.tiles_n) * p.BN + (int)rank * HBN;
+        for (int ks = k0; ks < k1; ++ks) {
+          mbar_wait(empty_bar(stage), phase ^ 1);
+          const uint32_t sa = smem_base + stage * stage_bytes;
+          mbar_expect_tx(full_bar(stage), 2u * b_bytes);
+          if (p.dbg_w) {  // timing experiment only: the same bytes as two contiguous bulk copies (one request each)
+            const char* src = reinterpret_cast<const char*>(p.dbg_w) + (size_t)((ks * 2 + (int)rank) & 63) * 2 * b_bytes;
+            bulk_load_1d(sa + off_w, src, b_bytes, full_bar(stage));
+            bulk_load_1d(sa + off_wlo, src + b_bytes, b_bytes, full_bar(stage));
+          } else {
+            tma_load_3d(sa + off_w, &map_w, full_bar(stage), ks * TC_BK, n0, 0);
+            tma_load_3d(sa + off_wlo, &map_wlo, full_bar(stage), ks * TC_BK, n0, 0);
+          }
+          if (++stage == NS) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
   } else {
     // ===================== splitter (warps 10..13): fp32 A tile -> bf16 hi / lo halves in this CTA's tensor memory ==========
     const int r = (warp & 3) * 32 + lane;
@@ -224,7 +240,7 @@ int conv2d_tc_pair_launch(const TcParams& t, int epi, int clusters, const CUtens
         return set_error(FRIDO_E_LAUNCH, "conv2d_tc(pair): cannot opt in to dynamic shared memory");
   }
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(2 * clusters); cfg.blockDim = dim3(TC_THREADS_X3); cfg.dynamicSmemBytes = TC_SMEM_BYTES; cfg.stream = s;
+  cfg.gridDim = dim3(2 * clusters); cfg.blockDim = dim3(TC2_THREADS); cfg.dynamicSmemBytes = TC_SMEM_BYTES; cfg.stream = s;
   cudaLaunchAttribute at[1];
   at[0].id = cudaLaunchAttributeClusterDimension;
   at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
