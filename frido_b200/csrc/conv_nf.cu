@@ -38,7 +38,7 @@ constexpr int NF_THREADS = 640;                 // 5 warpgroups: control | epilo
 constexpr int NF_TSLOTS = TC_BF_MAX_STAGES;     // tensor-memory operand slots (32 columns each)
 constexpr int NF_MAX_ASLOTS = 6;
 constexpr int NF_MAX_HALO_ROWS = 208;
-constexpr int NF_BAR_EXTRA = 256;               // barrier area grows to 512 B (40 slots used)
+constexpr int NF_BAR_EXTRA = 0;                 // the shared barrier area is 512 B (46 slots used here)
 constexpr int NF_SMEM_BYTES = TC_SMEM_BYTES + NF_BAR_EXTRA;
 constexpr int NF_GB_DEPTH = 4;                  // cp.async ring of SPADE gamma / beta: three steps (36 KB per SM) in flight ahead of
                                                 // the step in use - the maps stream from HBM and the latency needs the bytes
@@ -605,7 +605,7 @@ int conv2d_nf(const FridoConvParams* p, cudaStream_t s) {
     if (v >= 64 && v <= TC_BF_ACC_STRIDE && v % 64 == 0 && p->Cout % v == 0 && ring_budget / (v * 128) >= 2) bn = v;
   }
   // stream-K over operand UNITS (a chunk's 9 taps stay together: the halo tile is normalised once)
-  t.sk = 0; t.sk_per = 0; t.sk_ws = nullptr; t.sk_cnt = nullptr; t.pair = 0; t.dbg_w = nullptr; t.dbg = 0;
+  t.sk = 0; t.sk_per = 0; t.sk_ws = nullptr; t.sk_cnt = nullptr; t.pair = 0; t.dbg_w = nullptr; t.dbg = 0; t.a_stages = 0;
   int sk_grid = 0;
   {
     const char* sk_e = getenv("FRIDO_SK");

@@ -317,6 +317,227 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
   }
 }
 
+// ----------------------------------------------------------------------------
+// BF16x3 with DECOUPLED operand rings (default for engine 3).  The stage loop of the kernel above - MMA retires -> slot free ->
+// TMA issued -> tile lands -> split -> MMA - is ~1.9 us long, and with the four stages that the tensor-memory A slots allow a
+// k-step could not go below a quarter of that (measured: 2 / 3 / 4 stages = 600 / 397 / 336 us for the same conv; MMA-bound
+// would be 0.31 us per k-step).  Here every resource has its own ring and is released by its LAST reader:
+//   raw A tiles   a_stages (6-8) x 16 KB   filled by the A issuer (warp 0), released by the splitter as soon as it has read them
+//   W tiles       stages (3-4) x 2 tiles   filled by the W issuer (warp 14), released by the MMAs' commit
+//   split A       4 tensor-memory slots    filled by the splitter, released by the MMAs' commit
+// so the long TMA latency of the A tile is covered by six to eight tiles in flight instead of four.
+// ----------------------------------------------------------------------------
+constexpr int TCB_MAX_A = 8, TCB_MAX_W = 6;
+// barrier slots (8 bytes each): a_full[8] 0.. | a_empty[8] 8.. | (18..23: accumulator / stream-K slots of the epilogue role)
+//                               | w_full[6] 24.. | w_empty[6] 30.. | split[4] 36.. | t_empty[4] 40..
+template <int EPI>
+__global__ void __launch_bounds__(TC_THREADS_BF, 1)
+conv_tc_bf_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
+                  const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_wlo,
+                  const __grid_constant__ CUtensorMap map_x0, const __grid_constant__ CUtensorMap map_x1, const TcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t b_bytes = (uint32_t)p.BN * TC_BK * 2;
+  const uint32_t w_stage_bytes = 2u * b_bytes;
+  const int NA = p.a_stages, NW = p.stages;
+  const uint32_t w_ring = smem_base + (uint32_t)NA * TC_A_BYTES;
+  const uint32_t bar_base = smem_base + TC_SMEM_BUDGET + TC_STG_BYTES + TC_CSUM_BYTES;
+  auto a_full = [&](int s) { return bar_base + 8u * s; };
+  auto a_empty = [&](int s) { return bar_base + 8u * (8 + s); };
+  auto w_full = [&](int s) { return bar_base + 8u * (24 + s); };
+  auto w_empty = [&](int s) { return bar_base + 8u * (30 + s); };
+  auto split_bar = [&](int s) { return bar_base + 8u * (36 + s); };
+  auto t_empty = [&](int s) { return bar_base + 8u * (40 + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (TC_BAR_TFULL + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (TC_BAR_TEMPTY + a); };
+  const uint32_t tmem_slot = bar_base + 8u * TC_BAR_TMEM_SLOT;
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+  // warp index as a warp-UNIFORM value (shuffle from lane 0): the role branches below are then uniform control flow and the
+  // single-thread issue loops (TMA, MMA) compile to the uniform datapath instead of per-thread registers + R2UR moves
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+  const int lane = threadIdx.x & 31;
+  pdl_trigger();
+
+  const int Cin = p.c0 + p.c1;
+  const int kchunks = Cin / TC_BK;
+  const int taps = p.ksize * p.ksize;
+  const int ksteps_main = taps * kchunks;
+  const int ksteps = ksteps_main + (p.cx0 + p.cx1) / TC_BK;
+  const int m_tiles = p.tiles_x * p.tiles_y * p.tiles_b;
+  const int total_tiles = m_tiles * p.tiles_n;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&map_a0);
+    if (p.c1) prefetch_tmap(&map_a1);
+    if (p.cx0) prefetch_tmap(&map_x0);
+    if (p.cx1) prefetch_tmap(&map_x1);
+    prefetch_tmap(&map_w);
+    prefetch_tmap(&map_wlo);
+    for (int s = 0; s < TCB_MAX_A; ++s) { mbar_init(a_full(s), 1); mbar_init(a_empty(s), TC_SPLIT_WARPS); }
+    for (int s = 0; s < TCB_MAX_W; ++s) { mbar_init(w_full(s), 1); mbar_init(w_empty(s), 1); }
+    for (int s = 0; s < TC_BF_MAX_STAGES; ++s) { mbar_init(split_bar(s), TC_SPLIT_WARPS); mbar_init(t_empty(s), 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), TC_EPI_WARPS); }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+  pdl_wait();
+
+  if (warp == 0) {
+    // ===================== A-tile TMA issuer =====================
+    if (lane == 0) {
+      int sa = 0;
+      uint32_t pha = 0;
+      SegIter it(p, ksteps, total_tiles);
+      int tile, k0, k1;
+      while (it.next(tile, k0, k1)) {
+        int mt = tile / p.tiles_n;
+        const int tx = mt % p.tiles_x; mt /= p.tiles_x;
+        const int ty = mt % p.tiles_y;
+        const int tb = mt / p.tiles_y;
+        const int ox0 = tx * p.TW, oy0 = ty * p.TH, b0 = tb * p.TB;
+        // (tap, channel chunk) of k-step ks advance incrementally: no divisions in the loop
+        int tap = k0 < ksteps_main ? k0 / kchunks : 0, kc = k0 < ksteps_main ? k0 - tap * kchunks : 0;
+        int dy = tap / p.ksize, dx = tap - dy * p.ksize;
+        for (int ks = k0; ks < k1; ++ks) {
+          mbar_wait(a_empty(sa), pha ^ 1);
+          const uint32_t dst = smem_base + (uint32_t)sa * TC_A_BYTES;
+          mbar_expect_tx(a_full(sa), (p.dbg & 1) ? 0u : (uint32_t)TC_A_BYTES);
+          if (p.dbg & 1) {
+            // timing experiment: no A tile
+          } else if (ks < ksteps_main) {
+            const int ch = kc * TC_BK;
+            const int cx = ox0 * p.stride + dx - p.pad, cy = oy0 * p.stride + dy - p.pad;
+            if (ch < p.c0) tma_load_4d(dst, &map_a0, a_full(sa), ch, cx, cy, b0);
+            else           tma_load_4d(dst, &map_a1, a_full(sa), ch - p.c0, cx, cy, b0);
+            if (++kc == kchunks) { kc = 0; ++tap; if (++dx == p.ksize) { dx = 0; ++dy; } }
+          } else {  // side input: the pixel itself (a 1x1 tap), channels of x0 then x1
+            const int ch = (ks - ksteps_main) * TC_BK;
+            if (ch < p.cx0) tma_load_4d(dst, &map_x0, a_full(sa), ch, ox0 * p.stride, oy0 * p.stride, b0);
+            else            tma_load_4d(dst, &map_x1, a_full(sa), ch - p.cx0, ox0 * p.stride, oy0 * p.stride, b0);
+          }
+          if (++sa == NA) { sa = 0; pha ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer: the whole warp runs the loop converged, one elected lane issues =====================
+    {
+      const uint32_t idesc = umma_idesc_bf16(TC_BM, p.BN);
+      // shared-memory descriptor of a W tile = constant high word | (address >> 4) in the low 14 bits
+      const uint64_t desc_hi = umma_desc_sw64(0);
+      const uint32_t w_ring4 = w_ring >> 4, wst4 = w_stage_bytes >> 4, bb4 = b_bytes >> 4;
+      int sw = 0, ts = 0, acc = 0;
+      uint32_t phw = 0, pht = 0, acc_phase = 0;
+      SegIter it(p, ksteps, total_tiles);
+      int tile, k0, k1;
+      while (it.next(tile, k0, k1)) {
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1);  // epilogue has drained this accumulator
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)acc * TC_BF_ACC_STRIDE;
+        uint32_t accum = 0;
+        for (int ks = k0; ks < k1; ++ks) {
+          mbar_wait(w_full(sw), phw);
+          mbar_wait(split_bar(ts), pht);
+          tc_fence_after();
+          const uint32_t a0 = tmem_base + (uint32_t)(TC_BF_A_COL + ts * 32);
+          const uint64_t b0 = desc_hi | (uint64_t)(w_ring4 + (uint32_t)sw * wst4);   // (all W addresses stay below 256 KB: no carry)
+          umma_bf16_ts_elect(d_tmem, a0, b0, idesc, accum);               // k16 = 0: hi hi, lo hi, hi lo
+          umma_bf16_ts_elect(d_tmem, a0 + 16, b0, idesc, 1u);
+          umma_bf16_ts_elect(d_tmem, a0, b0 + bb4, idesc, 1u);
+          umma_bf16_ts_elect(d_tmem, a0 + 8, b0 + 2, idesc, 1u);          // k16 = 1: +8 columns of A, +32 bytes inside the W rows
+          umma_bf16_ts_elect(d_tmem, a0 + 24, b0 + 2, idesc, 1u);
+          umma_bf16_ts_elect(d_tmem, a0 + 8, b0 + bb4 + 2, idesc, 1u);
+          accum = 1u;
+          umma_commit_elect(w_empty(sw));   // frees the W stage ...
+          umma_commit_elect(t_empty(ts));   // ... and the tensor-memory operand slot when these MMAs retire
+          if (++sw == NW) { sw = 0; phw ^= 1; }
+          if (++ts == TC_BF_MAX_STAGES) { ts = 0; pht ^= 1; }
+        }
+        umma_commit_elect(tfull_bar(acc));  // accumulator ready for the epilogue
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else if (warp < 2 + TC_EPI_WARPS) {
+    tc_epilogue_role<EPI>(p, smem_raw, smem_base, bar_base, tmem_base, (uint32_t)TC_BF_ACC_STRIDE, ksteps, total_tiles);
+  } else if (warp == 14) {
+    // ===================== W-tile TMA issuer: hi and lo tiles of every k-step =====================
+    if (lane == 0) {
+      int sw = 0;
+      uint32_t phw = 0;
+      SegIter it(p, ksteps, total_tiles);
+      int tile, k0, k1;
+      while (it.next(tile, k0, k1)) {
+        const int n0 = (tile % p.tiles_n) * p.BN;
+        const int wb = p.w_batched ? (tile / p.tiles_n / (p.tiles_x * p.tiles_y)) * p.TB : 0;
+        for (int ks = k0; ks < k1; ++ks) {
+          mbar_wait(w_empty(sw), phw ^ 1);
+          const uint32_t sb = w_ring + (uint32_t)sw * w_stage_bytes;
+          mbar_expect_tx(w_full(sw), w_stage_bytes);
+          tma_load_3d(sb, &map_w, w_full(sw), ks * TC_BK, n0, wb);
+          tma_load_3d(sb + b_bytes, &map_wlo, w_full(sw), ks * TC_BK, n0, wb);
+          if (++sw == NW) { sw = 0; phw ^= 1; }
+        }
+      }
+    }
+  } else {
+    // ===================== splitter (warps 10..13): fp32 A tile (shared memory) -> bf16 hi / lo halves in tensor memory ==========
+    const int r = (warp & 3) * 32 + lane;
+    const uint32_t a_lane = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)TC_BF_A_COL;
+    int sa = 0, ts = 0;
+    uint32_t pha = 0, pht = 0;
+    SegIter it(p, ksteps, total_tiles);
+    int tile, k0, k1;
+    while (it.next(tile, k0, k1)) {
+      for (int ks = k0; ks < k1; ++ks) {
+        mbar_wait(a_full(sa), pha);
+        const uint8_t* srow = smem_raw + (smem_base - smem_u32(smem_raw)) + (size_t)sa * TC_A_BYTES + r * 128;
+        uint32_t hi[16], lo[16];
+        if (p.dbg & 4) {
+#pragma unroll
+          for (int c = 0; c < 16; ++c) { hi[c] = (uint32_t)(ks + c); lo[c] = (uint32_t)r; }
+        } else
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const float4 v = *reinterpret_cast<const float4*>(srow + ((c ^ (r & 7)) << 4));
+          const uint32_t h0 = pack_bf16x2(v.x, v.y), h1 = pack_bf16x2(v.z, v.w);
+          hi[2 * c] = h0; hi[2 * c + 1] = h1;
+          lo[2 * c] = pack_bf16x2(v.x - bf16_lo_to_f32(h0), v.y - bf16_hi_to_f32(h0));
+          lo[2 * c + 1] = pack_bf16x2(v.z - bf16_lo_to_f32(h1), v.w - bf16_hi_to_f32(h1));
+        }
+        // the raw tile is in registers: hand the shared-memory slot back to the A issuer right away
+        __syncwarp();
+        if (lane == 0) mbar_arrive(a_empty(sa));
+        mbar_wait(t_empty(ts), pht ^ 1);  // the MMAs that last read this tensor-memory slot have retired
+        tc_fence_after();
+        tmem_st16(a_lane + (uint32_t)(ts * 32), hi);
+        tmem_st16(a_lane + (uint32_t)(ts * 32 + 16), lo);
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(split_bar(ts));
+        if (++sa == NA) { sa = 0; pha ^= 1; }
+        if (++ts == TC_BF_MAX_STAGES) { ts = 0; pht ^= 1; }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
+
 int conv2d_tc_pair_launch(const TcParams& t, int epi, int clusters, const CUtensorMap& ma0, const CUtensorMap& ma1,
                           const CUtensorMap& mw, const CUtensorMap& mwlo, const CUtensorMap& mx0, const CUtensorMap& mx1,
                           cudaStream_t s);
@@ -403,7 +624,7 @@ int conv2d_tc(const FridoConvParams* p, cudaStream_t s) {
   }
   // Stream-K for launches that cannot fill the machine with whole tiles (8x8 / 16x16 levels, long K): compare the
   // data-parallel schedule chosen above with an even split of all (tile, k-step) iterations over the SMs, in clocks.
-  t.sk = 0; t.sk_per = 0; t.sk_ws = nullptr; t.sk_cnt = nullptr; t.pair = 0; t.dbg_w = nullptr; t.dbg = 0;
+  t.sk = 0; t.sk_per = 0; t.sk_ws = nullptr; t.sk_cnt = nullptr; t.pair = 0; t.dbg_w = nullptr; t.dbg = 0; t.a_stages = 0;
   if (const char* e = getenv("FRIDO_TC_DBG")) t.dbg = atoi(e);
   int sk_grid = 0;
   {
@@ -489,12 +710,17 @@ int conv2d_tc(const FridoConvParams* p, cudaStream_t s) {
                                                 conv_tc_kernel<2, EPI_BIAS_RV_CS>, conv_tc_kernel<2, EPI_BIAS_RES_CS>,
                                                 conv_tc_kernel<2, EPI_BIAS_GEGLU>, conv_tc_kernel<2, EPI_BIAS_CS>,
                                                 conv_tc_kernel<2, EPI_BIAS_PAIR>};
+  static const KernelFn bfd_kernels[EPI_COUNT] = {conv_tc_bf_kernel<EPI_GENERIC>, conv_tc_bf_kernel<EPI_BIAS>, conv_tc_bf_kernel<EPI_BIAS_RES>,
+                                                 conv_tc_bf_kernel<EPI_BIAS_RV_CS>, conv_tc_bf_kernel<EPI_BIAS_RES_CS>,
+                                                 conv_tc_bf_kernel<EPI_BIAS_GEGLU>, conv_tc_bf_kernel<EPI_BIAS_CS>,
+                                                 conv_tc_bf_kernel<EPI_BIAS_PAIR>};
   static DevOnce attr;
   if (attr.need()) {
     bool ok = cudaFuncSetAttribute(conv_tc_kernel<0, EPI_GENERIC>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES) == cudaSuccess &&
               cudaFuncSetAttribute(conv_tc_kernel<1, EPI_GENERIC>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES) == cudaSuccess;
     for (int i = 0; i < EPI_COUNT && ok; ++i)
-      ok = cudaFuncSetAttribute(bf_kernels[i], cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES) == cudaSuccess;
+      ok = cudaFuncSetAttribute(bf_kernels[i], cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES) == cudaSuccess &&
+           cudaFuncSetAttribute(bfd_kernels[i], cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES) == cudaSuccess;
     if (!ok) return set_error(FRIDO_E_LAUNCH, "conv2d_tc: cannot opt in to dynamic shared memory");
   }
   // epilogue variant (BF16x3 only): the feature set of this launch, if one of the specialised kernels covers it
@@ -544,6 +770,21 @@ int conv2d_tc(const FridoConvParams* p, cudaStream_t s) {
   if (const char* e = getenv("FRIDO_TC_STAGES")) { const int v = atoi(e); if (v >= 2 && v < t.stages) t.stages = v; }  // profiling aid
   const int total = m_tiles * t.tiles_n;
   const int grid = t.sk ? sk_grid : (total < sms ? total : sms);
+  // decoupled operand rings (default; FRIDO_TC_DECOUPLE=0 = the stage-coupled kernel): W ring of 3-4 stages, raw A ring of
+  // whatever is left of the operand budget (6 tiles at BN = 192, 8 below)
+  bool decouple = bf;
+  if (const char* e = getenv("FRIDO_TC_DECOUPLE")) decouple = decouple && atoi(e) != 0;
+  if (decouple) {
+    const int wsb = 2 * bn * TC_BK * 2;
+    int nw = 4;
+    int na = (TC_SMEM_BUDGET - nw * wsb) / TC_A_BYTES;
+    if (na < 4) { nw = 3; na = (TC_SMEM_BUDGET - nw * wsb) / TC_A_BYTES; }
+    if (na > TCB_MAX_A) na = TCB_MAX_A;
+    if (const char* e = getenv("FRIDO_TC_STAGES")) { const int v = atoi(e); if (v >= 2 && v < na) na = v; }  // profiling aid
+    t.stages = nw; t.a_stages = na;
+    launch_pdl(bfd_kernels[epi], dim3(grid), dim3(TC_THREADS_BF), TC_SMEM_BYTES, s, ma0, ma1, mw, mwlo, mx0, mx1, t);
+    return check_launch("conv2d_tc(bf16x3)");
+  }
   if (bf) launch_pdl(bf_kernels[epi], dim3(grid), dim3(TC_THREADS_BF), TC_SMEM_BYTES, s, ma0, ma1, mw, mwlo, mx0, mx1, t);
   else if (x3) launch_pdl(conv_tc_kernel<1, EPI_GENERIC>, dim3(grid), dim3(TC_THREADS_X3), TC_SMEM_BYTES, s, ma0, ma1, mw, mwlo, mx0, mx1, t);
   else launch_pdl(conv_tc_kernel<0, EPI_GENERIC>, dim3(grid), dim3(TC_THREADS), TC_SMEM_BYTES, s, ma0, ma1, mw, mwlo, mx0, mx1, t);

@@ -17,7 +17,7 @@ constexpr int TC_A_BYTES = TC_BM * TC_BK * 4;       // 16 KB
 constexpr int TC_SMEM_BUDGET = 200 * 1024;          // operand ring
 constexpr int TC_STG_BYTES = 4 * 4096;              // epilogue transpose staging, 4 KB per epilogue warp
 constexpr int TC_CSUM_BYTES = 4 * 256 * 2 * 4;          // per-tile channel sum / sum-of-squares accumulators [img<=4][BN<=256][2]
-constexpr int TC_SMEM_BYTES = TC_SMEM_BUDGET + TC_STG_BYTES + TC_CSUM_BYTES + 256 /*barriers*/ + 1024 /*align slack*/;  // < 227 KB
+constexpr int TC_SMEM_BYTES = TC_SMEM_BUDGET + TC_STG_BYTES + TC_CSUM_BYTES + 512 /*barriers*/ + 1024 /*align slack*/;  // < 227 KB
 constexpr int TC_EPI_WARPS = 8;
 constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;   // TMA, MMA, 8 epilogue warps
 constexpr int TC_BF_ACC_STRIDE = 192;  // BF16x3: accumulators at TMEM columns 0 / 192 (BN <= 192) ...
@@ -36,7 +36,8 @@ struct TcParams {
   int lTW, lTH;         // log2
   int tiles_x, tiles_y, tiles_b, tiles_n;
   int BN;
-  int stages;           // depth of the smem ring
+  int stages;           // depth of the smem ring (decoupled BF16x3 kernel: of the W ring)
+  int a_stages;         // decoupled BF16x3 kernel: depth of the raw A-tile ring
   int w_batched;        // weights have a per-image leading dim
   const float* bias;
   const float* rowvec; long long rowvec_sb;
@@ -213,6 +214,30 @@ __device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, u
       "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n"
       "}\n" ::"r"(tmem_d),
       "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// Warp-converged issue: ALL lanes of the issuing warp execute these with warp-uniform operands and one elected lane issues.
+// (Inside `if (lane == 0)` the compiler cannot prove the operands uniform: every tcgen05 instruction then gets R2UR moves and an
+// ELECT / BRA.U.ANY waterfall, and the 138-instruction k-step loop of the single issuing thread - not the tensor core, not the
+// operand feed - set the pace of the BF16x3 engine at ~700 clocks per k-step.)
+__device__ __forceinline__ void umma_bf16_ts_elect(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p, e;\n"
+      "elect.sync _|e, 0xffffffff;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_elect(uint32_t bar) {
+  asm volatile(
+      "{\n"
+      ".reg .pred e;\n"
+      "elect.sync _|e, 0xffffffff;\n"
+      "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n"
+      "}\n" ::"r"(bar)
       : "memory");
 }
 __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
