@@ -81,7 +81,7 @@ attn_flash_kernel(const __grid_constant__ CUtensorMap map_qh, const __grid_const
     if (PAIR) mbar_arrive_cluster(mapa_rank(bar, 0)); else mbar_arrive(bar);
   };
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = warp_idx_uniform();   // uniform role branches (see tc_common.cuh)
   const int lane = threadIdx.x & 31;
   pdl_trigger();
 
@@ -170,7 +170,7 @@ attn_flash_kernel(const __grid_constant__ CUtensorMap map_qh, const __grid_const
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (PAIR: leader CTA only; the peer's warp relays its `full` barriers) =====================
-    if (lane == 0 && rank == 0) {
+    if (rank == 0) {  // the whole warp runs the issue loop converged, one elected lane issues
       const uint32_t idesc_s = umma_idesc_bf16(PAIR ? 256 : 128, 128), idesc_o = umma_idesc_bf16(PAIR ? 256 : 128, p.DN);
       const uint32_t s_tmem = tmem_base + FA_S_COL;
       const uint32_t p_hi = smem_base + p_off, p_lo = p_hi + 32768;
@@ -179,9 +179,9 @@ attn_flash_kernel(const __grid_constant__ CUtensorMap map_qh, const __grid_const
       int stage = 0;
       uint32_t phase = 0;
       auto mma = [&](uint32_t d, uint64_t a, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
-        if (PAIR) umma_bf16_2cta(d, a, bdesc, idesc, acc); else umma_bf16(d, a, bdesc, idesc, acc);
+        if (PAIR) umma_bf16_2cta_elect(d, a, bdesc, idesc, acc); else umma_bf16_elect(d, a, bdesc, idesc, acc);
       };
-      auto commit = [&](uint32_t bar) { if (PAIR) umma_commit_2cta(bar); else umma_commit(bar); };
+      auto commit = [&](uint32_t bar) { if (PAIR) umma_commit_2cta_elect(bar); else umma_commit_elect(bar); };
       auto wait_stage = [&]() {
         mbar_wait(full_bar(stage), phase);
         if (PAIR) mbar_wait(peer_full(stage), phase);

@@ -209,7 +209,7 @@ conv_nf_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
   const uint32_t tmem_slot = bar_base + 8u * TC_BAR_TMEM_SLOT;
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = warp_idx_uniform();   // uniform: the role branches below are uniform control flow (see tc_common.cuh)
   const int lane = threadIdx.x & 31;
   pdl_trigger();
 
@@ -252,7 +252,9 @@ conv_nf_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
   if (warp < 4) {
     // ===================== control warpgroup: 0 = weight TMA, 1 = MMA issuer, 2 = halo TMA, 3 = idle =====================
     reg_dec<NF_REGS_CTRL>();
-    if (warp == 0 && lane == 0) {
+    // (nested so that the branches on the uniform warp index stay uniform control flow: `warp == 0 && lane == 0` is not)
+    if (warp == 0) {
+      if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
       NfCursor c(p, n_units, total_tiles);
@@ -270,7 +272,9 @@ conv_nf_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
           if (++stage == q.w_stages) { stage = 0; phase ^= 1; }
         }
       }
-    } else if (warp == 2 && lane == 0) {
+      }
+    } else if (warp == 2) {
+      if (lane == 0) {
       NfCursor c(p, n_units, total_tiles);
       for (c.advance(p, q); c.valid; c.advance(p, q)) {
         mbar_wait(a_empty(c.slot), c.phase ^ 1);
@@ -290,7 +294,9 @@ conv_nf_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
           else            tma_load_4d(dst, &map_x1, a_full(c.slot), ch - p.cx0, c.ox0, c.oy0, c.b0);
         }
       }
-    } else if (warp == 1 && lane == 0 && rank == 0) {
+      }
+    } else if (warp == 1 && rank == 0) {
+      // MMA issuer: the whole warp runs the loop converged, one elected lane issues (uniform datapath, no R2UR waterfalls)
       const bool pr = PAIR;
       const uint32_t idesc = umma_idesc_bf16(pr ? 2 * TC_BM : TC_BM, p.BN);
       int stage = 0, tslot = 0, acc = 0;
@@ -316,24 +322,24 @@ conv_nf_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
               const uint32_t ah = tmem_base + (uint32_t)(TC_BF_A_COL + tslot * 32 + k * 8), al = ah + 16;
               const uint64_t bh = umma_desc_sw64(sb + k * 32), bl = umma_desc_sw64(sb + b_bytes + k * 32);
               if (pr) {
-                umma_bf16_ts_2cta(d_tmem, ah, bh, idesc, (first && k == 0) ? 0u : 1u);
-                umma_bf16_ts_2cta(d_tmem, al, bh, idesc, 1u);
-                umma_bf16_ts_2cta(d_tmem, ah, bl, idesc, 1u);
+                umma_bf16_ts_2cta_elect(d_tmem, ah, bh, idesc, (first && k == 0) ? 0u : 1u);
+                umma_bf16_ts_2cta_elect(d_tmem, al, bh, idesc, 1u);
+                umma_bf16_ts_2cta_elect(d_tmem, ah, bl, idesc, 1u);
               } else {
-                umma_bf16_ts(d_tmem, ah, bh, idesc, (first && k == 0) ? 0u : 1u);
-                umma_bf16_ts(d_tmem, al, bh, idesc, 1u);
-                umma_bf16_ts(d_tmem, ah, bl, idesc, 1u);
+                umma_bf16_ts_elect(d_tmem, ah, bh, idesc, (first && k == 0) ? 0u : 1u);
+                umma_bf16_ts_elect(d_tmem, al, bh, idesc, 1u);
+                umma_bf16_ts_elect(d_tmem, ah, bl, idesc, 1u);
               }
             }
             first = false;
             // frees the weight stage and the tensor-memory operand slot when these MMAs retire (in both CTAs of a pair)
-            if (pr) { umma_commit_2cta(w_empty(stage)); umma_commit_2cta(t_empty(tslot)); }
-            else    { umma_commit(w_empty(stage)); umma_commit(t_empty(tslot)); }
+            if (pr) { umma_commit_2cta_elect(w_empty(stage)); umma_commit_2cta_elect(t_empty(tslot)); }
+            else    { umma_commit_elect(w_empty(stage)); umma_commit_elect(t_empty(tslot)); }
             if (++stage == q.w_stages) { stage = 0; phase ^= 1; }
             if (++tslot == NF_TSLOTS) { tslot = 0; tphase ^= 1; }
           }
         }
-        if (pr) umma_commit_2cta(tfull_bar(acc)); else umma_commit(tfull_bar(acc));  // accumulator ready for the epilogue(s)
+        if (pr) umma_commit_2cta_elect(tfull_bar(acc)); else umma_commit_elect(tfull_bar(acc));  // accumulator ready for the epilogue(s)
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }

@@ -38,7 +38,7 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_con
   const int NS = p.stages;
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = warp_idx_uniform();   // uniform role branches (see tc_common.cuh)
   const int lane = threadIdx.x & 31;
   const uint32_t rank = blockIdx.x & 1;  // cluster dims (2,1,1): rank in the pair
   pdl_trigger();
@@ -119,7 +119,7 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_con
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (leader CTA only) =====================
-    if (lane == 0 && rank == 0) {
+    if (rank == 0) {  // the whole warp runs the issue loop converged, one elected lane issues
       const uint32_t idesc = umma_idesc_bf16(2 * TC_BM, p.BN);
       int stage = 0, slot = 0;
       uint32_t phase = 0, sphase = 0;
@@ -139,16 +139,16 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_con
           for (int k = 0; k < TC_BK / 16; ++k) {
             const uint32_t ah = tmem_base + (uint32_t)(TC_BF_A_COL + slot * 32 + k * 8), al = ah + 16;
             const uint64_t bh = umma_desc_sw64(sa + off_w + k * 32), bl = umma_desc_sw64(sa + off_wlo + k * 32);
-            umma_bf16_ts_2cta(d_tmem, ah, bh, idesc, ((ks - k0) | k) ? 1u : 0u);
-            umma_bf16_ts_2cta(d_tmem, al, bh, idesc, 1u);
-            umma_bf16_ts_2cta(d_tmem, ah, bl, idesc, 1u);
+            umma_bf16_ts_2cta_elect(d_tmem, ah, bh, idesc, ((ks - k0) | k) ? 1u : 0u);
+            umma_bf16_ts_2cta_elect(d_tmem, al, bh, idesc, 1u);
+            umma_bf16_ts_2cta_elect(d_tmem, ah, bl, idesc, 1u);
           }
-          umma_commit_2cta(empty_bar(stage));  // frees the shared-memory ring slot in both CTAs
-          umma_commit_2cta(tfree_bar(slot));   // ... and the tensor-memory operand slot
+          umma_commit_2cta_elect(empty_bar(stage));  // frees the shared-memory ring slot in both CTAs
+          umma_commit_2cta_elect(tfree_bar(slot));   // ... and the tensor-memory operand slot
           if (++stage == NS) { stage = 0; phase ^= 1; }
           if (++slot == TC_BF_MAX_STAGES) { slot = 0; sphase ^= 1; }
         }
-        umma_commit_2cta(tfull_bar(acc));      // accumulator halves ready for both epilogues
+        umma_commit_2cta_elect(tfull_bar(acc));      // accumulator halves ready for both epilogues
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
