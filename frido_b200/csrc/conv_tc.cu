@@ -21,7 +21,7 @@
 #include "tc_common.cuh"
 
 #ifndef FRIDO_TC_PAIR_DEFAULT
-#define FRIDO_TC_PAIR_DEFAULT 1
+#define FRIDO_TC_PAIR_DEFAULT 0
 #endif
 
 namespace frido {
@@ -391,8 +391,8 @@ conv_tc_bf_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
   pdl_wait();
 
   if (warp == 0) {
-    // ===================== A-tile TMA issuer =====================
-    if (lane == 0) {
+    // ===================== A-tile TMA issuer (whole warp converged, elected lane issues) =====================
+    {
       int sa = 0;
       uint32_t pha = 0;
       SegIter it(p, ksteps, total_tiles);
@@ -409,19 +409,19 @@ conv_tc_bf_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
         for (int ks = k0; ks < k1; ++ks) {
           mbar_wait(a_empty(sa), pha ^ 1);
           const uint32_t dst = smem_base + (uint32_t)sa * TC_A_BYTES;
-          mbar_expect_tx(a_full(sa), (p.dbg & 1) ? 0u : (uint32_t)TC_A_BYTES);
+          mbar_expect_tx_elect(a_full(sa), (p.dbg & 1) ? 0u : (uint32_t)TC_A_BYTES);
           if (p.dbg & 1) {
             // timing experiment: no A tile
           } else if (ks < ksteps_main) {
             const int ch = kc * TC_BK;
             const int cx = ox0 * p.stride + dx - p.pad, cy = oy0 * p.stride + dy - p.pad;
-            if (ch < p.c0) tma_load_4d(dst, &map_a0, a_full(sa), ch, cx, cy, b0);
-            else           tma_load_4d(dst, &map_a1, a_full(sa), ch - p.c0, cx, cy, b0);
+            if (ch < p.c0) tma_load_4d_elect(dst, &map_a0, a_full(sa), ch, cx, cy, b0);
+            else           tma_load_4d_elect(dst, &map_a1, a_full(sa), ch - p.c0, cx, cy, b0);
             if (++kc == kchunks) { kc = 0; ++tap; if (++dx == p.ksize) { dx = 0; ++dy; } }
           } else {  // side input: the pixel itself (a 1x1 tap), channels of x0 then x1
             const int ch = (ks - ksteps_main) * TC_BK;
-            if (ch < p.cx0) tma_load_4d(dst, &map_x0, a_full(sa), ch, ox0 * p.stride, oy0 * p.stride, b0);
-            else            tma_load_4d(dst, &map_x1, a_full(sa), ch - p.cx0, ox0 * p.stride, oy0 * p.stride, b0);
+            if (ch < p.cx0) tma_load_4d_elect(dst, &map_x0, a_full(sa), ch, ox0 * p.stride, oy0 * p.stride, b0);
+            else            tma_load_4d_elect(dst, &map_x1, a_full(sa), ch - p.cx0, ox0 * p.stride, oy0 * p.stride, b0);
           }
           if (++sa == NA) { sa = 0; pha ^= 1; }
         }
@@ -468,8 +468,8 @@ conv_tc_bf_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
   } else if (warp < 2 + TC_EPI_WARPS) {
     tc_epilogue_role<EPI>(p, smem_raw, smem_base, bar_base, tmem_base, (uint32_t)TC_BF_ACC_STRIDE, ksteps, total_tiles);
   } else if (warp == 14) {
-    // ===================== W-tile TMA issuer: hi and lo tiles of every k-step =====================
-    if (lane == 0) {
+    // ===================== W-tile TMA issuer: hi and lo tiles of every k-step (converged warp, elected issue) ==========
+    {
       int sw = 0;
       uint32_t phw = 0;
       SegIter it(p, ksteps, total_tiles);
@@ -480,9 +480,9 @@ conv_tc_bf_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
         for (int ks = k0; ks < k1; ++ks) {
           mbar_wait(w_empty(sw), phw ^ 1);
           const uint32_t sb = w_ring + (uint32_t)sw * w_stage_bytes;
-          mbar_expect_tx(w_full(sw), w_stage_bytes);
-          tma_load_3d(sb, &map_w, w_full(sw), ks * TC_BK, n0, wb);
-          tma_load_3d(sb + b_bytes, &map_wlo, w_full(sw), ks * TC_BK, n0, wb);
+          mbar_expect_tx_elect(w_full(sw), w_stage_bytes);
+          tma_load_3d_elect(sb, &map_w, w_full(sw), ks * TC_BK, n0, wb);
+          tma_load_3d_elect(sb + b_bytes, &map_wlo, w_full(sw), ks * TC_BK, n0, wb);
           if (++sw == NW) { sw = 0; phw ^= 1; }
         }
       }
