@@ -122,8 +122,8 @@ attn_flash_kernel(const __grid_constant__ CUtensorMap map_qh, const __grid_const
   pdl_wait();
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
+    // ===================== TMA producer (whole warp converged, elected lane issues) =====================
+    {
       int stage = 0;
       uint32_t phase = 0;
       auto load_s = [&](int j) {
@@ -131,17 +131,17 @@ attn_flash_kernel(const __grid_constant__ CUtensorMap map_qh, const __grid_const
           mbar_wait(empty_bar(stage), phase ^ 1);
           const uint32_t sl = ring + stage * SLOT;
           if (PAIR) {  // own Q rows, this CTA's 64 of the 128 keys
-            mbar_expect_tx(full_bar(stage), 2u * 8192u + 2u * 4096u);
-            tma_load_3d(sl, &map_qh, full_bar(stage), c * 32, m0, b);
-            tma_load_3d(sl + 8192, &map_ql, full_bar(stage), c * 32, m0, b);
-            tma_load_3d(sl + 16384, &map_kh, full_bar(stage), c * 32, j * 128 + (int)rank * 64, b);
-            tma_load_3d(sl + 20480, &map_kl, full_bar(stage), c * 32, j * 128 + (int)rank * 64, b);
+            mbar_expect_tx_elect(full_bar(stage), 2u * 8192u + 2u * 4096u);
+            tma_load_3d_elect(sl, &map_qh, full_bar(stage), c * 32, m0, b);
+            tma_load_3d_elect(sl + 8192, &map_ql, full_bar(stage), c * 32, m0, b);
+            tma_load_3d_elect(sl + 16384, &map_kh, full_bar(stage), c * 32, j * 128 + (int)rank * 64, b);
+            tma_load_3d_elect(sl + 20480, &map_kl, full_bar(stage), c * 32, j * 128 + (int)rank * 64, b);
           } else {
-            mbar_expect_tx(full_bar(stage), 4u * 8192u);
-            tma_load_3d(sl, &map_qh, full_bar(stage), c * 32, m0, b);
-            tma_load_3d(sl + 8192, &map_ql, full_bar(stage), c * 32, m0, b);
-            tma_load_3d(sl + 16384, &map_kh, full_bar(stage), c * 32, j * 128, b);
-            tma_load_3d(sl + 24576, &map_kl, full_bar(stage), c * 32, j * 128, b);
+            mbar_expect_tx_elect(full_bar(stage), 4u * 8192u);
+            tma_load_3d_elect(sl, &map_qh, full_bar(stage), c * 32, m0, b);
+            tma_load_3d_elect(sl + 8192, &map_ql, full_bar(stage), c * 32, m0, b);
+            tma_load_3d_elect(sl + 16384, &map_kh, full_bar(stage), c * 32, j * 128, b);
+            tma_load_3d_elect(sl + 24576, &map_kl, full_bar(stage), c * 32, j * 128, b);
           }
           if (++stage == NS) { stage = 0; phase ^= 1; }
         }
@@ -153,13 +153,13 @@ attn_flash_kernel(const __grid_constant__ CUtensorMap map_qh, const __grid_const
             const uint32_t sl = ring + stage * SLOT;
             if (PAIR) {  // this CTA's DN/2 of the DN channels
               const int hdn = p.DN >> 1;
-              mbar_expect_tx(full_bar(stage), 2u * (uint32_t)hdn * 64u);
-              tma_load_3d(sl, &map_vh, full_bar(stage), j * 128 + ks * 32, dv0 + h * p.DN + (int)rank * hdn, b);
-              tma_load_3d(sl + 8192, &map_vl, full_bar(stage), j * 128 + ks * 32, dv0 + h * p.DN + (int)rank * hdn, b);
+              mbar_expect_tx_elect(full_bar(stage), 2u * (uint32_t)hdn * 64u);
+              tma_load_3d_elect(sl, &map_vh, full_bar(stage), j * 128 + ks * 32, dv0 + h * p.DN + (int)rank * hdn, b);
+              tma_load_3d_elect(sl + 8192, &map_vl, full_bar(stage), j * 128 + ks * 32, dv0 + h * p.DN + (int)rank * hdn, b);
             } else {
-              mbar_expect_tx(full_bar(stage), 2u * (uint32_t)p.DN * 64u);
-              tma_load_3d(sl, &map_vh, full_bar(stage), j * 128 + ks * 32, dv0 + h * p.DN, b);
-              tma_load_3d(sl + 16384, &map_vl, full_bar(stage), j * 128 + ks * 32, dv0 + h * p.DN, b);
+              mbar_expect_tx_elect(full_bar(stage), 2u * (uint32_t)p.DN * 64u);
+              tma_load_3d_elect(sl, &map_vh, full_bar(stage), j * 128 + ks * 32, dv0 + h * p.DN, b);
+              tma_load_3d_elect(sl + 16384, &map_vl, full_bar(stage), j * 128 + ks * 32, dv0 + h * p.DN, b);
             }
             if (++stage == NS) { stage = 0; phase ^= 1; }
           }

@@ -254,7 +254,7 @@ conv_nf_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
     reg_dec<NF_REGS_CTRL>();
     // (nested so that the branches on the uniform warp index stay uniform control flow: `warp == 0 && lane == 0` is not)
     if (warp == 0) {
-      if (lane == 0) {
+      {  // W-tile issuer: the whole warp runs the loop converged, one elected lane issues
       int stage = 0;
       uint32_t phase = 0;
       NfCursor c(p, n_units, total_tiles);
@@ -266,9 +266,9 @@ conv_nf_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
           const int col = c.chunk ? t * q.Cn + c.idx * TC_BK : q.taps * q.Cn + c.idx * TC_BK;
           mbar_wait(w_empty(stage), phase ^ 1);
           const uint32_t sb = smem_base + w_off + stage * w_stage_bytes;
-          mbar_expect_tx(w_full(stage), w_stage_bytes);
-          tma_load_3d(sb, &map_w, w_full(stage), col, n0, 0);
-          tma_load_3d(sb + b_bytes, &map_wlo, w_full(stage), col, n0, 0);
+          mbar_expect_tx_elect(w_full(stage), w_stage_bytes);
+          tma_load_3d_elect(sb, &map_w, w_full(stage), col, n0, 0);
+          tma_load_3d_elect(sb + b_bytes, &map_wlo, w_full(stage), col, n0, 0);
           if (++stage == q.w_stages) { stage = 0; phase ^= 1; }
         }
       }
