@@ -390,7 +390,7 @@ def run_ours(args):
             "clocks": clk,
             "roofline": {"bound": "tensor", "achieved": round(achieved, 2), "peak": peaks["bf16"], "unit": "TFLOP/s",
                          "frac": round(achieved / peaks["bf16"], 4), "traffic": _traffic(),
-                         "kernel": {"bf16x3": "frido::conv_tc_kernel<2> + conv_tc_pair_kernel + conv_nf_kernel (BF16x3 tcgen05 implicit-GEMM convs)",
+                         "kernel": {"bf16x3": "frido::conv_tc_bf_kernel + conv_nf_kernel (BF16x3 tcgen05 implicit-GEMM convs)",
                                     "tc3": "frido::conv_tc_kernel<1> (3xTF32)", "tc": "frido::conv_tc_kernel<0> (TF32)"}.get(eng, "conv"),
                          "note": f"algorithmic FLOPs (1x) of the {tc_n} tcgen05 conv launches of one stage-{ns - 1} UNet step at batch {B} "
                                  f"/ their summed CUDA-event time ({tc_ms:.2f} ms of a {step_ms:.2f} ms eager step); peak = {peaks['source']} "

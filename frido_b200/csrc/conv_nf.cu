@@ -274,7 +274,7 @@ conv_nf_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
       }
       }
     } else if (warp == 2) {
-      if (lane == 0) {
+      {  // halo-tile issuer: converged warp, elected issue
       NfCursor c(p, n_units, total_tiles);
       for (c.advance(p, q); c.valid; c.advance(p, q)) {
         mbar_wait(a_empty(c.slot), c.phase ^ 1);
@@ -283,15 +283,15 @@ conv_nf_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
         if (c.chunk) {
           // the (a, b) pairs of this chunk's 32 channels for the images of the tile ride on the same barrier
           const int nimg = q.has_norm ? min(p.TB, p.B - c.b0) : 0;
-          mbar_expect_tx(a_full(c.slot), (uint32_t)q.rows_h * 128u + (uint32_t)nimg * 256u);
-          if (ch < p.c0) tma_load_4d(dst, &map_a0, a_full(c.slot), ch, c.ox0 - q.hpad, c.oy0 - q.hpad, c.b0);
-          else           tma_load_4d(dst, &map_a1, a_full(c.slot), ch - p.c0, c.ox0 - q.hpad, c.oy0 - q.hpad, c.b0);
+          mbar_expect_tx_elect(a_full(c.slot), (uint32_t)q.rows_h * 128u + (uint32_t)nimg * 256u);
+          if (ch < p.c0) tma_load_4d_elect(dst, &map_a0, a_full(c.slot), ch, c.ox0 - q.hpad, c.oy0 - q.hpad, c.b0);
+          else           tma_load_4d_elect(dst, &map_a1, a_full(c.slot), ch - p.c0, c.ox0 - q.hpad, c.oy0 - q.hpad, c.b0);
           for (int i = 0; i < nimg; ++i)
-            bulk_load(dst + q.ab_off + i * 256, q.ab + ((size_t)(c.b0 + i) * q.Cn + ch) * 2, 256u, a_full(c.slot));
+            bulk_load_1d_elect(dst + q.ab_off + i * 256, q.ab + ((size_t)(c.b0 + i) * q.Cn + ch) * 2, 256u, a_full(c.slot));
         } else {  // side input: the output pixel itself, raw
-          mbar_expect_tx(a_full(c.slot), (uint32_t)TC_A_BYTES);
-          if (ch < p.cx0) tma_load_4d(dst, &map_x0, a_full(c.slot), ch, c.ox0, c.oy0, c.b0);
-          else            tma_load_4d(dst, &map_x1, a_full(c.slot), ch - p.cx0, c.ox0, c.oy0, c.b0);
+          mbar_expect_tx_elect(a_full(c.slot), (uint32_t)TC_A_BYTES);
+          if (ch < p.cx0) tma_load_4d_elect(dst, &map_x0, a_full(c.slot), ch, c.ox0, c.oy0, c.b0);
+          else            tma_load_4d_elect(dst, &map_x1, a_full(c.slot), ch - p.cx0, c.ox0, c.oy0, c.b0);
         }
       }
       }

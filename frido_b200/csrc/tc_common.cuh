@@ -186,6 +186,13 @@ __device__ __forceinline__ void tma_load_3d_elect(uint32_t dst, const CUtensorMa
       "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
+__device__ __forceinline__ void bulk_load_1d_elect(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile(
+      "{\n.reg .pred e;\nelect.sync _|e, 0xffffffff;\n"
+      "@e cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n}\n" ::"r"(dst), "l"(src), "r"(bytes),
+      "r"(bar)
+      : "memory");
+}
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }

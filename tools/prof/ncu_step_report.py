@@ -38,8 +38,8 @@ for k, (t, fl, n) in sorted(byop.items(), key=lambda kv: -kv[1][0])[:26]:
 print("\n| op | shape | us | algorithmic TFLOP/s | DRAM MB |\n|---|---|---:|---:|---:|")
 for t, o, by in sorted(detail, key=lambda x: -x[0])[:14]:
     print(f"| {o['tag']} | {o['shape']} | {t:.1f} | {o['flops']/t/1e6:.1f} | {by/1e6:.1f} |")
-tc = [kern['conv_tc_kernel'][i] + kern['conv_tc_pair_kernel'][i] + kern['conv_nf_kernel'][i] for i in range(4)]
-json.dump({"kernel": "frido::conv_tc_kernel + conv_tc_pair_kernel + conv_nf_kernel (BF16x3 tcgen05 implicit-GEMM convs)", "bytes_per_launch": round(tc[3] / tc[2]),
+tc = [kern['conv_tc_kernel'][i] + kern['conv_tc_bf_kernel'][i] + kern['conv_tc_pair_kernel'][i] + kern['conv_nf_kernel'][i] for i in range(4)]
+json.dump({"kernel": "frido::conv_tc_bf_kernel + conv_nf_kernel (+ conv_tc_kernel / conv_tc_pair_kernel where selected): BF16x3 tcgen05 implicit-GEMM convs", "bytes_per_launch": round(tc[3] / tc[2]),
            "launches": tc[2], "share_of_step_under_ncu": round(tc[0] / tot, 4),
            "source": "ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum over one eager stage-1 UNet step (batch 16), averaged over the tcgen05 conv launches"},
           open('profiles/traffic.json', 'w'), indent=1)
