@@ -20,6 +20,9 @@
 //   tile i overlaps the main loop of tile i+1.
 #include "tc_common.cuh"
 
+#ifndef FRIDO_TC_EPI16_DEFAULT
+#define FRIDO_TC_EPI16_DEFAULT 0
+#endif
 #ifndef FRIDO_TC_PAIR_DEFAULT
 #define FRIDO_TC_PAIR_DEFAULT 0
 #endif
@@ -330,8 +333,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
 constexpr int TCB_MAX_A = 8, TCB_MAX_W = 6;
 // barrier slots (8 bytes each): a_full[8] 0.. | a_empty[8] 8.. | (18..23: accumulator / stream-K slots of the epilogue role)
 //                               | w_full[6] 24.. | w_empty[6] 30.. | split[4] 36.. | t_empty[4] 40..
-template <int EPI>
-__global__ void __launch_bounds__(TC_THREADS_BF, 1)
+// NE = 8: warps 0 A issuer | 1 MMA | 2-9 epilogue | 10-13 splitter | 14 W issuer (480 threads)
+// NE = 16 (short-K launches, whose pace the epilogue sets): 0 A issuer | 1 MMA | 2 W issuer | 3 idle | 4-19 epilogue | 20-23
+//          splitter (768 threads, 80 registers each; 16 KB of the operand budget become staging tiles of the extra warps)
+template <int EPI, int NE>
+__global__ void __launch_bounds__(NE == 16 ? 768 : TC_THREADS_BF, 1)
 conv_tc_bf_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
                   const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_wlo,
                   const __grid_constant__ CUtensorMap map_x0, const __grid_constant__ CUtensorMap map_x1, const TcParams p) {
@@ -356,6 +362,7 @@ conv_tc_bf_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
   // warp index as a warp-UNIFORM value (shuffle from lane 0): the role branches below are then uniform control flow and the
   // single-thread issue loops (TMA, MMA) compile to the uniform datapath instead of per-thread registers + R2UR moves
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+  constexpr int EW0 = NE == 16 ? 4 : 2, W_ISSUER = NE == 16 ? 2 : 14;
   const int lane = threadIdx.x & 31;
   pdl_trigger();
 
@@ -377,7 +384,7 @@ conv_tc_bf_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
     for (int s = 0; s < TCB_MAX_A; ++s) { mbar_init(a_full(s), 1); mbar_init(a_empty(s), TC_SPLIT_WARPS); }
     for (int s = 0; s < TCB_MAX_W; ++s) { mbar_init(w_full(s), 1); mbar_init(w_empty(s), 1); }
     for (int s = 0; s < TC_BF_MAX_STAGES; ++s) { mbar_init(split_bar(s), TC_SPLIT_WARPS); mbar_init(t_empty(s), 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), TC_EPI_WARPS); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), NE); }
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -465,9 +472,9 @@ conv_tc_bf_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
-  } else if (warp < 2 + TC_EPI_WARPS) {
-    tc_epilogue_role<EPI>(p, smem_raw, smem_base, bar_base, tmem_base, (uint32_t)TC_BF_ACC_STRIDE, ksteps, total_tiles);
-  } else if (warp == 14) {
+  } else if (warp >= EW0 && warp < EW0 + NE) {
+    tc_epilogue_role<EPI, EW0, NE>(p, smem_raw, smem_base, bar_base, tmem_base, (uint32_t)TC_BF_ACC_STRIDE, ksteps, total_tiles);
+  } else if (warp == W_ISSUER) {
     // ===================== W-tile TMA issuer: hi and lo tiles of every k-step (converged warp, elected issue) ==========
     {
       int sw = 0;
@@ -487,8 +494,8 @@ conv_tc_bf_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
         }
       }
     }
-  } else {
-    // ===================== splitter (warps 10..13): fp32 A tile (shared memory) -> bf16 hi / lo halves in tensor memory ==========
+  } else if (warp >= EW0 + NE) {
+    // ===================== splitter (4 warps): fp32 A tile (shared memory) -> bf16 hi / lo halves in tensor memory ==========
     const int r = (warp & 3) * 32 + lane;
     const uint32_t a_lane = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)TC_BF_A_COL;
     int sa = 0, ts = 0;
@@ -710,17 +717,19 @@ int conv2d_tc(const FridoConvParams* p, cudaStream_t s) {
                                                 conv_tc_kernel<2, EPI_BIAS_RV_CS>, conv_tc_kernel<2, EPI_BIAS_RES_CS>,
                                                 conv_tc_kernel<2, EPI_BIAS_GEGLU>, conv_tc_kernel<2, EPI_BIAS_CS>,
                                                 conv_tc_kernel<2, EPI_BIAS_PAIR>};
-  static const KernelFn bfd_kernels[EPI_COUNT] = {conv_tc_bf_kernel<EPI_GENERIC>, conv_tc_bf_kernel<EPI_BIAS>, conv_tc_bf_kernel<EPI_BIAS_RES>,
-                                                 conv_tc_bf_kernel<EPI_BIAS_RV_CS>, conv_tc_bf_kernel<EPI_BIAS_RES_CS>,
-                                                 conv_tc_bf_kernel<EPI_BIAS_GEGLU>, conv_tc_bf_kernel<EPI_BIAS_CS>,
-                                                 conv_tc_bf_kernel<EPI_BIAS_PAIR>};
+  static const KernelFn bfd_kernels[2 * EPI_COUNT] = {
+      conv_tc_bf_kernel<EPI_GENERIC, 8>, conv_tc_bf_kernel<EPI_BIAS, 8>, conv_tc_bf_kernel<EPI_BIAS_RES, 8>, conv_tc_bf_kernel<EPI_BIAS_RV_CS, 8>,
+      conv_tc_bf_kernel<EPI_BIAS_RES_CS, 8>, conv_tc_bf_kernel<EPI_BIAS_GEGLU, 8>, conv_tc_bf_kernel<EPI_BIAS_CS, 8>, conv_tc_bf_kernel<EPI_BIAS_PAIR, 8>,
+      conv_tc_bf_kernel<EPI_GENERIC, 16>, conv_tc_bf_kernel<EPI_BIAS, 16>, conv_tc_bf_kernel<EPI_BIAS_RES, 16>, conv_tc_bf_kernel<EPI_BIAS_RV_CS, 16>,
+      conv_tc_bf_kernel<EPI_BIAS_RES_CS, 16>, conv_tc_bf_kernel<EPI_BIAS_GEGLU, 16>, conv_tc_bf_kernel<EPI_BIAS_CS, 16>, conv_tc_bf_kernel<EPI_BIAS_PAIR, 16>};
   static DevOnce attr;
   if (attr.need()) {
     bool ok = cudaFuncSetAttribute(conv_tc_kernel<0, EPI_GENERIC>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES) == cudaSuccess &&
               cudaFuncSetAttribute(conv_tc_kernel<1, EPI_GENERIC>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES) == cudaSuccess;
     for (int i = 0; i < EPI_COUNT && ok; ++i)
       ok = cudaFuncSetAttribute(bf_kernels[i], cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES) == cudaSuccess &&
-           cudaFuncSetAttribute(bfd_kernels[i], cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES) == cudaSuccess;
+           cudaFuncSetAttribute(bfd_kernels[i], cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES) == cudaSuccess &&
+           cudaFuncSetAttribute(bfd_kernels[EPI_COUNT + i], cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES) == cudaSuccess;
     if (!ok) return set_error(FRIDO_E_LAUNCH, "conv2d_tc: cannot opt in to dynamic shared memory");
   }
   // epilogue variant (BF16x3 only): the feature set of this launch, if one of the specialised kernels covers it
@@ -775,14 +784,22 @@ int conv2d_tc(const FridoConvParams* p, cudaStream_t s) {
   bool decouple = bf;
   if (const char* e = getenv("FRIDO_TC_DECOUPLE")) decouple = decouple && atoi(e) != 0;
   if (decouple) {
+    // 16 epilogue warps for short K loops (the epilogue of a 128 x BN tile outlasts a main loop of fewer than ~48 k-steps);
+    // FRIDO_TC_EPI16 = 0 never | 1 by that rule (default) | 2 always
+    const int ksteps_all = p->ksize * p->ksize * (Cin / TC_BK) + (p->cx0 + p->cx1) / TC_BK;
+    int e16 = FRIDO_TC_EPI16_DEFAULT;
+    if (const char* e = getenv("FRIDO_TC_EPI16")) e16 = atoi(e);
+    const bool wide_epi = e16 == 2 || (e16 == 1 && ksteps_all <= 48);
+    const int budget = TC_SMEM_BUDGET - (wide_epi ? 8 * 2048 : 0);
     const int wsb = 2 * bn * TC_BK * 2;
     int nw = 4;
-    int na = (TC_SMEM_BUDGET - nw * wsb) / TC_A_BYTES;
-    if (na < 4) { nw = 3; na = (TC_SMEM_BUDGET - nw * wsb) / TC_A_BYTES; }
+    int na = (budget - nw * wsb) / TC_A_BYTES;
+    if (na < 4) { nw = 3; na = (budget - nw * wsb) / TC_A_BYTES; }
     if (na > TCB_MAX_A) na = TCB_MAX_A;
     if (const char* e = getenv("FRIDO_TC_STAGES")) { const int v = atoi(e); if (v >= 2 && v < na) na = v; }  // profiling aid
     t.stages = nw; t.a_stages = na;
-    launch_pdl(bfd_kernels[epi], dim3(grid), dim3(TC_THREADS_BF), TC_SMEM_BYTES, s, ma0, ma1, mw, mwlo, mx0, mx1, t);
+    launch_pdl(bfd_kernels[(wide_epi ? EPI_COUNT : 0) + epi], dim3(grid), dim3(wide_epi ? 768 : TC_THREADS_BF), TC_SMEM_BYTES, s, ma0, ma1, mw, mwlo,
+               mx0, mx1, t);
     return check_launch("conv2d_tc(bf16x3)");
   }
   if (bf) launch_pdl(bf_kernels[epi], dim3(grid), dim3(TC_THREADS_BF), TC_SMEM_BYTES, s, ma0, ma1, mw, mwlo, mx0, mx1, t);

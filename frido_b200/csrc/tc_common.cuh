@@ -407,7 +407,9 @@ constexpr int TC_BAR_TFULL = 3 * TC_MAX_STAGES, TC_BAR_TEMPTY = 3 * TC_MAX_STAGE
 // `ksteps` is the length of a tile's K loop in the units the work iterator counts (k-steps in conv_tc.cu, operand units in
 // conv_nf.cu); the stream-K bookkeeping only needs it to be the same everywhere.
 // EW0 = index of the first of the eight epilogue warps (a multiple of 2 so that warp & 3 walks the TMEM lane quarters).
-template <int EPI, int EW0 = 2>
+// NE = number of epilogue warps (8, or 16 for the short-K variant of the decoupled kernel: warp w then handles a column QUARTER of
+// its TMEM lane quarter; the staging tiles of the extra warps grow downwards into the operand budget, which that kernel leaves free)
+template <int EPI, int EW0 = 2, int NE = TC_EPI_WARPS>
 __device__ __forceinline__ void tc_epilogue_role(const TcParams& p, uint8_t* smem_raw, uint32_t smem_base, uint32_t bar_base,
                                                  uint32_t tmem_base, uint32_t acc_stride, int ksteps, int total_tiles) {
   const int warp = threadIdx.x >> 5;
@@ -421,14 +423,14 @@ __device__ __forceinline__ void tc_epilogue_role(const TcParams& p, uint8_t* sme
   // Transposed outputs (V^T: o_sp == 1) are already coalesced across lanes and go out directly.
   const int ew = warp - EW0;
   const int q = warp & 3;            // TMEM lane quarter this warp may access
-  const int half = ew >> 2;
+  const int half = ew >> 2;            // column part of this warp: 0..NE/4-1
   const int row = q * 32 + lane;     // tile row owned by this thread (direct path)
-  float4* stg = reinterpret_cast<float4*>(smem_raw + (smem_base - smem_u32(smem_raw)) + TC_SMEM_BUDGET) + ew * 128;
+  float4* stg = reinterpret_cast<float4*>(smem_raw + (smem_base - smem_u32(smem_raw)) + TC_SMEM_BUDGET - (NE - TC_EPI_WARPS) * 2048) + ew * 128;
   float* cacc = reinterpret_cast<float*>(smem_raw + (smem_base - smem_u32(smem_raw)) + TC_SMEM_BUDGET + TC_STG_BYTES);
   const int et = threadIdx.x - 32 * EW0;   // 0..255 among the epilogue warps
   const int img_q = (q * 32) >> (p.lTW + p.lTH);  // image slot of this warp's rows inside the tile (all 32 rows share it)
   const int sub = lane >> 2, c4 = lane & 3;
-  const int hcols = p.BN >> 1;
+  const int hcols = p.BN / (NE / 4);   // columns per warp (a multiple of 16 for every tile width the launchers pick)
   const int col_lo = half * hcols;
   constexpr bool GEN = EPI == EPI_GENERIC;
   const bool geglu = GEN ? (p.act == FRIDO_ACT_GEGLU || p.act == FRIDO_ACT_GEGLU_FAST) : (EPI == EPI_BIAS_GEGLU);
@@ -480,14 +482,14 @@ __device__ __forceinline__ void tc_epilogue_role(const TcParams& p, uint8_t* sme
       c_first = (tile * ksteps) / p.sk_per;
       c_last = ((tile + 1) * ksteps - 1) / p.sk_per;
       __threadfence();
-      asm volatile("bar.sync 1, 256;" ::: "memory");
+      asm volatile("bar.sync 1, %0;" ::"n"(32 * NE) : "memory");
       if (et == 0) {
         const int old = atomicAdd(p.sk_cnt + tile, 1);
         const bool last = old == c_last - c_first;
         if (last) p.sk_cnt[tile] = 0;  // every contributor has arrived: leave the counter ready for the next launch
         *sk_flag = last ? 1u : 0u;
       }
-      asm volatile("bar.sync 1, 256;" ::: "memory");
+      asm volatile("bar.sync 1, %0;" ::"n"(32 * NE) : "memory");
       if (*sk_flag == 0u) continue;
       __threadfence();
       from_ws = true;
@@ -541,8 +543,8 @@ __device__ __forceinline__ void tc_epilogue_role(const TcParams& p, uint8_t* sme
         obase[j] = (ox < p.Wout && oy < p.Hout && b < p.B) ? (long long)b * p.o_sb + ((long long)oy * p.Wout + ox) * p.o_sp : -1;
       }
       if (has_cs) {
-        for (int i = et; i < p.TB * p.BN * 2; i += 32 * TC_EPI_WARPS) cacc[i] = 0.f;
-        asm volatile("bar.sync 1, 256;" ::: "memory");
+        for (int i = et; i < p.TB * p.BN * 2; i += 32 * NE) cacc[i] = 0.f;
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * NE) : "memory");
       }
       // the bias slice of a chunk is fetched one chunk ahead: an L2 round trip is longer than a whole chunk (ncu: the first
       // use of the bias was the epilogue's top stall)
@@ -634,8 +636,8 @@ __device__ __forceinline__ void tc_epilogue_role(const TcParams& p, uint8_t* sme
         __syncwarp();
       }
       if (has_cs) {
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-        for (int i = et; i < p.TB * p.BN; i += 32 * TC_EPI_WARPS) {
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * NE) : "memory");
+        for (int i = et; i < p.TB * p.BN; i += 32 * NE) {
           const int im = i / p.BN, col = i - im * p.BN;
           const int b = tb * p.TB + im;
           if (b < p.B) {

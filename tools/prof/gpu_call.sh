@@ -1,9 +1,9 @@
 mkdir -p gpurun_out
-T=r02T
-FRIDO_TC_PAIR=0 FRIDO_SK=0 timeout 200 ncu --set full --clock-control none --import-source on -k regex:conv_tc_bf -s 3 -c 1 -o gpurun_out/${T}_conv python tools/prof/conv_bench.py 9 > gpurun_out/${T}_ncu_conv.log 2>&1; tail -2 gpurun_out/${T}_ncu_conv.log
-timeout 200 ncu --set full --clock-control none --import-source on -k regex:conv_nf -s 4 -c 1 -o gpurun_out/${T}_nf env FRIDO_SK=0 NB_ONLY=nf python tools/prof/nf_bench.py 0 > gpurun_out/${T}_ncu_nf.log 2>&1; tail -2 gpurun_out/${T}_ncu_nf.log
-timeout 200 ncu --set full --clock-control none --import-source on -k regex:attn_flash -s 3 -c 1 -o gpurun_out/${T}_flash python tools/prof/flash_bench.py 16x1024x384 > gpurun_out/${T}_ncu_flash.log 2>&1; tail -2 gpurun_out/${T}_ncu_flash.log
-for st in 1 0; do
-PSTAGE=$st timeout 400 ncu --profile-from-start off --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none --csv --log-file gpurun_out/${T}_step_s$st.csv python tools/prof/ncu_step.py > gpurun_out/${T}_ncu_step_s$st.log 2>&1
-cp gpurun_out/step_ops.json gpurun_out/${T}_step_ops_s$st.json
-done
+T=r02V
+FRIDO_TC_EPI16=2 timeout -k 5 300 python -m pytest tests/test_gpu_tc.py -x -q --timeout=60 -p no:cacheprovider > gpurun_out/${T}_k.log 2>&1; echo "rc=$?" >> gpurun_out/${T}_k.log
+tail -3 gpurun_out/${T}_k.log
+if grep -q "rc=0" gpurun_out/${T}_k.log; then
+  for e in 0 2; do echo "== EPI16=$e" >> gpurun_out/${T}.log; FRIDO_TC_EPI16=$e LB_SEL=1,3,4,5,7,8,10,11 timeout 150 python tools/prof/lin_bench.py >> gpurun_out/${T}.log 2>&1; done
+  for e in 0 2; do echo "== conv EPI16=$e" >> gpurun_out/${T}.log; FRIDO_TC_EPI16=$e FRIDO_SK=0 timeout 100 python tools/prof/conv_bench.py 9 7 >> gpurun_out/${T}.log 2>&1; done
+  cat gpurun_out/${T}.log
+fi
