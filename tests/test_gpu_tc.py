@@ -204,3 +204,46 @@ def test_tc_rejects_unsupported_shapes(dev):
     P.conv(Src.nhwc(x, 8, 8), w, out, B=1, Hin=8, Win=8, Hout=8, Wout=8, Cout=64, ksize=3, pad=1, engine=1)
     with pytest.raises(L.FridoError):
         P.run()
+
+
+@pytest.mark.parametrize("variant", ["coupled", "epi16"])
+@pytest.mark.parametrize("case", [CASES[1], CASES[3], CASES[7]])
+def test_bf16x3_kernel_variants_bit_identical(dev, case, variant):
+    """Engine 3 has three kernels for the same launch: the default (decoupled operand rings, warp-uniform issue), the
+    stage-coupled one (FRIDO_TC_DECOUPLE=0) and the 16-epilogue-warp variant (FRIDO_TC_EPI16=2).  The K order of every output
+    element is the same in all of them: results must be bit-identical."""
+    import os
+    from frido_b200.program import Program, Src
+    B, C0, C1, Cout, H, W, k = case
+    g = torch.Generator().manual_seed(5 + Cout + H)
+    x = torch.randn(B, C0 + C1, H, W, generator=g)
+    w = torch.randn(Cout, C0 + C1, k, k, generator=g) / np.sqrt((C0 + C1) * k * k)
+    bias = torch.randn(Cout, generator=g)
+    res = torch.randn(B, Cout, H, W, generator=g)
+
+    def run(env):
+        old = {k_: os.environ.get(k_) for k_ in ("FRIDO_TC_DECOUPLE", "FRIDO_TC_EPI16", "FRIDO_SK")}
+        os.environ.update(env)
+        os.environ["FRIDO_SK"] = "0"
+        try:
+            P = Program(dev, "variants")
+            out = torch.zeros(B, H * W, Cout, device=dev)
+            P.conv(Src.nhwc(_nhwc(x).to(dev), H, W), _pack(w).to(dev), out, B=B, Hin=H, Win=W, Hout=H, Wout=W, Cout=Cout, ksize=k,
+                   pad=k // 2, bias=bias.to(dev), res=_nhwc(res).to(dev).view(B, H * W, Cout), engine=3)
+            _run(P, dev)
+            P.run()
+            torch.cuda.synchronize(dev)
+            return out.cpu()
+        finally:
+            for k_, v in old.items():
+                if v is None:
+                    os.environ.pop(k_, None)
+                else:
+                    os.environ[k_] = v
+
+    base = run({"FRIDO_TC_DECOUPLE": "1", "FRIDO_TC_EPI16": "0"})
+    other = run({"FRIDO_TC_DECOUPLE": "0"} if variant == "coupled" else {"FRIDO_TC_DECOUPLE": "1", "FRIDO_TC_EPI16": "2"})
+    ref = (F.conv2d(x.double(), w.double(), bias.double(), padding=k // 2) + res.double())
+    got = base.view(B, H, W, Cout).permute(0, 3, 1, 2).double()
+    assert (got - ref).abs().max().item() < tol3((C0 + C1) * k * k, ref.abs().max().item()) + 1e-4
+    assert torch.equal(base, other), variant
