@@ -1,6 +1,4 @@
 mkdir -p gpurun_out
-T=r02X
-for c in t2i_clip sg2i_vg l2i_512; do
-  FRIDO_BENCH_GPU_EAGER=0 timeout -k 5 700 python bench.py --config $c --steps 2 --warmup 3 > gpurun_out/${T}_bench_$c.json 2> gpurun_out/${T}_bench_$c.err
-  echo "$c rc=$?"; head -c 300 gpurun_out/${T}_bench_$c.json | tail -c 200; echo
-done
+T=r02Y
+timeout -k 5 300 python -m pytest tests/test_gpu_tc.py -x -q --timeout=60 -p no:cacheprovider -k "variants" > gpurun_out/${T}_k.log 2>&1; echo "rc=$?" >> gpurun_out/${T}_k.log
+tail -3 gpurun_out/${T}_k.log
