@@ -1,4 +1,3 @@
 mkdir -p gpurun_out
-T=r02Y
-timeout -k 5 300 python -m pytest tests/test_gpu_tc.py -x -q --timeout=60 -p no:cacheprovider -k "variants" > gpurun_out/${T}_k.log 2>&1; echo "rc=$?" >> gpurun_out/${T}_k.log
-tail -3 gpurun_out/${T}_k.log
+T=r02AA
+timeout 420 python tools/prof/drift.py --steps 200 --out gpurun_out/${T}_drift.json > gpurun_out/${T}_drift.log 2>&1; head -12 gpurun_out/${T}_drift.json
