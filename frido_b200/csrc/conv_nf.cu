@@ -596,7 +596,7 @@ int conv2d_nf(const FridoConvParams* p, cudaStream_t s) {
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int ring_budget = TC_SMEM_BUDGET - q.a_slots * q.slot_bytes - (q.has_gb ? NF_GB_DEPTH * NF_GB_STEP_BYTES : 0) -
                           NF_DESC_BYTES;
-  auto stage_clk = [&](int n) { return 256 + 5 * n / 2; };  // per k-step, as conv_tc.cu's BF16x3 model
+  auto stage_clk = [&](int n) { return bf_stage_clk(n); };  // per k-step, as conv_tc.cu's BF16x3 model
   const int cands[3] = {192, 128, 64};
   int bn = 64;
   double best_cost = 1e30;

@@ -621,7 +621,7 @@ int conv2d_tc(const FridoConvParams* p, cudaStream_t s) {
     int clk = mma_per_stage[mode] * cands[i] / 2;
     if (clk < floor_clk[mode]) clk = floor_clk[mode];
     // BF16x3 is bound by shared-memory bandwidth (128 B/clk): TMA writes 16 KB + 128*BN, splitter reads 16 KB, MMAs read 192*BN
-    if (mode == 2) clk = 256 + 5 * cands[i] / 2;
+    if (mode == 2) clk = bf_stage_clk(cands[i]);
     const double cost = (double)waves * clk;
     if (cost < best_cost) { best_cost = cost; bn = cands[i]; }
   }
@@ -641,7 +641,7 @@ int conv2d_tc(const FridoConvParams* p, cudaStream_t s) {
     auto stage_clk = [&](int n) {
       int clk = mma_per_stage[mode] * n / 2;
       if (clk < floor_clk[mode]) clk = floor_clk[mode];
-      if (mode == 2) clk = 256 + 5 * n / 2;
+      if (mode == 2) clk = bf_stage_clk(n);
       return clk;
     };
     const int64_t dp_tiles = (int64_t)m_tiles * (p->Cout / bn);

@@ -710,6 +710,17 @@ inline EncodeTiledFn get_encode() {
   return fn;
 }
 
+// Clocks per 32-wide k-step of the BF16x3 kernels as a function of the tile width (fit to tools/prof/conv_bench.py sweeps):
+// FRIDO_TC_CLK="A,B" overrides intercept and slope-per-2-columns (tuning aid).
+inline int bf_stage_clk(int n) {
+  static int A = -1, B = 0;
+  if (A < 0) {
+    A = 450; B = 4;   // decoupled, uniform-issue kernels: ~520 clocks at BN = 64, ~810 at BN = 192 (was 256 + 2.5 n for the round-1 kernel)
+    if (const char* e = getenv("FRIDO_TC_CLK")) { int a = 0, b = 0; if (sscanf(e, "%d,%d", &a, &b) == 2 && a > 0 && b > 0) { A = a; B = b; } }
+  }
+  return A + B * n / 2;
+}
+
 inline int next_pow2(int v) { int p = 1; while (p < v) p <<= 1; return p; }
 
 // rank-4 fp32 map (C, W, H, B) with a {32, bw, bh, bb} box, SWIZZLE_128B
