@@ -1,6 +1,6 @@
 mkdir -p gpurun_out
-T=r02AD
-timeout -k 5 500 python -m pytest tests/test_gpu_tc.py tests/test_gpu_nf.py tests/test_gpu_benched.py -x -q --timeout=300 > gpurun_out/${T}_k.log 2>&1; echo "rc=$?" >> gpurun_out/${T}_k.log
-tail -3 gpurun_out/${T}_k.log
-timeout -k 5 300 python -m pytest tests/test_gpu_model.py -x -q --timeout=300 -k "golden or full_size or fusion" > gpurun_out/${T}_m.log 2>&1; echo "rc=$?" >> gpurun_out/${T}_m.log
-tail -3 gpurun_out/${T}_m.log
+T=r02AE
+for v in 0 1; do for st in 0 1; do
+FRIDO_FUSE_NORM_1X1=$v PSTAGE=$st timeout 200 python tools/prof/perop.py > gpurun_out/${T}_perop_s${st}_1x1_$v.log 2>&1
+echo "1x1=$v s$st: $(grep GRAPH gpurun_out/${T}_perop_s${st}_1x1_$v.log | cut -c1-60)"
+done; done
